@@ -1,0 +1,213 @@
+/*
+ * rocco_b200 -- C-ABI of the B200-native consensus-selection hot path.
+ *
+ * This is the drop-in boundary for ROCCO's three hot-path extensions:
+ *
+ *   reference interface (under /root/reference/rocco)            replaced by
+ *   -----------------------------------------------------------  -----------------------------------------
+ *   native/baseline_backend.h:11-22                               rocco_crossfit_whittaker_baseline_f64
+ *     rocco_crossfit_whittaker_baseline_f64 / _matrix_f64         rocco_crossfit_whittaker_baseline_matrix_f64
+ *   native/wls_backend.h:11-28  rocco_score_centered_wls_f64      rocco_score_centered_wls_f64
+ *   _chain_dp.c:9-213 (kernel inline in the CPython wrapper;      rocco_solve_penalized_chain_f64
+ *     no C-ABI upstream)
+ *   dp.py:89-164  calibrate_selection_penalty (62 DP passes       rocco_calibrate_selection_penalty_f64
+ *     driven from Python)
+ *   inference.py:302-379 score_loci_wls (log2p1 -> row median     rocco_score_loci_wls_f64 / _f32
+ *     -> baseline -> centered WLS, four m x n temporaries)
+ *   rocco.py:243-355 column statistics over the sample axis       rocco_column_stat_f64
+ *   rocco.py:139-191 mask -> merged intervals                     rocco_mask_to_intervals_u8
+ *
+ * The first three keep the reference's exact symbol names, argument order and status codes and
+ * take HOST pointers, so the reference's own CPython wrappers (_baseline.c, _wls.c) link against
+ * librocco_b200.so unchanged.  Everything is plain pointers and sizes; there are
+ * no torch types here.  The `*_dev` entry points take DEVICE pointers and a CUDA stream so the
+ * stages chain on the GPU without host round trips; they are what the Python host side and the
+ * benchmark use.
+ *
+ * Status codes (reference: wls_backend.c:779-788, _wls.c:133-150, _baseline.c:96-101):
+ *    0  ok        -1  allocation failure (-> MemoryError)      -2  invalid input (-> ValueError)
+ *   -3  CUDA runtime error (-> RuntimeError; text from rocco_b200_last_error())
+ *   -4  non-finite values in the input / result (-> ValueError, inference.py:45,207,289-298)
+ * There is NO CPU fallback: without a CUDA device every compute entry returns -3.
+ */
+#ifndef ROCCO_B200_H
+#define ROCCO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ library / device */
+const char *rocco_b200_version(void);
+const char *rocco_b200_last_error(void);          /* thread-local text of the last -3 */
+int rocco_b200_device_count(void);                /* 0 when no CUDA device is visible */
+int rocco_b200_set_device(int device);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+unsigned long long rocco_b200_kernel_launches(void);
+
+/* ------------------------------------------------------------------ reference-named host entries */
+int rocco_crossfit_whittaker_baseline_f64(
+    const double *y_values, size_t value_count, double penalty_lambda, double *baseline_out);
+int rocco_crossfit_whittaker_baseline_matrix_f64(
+    const double *matrix_values, size_t row_count, size_t column_count,
+    double penalty_lambda, double *baseline_out);
+int rocco_score_centered_wls_f64(
+    const double *centered_matrix, size_t sample_count, size_t locus_count,
+    double lower_bound_z, double prior_df, double min_effect, int use_min_effect,
+    int spatial_window, double precision_floor_ratio,
+    double *mean_out, double *raw_variance_out, double *prior_variance_out,
+    double *moderated_variance_out, double *standard_error_out, double *scores_out,
+    double *degrees_of_freedom_out, int *resolved_window_out);
+
+/* ------------------------------------------------------------------ chain DP + multiplier search */
+typedef struct rocco_b200_chain_result {
+    double selection_penalty;     /* lambda the mask was solved at                              */
+    double penalized_objective;   /* sum (s-lambda) z - sum c |dz|   (reference: DP best value)  */
+    double objective;             /* -sum s z + sum c |dz|           (dp.py:16-34)               */
+    long long selected_count;     /* sum z                                                       */
+    long long switch_count;       /* number of 0/1 boundaries in the mask                        */
+    long long exact_tie_bins;     /* decisions that needed the (value, fewer-count) tie-break    */
+    long long near_tie_bins;      /* decisions within 1e-9*(1+|c|) of a threshold (documented)   */
+    int dp_passes;                /* DP evaluations spent (reference: 62 per budget search)      */
+    int search_rounds;            /* batched launches spent                                      */
+    int status;                   /* 0, or -2 / -4 for this chromosome                           */
+    int reserved;
+} rocco_b200_chain_result;
+
+/* One DP solve at a fixed multiplier.  `switch_costs` has length n-1 (may be NULL when n == 1).
+ * Replaces _chain_dp.solve_penalized_chain(scores, switch_costs, selection_penalty).           */
+int rocco_solve_penalized_chain_f64(
+    const double *scores, const double *switch_costs, size_t n, double selection_penalty,
+    uint8_t *solution_out, double *penalized_objective_out, long long *selected_count_out);
+
+/* dp.py:89-164: bracket + `max_iter` dyadic bisection steps; returns the upper end and its mask. */
+int rocco_calibrate_selection_penalty_f64(
+    const double *scores, const double *switch_costs, size_t n, long long target_count,
+    int max_iter, double *selection_penalty_out, uint8_t *solution_out,
+    double *penalized_objective_out, long long *selected_count_out);
+
+/* Device-resident, many chromosomes per call.  Chromosome c owns scores[offset_c .. offset_c+n_c).
+ * mode: 0 = fixed multiplier `selection_penalty`, 1 = budget search to `target_count`.
+ * `cost_sum` is sum(switch_costs) as the caller's host library computes it (dp.py:110-111 uses
+ * numpy.sum, whose rounding defines the bracket); gamma is the constant switch cost
+ * (dp.py:37-46).  d_switch_costs, when not NULL, is a per-bin cost vector laid out like scores
+ * (entry i = cost between bins i and i+1 of that chromosome; the last entry of each is unused). */
+typedef struct rocco_b200_chain_task {
+    size_t offset;
+    size_t n;
+    double gamma;
+    double cost_sum;
+    double selection_penalty;
+    long long target_count;
+    int mode;
+    int max_iter;
+} rocco_b200_chain_task;
+
+int rocco_b200_chain_solve_batch_dev(
+    const double *d_scores, const double *d_switch_costs,
+    const rocco_b200_chain_task *tasks, int task_count,
+    uint8_t *d_masks_out,                 /* same layout as d_scores, one byte per bin */
+    rocco_b200_chain_result *results_out, /* host, task_count entries                   */
+    int levels_per_round,                 /* bisection levels evaluated per launch (1..8); 0 = default */
+    void *cuda_stream);
+
+/* Multiplier sweep: counts and objectives for `lambda_count` multipliers in one launch set
+ * (BASELINE.json config 5).  Outputs are host arrays of lambda_count entries. */
+int rocco_b200_chain_sweep_dev(
+    const double *d_scores, size_t n, double gamma,
+    const double *lambdas, int lambda_count,
+    long long *selected_count_out, double *penalized_objective_out, double *objective_out,
+    void *cuda_stream);
+
+/* ------------------------------------------------------------------ mask -> merged intervals */
+/* rocco.py:179-191 + 74-95: bins with mask > 0, the LAST bin dropped, adjacent bins merged,
+ * runs shorter than min_length_bp removed.  Emits (start, end) = (first + i*step, first + j*step).
+ * Returns the number of intervals (>= 0) or a negative status; capacity is in intervals. */
+long long rocco_mask_to_intervals_u8(
+    const uint8_t *mask, size_t n, long long first_start, long long step, long long min_length_bp,
+    long long *starts_out, long long *ends_out, size_t capacity);
+long long rocco_b200_mask_to_intervals_dev(
+    const uint8_t *d_mask, size_t n, long long first_start, long long step, long long min_length_bp,
+    long long *starts_out, long long *ends_out, size_t capacity, void *cuda_stream);
+
+/* Batched form: chromosome c occupies mask[offsets[c] .. offsets[c]+lengths[c]) (ascending, disjoint,
+ * padding bytes zero).  One pass over the concatenated masks; outputs are bin indices relative to
+ * each chromosome (end exclusive) plus the chromosome index of every run. */
+long long rocco_b200_mask_to_runs_batch_dev(
+    const uint8_t *d_mask, const size_t *offsets, const size_t *lengths, int chrom_count,
+    long long *start_bin_out, long long *end_bin_out, int *chrom_index_out, size_t capacity,
+    void *cuda_stream);
+
+/* numpy.sum of a float64 vector / of n copies of one value, restated bit-exactly (host helpers:
+ * dp.py:110-111 builds the search bracket from numpy.sum(switch_costs)). */
+double rocco_b200_numpy_sum_f64(const double *values, size_t n);
+double rocco_b200_numpy_sum_const_f64(double value, size_t n);
+
+/* ------------------------------------------------------------------ scoring */
+typedef struct rocco_b200_score_params {
+    double lower_bound_z;           /* inference.py:304 default 1.0                 */
+    double prior_df;                /* 5.0 (function default) / 6.0 (CLI default)   */
+    double min_effect;
+    int use_min_effect;
+    int spatial_window;             /* 31                                           */
+    double precision_floor_ratio;   /* 0.01                                         */
+    int baseline_window;            /* 101 (inference.py:185-228)                   */
+    int reserved;
+} rocco_b200_score_params;
+
+void rocco_b200_default_score_params(rocco_b200_score_params *p);
+
+/* Optional per-locus detail outputs (device or host according to the entry point); any may be NULL. */
+typedef struct rocco_b200_score_outputs {
+    double *scores;
+    double *mean;
+    double *raw_variance;
+    double *prior_variance;
+    double *moderated_variance;
+    double *standard_error;
+    double *centered_matrix;        /* m x n, optional                               */
+    double total_df;                /* out */
+    int resolved_spatial_window;    /* out */
+    int baseline_window;            /* out */
+    double baseline_lambda;         /* out */
+} rocco_b200_score_outputs;
+
+/* Full score_loci_wls on host buffers (H2D / D2H inside). matrix is row-major [sample, locus]. */
+int rocco_score_loci_wls_f64(const double *matrix, size_t m, size_t n,
+                             const rocco_b200_score_params *params, rocco_b200_score_outputs *out);
+int rocco_score_loci_wls_f32(const float *matrix, size_t m, size_t n,
+                             const rocco_b200_score_params *params, rocco_b200_score_outputs *out);
+
+/* Device-resident variants; dtype: 0 = float64 input, 1 = float32 input. Output pointers are device. */
+int rocco_b200_score_loci_wls_dev(const void *d_matrix, int dtype, size_t m, size_t n,
+                                  const rocco_b200_score_params *params,
+                                  rocco_b200_score_outputs *out, void *cuda_stream);
+int rocco_b200_crossfit_baseline_dev(const double *d_rows, size_t m, size_t n, double penalty_lambda,
+                                     double *d_out, void *cuda_stream);
+int rocco_b200_score_centered_wls_dev(const double *d_centered, size_t m, size_t n,
+                                      const rocco_b200_score_params *params,
+                                      rocco_b200_score_outputs *out, void *cuda_stream);
+
+/* ------------------------------------------------------------------ column statistics */
+enum {
+    ROCCO_STAT_MEDIAN = 0,     /* np.median                                   (rocco.py:265)  */
+    ROCCO_STAT_QUANTILE = 1,   /* np.quantile(method="nearest"), arg0 = q     (rocco.py:267)  */
+    ROCCO_STAT_TMEAN = 2,      /* nearest-rank trimmed mean, arg0 = tprop     (rocco.py:273)  */
+    ROCCO_STAT_MEAN = 3,       /*                                             (rocco.py:299)  */
+    ROCCO_STAT_MAD = 4,        /* median |x - median|, scale 1                (rocco.py:325)  */
+    ROCCO_STAT_IQR = 5,        /* percentile(arg1) - percentile(arg0), linear (rocco.py:327)  */
+    ROCCO_STAT_STD = 6,        /* ddof 0                                      (rocco.py:329)  */
+    ROCCO_STAT_TSTD = 7        /* ddof 1 inside nearest-rank limits, arg0 = tprop (rocco.py:331) */
+};
+int rocco_column_stat_f64(const double *matrix, size_t m, size_t n, int stat,
+                          double arg0, double arg1, double power, double *out);
+int rocco_b200_column_stat_dev(const void *d_matrix, int dtype, size_t m, size_t n, int stat,
+                               double arg0, double arg1, double power, double *d_out, void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROCCO_B200_H */

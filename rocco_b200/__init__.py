@@ -1,0 +1,15 @@
+"""rocco_b200 -- B200-native (sm_100a) implementation of ROCCO's consensus-selection hot path.
+
+Drop-in for that path only: the names below are the ones a user of the reference imports
+(``from rocco import *``, reference ``rocco/__init__.py:1-7``); everything else of ROCCO (BAM/bigWig
+reading, CLI, budget bootstrap, narrowPeak) is out of scope.
+"""
+from ._version import __version__
+from .dp import (build_switch_costs, calibrate_selection_penalty, objective_value, solve_chrom_exact,
+                 solve_penalized_chain)
+from .rocco import chrom_solution_to_bed, combine_chrom_results
+
+__all__ = [
+    "__version__", "build_switch_costs", "calibrate_selection_penalty", "objective_value",
+    "solve_chrom_exact", "solve_penalized_chain", "chrom_solution_to_bed", "combine_chrom_results",
+]

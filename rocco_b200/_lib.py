@@ -1,0 +1,150 @@
+"""ctypes binding of ``librocco_b200.so`` (the C-ABI declared in ``include/rocco_b200.h``).
+
+There is no CPU fallback anywhere in this package: if the shared library is missing or no CUDA
+device is visible, every compute entry raises ``RuntimeError`` -- mirroring the reference's
+"Make sure native C extensions are built and available" (dp.py:73-74, inference.py:244-245).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_double, c_int, c_longlong, c_size_t, c_ubyte, c_ulonglong, c_void_p
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librocco_b200.so")
+
+ST_NOMEM, ST_INVALID, ST_CUDA, ST_NONFINITE = -1, -2, -3, -4
+
+
+class ChainResult(Structure):
+    _fields_ = [
+        ("selection_penalty", c_double), ("penalized_objective", c_double), ("objective", c_double),
+        ("selected_count", c_longlong), ("switch_count", c_longlong), ("exact_tie_bins", c_longlong),
+        ("near_tie_bins", c_longlong), ("dp_passes", c_int), ("search_rounds", c_int),
+        ("status", c_int), ("reserved", c_int),
+    ]
+
+
+class ChainTask(Structure):
+    _fields_ = [
+        ("offset", c_size_t), ("n", c_size_t), ("gamma", c_double), ("cost_sum", c_double),
+        ("selection_penalty", c_double), ("target_count", c_longlong), ("mode", c_int), ("max_iter", c_int),
+    ]
+
+
+class ScoreParams(Structure):
+    _fields_ = [
+        ("lower_bound_z", c_double), ("prior_df", c_double), ("min_effect", c_double),
+        ("use_min_effect", c_int), ("spatial_window", c_int), ("precision_floor_ratio", c_double),
+        ("baseline_window", c_int), ("reserved", c_int),
+    ]
+
+
+class ScoreOutputs(Structure):
+    _fields_ = [
+        ("scores", c_void_p), ("mean", c_void_p), ("raw_variance", c_void_p), ("prior_variance", c_void_p),
+        ("moderated_variance", c_void_p), ("standard_error", c_void_p), ("centered_matrix", c_void_p),
+        ("total_df", c_double), ("resolved_spatial_window", c_int), ("baseline_window", c_int),
+        ("baseline_lambda", c_double),
+    ]
+
+
+_lib = None
+
+
+def _declare(lib):
+    dp, u8p, llp, ip = POINTER(c_double), POINTER(c_ubyte), POINTER(c_longlong), POINTER(c_int)
+    sig = {
+        "rocco_b200_version": (c_char_p, []),
+        "rocco_b200_last_error": (c_char_p, []),
+        "rocco_b200_device_count": (c_int, []),
+        "rocco_b200_set_device": (c_int, [c_int]),
+        "rocco_b200_kernel_launches": (c_ulonglong, []),
+        "rocco_b200_numpy_sum_f64": (c_double, [c_void_p, c_size_t]),
+        "rocco_b200_numpy_sum_const_f64": (c_double, [c_double, c_size_t]),
+        "rocco_solve_penalized_chain_f64": (c_int, [c_void_p, c_void_p, c_size_t, c_double, c_void_p, dp, llp]),
+        "rocco_calibrate_selection_penalty_f64": (
+            c_int, [c_void_p, c_void_p, c_size_t, c_longlong, c_int, dp, c_void_p, dp, llp]),
+        "rocco_b200_chain_solve_batch_dev": (
+            c_int, [c_void_p, c_void_p, POINTER(ChainTask), c_int, c_void_p, POINTER(ChainResult), c_int, c_void_p]),
+        "rocco_b200_chain_sweep_dev": (
+            c_int, [c_void_p, c_size_t, c_double, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+        "rocco_mask_to_intervals_u8": (
+            c_longlong, [c_void_p, c_size_t, c_longlong, c_longlong, c_longlong, c_void_p, c_void_p, c_size_t]),
+        "rocco_b200_mask_to_intervals_dev": (
+            c_longlong, [c_void_p, c_size_t, c_longlong, c_longlong, c_longlong, c_void_p, c_void_p, c_size_t, c_void_p]),
+        "rocco_b200_mask_to_runs_batch_dev": (
+            c_longlong, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+        "rocco_crossfit_whittaker_baseline_f64": (c_int, [c_void_p, c_size_t, c_double, c_void_p]),
+        "rocco_crossfit_whittaker_baseline_matrix_f64": (c_int, [c_void_p, c_size_t, c_size_t, c_double, c_void_p]),
+        "rocco_score_centered_wls_f64": (
+            c_int, [c_void_p, c_size_t, c_size_t, c_double, c_double, c_double, c_int, c_int, c_double,
+                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, dp, ip]),
+        "rocco_b200_default_score_params": (None, [POINTER(ScoreParams)]),
+        "rocco_score_loci_wls_f64": (c_int, [c_void_p, c_size_t, c_size_t, POINTER(ScoreParams), POINTER(ScoreOutputs)]),
+        "rocco_score_loci_wls_f32": (c_int, [c_void_p, c_size_t, c_size_t, POINTER(ScoreParams), POINTER(ScoreOutputs)]),
+        "rocco_b200_score_loci_wls_dev": (
+            c_int, [c_void_p, c_int, c_size_t, c_size_t, POINTER(ScoreParams), POINTER(ScoreOutputs), c_void_p]),
+        "rocco_b200_crossfit_baseline_dev": (c_int, [c_void_p, c_size_t, c_size_t, c_double, c_void_p, c_void_p]),
+        "rocco_b200_score_centered_wls_dev": (
+            c_int, [c_void_p, c_size_t, c_size_t, POINTER(ScoreParams), POINTER(ScoreOutputs), c_void_p]),
+        "rocco_column_stat_f64": (c_int, [c_void_p, c_size_t, c_size_t, c_int, c_double, c_double, c_double, c_void_p]),
+        "rocco_b200_column_stat_dev": (
+            c_int, [c_void_p, c_int, c_size_t, c_size_t, c_int, c_double, c_double, c_double, c_void_p, c_void_p]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)          # AttributeError here = header/library mismatch: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    return sig
+
+
+def load():
+    """Load (once) and return the shared library; raises RuntimeError when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found. Make sure native CUDA extensions are built and available "
+                "(python -c 'import __graft_entry__ as g; g.build()' or make -C rocco_b200/csrc).")
+        lib = ctypes.CDLL(LIB_PATH)
+        lib._signatures = _declare(lib)
+        _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    return load().rocco_b200_last_error().decode("utf-8", "replace")
+
+
+def check(status: int, what: str = "rocco_b200") -> None:
+    """Map C-ABI status codes onto the reference's exceptions (_wls.c:133-150, _baseline.c:96-101)."""
+    if status == 0:
+        return
+    if status == ST_NOMEM:
+        raise MemoryError(f"{what}: device/host allocation failed ({last_error()})")
+    if status == ST_INVALID:
+        raise ValueError(f"{what}: invalid inputs")
+    if status == ST_NONFINITE:
+        raise ValueError(f"{what}: non-finite values")
+    raise RuntimeError(f"{what}: CUDA error: {last_error()}")
+
+
+def require_device() -> None:
+    if load().rocco_b200_device_count() <= 0:
+        raise RuntimeError("rocco_b200: no CUDA device visible and there is no CPU fallback")
+
+
+def np_ptr(a: np.ndarray) -> c_void_p:
+    return c_void_p(a.ctypes.data)
+
+
+def kernel_launches() -> int:
+    return int(load().rocco_b200_kernel_launches())
+
+
+def numpy_sum_const(value: float, n: int) -> float:
+    """numpy.sum(numpy.full(n, value)) without materialising the vector (dp.py:110-111 bracket)."""
+    return float(load().rocco_b200_numpy_sum_const_f64(float(value), int(n)))

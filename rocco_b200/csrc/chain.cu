@@ -1,0 +1,934 @@
+// Two-state chain DP as a parallel scan of clamp-add maps, and the batched multiplier search.
+//
+// Replaces /root/reference/rocco/_chain_dp.c:109-186 (sequential Viterbi with back-pointers) and
+// /root/reference/rocco/dp.py:89-164 (bisection driven from Python, 62 DP passes).
+//
+// With V0/V1 the best values ending unselected/selected, d = V1 - V0 obeys
+//     d_0 = s_0 - lambda,     d_i = min(max(d_{i-1}, -c_{i-1}), c_{i-1}) + (s_i - lambda)
+// and the back-pointers collapse to: z_{n-1} = [d_{n-1} > 0];  z_i = 1 if d_i > c_i, 0 if d_i < -c_i,
+// else z_{i+1}.  Each step is a map x -> min(max(x + p, lo), hi); such maps are closed under
+// composition, so the forward sweep is an associative scan (per-thread serial compose, warp-shuffle
+// scan, decoupled look-back across tiles) and the backward pointer chase becomes a "nearest decided
+// bin to the right" propagation resolved inside the tile, with only the undecided tile suffix
+// deferred to a tiny per-chromosome pass.
+//
+// Tie-break fidelity: the reference compares (value, fewer selected bins) lexicographically.  Values
+// here are either plain doubles (VD, fast path) or (double, int) pairs ordered lexicographically (VL).
+// The fast path counts every decision that lands exactly on a threshold; if any occurred for a
+// multiplier, that multiplier is re-solved with VL, which is the reference's rule restated on d.
+#include "common.cuh"
+
+#include <math.h>
+
+#include <algorithm>
+
+namespace rb {
+namespace chain {
+
+constexpr int THREADS = 256;
+constexpr int ITEMS = 16;
+constexpr int TILE = THREADS * ITEMS;   // 4096 bins per tile
+constexpr int WARPS = THREADS / 32;
+constexpr int PAD_STRIDE = ITEMS + 1;   // smem padding: conflict-free blocked reads
+constexpr int MAX_LEVELS = 8;
+constexpr int MAX_SLOTS = 256;          // multipliers per launch set
+
+// ------------------------------------------------------------------ value types
+struct VD { double v; };
+struct VL { double v; int k; };          // k = selected-count difference; fewer is better
+
+__device__ __forceinline__ VD v_make(VD *, double v, int) { return VD{v}; }
+__device__ __forceinline__ VL v_make(VL *, double v, int k) { return VL{v, k}; }
+__device__ __forceinline__ VD v_add(VD a, VD b) { return VD{a.v + b.v}; }
+__device__ __forceinline__ VL v_add(VL a, VL b) { return VL{a.v + b.v, a.k + b.k}; }
+// strict "a is worse than b"
+__device__ __forceinline__ bool v_lt(VD a, VD b) { return a.v < b.v; }
+__device__ __forceinline__ bool v_lt(VL a, VL b) { return a.v < b.v || (a.v == b.v && a.k > b.k); }
+__device__ __forceinline__ bool v_eq(VD a, VD b) { return a.v == b.v; }
+__device__ __forceinline__ bool v_eq(VL a, VL b) { return a.v == b.v && a.k == b.k; }
+template <typename V> __device__ __forceinline__ V v_max(V a, V b) { return v_lt(a, b) ? b : a; }
+template <typename V> __device__ __forceinline__ V v_min(V a, V b) { return v_lt(b, a) ? b : a; }
+template <typename V> __device__ __forceinline__ V v_clamp(V x, V lo, V hi) { return v_min(v_max(x, lo), hi); }
+__device__ __forceinline__ VD v_shfl_up(VD a, int d) { return VD{__shfl_up_sync(0xffffffffu, a.v, d)}; }
+__device__ __forceinline__ VL v_shfl_up(VL a, int d) {
+    return VL{__shfl_up_sync(0xffffffffu, a.v, d), __shfl_up_sync(0xffffffffu, a.k, d)};
+}
+
+template <typename V> struct Map { V p, lo, hi; };   // x -> min(max(x + p, lo), hi)
+
+template <typename V> __device__ __forceinline__ Map<V> map_identity() {
+    V *t = nullptr;
+    return Map<V>{v_make(t, 0.0, 0), v_make(t, -INFINITY, 0), v_make(t, INFINITY, 0)};
+}
+template <typename V> __device__ __forceinline__ Map<V> map_const(V a) {
+    V *t = nullptr;
+    return Map<V>{v_make(t, 0.0, 0), a, a};
+}
+// apply f first, then g
+template <typename V> __device__ __forceinline__ Map<V> map_compose(const Map<V> &f, const Map<V> &g) {
+    Map<V> r;
+    r.p = v_add(f.p, g.p);
+    r.lo = v_clamp(v_add(f.lo, g.p), g.lo, g.hi);
+    r.hi = v_clamp(v_add(f.hi, g.p), g.lo, g.hi);
+    return r;
+}
+template <typename V> __device__ __forceinline__ V map_apply(const Map<V> &f, V x) {
+    return v_clamp(v_add(x, f.p), f.lo, f.hi);
+}
+// one DP step appended to f: clamp to [-c, c], then add a
+template <typename V> __device__ __forceinline__ Map<V> map_step(const Map<V> &f, V a, V cneg, V cpos) {
+    Map<V> r;
+    r.p = v_add(f.p, a);
+    r.lo = v_add(v_clamp(f.lo, cneg, cpos), a);
+    r.hi = v_add(v_clamp(f.hi, cneg, cpos), a);
+    return r;
+}
+template <typename V> __device__ __forceinline__ Map<V> map_shfl_up(const Map<V> &m, int d) {
+    return Map<V>{v_shfl_up(m.p, d), v_shfl_up(m.lo, d), v_shfl_up(m.hi, d)};
+}
+// L2-coherent reads of look-back payloads written by other blocks
+__device__ __forceinline__ VD v_ldcg(const VD *p) { return VD{__ldcg(&p->v)}; }
+__device__ __forceinline__ VL v_ldcg(const VL *p) { return VL{__ldcg(&p->v), __ldcg(&p->k)}; }
+template <typename V> __device__ __forceinline__ Map<V> map_ldcg(const Map<V> *m) {
+    return Map<V>{v_ldcg(&m->p), v_ldcg(&m->lo), v_ldcg(&m->hi)};
+}
+
+// ------------------------------------------------------------------ device-side descriptors
+struct ChromDev {
+    long long offset;       // element offset of this chromosome in the concatenated arrays
+    long long n;
+    double gamma;
+    double cost_sum;
+    long long target;
+    int tile0;              // first tile index
+    int ntiles;
+    int mode;               // 0 fixed multiplier, 1 budget search
+    int max_iter;
+};
+
+enum Phase : int { PH_BRACKET = 0, PH_BISECT = 1, PH_DONE = 2, PH_HOST = 3, PH_MANUAL = 4 };
+
+struct SearchDev {
+    double lower, upper;
+    double smin, smax;
+    int phase;
+    int iters_left;
+    int levels;             // levels (=> 2^levels - 1 slots) of the round in flight
+    int nslots;             // active multipliers this round
+    int need_lex;
+    int passes;
+    int rounds;
+    int pad;
+};
+
+struct TileOut { int cnt; int pend; int head; int ties; };   // head: 0/1 value, 2 = whole tile undecided
+
+struct Params {
+    const double *scores;
+    const double *costs;        // nullable
+    const ChromDev *chroms;
+    SearchDev *search;
+    const int *tile_chrom;
+    double *lam;                // [nchrom][MAX_SLOTS]
+    long long *counts;          // [nchrom][MAX_SLOTS]
+    long long *tiecnt;          // [nchrom][MAX_SLOTS]
+    int *flags;                 // [slot][tile]  (epoch<<2 | state)
+    void *agg;                  // [slot][tile] Map<V>
+    void *incl;                 // [slot][tile] V
+    TileOut *tout;              // [slot][tile]
+    int *ticket;
+    uint8_t *mask;              // EMIT only
+    int *zin;                   // [tile]  EMIT: value flowing into the tile from the right
+    long long *near_ties;       // [nchrom] EMIT only
+    int ntiles;
+    int nchrom;
+    int slots_per_block;        // multipliers handled sequentially by one block
+    int ngroups;                // ceil(max nslots / slots_per_block)
+    int epoch;
+    int lex_pass;               // 1: only chromosomes with need_lex
+};
+
+// ------------------------------------------------------------------ the tile kernel
+template <typename V, bool VEC_COST, bool EMIT>
+__global__ void __launch_bounds__(THREADS) k_chain_tiles(Params P)
+{
+    extern __shared__ double smem[];
+    double *s_sc = smem;                               // TILE + THREADS (padded)
+    double *s_cs = smem + (TILE + THREADS);            // VEC_COST only: TILE + 1 + padding
+    __shared__ Map<V> s_wtot[WARPS];
+    __shared__ V s_din;
+    __shared__ int s_ticket;
+    __shared__ int s_whas[WARPS], s_whead[WARPS];
+    __shared__ int s_red[WARPS][4];
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_ticket = atomicAdd(P.ticket, 1);
+    __syncthreads();
+    const int ticket = s_ticket;
+    const int group = ticket % P.ngroups;
+    const int tile = ticket / P.ngroups;
+    const int c = P.tile_chrom[tile];
+    const ChromDev cd = P.chroms[c];
+    const SearchDev sd = P.search[c];
+    if (P.lex_pass ? (sd.need_lex == 0) : (sd.phase == PH_DONE && !EMIT) || sd.phase == PH_HOST) return;
+    const int slot0 = group * P.slots_per_block;
+    if (slot0 >= sd.nslots) return;
+    const int slot1 = min(sd.nslots, slot0 + P.slots_per_block);
+
+    const long long s0 = (long long)(tile - cd.tile0) * TILE;     // first bin of this tile
+    const int len = (int)min((long long)TILE, cd.n - s0);
+    const bool first_tile = (tile == cd.tile0);
+    const bool last_tile = (s0 + len == cd.n);
+    const double *gsc = P.scores + cd.offset + s0;
+
+    // stage scores (coalesced) into the padded blocked layout
+    for (int e = tid; e < TILE; e += THREADS) {
+        double v = (e < len) ? __ldg(gsc + e) : 0.0;
+        s_sc[e + e / ITEMS] = v;
+    }
+    if (VEC_COST) {
+        // s_cs[e] = cost between bins (s0+e-1) and (s0+e);  e in [0, TILE]
+        const double *gcs = P.costs + cd.offset + s0 - 1;
+        for (int e = tid; e <= TILE; e += THREADS) {
+            double v = 0.0;
+            if (e <= len && (s0 + e) >= 1 && (s0 + e) < cd.n) v = __ldg(gcs + e);
+            s_cs[e + e / ITEMS] = v;
+        }
+    }
+    __syncthreads();
+
+    double sc[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) sc[j] = s_sc[tid * PAD_STRIDE + j];
+    const int base = tid * ITEMS;
+    const int cnt = max(0, min(ITEMS, len - base));               // valid items of this thread
+    const unsigned vm = (cnt >= 32) ? 0xffffffffu : ((1u << cnt) - 1u);
+    V *tv = nullptr;
+
+    for (int slot = slot0; slot < slot1; ++slot) {
+        const double lam = P.lam[(size_t)c * MAX_SLOTS + slot];
+        const size_t sidx = (size_t)slot * P.ntiles + tile;
+
+        // ---- pass 1: compose this thread's maps
+        Map<V> m = map_identity<V>();
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            if (j < cnt) {
+                const V a = v_make(tv, sc[j] - lam, 1);
+                if (first_tile && base + j == 0) {
+                    m = map_const<V>(a);
+                } else {
+                    const double cc = VEC_COST ? s_cs[(base + j) + (base + j) / ITEMS] : cd.gamma;
+                    m = map_step<V>(m, a, v_make(tv, -cc, 0), v_make(tv, cc, 0));
+                }
+            }
+        }
+        // ---- block scan (inclusive within warp)
+        Map<V> inc = m;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            Map<V> o = map_shfl_up<V>(inc, d);
+            if (lane >= d) inc = map_compose<V>(o, inc);
+        }
+        if (lane == 31) s_wtot[wid] = inc;
+        Map<V> excl = map_shfl_up<V>(inc, 1);
+        if (lane == 0) excl = map_identity<V>();
+        __syncthreads();
+        Map<V> wpre = map_identity<V>();
+        for (int w = 0; w < wid; ++w) wpre = map_compose<V>(wpre, s_wtot[w]);
+        excl = map_compose<V>(wpre, excl);
+
+        // ---- publish + decoupled look-back (one thread)
+        if (tid == 0) {
+            Map<V> A = s_wtot[0];
+            for (int w = 1; w < WARPS; ++w) A = map_compose<V>(A, s_wtot[w]);
+            Map<V> *gagg = reinterpret_cast<Map<V> *>(P.agg);
+            V *gincl = reinterpret_cast<V *>(P.incl);
+            V din = v_make(tv, 0.0, 0);
+            const bool is_const = v_eq(A.lo, A.hi);
+            if (first_tile || is_const) {
+                gincl[sidx] = A.lo;
+                st_release_i32(P.flags + sidx, (P.epoch << 2) | 2);
+            } else {
+                gagg[sidx] = A;
+                st_release_i32(P.flags + sidx, (P.epoch << 2) | 1);
+            }
+            if (!first_tile) {
+                Map<V> acc = map_identity<V>();
+                size_t j = sidx - 1;
+                for (;;) {
+                    int f = ld_acquire_i32(P.flags + j);
+                    if ((f >> 2) != P.epoch || (f & 3) == 0) { __nanosleep(20); continue; }
+                    if ((f & 3) == 2) {
+                        V x = v_ldcg(gincl + j);
+                        din = map_apply<V>(acc, x);
+                        break;
+                    }
+                    Map<V> a = map_ldcg<V>(gagg + j);
+                    acc = map_compose<V>(a, acc);
+                    --j;
+                }
+                if (!is_const) {
+                    gincl[sidx] = map_apply<V>(A, din);
+                    st_release_i32(P.flags + sidx, (P.epoch << 2) | 2);
+                }
+            }
+            s_din = din;
+        }
+        __syncthreads();
+
+        // ---- pass 2: actual d values, decisions
+        V x = map_apply<V>(excl, s_din);
+        unsigned dec = 0, val = 0;
+        int ties = 0, near = 0;
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            if (j < cnt) {
+                const V a = v_make(tv, sc[j] - lam, 1);
+                const long long gi = s0 + base + j;
+                if (gi == 0) {
+                    x = a;
+                } else {
+                    const double cc = VEC_COST ? s_cs[(base + j) + (base + j) / ITEMS] : cd.gamma;
+                    x = v_add(v_clamp(x, v_make(tv, -cc, 0), v_make(tv, cc, 0)), a);
+                }
+                if (gi == cd.n - 1) {                 // terminal choice (_chain_dp.c:167-179)
+                    dec |= 1u << j;
+                    if (v_lt(v_make(tv, 0.0, 0), x)) val |= 1u << j;
+                    ties += (x.v == 0.0);
+                } else {
+                    const double cr = VEC_COST ? s_cs[(base + j + 1) + (base + j + 1) / ITEMS] : cd.gamma;
+                    if (v_lt(v_make(tv, cr, 0), x)) { dec |= 1u << j; val |= 1u << j; }
+                    else if (v_lt(x, v_make(tv, -cr, 0))) { dec |= 1u << j; }
+                    ties += (x.v == cr) || (x.v == -cr);
+                    if (EMIT) {
+                        const double tol = 1.0e-9 * (1.0 + fabs(cr));
+                        near += (fabs(x.v - cr) <= tol) || (fabs(x.v + cr) <= tol);
+                    }
+                }
+            }
+        }
+
+        // ---- backward: nearest decided bin to the right
+        const int has = dec != 0;
+        const int headv = has ? ((val >> (__ffs(dec) - 1)) & 1) : 0;
+        const unsigned D = __ballot_sync(0xffffffffu, has);
+        const unsigned Hv = __ballot_sync(0xffffffffu, headv);
+        if (lane == 0) {
+            s_whas[wid] = D != 0;
+            s_whead[wid] = D ? ((Hv >> (__ffs(D) - 1)) & 1) : 0;
+        }
+        __syncthreads();
+        int known = 0, zin = 0;
+        {
+            const unsigned above = D & ~((2u << lane) - 1u);
+            if (above) { known = 1; zin = (Hv >> (__ffs(above) - 1)) & 1; }
+            else {
+                for (int w = wid + 1; w < WARPS; ++w)
+                    if (s_whas[w]) { known = 1; zin = s_whead[w]; break; }
+            }
+        }
+        unsigned z = 0;
+        {
+            int cur = known ? zin : 0;
+#pragma unroll
+            for (int j = ITEMS - 1; j >= 0; --j) {
+                if ((dec >> j) & 1u) cur = (val >> j) & 1u;
+                z |= (unsigned)cur << j;
+            }
+        }
+        z &= vm;
+        unsigned pm = 0;                         // items that copy the (unknown) value from the right
+        if (!known) pm = (dec ? ~((2u << (31 - __clz(dec))) - 1u) : 0xffffffffu) & vm;
+
+        int r_cnt = __popc(z), r_pend = __popc(pm), r_ties = ties, r_near = near;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            r_cnt += __shfl_xor_sync(0xffffffffu, r_cnt, d);
+            r_pend += __shfl_xor_sync(0xffffffffu, r_pend, d);
+            r_ties += __shfl_xor_sync(0xffffffffu, r_ties, d);
+            r_near += __shfl_xor_sync(0xffffffffu, r_near, d);
+        }
+        if (lane == 0) { s_red[wid][0] = r_cnt; s_red[wid][1] = r_pend; s_red[wid][2] = r_ties; s_red[wid][3] = r_near; }
+
+        if (EMIT) {
+            uint8_t *gm = P.mask + cd.offset + s0 + base;
+            if (cnt == ITEMS && ((reinterpret_cast<uintptr_t>(gm) & 15) == 0)) {
+                uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int j = 0; j < ITEMS; ++j) w[j >> 2] |= ((z >> j) & 1u) << (8 * (j & 3));
+                *reinterpret_cast<uint4 *>(gm) = make_uint4(w[0], w[1], w[2], w[3]);
+            } else {
+                for (int j = 0; j < cnt; ++j) gm[j] = (uint8_t)((z >> j) & 1u);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            TileOut o{0, 0, 0, 0};
+            int nr = 0, any = 0;
+            for (int w = 0; w < WARPS; ++w) {
+                o.cnt += s_red[w][0]; o.pend += s_red[w][1]; o.ties += s_red[w][2]; nr += s_red[w][3];
+                any |= s_whas[w];
+            }
+            o.head = any ? (int)(z & 1u) : 2;
+            P.tout[sidx] = o;
+            if (EMIT && nr) atomicAdd(reinterpret_cast<unsigned long long *>(P.near_ties + c), (unsigned long long)nr);
+        }
+        __syncthreads();
+    }
+    (void)last_tile;
+}
+
+// ------------------------------------------------------------------ per-chromosome finish + search controller
+// One block per chromosome, one warp per multiplier slot (looping when there are more slots than warps).
+__device__ void gen_tree(const SearchDev &sd, double *lam, int levels)
+{
+    // heap-ordered complete tree of the next `levels` bisection midpoints; every midpoint is formed
+    // with the reference's own expression (lower + upper) / 2.0 on the bracket it would see (dp.py:143)
+    double lo[1 << MAX_LEVELS], hi[1 << MAX_LEVELS];
+    lo[1] = sd.lower; hi[1] = sd.upper;
+    const int nodes = (1 << levels) - 1;
+    for (int i = 1; i <= nodes; ++i) {
+        const double mid = (lo[i] + hi[i]) / 2.0;
+        lam[i - 1] = mid;
+        if (2 * i + 1 <= nodes) {
+            lo[2 * i] = lo[i]; hi[2 * i] = mid;
+            lo[2 * i + 1] = mid; hi[2 * i + 1] = hi[i];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_chain_finish(Params P, int emit)
+{
+    const int c = blockIdx.x;
+    const ChromDev cd = P.chroms[c];
+    SearchDev sd = P.search[c];
+    if (blockIdx.x == 0 && threadIdx.x == 0) *P.ticket = 0;
+    const bool active = P.lex_pass ? (sd.need_lex != 0)
+                                   : !((sd.phase == PH_DONE && !emit) || sd.phase == PH_HOST);
+    if (!active) return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __shared__ int s_anytie;
+    if (threadIdx.x == 0) s_anytie = 0;
+    __syncthreads();
+
+    for (int slot = wid; slot < sd.nslots; slot += nw) {
+        const TileOut *to = P.tout + (size_t)slot * P.ntiles + cd.tile0;
+        long long total = 0;
+        int ties = 0;
+        int carry = 0;                                   // value flowing in from the right of the chunk
+        for (int hi = cd.ntiles; hi > 0; hi -= 32) {     // chunks of 32 tiles, right to left
+            const int t = hi - 32 + lane;                // this lane's tile (may be < 0)
+            int h = 2, pend = 0, cnt = 0, tt = 0;
+            if (t >= 0) {
+                const TileOut me = to[t];
+                cnt = me.cnt; pend = me.pend; tt = me.ties;
+                if (t + 1 < cd.ntiles) h = to[t + 1].head;   // head of the right neighbour
+            }
+            const unsigned D = __ballot_sync(0xffffffffu, h != 2);
+            const unsigned Hv = __ballot_sync(0xffffffffu, h == 1);
+            const unsigned at_or_above = D >> lane;
+            const int zin = at_or_above ? ((Hv >> (lane + __ffs(at_or_above) - 1)) & 1) : carry;
+            if (t >= 0) {
+                total += cnt + (zin ? pend : 0);
+                ties += tt;
+                if (emit && slot == 0) P.zin[cd.tile0 + t] = zin;
+            }
+            carry = __shfl_sync(0xffffffffu, zin, 0);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            total += __shfl_xor_sync(0xffffffffu, total, d);
+            ties += __shfl_xor_sync(0xffffffffu, ties, d);
+        }
+        if (lane == 0) {
+            P.counts[(size_t)c * MAX_SLOTS + slot] = total;
+            P.tiecnt[(size_t)c * MAX_SLOTS + slot] = ties;
+            if (ties) atomicOr(&s_anytie, 1);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+
+    // ---- controller (thread 0)
+    if (!P.lex_pass && s_anytie) {                      // exact ties: redo these multipliers with VL
+        sd.need_lex = 1;
+        P.search[c] = sd;
+        return;
+    }
+    sd.need_lex = 0;
+    sd.passes += sd.nslots;
+    sd.rounds += 1;
+    const long long *cnt = P.counts + (size_t)c * MAX_SLOTS;
+    double *lam = P.lam + (size_t)c * MAX_SLOTS;
+    if (sd.phase == PH_BRACKET) {
+        // dp.py:113-138: the bracket ends must give count > target (lower) and count <= target (upper)
+        if (cnt[0] <= cd.target || cnt[1] > cd.target) {
+            sd.phase = PH_HOST;                           // expansion loop handled by the host driver
+        } else {
+            sd.phase = PH_BISECT;
+        }
+    } else if (sd.phase == PH_BISECT) {
+        int i = 1;
+        for (int l = 0; l < sd.levels; ++l) {             // dp.py:141-162
+            const double mid = lam[i - 1];
+            if (cnt[i - 1] > cd.target) { sd.lower = mid; i = 2 * i + 1; }
+            else { sd.upper = mid; i = 2 * i; }
+        }
+        sd.iters_left -= sd.levels;
+    }
+    if (sd.phase == PH_BISECT) {
+        if (sd.iters_left <= 0) {
+            sd.phase = PH_DONE;
+            sd.nslots = 1;
+            lam[0] = sd.upper;                            // dp.py:164 returns the upper end
+        } else {
+            const int lv = min(sd.levels > 0 ? sd.levels : 1, sd.iters_left);
+            sd.levels = lv;
+            sd.nslots = (1 << lv) - 1;
+            gen_tree(sd, lam, lv);
+        }
+    }
+    P.search[c] = sd;
+}
+
+// Bracket initialisation: lower = min(s) - sum(c) - 1, upper = max(s) + sum(c) + 1 (dp.py:110-111).
+__global__ void __launch_bounds__(256) k_chain_minmax(const double *scores, const ChromDev *chroms, SearchDev *search,
+                                                      double *partial /* [nchrom][gridDim.y][2] */)
+{
+    const int c = blockIdx.x;
+    const ChromDev cd = chroms[c];
+    const double *s = scores + cd.offset;
+    double lo = INFINITY, hi = -INFINITY;
+    int bad = 0;
+    for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < cd.n; i += (long long)gridDim.y * blockDim.x) {
+        const double v = s[i];
+        lo = fmin(lo, v); hi = fmax(hi, v);
+        bad |= !isfinite(v);
+    }
+    __shared__ double s_lo[8], s_hi[8];
+    __shared__ int s_bad;
+    if (threadIdx.x == 0) s_bad = 0;
+    __syncthreads();
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+    }
+    if (bad) atomicOr(&s_bad, 1);
+    if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) { lo = fmin(lo, s_lo[w]); hi = fmax(hi, s_hi[w]); }
+        double *p = partial + ((size_t)c * gridDim.y + blockIdx.y) * 2;
+        p[0] = s_bad ? NAN : lo;
+        p[1] = hi;
+    }
+}
+
+__global__ void k_chain_init(const ChromDev *chroms, SearchDev *search, double *lam, const double *partial,
+                             int nparts, int levels, int nchrom)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchrom) return;
+    const ChromDev cd = chroms[c];
+    SearchDev sd;
+    double lo = INFINITY, hi = -INFINITY;
+    bool bad = false;
+    for (int k = 0; k < nparts; ++k) {
+        const double a = partial[((size_t)c * nparts + k) * 2], b = partial[((size_t)c * nparts + k) * 2 + 1];
+        if (isnan(a)) bad = true;
+        lo = fmin(lo, a); hi = fmax(hi, b);
+    }
+    sd.smin = bad ? NAN : lo; sd.smax = hi;
+    sd.need_lex = 0; sd.passes = 0; sd.rounds = 0; sd.pad = 0;
+    double *l = lam + (size_t)c * MAX_SLOTS;
+    if (cd.mode == 0) {
+        sd.phase = PH_DONE; sd.lower = sd.upper = l[0];     // host stored the fixed multiplier in slot 0
+        sd.iters_left = 0; sd.levels = 0; sd.nslots = 1;
+    } else {
+        sd.lower = lo - cd.cost_sum - 1.0;
+        sd.upper = hi + cd.cost_sum + 1.0;
+        sd.phase = PH_BRACKET; sd.iters_left = cd.max_iter; sd.levels = levels; sd.nslots = 2;
+        l[0] = sd.lower; l[1] = sd.upper;
+        if (cd.max_iter <= 0) { /* bracket only */ }
+    }
+    search[c] = sd;
+}
+
+// After the bracket round, PH_BRACKET -> PH_BISECT transitions generate the first tree inside k_chain_finish.
+
+// ------------------------------------------------------------------ finalize: patch undecided suffixes, objective sums
+struct FinalPart { double sum_sz; double sum_cost; long long count; long long switches; };
+
+template <bool VEC_COST>
+__global__ void __launch_bounds__(THREADS) k_chain_finalize(Params P, FinalPart *parts /* [tile] */)
+{
+    const int tile = blockIdx.x;
+    const int c = P.tile_chrom[tile];
+    const ChromDev cd = P.chroms[c];
+    const long long s0 = (long long)(tile - cd.tile0) * TILE;
+    const int len = (int)min((long long)TILE, cd.n - s0);
+    const TileOut to = P.tout[tile];                      // slot 0
+    const int zin = P.zin[tile];
+    const int pend_from = len - to.pend;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint8_t *gm = P.mask + cd.offset + s0;
+    const double *gs = P.scores + cd.offset + s0;
+    const bool last_tile = (s0 + len == cd.n);
+
+    __shared__ uint8_t s_z[TILE + 1];
+    for (int e = tid; e < len; e += THREADS) {
+        uint8_t z = gm[e];
+        if (e >= pend_from) { z = (uint8_t)zin; if (zin) gm[e] = 1; }
+        s_z[e] = z;
+    }
+    if (tid == 0) s_z[len] = last_tile ? 255 : (uint8_t)zin;      // right neighbour of the tile's last bin
+    __syncthreads();
+    double ssz = 0.0, scost = 0.0;
+    long long cntv = 0, sw = 0;
+    for (int e = tid; e < len; e += THREADS) {
+        const int z = s_z[e];
+        if (z) { ssz += gs[e]; ++cntv; }
+        const int zr = s_z[e + 1];
+        if (zr != 255 && zr != z) {
+            ++sw;
+            if (VEC_COST) scost += P.costs[cd.offset + s0 + e];
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        ssz += __shfl_xor_sync(0xffffffffu, ssz, d);
+        scost += __shfl_xor_sync(0xffffffffu, scost, d);
+        cntv += __shfl_xor_sync(0xffffffffu, cntv, d);
+        sw += __shfl_xor_sync(0xffffffffu, sw, d);
+    }
+    __shared__ double r_a[WARPS], r_b[WARPS];
+    __shared__ long long r_c[WARPS], r_d[WARPS];
+    if (lane == 0) { r_a[wid] = ssz; r_b[wid] = scost; r_c[wid] = cntv; r_d[wid] = sw; }
+    __syncthreads();
+    if (tid == 0) {
+        FinalPart fp{0.0, 0.0, 0, 0};
+        for (int w = 0; w < WARPS; ++w) { fp.sum_sz += r_a[w]; fp.sum_cost += r_b[w]; fp.count += r_c[w]; fp.switches += r_d[w]; }
+        parts[tile] = fp;
+    }
+}
+
+__global__ void k_chain_results(Params P, const FinalPart *parts, rocco_b200_chain_result *out, int vec_cost)
+{
+    const int c = blockIdx.x;
+    const ChromDev cd = P.chroms[c];
+    const SearchDev sd = P.search[c];
+    // fixed order, one warp: deterministic sums
+    const int lane = threadIdx.x;
+    double ssz = 0.0, scost = 0.0;
+    long long cnt = 0, sw = 0;
+    for (int t = lane; t < cd.ntiles; t += 32) {
+        const FinalPart fp = parts[cd.tile0 + t];
+        ssz += fp.sum_sz; scost += fp.sum_cost; cnt += fp.count; sw += fp.switches;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        ssz += __shfl_xor_sync(0xffffffffu, ssz, d);
+        scost += __shfl_xor_sync(0xffffffffu, scost, d);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+        sw += __shfl_xor_sync(0xffffffffu, sw, d);
+    }
+    if (lane == 0) {
+        rocco_b200_chain_result r;
+        const double lam = P.lam[(size_t)c * MAX_SLOTS];
+        const double tv = vec_cost ? scost : cd.gamma * (double)sw;
+        r.selection_penalty = lam;
+        r.penalized_objective = ssz - lam * (double)cnt - tv;
+        r.objective = -ssz + tv;
+        r.selected_count = cnt;
+        r.switch_count = sw;
+        r.exact_tie_bins = P.tiecnt[(size_t)c * MAX_SLOTS];
+        r.near_tie_bins = P.near_ties[c];
+        r.dp_passes = sd.passes;
+        r.search_rounds = sd.rounds;
+        r.status = isnan(sd.smin) ? ST_NONFINITE : 0;
+        r.reserved = 0;
+        out[c] = r;
+    }
+}
+
+// ------------------------------------------------------------------ host driver
+struct Workspace {
+    ChromDev *d_chroms = nullptr;
+    SearchDev *d_search = nullptr;
+    int *d_tile_chrom = nullptr;
+    double *d_lam = nullptr;
+    long long *d_counts = nullptr, *d_tiecnt = nullptr, *d_near = nullptr;
+    int *d_flags = nullptr;
+    void *d_agg = nullptr, *d_incl = nullptr;
+    TileOut *d_tout = nullptr;
+    int *d_ticket = nullptr, *d_zin = nullptr;
+    double *d_partial = nullptr;
+    FinalPart *d_parts = nullptr;
+    rocco_b200_chain_result *d_results = nullptr;
+};
+
+static size_t smem_bytes(bool vec) { return (size_t)(TILE + THREADS) * sizeof(double) * (vec ? 2 : 1) + (vec ? 64 : 0); }
+
+template <typename V, bool VEC, bool EMIT>
+static int launch_tiles(const Params &P, int blocks, cudaStream_t st)
+{
+    static bool attr_set = false;
+    const size_t sm = smem_bytes(VEC);
+    if (!attr_set) {
+        RB_CUDA(cudaFuncSetAttribute(k_chain_tiles<V, VEC, EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        attr_set = true;
+    }
+    k_chain_tiles<V, VEC, EMIT><<<blocks, THREADS, sm, st>>>(P);
+    RB_LAUNCH_CHECK();
+    return 0;
+}
+
+template <bool EMIT>
+static int launch_round(Params P, bool vec, int nslots_max, int &epoch, cudaStream_t st)
+{
+    P.ngroups = (nslots_max + P.slots_per_block - 1) / P.slots_per_block;
+    const int blocks = P.ntiles * P.ngroups;
+    for (int lex = 0; lex < 2; ++lex) {
+        P.lex_pass = lex;
+        P.epoch = ++epoch;
+        if (lex == 0) {
+            if (vec) RB_TRY((launch_tiles<VD, true, EMIT>(P, blocks, st)));
+            else RB_TRY((launch_tiles<VD, false, EMIT>(P, blocks, st)));
+        } else {
+            if (vec) RB_TRY((launch_tiles<VL, true, EMIT>(P, blocks, st)));
+            else RB_TRY((launch_tiles<VL, false, EMIT>(P, blocks, st)));
+        }
+        k_chain_finish<<<P.nchrom, 256, 0, st>>>(P, EMIT ? 1 : 0);
+        RB_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+static int solve_batch(const double *d_scores, const double *d_costs, const rocco_b200_chain_task *tasks, int ntask,
+                       uint8_t *d_masks, rocco_b200_chain_result *results, int levels, cudaStream_t st)
+{
+    if (ntask <= 0) return 0;
+    if (!d_scores || !tasks || !d_masks || !results) return ST_INVALID;
+    if (levels <= 0) levels = 3;
+    levels = std::min(levels, MAX_LEVELS);
+    RB_TRY(ensure_device());
+
+    std::vector<ChromDev> chroms(ntask);
+    std::vector<int> tile_chrom;
+    int ntiles = 0, max_iter = 0;
+    bool any_search = false;
+    for (int c = 0; c < ntask; ++c) {
+        const rocco_b200_chain_task &t = tasks[c];
+        if (t.n == 0 || !(t.gamma >= 0.0) || t.n > (size_t)1 << 40) return ST_INVALID;
+        ChromDev &cd = chroms[c];
+        cd.offset = (long long)t.offset; cd.n = (long long)t.n; cd.gamma = t.gamma; cd.cost_sum = t.cost_sum;
+        cd.mode = t.mode; cd.max_iter = t.max_iter;
+        long long target = std::max<long long>(0, std::min<long long>(t.target_count, (long long)t.n));
+        cd.target = target;
+        if (t.mode == 1 && target == (long long)t.n) cd.mode = 2;    // dp.py:102-108: solve at lambda = 0
+        cd.tile0 = ntiles;
+        cd.ntiles = (int)((t.n + TILE - 1) / TILE);
+        ntiles += cd.ntiles;
+        for (int k = 0; k < cd.ntiles; ++k) tile_chrom.push_back(c);
+        if (cd.mode == 1) { any_search = true; max_iter = std::max(max_iter, t.max_iter); }
+    }
+    const bool vec = d_costs != nullptr;
+    const int max_slots = any_search ? std::max(2, (1 << levels) - 1) : 1;
+    const int slots_per_block = std::min(max_slots, 8);
+
+    Arena ar(st);
+    Workspace w;
+    RB_TRY(ar.alloc(&w.d_chroms, ntask));
+    RB_TRY(ar.alloc(&w.d_search, ntask));
+    RB_TRY(ar.alloc(&w.d_tile_chrom, ntiles));
+    RB_TRY(ar.alloc(&w.d_lam, (size_t)ntask * MAX_SLOTS));
+    RB_TRY(ar.alloc(&w.d_counts, (size_t)ntask * MAX_SLOTS));
+    RB_TRY(ar.alloc(&w.d_tiecnt, (size_t)ntask * MAX_SLOTS));
+    RB_TRY(ar.alloc(&w.d_near, ntask));
+    RB_TRY(ar.alloc(&w.d_flags, (size_t)max_slots * ntiles));
+    char *agg_bytes = nullptr, *incl_bytes = nullptr;
+    RB_TRY(ar.alloc(&agg_bytes, (size_t)max_slots * ntiles * sizeof(Map<VL>)));
+    RB_TRY(ar.alloc(&incl_bytes, (size_t)max_slots * ntiles * sizeof(VL)));
+    w.d_agg = agg_bytes; w.d_incl = incl_bytes;
+    RB_TRY(ar.alloc(&w.d_tout, (size_t)max_slots * ntiles));
+    RB_TRY(ar.alloc(&w.d_ticket, 1));
+    RB_TRY(ar.alloc(&w.d_zin, ntiles));
+    const int nparts = 64;
+    RB_TRY(ar.alloc(&w.d_partial, (size_t)ntask * nparts * 2));
+    RB_TRY(ar.alloc(&w.d_parts, ntiles));
+    RB_TRY(ar.alloc(&w.d_results, ntask));
+
+    // modes: 0 fixed (lambda given), 2 fixed at 0.0; both are PH_DONE from the start
+    std::vector<double> lam0((size_t)ntask * MAX_SLOTS, 0.0);
+    for (int c = 0; c < ntask; ++c) {
+        if (chroms[c].mode == 0) lam0[(size_t)c * MAX_SLOTS] = tasks[c].selection_penalty;
+        if (chroms[c].mode == 2) { chroms[c].mode = 0; lam0[(size_t)c * MAX_SLOTS] = 0.0; }
+    }
+    RB_CUDA(cudaMemcpyAsync(w.d_chroms, chroms.data(), sizeof(ChromDev) * ntask, cudaMemcpyHostToDevice, st));
+    RB_CUDA(cudaMemcpyAsync(w.d_tile_chrom, tile_chrom.data(), sizeof(int) * ntiles, cudaMemcpyHostToDevice, st));
+    RB_CUDA(cudaMemcpyAsync(w.d_lam, lam0.data(), sizeof(double) * lam0.size(), cudaMemcpyHostToDevice, st));
+    RB_CUDA(cudaMemsetAsync(w.d_flags, 0, sizeof(int) * (size_t)max_slots * ntiles, st));
+    RB_CUDA(cudaMemsetAsync(w.d_ticket, 0, sizeof(int), st));
+    RB_CUDA(cudaMemsetAsync(w.d_near, 0, sizeof(long long) * ntask, st));
+    RB_CUDA(cudaMemsetAsync(w.d_tiecnt, 0, sizeof(long long) * (size_t)ntask * MAX_SLOTS, st));
+
+    k_chain_minmax<<<dim3(ntask, nparts), 256, 0, st>>>(d_scores, w.d_chroms, w.d_search, w.d_partial);
+    RB_LAUNCH_CHECK();
+    k_chain_init<<<(ntask + 63) / 64, 64, 0, st>>>(w.d_chroms, w.d_search, w.d_lam, w.d_partial, nparts, levels, ntask);
+    RB_LAUNCH_CHECK();
+
+    Params P{};
+    P.scores = d_scores; P.costs = d_costs; P.chroms = w.d_chroms; P.search = w.d_search;
+    P.tile_chrom = w.d_tile_chrom; P.lam = w.d_lam; P.counts = w.d_counts; P.tiecnt = w.d_tiecnt;
+    P.flags = w.d_flags; P.agg = w.d_agg; P.incl = w.d_incl; P.tout = w.d_tout; P.ticket = w.d_ticket;
+    P.mask = d_masks; P.zin = w.d_zin; P.near_ties = w.d_near; P.ntiles = ntiles; P.nchrom = ntask;
+    P.slots_per_block = slots_per_block;
+    int epoch = 0;
+
+    std::vector<SearchDev> hsearch(ntask);
+    if (any_search) {
+        RB_TRY((launch_round<false>(P, vec, 2, epoch, st)));                 // bracket ends
+        // PH_BRACKET -> PH_BISECT generates the first tree in the same finish kernel
+        const int rounds = (max_iter + levels - 1) / levels;
+        for (int r = 0; r < rounds; ++r) RB_TRY((launch_round<false>(P, vec, max_slots, epoch, st)));
+        // rare: bracket expansion (dp.py:119-125, 132-138) is driven from the host with single solves
+        RB_CUDA(cudaMemcpyAsync(hsearch.data(), w.d_search, sizeof(SearchDev) * ntask, cudaMemcpyDeviceToHost, st));
+        RB_CUDA(cudaStreamSynchronize(st));
+        bool any_host = false;
+        for (int c = 0; c < ntask; ++c) any_host |= (hsearch[c].phase == PH_HOST);
+        if (any_host) {
+            std::vector<double> hl((size_t)ntask * MAX_SLOTS);
+            std::vector<long long> hc((size_t)ntask * MAX_SLOTS);
+            auto eval = [&](int c, double lamv, long long &count) -> int {
+                // PH_MANUAL for chromosome c only; everything else parked as PH_HOST (skipped)
+                for (int k = 0; k < ntask; ++k) {
+                    hsearch[k].phase = (k == c) ? PH_MANUAL : PH_HOST;
+                    hsearch[k].nslots = 1; hsearch[k].need_lex = 0;
+                }
+                RB_CUDA(cudaMemcpyAsync(w.d_search, hsearch.data(), sizeof(SearchDev) * ntask, cudaMemcpyHostToDevice, st));
+                RB_CUDA(cudaMemcpyAsync(w.d_lam + (size_t)c * MAX_SLOTS, &lamv, sizeof(double), cudaMemcpyHostToDevice, st));
+                RB_TRY((launch_round<false>(P, vec, 1, epoch, st)));
+                RB_CUDA(cudaMemcpyAsync(&count, w.d_counts + (size_t)c * MAX_SLOTS, sizeof(long long), cudaMemcpyDeviceToHost, st));
+                RB_CUDA(cudaStreamSynchronize(st));
+                return 0;
+            };
+            std::vector<SearchDev> fin = hsearch;
+            std::vector<SearchDev> saved = hsearch;
+            for (int c = 0; c < ntask; ++c) {
+                if (saved[c].phase != PH_HOST) continue;
+                const long long target = chroms[c].target;
+                double lower = saved[c].lower, upper = saved[c].upper;
+                long long cl = 0, cu = 0;
+                int passes = 0;
+                RB_TRY(eval(c, lower, cl)); ++passes;
+                while (cl <= target) { lower -= std::max(1.0, fabs(lower)); RB_TRY(eval(c, lower, cl)); ++passes; if (passes > 4096) return ST_INVALID; }
+                RB_TRY(eval(c, upper, cu)); ++passes;
+                while (cu > target) { upper += std::max(1.0, fabs(upper)); RB_TRY(eval(c, upper, cu)); ++passes; if (passes > 4096) return ST_INVALID; }
+                for (int it = 0; it < chroms[c].max_iter; ++it) {
+                    const double mid = (lower + upper) / 2.0;
+                    long long cm = 0;
+                    RB_TRY(eval(c, mid, cm)); ++passes;
+                    if (cm > target) lower = mid; else upper = mid;
+                }
+                fin[c] = saved[c];
+                fin[c].lower = lower; fin[c].upper = upper; fin[c].passes = passes; fin[c].rounds = passes;
+            }
+            for (int c = 0; c < ntask; ++c) {
+                if (saved[c].phase != PH_HOST) fin[c] = saved[c];
+                fin[c].phase = PH_DONE; fin[c].nslots = 1; fin[c].need_lex = 0;
+                hl[(size_t)c * MAX_SLOTS] = fin[c].upper;
+            }
+            RB_CUDA(cudaMemcpyAsync(w.d_search, fin.data(), sizeof(SearchDev) * ntask, cudaMemcpyHostToDevice, st));
+            for (int c = 0; c < ntask; ++c)
+                RB_CUDA(cudaMemcpyAsync(w.d_lam + (size_t)c * MAX_SLOTS, &hl[(size_t)c * MAX_SLOTS], sizeof(double),
+                                        cudaMemcpyHostToDevice, st));
+        }
+    }
+
+    // final solve at the chosen multiplier, mask emitted
+    RB_TRY((launch_round<true>(P, vec, 1, epoch, st)));
+    if (vec) k_chain_finalize<true><<<ntiles, THREADS, 0, st>>>(P, w.d_parts);
+    else k_chain_finalize<false><<<ntiles, THREADS, 0, st>>>(P, w.d_parts);
+    RB_LAUNCH_CHECK();
+    k_chain_results<<<ntask, 32, 0, st>>>(P, w.d_parts, w.d_results, vec ? 1 : 0);
+    RB_LAUNCH_CHECK();
+    RB_CUDA(cudaMemcpyAsync(results, w.d_results, sizeof(rocco_b200_chain_result) * ntask, cudaMemcpyDeviceToHost, st));
+    RB_CUDA(cudaStreamSynchronize(st));
+    for (int c = 0; c < ntask; ++c)
+        if (results[c].status == ST_NONFINITE) return ST_NONFINITE;
+    return 0;
+}
+
+}  // namespace chain
+}  // namespace rb
+
+// ====================================================================== C-ABI
+using namespace rb;
+
+extern "C" __attribute__((visibility("default"))) int rocco_b200_chain_solve_batch_dev(
+    const double *d_scores, const double *d_switch_costs, const rocco_b200_chain_task *tasks, int task_count,
+    uint8_t *d_masks_out, rocco_b200_chain_result *results_out, int levels_per_round, void *cuda_stream)
+{
+    return chain::solve_batch(d_scores, d_switch_costs, tasks, task_count, d_masks_out, results_out,
+                              levels_per_round, (cudaStream_t)cuda_stream);
+}
+
+static int host_chain(const double *scores, const double *costs, size_t n, int mode, double lam, long long target,
+                      int max_iter, uint8_t *mask_out, rocco_b200_chain_result *res)
+{
+    if (!scores || !mask_out || n == 0) return ST_INVALID;
+    if (n > 1 && !costs) return ST_INVALID;
+    RB_TRY(ensure_device());
+    cudaStream_t st = 0;
+    Arena ar(st);
+    double *d_s = nullptr, *d_c = nullptr;
+    uint8_t *d_m = nullptr;
+    RB_TRY(ar.alloc(&d_s, n));
+    RB_TRY(ar.alloc(&d_c, n));
+    RB_TRY(ar.alloc(&d_m, n));
+    RB_CUDA(cudaMemcpyAsync(d_s, scores, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    RB_CUDA(cudaMemsetAsync(d_c, 0, n * sizeof(double), st));
+    double csum = 0.0;
+    if (n > 1) {
+        RB_CUDA(cudaMemcpyAsync(d_c, costs, (n - 1) * sizeof(double), cudaMemcpyHostToDevice, st));
+        for (size_t i = 0; i + 1 < n; ++i)
+            if (!(costs[i] >= 0.0)) return ST_INVALID;      // negative / NaN switch costs are outside the clamp-map form
+        csum = numpy_sum_f64(costs, n - 1);                  // dp.py:110-111 uses numpy.sum; its rounding defines the bracket
+    }
+    rocco_b200_chain_task t{};
+    t.offset = 0; t.n = n; t.gamma = 0.0; t.cost_sum = csum; t.selection_penalty = lam;
+    t.target_count = target; t.mode = mode; t.max_iter = max_iter;
+    int s = chain::solve_batch(d_s, d_c, &t, 1, d_m, res, 0, st);
+    if (s != 0) return s;
+    RB_CUDA(cudaMemcpyAsync(mask_out, d_m, n, cudaMemcpyDeviceToHost, st));
+    RB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int rocco_solve_penalized_chain_f64(
+    const double *scores, const double *switch_costs, size_t n, double selection_penalty,
+    uint8_t *solution_out, double *penalized_objective_out, long long *selected_count_out)
+{
+    rocco_b200_chain_result r{};
+    int s = host_chain(scores, switch_costs, n, 0, selection_penalty, 0, 0, solution_out, &r);
+    if (s != 0) return s;
+    if (penalized_objective_out) *penalized_objective_out = r.penalized_objective;
+    if (selected_count_out) *selected_count_out = r.selected_count;
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int rocco_calibrate_selection_penalty_f64(
+    const double *scores, const double *switch_costs, size_t n, long long target_count, int max_iter,
+    double *selection_penalty_out, uint8_t *solution_out, double *penalized_objective_out,
+    long long *selected_count_out)
+{
+    rocco_b200_chain_result r{};
+    int s = host_chain(scores, switch_costs, n, 1, 0.0, target_count, max_iter, solution_out, &r);
+    if (s != 0) return s;
+    if (selection_penalty_out) *selection_penalty_out = r.selection_penalty;
+    if (penalized_objective_out) *penalized_objective_out = r.penalized_objective;
+    if (selected_count_out) *selected_count_out = r.selected_count;
+    return 0;
+}

@@ -1,0 +1,137 @@
+// Shared helpers for the rocco_b200 CUDA library (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "../../include/rocco_b200.h"
+
+namespace rb {
+
+constexpr int ST_OK = 0, ST_NOMEM = -1, ST_INVALID = -2, ST_CUDA = -3, ST_NONFINITE = -4;
+
+void set_error(const char *fmt, ...);
+extern std::atomic<unsigned long long> g_launches;
+inline void count_launch(int k = 1) { g_launches.fetch_add((unsigned long long)k, std::memory_order_relaxed); }
+
+#define RB_CUDA(expr)                                                                        \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            ::rb::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return (_e == cudaErrorMemoryAllocation) ? ::rb::ST_NOMEM : ::rb::ST_CUDA;       \
+        }                                                                                    \
+    } while (0)
+
+#define RB_LAUNCH_CHECK()                                                                    \
+    do {                                                                                     \
+        ::rb::count_launch();                                                                \
+        RB_CUDA(cudaGetLastError());                                                         \
+    } while (0)
+
+#define RB_TRY(expr)                  \
+    do {                              \
+        int _s = (expr);              \
+        if (_s != 0) return _s;       \
+    } while (0)
+
+// Stream-ordered scratch: every buffer is freed (stream-ordered) when the arena dies.
+class Arena {
+  public:
+    explicit Arena(cudaStream_t s) : stream_(s) {}
+    ~Arena() { release(); }
+    Arena(const Arena &) = delete;
+    Arena &operator=(const Arena &) = delete;
+    template <typename T> int alloc(T **out, size_t count) {
+        void *p = nullptr;
+        size_t bytes = count * sizeof(T);
+        if (bytes == 0) bytes = 16;
+        cudaError_t e = cudaMallocAsync(&p, bytes, stream_);
+        if (e != cudaSuccess) {
+            set_error("cudaMallocAsync(%zu bytes) -> %s", bytes, cudaGetErrorString(e));
+            (void)cudaGetLastError();
+            *out = nullptr;
+            return e == cudaErrorMemoryAllocation ? ST_NOMEM : ST_CUDA;
+        }
+        ptrs_.push_back(p);
+        *out = static_cast<T *>(p);
+        return 0;
+    }
+    void release() {
+        for (void *p : ptrs_) cudaFreeAsync(p, stream_);
+        ptrs_.clear();
+    }
+
+  private:
+    cudaStream_t stream_;
+    std::vector<void *> ptrs_;
+};
+
+// Pinned host staging that is released on scope exit.
+template <typename T> class Pinned {
+  public:
+    Pinned() = default;
+    ~Pinned() { if (p_) cudaFreeHost(p_); }
+    int alloc(size_t count) {
+        cudaError_t e = cudaMallocHost(&p_, (count ? count : 1) * sizeof(T));
+        if (e != cudaSuccess) {
+            set_error("cudaMallocHost -> %s", cudaGetErrorString(e));
+            (void)cudaGetLastError();
+            p_ = nullptr;
+            return ST_NOMEM;
+        }
+        return 0;
+    }
+    T *get() { return static_cast<T *>(p_); }
+    T &operator[](size_t i) { return static_cast<T *>(p_)[i]; }
+
+  private:
+    void *p_ = nullptr;
+};
+
+int ensure_device();     // returns 0 or ST_CUDA when no usable device
+int sm_count();
+
+// ---------------------------------------------------------------- device helpers
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
+
+__device__ __forceinline__ double shfl_up_f64(double v, int delta) {
+    return __shfl_up_sync(0xffffffffu, v, delta);
+}
+__device__ __forceinline__ double shfl_f64(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+__device__ __forceinline__ void st_release_i32(int *p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_i32(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// streaming 128-bit loads (read-once data: do not allocate in L1)
+__device__ __forceinline__ double2 ld_stream_f64x2(const double *p) {
+    double2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float4 ld_stream_f32x4(const float *p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
+}  // namespace rb
+
+namespace rb {
+// numpy.sum of a contiguous float64 vector, restated (pairwise halving down to blocks of <= 128 summed with 8
+// accumulators): dp.py:110-111 builds the search bracket from numpy.sum(switch_costs).
+double numpy_sum_f64(const double *a, size_t n);
+double numpy_sum_const_f64(double value, size_t n);
+}  // namespace rb

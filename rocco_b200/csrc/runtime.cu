@@ -1,0 +1,126 @@
+// Library plumbing: error text, device selection, launch counter, numpy-compatible summation.
+#include "common.cuh"
+
+#include <stdarg.h>
+
+#include <map>
+
+namespace rb {
+
+static thread_local char g_err[512] = "";
+std::atomic<unsigned long long> g_launches{0};
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int ensure_device()
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        set_error("no CUDA device available (%s); rocco_b200 has no CPU fallback",
+                  e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        return ST_CUDA;
+    }
+    return 0;
+}
+
+int sm_count()
+{
+    static int cached = 0;
+    if (cached == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            cached = n;
+        else
+            cached = 148;
+    }
+    return cached;
+}
+
+// numpy/_core/src/umath/loops_utils.h.src  DOUBLE_pairwise_sum, restated
+static double pairwise(const double *a, size_t n)
+{
+    if (n < 8) {
+        double r = 0.0;
+        for (size_t i = 0; i < n; ++i) r += a[i];
+        return r;
+    }
+    if (n <= 128) {
+        double r[8];
+        for (int k = 0; k < 8; ++k) r[k] = a[k];
+        size_t i = 8;
+        for (; i < n - (n % 8); i += 8)
+            for (int k = 0; k < 8; ++k) r[k] += a[i + k];
+        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; ++i) res += a[i];
+        return res;
+    }
+    size_t n2 = n / 2;
+    n2 -= n2 % 8;
+    return pairwise(a, n2) + pairwise(a + n2, n - n2);
+}
+
+double numpy_sum_f64(const double *a, size_t n)
+{
+    if (n == 0) return 0.0;
+    return pairwise(a, n);
+}
+
+static double pairwise_const(double v, size_t n, std::map<size_t, double> &memo)
+{
+    if (n <= 128) {
+        double buf[128];
+        for (size_t i = 0; i < n; ++i) buf[i] = v;
+        return pairwise(buf, n);
+    }
+    auto it = memo.find(n);
+    if (it != memo.end()) return it->second;
+    size_t n2 = n / 2;
+    n2 -= n2 % 8;
+    const double r = pairwise_const(v, n2, memo) + pairwise_const(v, n - n2, memo);
+    memo[n] = r;
+    return r;
+}
+
+double numpy_sum_const_f64(double value, size_t n)
+{
+    if (n == 0) return 0.0;
+    std::map<size_t, double> memo;
+    return pairwise_const(value, n, memo);
+}
+
+}  // namespace rb
+
+#define RB_API __attribute__((visibility("default")))
+extern "C" {
+
+RB_API const char *rocco_b200_version(void) { return "0.1.0"; }
+RB_API const char *rocco_b200_last_error(void) { return rb::g_err; }
+
+RB_API int rocco_b200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    return n;
+}
+
+RB_API int rocco_b200_set_device(int device)
+{
+    RB_TRY(rb::ensure_device());
+    RB_CUDA(cudaSetDevice(device));
+    return 0;
+}
+
+RB_API unsigned long long rocco_b200_kernel_launches(void) { return rb::g_launches.load(); }
+
+RB_API double rocco_b200_numpy_sum_f64(const double *a, size_t n) { return rb::numpy_sum_f64(a, n); }
+RB_API double rocco_b200_numpy_sum_const_f64(double value, size_t n) { return rb::numpy_sum_const_f64(value, n); }
+}

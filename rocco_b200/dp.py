@@ -1,0 +1,97 @@
+"""Host-side mirror of the reference's ``rocco/dp.py`` (same names, arguments, return types).
+
+The chain DP and the budget search run on the GPU (``csrc/chain.cu``); this module only keeps the
+reference's Python-level contract: ``dp.py:16-34`` objective_value, ``37-46`` build_switch_costs,
+``49-86`` solve_penalized_chain, ``89-164`` calibrate_selection_penalty, ``167-228`` solve_chrom_exact.
+"""
+from __future__ import annotations
+
+import ctypes
+import logging
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+
+from . import _chain_dp, _lib
+
+logger = logging.getLogger(__name__)
+
+
+def objective_value(solution: np.ndarray, scores: np.ndarray, switch_costs) -> float:
+    solution_ = np.asarray(solution, dtype=np.float64)
+    scores_ = np.asarray(scores, dtype=np.float64)
+    if np.isscalar(switch_costs):
+        switch_costs_ = np.full(max(solution_.shape[0] - 1, 0), float(switch_costs), dtype=np.float64)
+    else:
+        switch_costs_ = np.asarray(switch_costs, dtype=np.float64)
+    penalty = 0.0
+    if solution_.shape[0] > 1:
+        penalty = float(switch_costs_ @ np.abs(np.diff(solution_, 1)))
+    return float(-(scores_ @ solution_) + penalty)
+
+
+def build_switch_costs(scores: np.ndarray, gamma: float = 1.0) -> np.ndarray:
+    scores_ = np.asarray(scores, dtype=np.float64)
+    if scores_.ndim != 1:
+        raise ValueError("`scores` must be a one-dimensional array")
+    if scores_.shape[0] <= 1:
+        return np.zeros(0, dtype=np.float64)
+    return np.full(scores_.shape[0] - 1, float(gamma), dtype=np.float64)
+
+
+def solve_penalized_chain(scores, switch_costs, selection_penalty: float) -> Tuple[np.ndarray, float, int]:
+    r"""max_z sum (s_j - lambda) z_j - sum c_j |z_{j+1} - z_j|, ties -> fewer selected (dp.py:49-86)."""
+    scores_ = np.ascontiguousarray(scores, dtype=np.float64)
+    switch_costs_ = np.ascontiguousarray(switch_costs, dtype=np.float64)
+    solution, penalized_objective, selected_count = _chain_dp.solve_penalized_chain(
+        scores_, switch_costs_, float(selection_penalty))
+    return np.asarray(solution, dtype=np.uint8), float(penalized_objective), int(selected_count)
+
+
+def calibrate_selection_penalty(scores, switch_costs, target_count: int, max_iter: int = 60
+                                ) -> Tuple[float, np.ndarray, float, int]:
+    r"""Bisection on DP solutions (dp.py:89-164), evaluated as a batched bisection tree on the GPU:
+    the same (lower+upper)/2 lattice, several levels per launch."""
+    scores_ = np.ascontiguousarray(scores, dtype=np.float64)
+    switch_costs_ = np.ascontiguousarray(switch_costs, dtype=np.float64)
+    n = scores_.shape[0]
+    if scores_.ndim != 1 or switch_costs_.ndim != 1:
+        raise ValueError("`scores` and `switch_costs` must be one-dimensional")
+    if n == 0:
+        raise ValueError("`scores` cannot be empty")
+    if n > 1 and switch_costs_.shape[0] != n - 1:
+        raise ValueError("`switch_costs` must have length len(scores) - 1")
+    lib = _lib.load()
+    _lib.require_device()
+    solution = np.zeros(n, dtype=np.uint8)
+    lam, val, cnt = ctypes.c_double(0.0), ctypes.c_double(0.0), ctypes.c_longlong(0)
+    st = lib.rocco_calibrate_selection_penalty_f64(
+        _lib.np_ptr(scores_), _lib.np_ptr(switch_costs_) if n > 1 else None, n, int(target_count), int(max_iter),
+        ctypes.byref(lam), _lib.np_ptr(solution), ctypes.byref(val), ctypes.byref(cnt))
+    _lib.check(st, "calibrate_selection_penalty")
+    return float(lam.value), solution, float(val.value), int(cnt.value)
+
+
+def solve_chrom_exact(
+    scores: np.ndarray,
+    budget: Optional[float] = None,
+    gamma: float = 1.0,
+    selection_penalty: Optional[float] = None,
+    return_details: bool = False,
+) -> Tuple[np.ndarray, float] | Tuple[np.ndarray, float, Dict[str, float]]:
+    r"""Solve one chromosome with the exact penalized-chain DP (dp.py:167-228).
+
+    ``scores`` may be a NumPy array or a CUDA ``torch.Tensor`` (float64); the latter skips the host
+    round trip but NumPy arrays are still returned."""
+    from .pipeline import solve_chromosomes
+
+    res = solve_chromosomes([scores], budgets=[budget], gammas=[gamma], selection_penalties=[selection_penalty])[0]
+    solution = res["solution"]
+    if not return_details:
+        return solution, res["objective"]
+    return solution, res["objective"], {
+        "penalized_objective": float(res["penalized_objective"]),
+        "selected_count": int(res["selected_count"]),
+        "selected_fraction": float(res["selected_count"] / solution.shape[0]),
+        "selection_penalty": float(res["selection_penalty"]),
+    }

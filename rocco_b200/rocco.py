@@ -1,0 +1,135 @@
+"""Host-side mirror of the hot-path functions of the reference's ``rocco/rocco.py``.
+
+* ``chrom_solution_to_bed`` (rocco.py:139-191), ``_merge_bed_records`` (74-95), ``_write_bed_records``
+  (98-110), ``combine_chrom_results`` (194-240): the per-bin Python loop over the mask is replaced by
+  run detection on the GPU (``csrc/bed.cu``); text I/O stays on the host.
+* ``score_central_tendency_chrom`` (243-304) / ``score_dispersion_chrom`` (307-355): column-wise
+  order statistics over the sample axis on the GPU (``csrc/colstats.cu``).
+"""
+from __future__ import annotations
+
+import ctypes
+import logging
+import os
+from typing import Tuple
+
+import numpy as np
+
+from . import _lib
+
+logger = logging.getLogger(__name__)
+
+
+def _read_bed_records(bed_file: str) -> tuple[list[tuple[str, int, int]], bool]:
+    records: list[tuple[str, int, int]] = []
+    saw_extra_columns = False
+    with open(bed_file, "r", encoding="utf-8") as handle:
+        for line_num, line in enumerate(handle, start=1):
+            line_ = line.strip()
+            if line_ == "":
+                continue
+            fields = line_.split("\t")
+            if len(fields) < 3:
+                raise ValueError(f"BED row {line_num} in {bed_file} has fewer than 3 columns.")
+            if len(fields) > 3:
+                saw_extra_columns = True
+            records.append((str(fields[0]), int(fields[1]), int(fields[2])))
+    return records, saw_extra_columns
+
+
+def _merge_bed_records(records, min_length_bp: int | None = None):
+    """Sort by (chrom string, start, end) and merge records with start <= previous end."""
+    if len(records) == 0:
+        return []
+    merged: list[list] = []
+    for chrom, start, end in sorted(records, key=lambda x: (x[0], x[1], x[2])):
+        if merged and chrom == merged[-1][0] and int(start) <= int(merged[-1][2]):
+            merged[-1][2] = max(int(merged[-1][2]), int(end))
+            continue
+        merged.append([chrom, int(start), int(end)])
+    return [(str(c), int(s), int(e)) for c, s, e in merged
+            if min_length_bp is None or (int(e) - int(s)) >= int(min_length_bp)]
+
+
+def _write_bed_records(records, output_file: str, name_features: bool = False) -> str:
+    with open(output_file, "w", encoding="utf-8") as handle:
+        if name_features:
+            handle.write("".join(f"{c}\t{s}\t{e}\t{c}_{s}_{e}\n" for c, s, e in records))
+        else:
+            handle.write("".join(f"{c}\t{s}\t{e}\n" for c, s, e in records))
+    return output_file
+
+
+def solution_runs(solution) -> Tuple[np.ndarray, np.ndarray]:
+    """Maximal runs of selected bins among bins 0..n-2 (the last bin is never emitted), on the GPU.
+
+    Returns (first_bin, last_bin + 1) index arrays."""
+    sol = np.asarray(solution)
+    mask = np.ascontiguousarray(sol if sol.dtype == np.uint8 else (sol > 0.50), dtype=np.uint8)
+    if sol.dtype == np.uint8 and mask.max(initial=0) > 1:
+        mask = (mask > 0).astype(np.uint8)
+    n = mask.shape[0]
+    if n == 0:
+        return np.zeros(0, np.int64), np.zeros(0, np.int64)
+    lib = _lib.load()
+    _lib.require_device()
+    cap = n // 2 + 1
+    starts = np.empty(cap, dtype=np.int64)
+    ends = np.empty(cap, dtype=np.int64)
+    k = lib.rocco_mask_to_intervals_u8(_lib.np_ptr(mask), n, 0, 1, 0, _lib.np_ptr(starts), _lib.np_ptr(ends), cap)
+    if k < 0:
+        _lib.check(int(k), "chrom_solution_to_bed")
+    return starts[:k], ends[:k]
+
+
+def chrom_solution_to_bed(chromosome, intervals, solution, ID=None, check_gaps_intervals=True,
+                          min_length_bp=None) -> str:
+    r"""Convert the decision vector of one chromosome to a BED file in the current directory
+    (rocco.py:139-191).  Selected bins (> 0.5) become (intervals[i], intervals[i+1]); the last bin is
+    dropped; adjacent records merge; records shorter than ``min_length_bp`` are removed."""
+    if len(intervals) != len(solution):
+        raise ValueError(
+            f"Intervals and solution must have the same length at the pre-merge stage: {len(intervals)} != {len(solution)}")
+    intervals_ = np.asarray(intervals)
+    if check_gaps_intervals:
+        gaps = np.unique(np.diff(intervals_))
+        if len(gaps) > 1:
+            raise ValueError(f"Intervals must be contiguous: {set(gaps.tolist())}")
+    step_ = intervals_[1] - intervals_[0]  # noqa: F841  (kept: the reference evaluates it, so len < 2 raises)
+    output_file = f"rocco_{chromosome}.bed" if ID is None else f"rocco_{ID}_{chromosome}.bed"
+    first, last = solution_runs(solution)
+    starts = intervals_[first]
+    ends = intervals_[last]
+    records = [(str(chromosome), int(s), int(e)) for s, e in zip(starts.tolist(), ends.tolist())]
+    if len(records) > 1 and not np.all(starts[1:] > ends[:-1]):
+        records = _merge_bed_records(records)          # non-monotone interval tables: full reference merge
+    if min_length_bp is not None:
+        records = [r for r in records if (r[2] - r[1]) >= int(min_length_bp)]
+    return _write_bed_records(records, output_file)
+
+
+def combine_chrom_results(chrom_bed_files: list, output_file: str, name_features: bool = False) -> str:
+    r"""Concatenate per-chromosome BED files, sort by (chrom string, start, end), merge, write
+    (rocco.py:194-240)."""
+    printed_colct_msg = False
+    if os.path.exists(output_file):
+        logger.info(f"Removing existing output file: {output_file}")
+        try:
+            os.remove(output_file)
+        except OSError:
+            logger.info(f"Could not remove existing output file: {output_file}.")
+    combined_records: list[tuple[str, int, int]] = []
+    for chrom_bed_file in chrom_bed_files:
+        if not os.path.exists(chrom_bed_file):
+            raise FileNotFoundError(f"File does not exist: {chrom_bed_file}")
+        try:
+            chrom_records, saw_extra_columns = _read_bed_records(chrom_bed_file)
+        except Exception as e:
+            logger.info(f"Could not read BED file: {chrom_bed_file}\n{e}\n")
+            raise
+        if saw_extra_columns and not printed_colct_msg:
+            logger.info("More than 3 columns detected in the input BED files. Extra columns will be ignored.")
+            printed_colct_msg = True
+        combined_records.extend(chrom_records)
+    merged_records = _merge_bed_records(combined_records)
+    return _write_bed_records(merged_records, output_file, name_features=name_features)

@@ -1,0 +1,63 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every declared symbol,
+the numpy.sum restatement that defines the search bracket (dp.py:110-111) is bit-exact, layout and
+budget-target rules, BED merge/sort semantics.  No kernel is launched here."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from rocco_b200 import _lib
+    lib = _lib.load()                       # raises if the .so is missing or a symbol is absent
+    header = open(os.path.join(REPO, "include", "rocco_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(rocco_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 20
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/rocco_b200.h but not exported"
+    assert lib.rocco_b200_version().decode() == "0.1.0"
+
+
+def test_compute_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import rocco_b200
+    with pytest.raises(RuntimeError):
+        rocco_b200.solve_penalized_chain(np.zeros(4), np.ones(3), 0.0)
+    with pytest.raises(RuntimeError):
+        rocco_b200.chrom_solution_to_bed("c", np.arange(0, 200, 50), np.array([1, 1, 0, 0], dtype=np.uint8))
+
+
+def test_numpy_sum_restatement_is_bit_exact():
+    from rocco_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    for n in [1, 2, 7, 8, 9, 127, 128, 129, 130, 255, 256, 1000, 4097, 65537, 934199, 1172352, 4979128]:
+        a = rng.uniform(0, 3, size=n)
+        assert lib.rocco_b200_numpy_sum_f64(a.ctypes.data, n) == float(np.sum(a))
+        for g in (1.0, 6.86, 0.1, 2.5, 1e-3):
+            assert _lib.numpy_sum_const(g, n) == float(np.sum(np.full(n, g))), (n, g)
+
+
+def test_layout_and_budget_target():
+    from rocco_b200.pipeline import layout_offsets, target_count_for_budget
+    offs, total = layout_offsets([5, 16, 17, 1])
+    assert offs == [0, 16, 32, 64] and total == 80
+    # SURVEY.md appendix D item 12
+    assert target_count_for_budget(934200, 0.02) == 18684
+    assert target_count_for_budget(1172353, 0.045) == 52755
+    assert target_count_for_budget(3120818, 0.015) == 46812
+    assert target_count_for_budget(4979129, 0.03) == 149373
+
+
+def test_merge_sorts_chromosomes_lexicographically(oracle):
+    from rocco_b200.rocco import _merge_bed_records
+    recs = [("chr2", 5, 10), ("chr10", 0, 5), ("chr1", 50, 60), ("chr1", 55, 70), ("chr1", 70, 80), ("chr10", 5, 7)]
+    want = oracle.merge_bed_records(recs)
+    assert _merge_bed_records(recs) == want == [("chr1", 50, 80), ("chr10", 0, 7), ("chr2", 5, 10)]
+    assert _merge_bed_records(recs, min_length_bp=10) == oracle.merge_bed_records(recs, 10)
