@@ -114,6 +114,11 @@ int rocco_b200_chain_solve_batch_dev(
     int levels_per_round,                 /* bisection levels evaluated per launch (1..8); 0 = default */
     void *cuda_stream);
 
+/* Chromosomes of at most `max_bins` (<= 4096, the default) bins are solved by replaying the
+ * reference's sequential recurrence operation for operation (bit-identical value / count / mask);
+ * longer ones use the parallel scan.  Returns the previous setting.  0 forces the scan everywhere. */
+int rocco_b200_chain_set_seq_max(int max_bins);
+
 /* Multiplier sweep: counts and objectives for `lambda_count` multipliers in one launch set
  * (BASELINE.json config 5).  Outputs are host arrays of lambda_count entries. */
 int rocco_b200_chain_sweep_dev(

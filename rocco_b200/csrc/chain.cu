@@ -104,6 +104,8 @@ struct ChromDev {
     int ntiles;
     int mode;               // 0 fixed multiplier, 1 budget search
     int max_iter;
+    int seq;                // 1: short chromosome solved by the exact sequential kernel (one tile)
+    int pad;
 };
 
 enum Phase : int { PH_BRACKET = 0, PH_BISECT = 1, PH_DONE = 2, PH_HOST = 3, PH_MANUAL = 4 };
@@ -140,6 +142,8 @@ struct Params {
     uint8_t *mask;              // EMIT only
     int *zin;                   // [tile]  EMIT: value flowing into the tile from the right
     long long *near_ties;       // [nchrom] EMIT only
+    uint8_t *bt;                // [ntiles * TILE] back-pointers of the sequential kernel (EMIT only)
+    double *seq_value;          // [nchrom] DP best value of the sequential kernel (EMIT only)
     int ntiles;
     int nchrom;
     int slots_per_block;        // multipliers handled sequentially by one block
@@ -170,6 +174,7 @@ __global__ void __launch_bounds__(THREADS) k_chain_tiles(Params P)
     const int c = P.tile_chrom[tile];
     const ChromDev cd = P.chroms[c];
     const SearchDev sd = P.search[c];
+    if (cd.seq) return;
     if (P.lex_pass ? (sd.need_lex == 0) : (sd.phase == PH_DONE && !EMIT) || sd.phase == PH_HOST) return;
     const int slot0 = group * P.slots_per_block;
     if (slot0 >= sd.nslots) return;
@@ -379,6 +384,63 @@ __global__ void __launch_bounds__(THREADS) k_chain_tiles(Params P)
     (void)last_tile;
 }
 
+
+// ------------------------------------------------------------------ short chromosomes: exact sequential emulation
+// For n <= TILE the reference's recurrence is replayed operation for operation (_chain_dp.c:109-186):
+// same association order, same (value, fewer-count) comparisons, so value/count/mask are the
+// reference's bits.  This matters because on short inputs the 60-step bisection converges to
+// neighbouring doubles around a breakpoint, where the reference's decisions are rounding-determined.
+// One thread per (chromosome, multiplier); the threads of a block read the same scores (broadcast).
+template <bool VEC_COST, bool EMIT>
+__global__ void __launch_bounds__(256) k_chain_seq(Params P)
+{
+    const int c = blockIdx.x;
+    const ChromDev cd = P.chroms[c];
+    if (!cd.seq) return;
+    const SearchDev sd = P.search[c];
+    if ((sd.phase == PH_DONE && !EMIT) || sd.phase == PH_HOST) return;
+    const int slot = threadIdx.x;
+    if (slot >= sd.nslots) return;
+    const double lam = P.lam[(size_t)c * MAX_SLOTS + slot];
+    const double *s = P.scores + cd.offset;
+    const double *cs = VEC_COST ? P.costs + cd.offset : nullptr;
+    uint8_t *bt = EMIT ? P.bt + (size_t)cd.tile0 * TILE : nullptr;
+    const int n = (int)cd.n;
+    double v0 = 0.0, v1 = s[0] - lam;
+    long long k0 = 0, k1 = 1;
+    for (int i = 1; i < n; ++i) {
+        const double cc = VEC_COST ? cs[i - 1] : cd.gamma;
+        const double si = s[i];
+        const double off_leave = v1 - cc;
+        const double on_keep = v1 + si - lam;
+        const double on_enter = v0 - cc + si - lam;
+        const bool leave = (off_leave > v0) || (off_leave == v0 && k1 < k0);
+        const bool enter = (on_enter > on_keep) || (on_enter == on_keep && (k0 + 1) < (k1 + 1));
+        const double nv0 = leave ? off_leave : v0;
+        const long long nk0 = leave ? k1 : k0;
+        const double nv1 = enter ? on_enter : on_keep;
+        const long long nk1 = (enter ? k0 : k1) + 1;
+        if (EMIT) bt[i] = (uint8_t)((leave ? 1 : 0) | (enter ? 0 : 2));   // bit0: pred of state 0, bit1: pred of state 1
+        v0 = nv0; k0 = nk0; v1 = nv1; k1 = nk1;
+    }
+    const bool end_on = (v1 > v0) || (v1 == v0 && k1 < k0);
+    const long long cnt = end_on ? k1 : k0;
+    P.counts[(size_t)c * MAX_SLOTS + slot] = cnt;
+    P.tiecnt[(size_t)c * MAX_SLOTS + slot] = 0;
+    if (EMIT && slot == 0) {
+        uint8_t *m = P.mask + cd.offset;
+        int st = end_on ? 1 : 0;
+        m[n - 1] = (uint8_t)st;
+        for (int i = n - 1; i > 0; --i) {
+            st = st ? ((bt[i] >> 1) & 1) : (bt[i] & 1);
+            m[i - 1] = (uint8_t)st;
+        }
+        P.seq_value[c] = end_on ? v1 : v0;
+        P.tout[cd.tile0] = TileOut{(int)cnt, 0, (int)m[0], 0};
+        P.zin[cd.tile0] = 0;
+    }
+}
+
 // ------------------------------------------------------------------ per-chromosome finish + search controller
 // One block per chromosome, one warp per multiplier slot (looping when there are more slots than warps).
 __device__ void gen_tree(const SearchDev &sd, double *lam, int levels)
@@ -406,13 +468,14 @@ __global__ void __launch_bounds__(256) k_chain_finish(Params P, int emit)
     if (blockIdx.x == 0 && threadIdx.x == 0) *P.ticket = 0;
     const bool active = P.lex_pass ? (sd.need_lex != 0)
                                    : !((sd.phase == PH_DONE && !emit) || sd.phase == PH_HOST);
+    // (sequential-kernel chromosomes never set need_lex: their counts are already the reference's)
     if (!active) return;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     __shared__ int s_anytie;
     if (threadIdx.x == 0) s_anytie = 0;
     __syncthreads();
 
-    for (int slot = wid; slot < sd.nslots; slot += nw) {
+    for (int slot = wid; slot < sd.nslots && !cd.seq; slot += nw) {
         const TileOut *to = P.tout + (size_t)slot * P.ntiles + cd.tile0;
         long long total = 0;
         int ties = 0;
@@ -457,8 +520,10 @@ __global__ void __launch_bounds__(256) k_chain_finish(Params P, int emit)
         return;
     }
     sd.need_lex = 0;
-    sd.passes += sd.nslots;
-    sd.rounds += 1;
+    if (!emit) {                                        // the final mask-emitting solve re-evaluates `upper`
+        sd.passes += sd.nslots;
+        sd.rounds += 1;
+    }
     const long long *cnt = P.counts + (size_t)c * MAX_SLOTS;
     double *lam = P.lam + (size_t)c * MAX_SLOTS;
     if (sd.phase == PH_BRACKET) {
@@ -639,13 +704,13 @@ __global__ void k_chain_results(Params P, const FinalPart *parts, rocco_b200_cha
         const double lam = P.lam[(size_t)c * MAX_SLOTS];
         const double tv = vec_cost ? scost : cd.gamma * (double)sw;
         r.selection_penalty = lam;
-        r.penalized_objective = ssz - lam * (double)cnt - tv;
+        r.penalized_objective = cd.seq ? P.seq_value[c] : ssz - lam * (double)cnt - tv;
         r.objective = -ssz + tv;
         r.selected_count = cnt;
         r.switch_count = sw;
         r.exact_tie_bins = P.tiecnt[(size_t)c * MAX_SLOTS];
         r.near_tie_bins = P.near_ties[c];
-        r.dp_passes = sd.passes;
+        r.dp_passes = sd.passes + (cd.mode == 0 ? 1 : 0);
         r.search_rounds = sd.rounds;
         r.status = isnan(sd.smin) ? ST_NONFINITE : 0;
         r.reserved = 0;
@@ -654,6 +719,9 @@ __global__ void k_chain_results(Params P, const FinalPart *parts, rocco_b200_cha
 }
 
 // ------------------------------------------------------------------ host driver
+// chromosomes of at most this many bins (<= TILE) use the exact sequential kernel
+static std::atomic<int> g_seq_max{TILE};
+
 struct Workspace {
     ChromDev *d_chroms = nullptr;
     SearchDev *d_search = nullptr;
@@ -686,13 +754,18 @@ static int launch_tiles(const Params &P, int blocks, cudaStream_t st)
 }
 
 template <bool EMIT>
-static int launch_round(Params P, bool vec, int nslots_max, int &epoch, cudaStream_t st)
+static int launch_round(Params P, bool vec, int nslots_max, int &epoch, bool any_seq, cudaStream_t st)
 {
     P.ngroups = (nslots_max + P.slots_per_block - 1) / P.slots_per_block;
     const int blocks = P.ntiles * P.ngroups;
     for (int lex = 0; lex < 2; ++lex) {
         P.lex_pass = lex;
         P.epoch = ++epoch;
+        if (lex == 0 && any_seq) {
+            if (vec) k_chain_seq<true, EMIT><<<P.nchrom, 256, 0, st>>>(P);
+            else k_chain_seq<false, EMIT><<<P.nchrom, 256, 0, st>>>(P);
+            RB_LAUNCH_CHECK();
+        }
         if (lex == 0) {
             if (vec) RB_TRY((launch_tiles<VD, true, EMIT>(P, blocks, st)));
             else RB_TRY((launch_tiles<VD, false, EMIT>(P, blocks, st)));
@@ -718,7 +791,7 @@ static int solve_batch(const double *d_scores, const double *d_costs, const rocc
     std::vector<ChromDev> chroms(ntask);
     std::vector<int> tile_chrom;
     int ntiles = 0, max_iter = 0;
-    bool any_search = false;
+    bool any_search = false, any_seq = false;
     for (int c = 0; c < ntask; ++c) {
         const rocco_b200_chain_task &t = tasks[c];
         if (t.n == 0 || !(t.gamma >= 0.0) || t.n > (size_t)1 << 40) return ST_INVALID;
@@ -728,6 +801,9 @@ static int solve_batch(const double *d_scores, const double *d_costs, const rocc
         long long target = std::max<long long>(0, std::min<long long>(t.target_count, (long long)t.n));
         cd.target = target;
         if (t.mode == 1 && target == (long long)t.n) cd.mode = 2;    // dp.py:102-108: solve at lambda = 0
+        cd.seq = ((long long)t.n <= (long long)g_seq_max.load()) ? 1 : 0;
+        cd.pad = 0;
+        any_seq |= cd.seq != 0;
         cd.tile0 = ntiles;
         cd.ntiles = (int)((t.n + TILE - 1) / TILE);
         ntiles += cd.ntiles;
@@ -759,6 +835,10 @@ static int solve_batch(const double *d_scores, const double *d_costs, const rocc
     RB_TRY(ar.alloc(&w.d_partial, (size_t)ntask * nparts * 2));
     RB_TRY(ar.alloc(&w.d_parts, ntiles));
     RB_TRY(ar.alloc(&w.d_results, ntask));
+    uint8_t *d_bt = nullptr;
+    double *d_seqv = nullptr;
+    RB_TRY(ar.alloc(&d_bt, any_seq ? (size_t)ntiles * TILE : 16));
+    RB_TRY(ar.alloc(&d_seqv, ntask));
 
     // modes: 0 fixed (lambda given), 2 fixed at 0.0; both are PH_DONE from the start
     std::vector<double> lam0((size_t)ntask * MAX_SLOTS, 0.0);
@@ -785,14 +865,15 @@ static int solve_batch(const double *d_scores, const double *d_costs, const rocc
     P.flags = w.d_flags; P.agg = w.d_agg; P.incl = w.d_incl; P.tout = w.d_tout; P.ticket = w.d_ticket;
     P.mask = d_masks; P.zin = w.d_zin; P.near_ties = w.d_near; P.ntiles = ntiles; P.nchrom = ntask;
     P.slots_per_block = slots_per_block;
+    P.bt = d_bt; P.seq_value = d_seqv;
     int epoch = 0;
 
     std::vector<SearchDev> hsearch(ntask);
     if (any_search) {
-        RB_TRY((launch_round<false>(P, vec, 2, epoch, st)));                 // bracket ends
+        RB_TRY((launch_round<false>(P, vec, 2, epoch, any_seq, st)));                 // bracket ends
         // PH_BRACKET -> PH_BISECT generates the first tree in the same finish kernel
         const int rounds = (max_iter + levels - 1) / levels;
-        for (int r = 0; r < rounds; ++r) RB_TRY((launch_round<false>(P, vec, max_slots, epoch, st)));
+        for (int r = 0; r < rounds; ++r) RB_TRY((launch_round<false>(P, vec, max_slots, epoch, any_seq, st)));
         // rare: bracket expansion (dp.py:119-125, 132-138) is driven from the host with single solves
         RB_CUDA(cudaMemcpyAsync(hsearch.data(), w.d_search, sizeof(SearchDev) * ntask, cudaMemcpyDeviceToHost, st));
         RB_CUDA(cudaStreamSynchronize(st));
@@ -809,7 +890,7 @@ static int solve_batch(const double *d_scores, const double *d_costs, const rocc
                 }
                 RB_CUDA(cudaMemcpyAsync(w.d_search, hsearch.data(), sizeof(SearchDev) * ntask, cudaMemcpyHostToDevice, st));
                 RB_CUDA(cudaMemcpyAsync(w.d_lam + (size_t)c * MAX_SLOTS, &lamv, sizeof(double), cudaMemcpyHostToDevice, st));
-                RB_TRY((launch_round<false>(P, vec, 1, epoch, st)));
+                RB_TRY((launch_round<false>(P, vec, 1, epoch, any_seq, st)));
                 RB_CUDA(cudaMemcpyAsync(&count, w.d_counts + (size_t)c * MAX_SLOTS, sizeof(long long), cudaMemcpyDeviceToHost, st));
                 RB_CUDA(cudaStreamSynchronize(st));
                 return 0;
@@ -848,7 +929,7 @@ static int solve_batch(const double *d_scores, const double *d_costs, const rocc
     }
 
     // final solve at the chosen multiplier, mask emitted
-    RB_TRY((launch_round<true>(P, vec, 1, epoch, st)));
+    RB_TRY((launch_round<true>(P, vec, 1, epoch, any_seq, st)));
     if (vec) k_chain_finalize<true><<<ntiles, THREADS, 0, st>>>(P, w.d_parts);
     else k_chain_finalize<false><<<ntiles, THREADS, 0, st>>>(P, w.d_parts);
     RB_LAUNCH_CHECK();
@@ -866,6 +947,13 @@ static int solve_batch(const double *d_scores, const double *d_costs, const rocc
 
 // ====================================================================== C-ABI
 using namespace rb;
+
+extern "C" __attribute__((visibility("default"))) int rocco_b200_chain_set_seq_max(int max_bins)
+{
+    const int prev = chain::g_seq_max.load();
+    chain::g_seq_max.store(std::max(0, std::min(max_bins, chain::TILE)));
+    return prev;
+}
 
 extern "C" __attribute__((visibility("default"))) int rocco_b200_chain_solve_batch_dev(
     const double *d_scores, const double *d_switch_costs, const rocco_b200_chain_task *tasks, int task_count,

@@ -11,13 +11,23 @@ def rb():
     return rocco_b200
 
 
+@pytest.fixture(params=["scan", "default"])
+def path_mode(request):
+    """'scan' forces the parallel clamp-map scan even on short inputs; 'default' lets chromosomes of
+    <= 4096 bins take the exact sequential kernel."""
+    from rocco_b200 import _lib
+    prev = _lib.load().rocco_b200_chain_set_seq_max(0 if request.param == "scan" else 4096)
+    yield request.param
+    _lib.load().rocco_b200_chain_set_seq_max(prev)
+
+
 def _scores(n, seed, peak_frac=0.03):
     rng = np.random.default_rng(seed)
     return rng.normal(size=n) - 0.8 + 4.0 * (rng.random(n) < peak_frac) * rng.random(n)
 
 
 # ------------------------------------------------------------------ fixed multiplier
-def test_bruteforce_vectors(rb, golden):
+def test_bruteforce_vectors(rb, golden, path_mode):
     """reference tests/test_rocco.py:397-415 (n = 9, random costs, four multipliers)"""
     s, c = golden["dp_bf_scores"], golden["dp_bf_costs"]
     for k in range(4):
@@ -30,7 +40,7 @@ def test_bruteforce_vectors(rb, golden):
 
 
 @pytest.mark.parametrize("n", [1, 2, 3, 17, 4095, 4096, 4097, 8192, 12289, 70001])
-def test_fixed_multiplier_matches_oracle_across_tile_edges(rb, oracle, n):
+def test_fixed_multiplier_matches_oracle_across_tile_edges(rb, oracle, n, path_mode):
     s = _scores(n, seed=n)
     rng = np.random.default_rng(n + 1)
     for costs in (np.full(max(n - 1, 0), 1.0), rng.uniform(0.0, 2.5, size=max(n - 1, 0)), np.full(max(n - 1, 0), 40.0)):
@@ -65,7 +75,7 @@ def test_tie_break_cases_match_reference_golden(rb, golden, tag):
         assert abs(o - obj) <= 1e-9 and abs(det["penalized_objective"] - pen) <= 1e-9
 
 
-def test_integer_scores_exact_ties_random(rb, oracle):
+def test_integer_scores_exact_ties_random(rb, oracle, path_mode):
     rng = np.random.default_rng(5)
     for trial in range(12):
         n = int(rng.integers(2, 9000))
@@ -76,6 +86,24 @@ def test_integer_scores_exact_ties_random(rb, oracle):
             got = rb.solve_penalized_chain(s, c, pen)
             assert np.array_equal(got[0], want[0]), (trial, n, pen)
             assert got[2] == want[2] and got[1] == want[1]
+
+
+def test_short_inputs_replay_reference_bits(rb, oracle):
+    """n <= 4096: value, count, mask and the searched multiplier are the reference's bits, even where
+    the 60-step bisection has converged to neighbouring doubles around a breakpoint."""
+    rng = np.random.default_rng(12)
+    for trial in range(25):
+        n = int(rng.integers(1, 4097))
+        s = np.round(rng.normal(size=n) * 2.0, int(rng.integers(0, 4)))
+        gamma = float(rng.choice([0.0, 0.5, 1.0, 6.86]))
+        budget = float(rng.choice([0.01, 0.1, 0.3, 0.9]))
+        want_sol, want_obj, want = oracle.solve_chrom_exact(s, budget=budget, gamma=gamma, return_details=True)
+        sol, obj, det = rb.solve_chrom_exact(s, budget=budget, gamma=gamma, return_details=True)
+        assert np.array_equal(sol, want_sol), (trial, n, gamma, budget)
+        assert det["selection_penalty"] == want["selection_penalty"]
+        assert det["penalized_objective"] == want["penalized_objective"]
+        assert det["selected_count"] == want["selected_count"]
+        assert abs(obj - want_obj) <= 1e-9 * max(1.0, abs(want_obj))
 
 
 # ------------------------------------------------------------------ budget search
@@ -111,7 +139,10 @@ def test_budget_search_matches_oracle(rb, oracle, n, gamma, budget, seed):
         got = solve_chromosomes([s], [budget], [gamma], levels_per_round=levels)[0]
         assert np.array_equal(got["solution"], want_sol), (levels, int(np.sum(got["solution"] != want_sol)))
         assert got["selected_count"] == want["selected_count"] <= int(np.floor(n * budget))
-        assert got["selection_penalty"] == want["selection_penalty"], (got["selection_penalty"], want["selection_penalty"])
+        # Long inputs use the scan: its decisions differ from the reference's only inside the reference's own
+        # rounding noise around a breakpoint, which can move the returned lattice point by a few steps
+        # (bracket width / 2^60 each) without changing the mask.  Gate: <= 1e-9 absolute.
+        assert abs(got["selection_penalty"] - want["selection_penalty"]) <= 1e-9, (got["selection_penalty"], want["selection_penalty"])
         assert abs(got["objective"] - want_obj) <= 1e-6 * abs(want_obj)
         assert got["dp_passes"] == 62
 
@@ -122,7 +153,7 @@ def test_calibrate_with_vector_costs_matches_oracle(rb, oracle):
     c = np.random.default_rng(10).uniform(0.1, 3.0, size=n - 1)
     want = oracle.calibrate_selection_penalty(s, c, 900)
     got = rb.calibrate_selection_penalty(s, c, 900)
-    assert got[0] == want[0] and got[3] == want[3]
+    assert abs(got[0] - want[0]) <= 1e-9 and got[3] == want[3]
     assert np.array_equal(got[1], want[1])
     assert abs(got[2] - want[2]) <= 1e-6 * abs(want[2])
     # target == n short-circuits to lambda = 0 (dp.py:102-108)
@@ -143,7 +174,7 @@ def test_many_chromosomes_one_launch_set(rb, oracle):
         sol, obj, det = oracle.solve_chrom_exact(sc[i], budget=budgets[i], gamma=gammas[i],
                                                  selection_penalty=pens[i], return_details=True)
         assert np.array_equal(got[i]["solution"], sol), i
-        assert got[i]["selection_penalty"] == det["selection_penalty"]
+        assert abs(got[i]["selection_penalty"] - det["selection_penalty"]) <= 1e-9
         assert got[i]["selected_count"] == det["selected_count"]
 
 
