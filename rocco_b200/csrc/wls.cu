@@ -1,0 +1,657 @@
+// EB-moderated WLS locus scoring on a centered matrix, and the score_loci_wls chain around it.
+//
+// Replaces /root/reference/rocco/native/wls_backend.c:
+//   610-742  rolling AR(1) innovation variance   -> k_rollvar   (direct window sums + short slides)
+//   394-608  monotone variance-vs-|signal| trend -> exact order statistics per sample row, PAVA on <= 32 knots
+//   744-947  posterior precision + combine       -> k_combine   (fused column reduction over the sample axis)
+// and the Python driver inference.py:302-379.
+#include "common.cuh"
+#include "score.cuh"
+
+#include <cub/cub.cuh>
+#include <math.h>
+
+#include <algorithm>
+
+namespace rb {
+namespace score {
+
+constexpr int MAX_KNOTS = 64;
+
+int resolve_spatial_window(long long n, int requested)          // wls_backend.c:232-260
+{
+    if (n < 5) return 0;
+    long long w = requested > 0 ? requested : 31;
+    if (w < 5) w = 5;
+    if (w > n) w = n;
+    if ((w & 1) == 0) w = (w == n) ? (w - 1) : (w + 1);
+    return (w < 5) ? 0 : (int)w;
+}
+
+int resolve_baseline_window(long long n, int target)             // inference.py:50-62
+{
+    if (n < 25) return 0;
+    long long w = std::max(3, target);
+    if (w > n) w = n;
+    if ((w % 2) == 0) w = (w == n) ? w - 1 : w + 1;
+    return (int)std::max<long long>(0, w);
+}
+
+double whittaker_lambda(int block)                                // inference.py:65-76
+{
+    int b = std::max(3, block);
+    if ((b % 2) == 0) b += 1;
+    const double w_hat = (double)b * 0.15915494;
+    return 7.0 * pow(w_hat, 4.0);                                 // CPython float ** 4 is libm pow
+}
+
+// ------------------------------------------------------------------ small helpers
+__device__ __forceinline__ double load_logx(const void *x, int in_f32, long long idx)
+{
+    const double v = in_f32 ? (double)reinterpret_cast<const float *>(x)[idx] : reinterpret_cast<const double *>(x)[idx];
+    return log2(fmax(v, 0.0) + 1.0);
+}
+
+// in-place bitonic sort of `len` (power of two) doubles in shared memory
+__device__ void bitonic_sort(double *s, int len)
+{
+    for (int k = 2; k <= len; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < len; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const double a = s[i], b = s[ixj];
+                    const bool up = ((i & k) == 0);
+                    if ((a > b) == up) { s[i] = b; s[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+constexpr int PILOT_CAP = 4096;
+
+// inference.py:333  np.median(matrix, axis=1): exact for n <= 4096, sampled above (see score.cuh)
+__global__ void __launch_bounds__(256) k_pilot(const void *x, int in_f32, long long n, long long row_stride, double *pilot)
+{
+    __shared__ double s[PILOT_CAP];
+    const long long row = blockIdx.x;
+    const int take = (int)min((long long)PILOT_CAP, n);
+    int len = 1;
+    while (len < take) len <<= 1;
+    for (int k = threadIdx.x; k < len; k += blockDim.x) {
+        double v = INFINITY;
+        if (k < take) {
+            const long long i = (n <= PILOT_CAP) ? k : (long long)(((double)k + 0.5) * ((double)n / (double)PILOT_CAP));
+            v = load_logx(x, in_f32, row * row_stride + min(i, n - 1));
+            if (!(v == v)) v = INFINITY;
+        }
+        s[k] = v;
+    }
+    __syncthreads();
+    bitonic_sort(s, len);
+    if (threadIdx.x == 0) {
+        pilot[row] = (take & 1) ? s[take / 2] : (s[take / 2 - 1] + s[take / 2]) / 2.0;
+    }
+}
+
+int pilot_offsets(const void *d_x, int in_f32, long long rows, long long n, long long row_stride, double *d_pilot,
+                  cudaStream_t st)
+{
+    k_pilot<<<(unsigned)rows, 256, 0, st>>>(d_x, in_f32, n, row_stride, d_pilot);
+    RB_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------ rolling AR(1) innovation variance
+constexpr int RV_ITEMS = 8;
+
+struct WinSums { double s1, s2, sl; };
+
+__device__ __forceinline__ double ar1_variance(const WinSums &ws, double first, double last, double wd, double pairs)
+{
+    // wls_backend.c:665-712, same association order (intrinsics keep nvcc from contracting into FMAs)
+    const double sum_head = __dsub_rn(ws.s1, last);
+    const double sum_tail = __dsub_rn(ws.s1, first);
+    const double mu = ws.s1 / wd;
+    double g0 = __dsub_rn(ws.s2, __dmul_rn(__dmul_rn(wd, mu), mu));
+    const double shrink = 1.0 / (wd + 1.0);
+    if (g0 < 0.0) g0 = 0.0;
+    double g1 = __dsub_rn(ws.sl, __dmul_rn(mu, sum_head));
+    g1 = __dsub_rn(g1, __dmul_rn(mu, sum_tail));
+    g1 = __dadd_rn(g1, __dmul_rn(__dmul_rn(pairs, mu), mu));
+    const double flo = __dmul_rn(1.0e-4, __dadd_rn(g0, 1.0));
+    const double den = __dadd_rn(__dmul_rn(g0, __dadd_rn(1.0, shrink)), flo);
+    const double eps = __dmul_rn(1.0e-12, __dadd_rn(g0, 1.0));
+    double beta = 0.0;
+    if (den > eps) beta = g1 / den;
+    if (beta > 0.99) beta = 0.99; else if (beta < 0.0) beta = 0.0;
+    const double gam0 = g0 / wd;
+    double omb = __dsub_rn(1.0, __dmul_rn(beta, beta));
+    if (omb < 0.0) omb = 0.0;
+    return fmax(__dmul_rn(gam0, omb), 0.0);
+}
+
+__global__ void __launch_bounds__(256) k_rollvar(const double *__restrict__ C, long long n, long long row_stride, int w,
+                                                 double *__restrict__ V)
+{
+    const long long row = blockIdx.y;
+    const double *c = C + row * row_stride;
+    double *v = V + row * row_stride;
+    const long long j0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * RV_ITEMS;
+    if (j0 >= n) return;
+    const long long half = w / 2, last = n - w;
+    const double wd = (double)w, pairs = (double)(w - 1);
+    WinSums ws{0.0, 0.0, 0.0};
+    long long tprev = -1;
+    double cur = 0.0;
+#pragma unroll 1
+    for (int jj = 0; jj < RV_ITEMS; ++jj) {
+        const long long j = j0 + jj;
+        if (j >= n) break;
+        long long t = j - half;
+        if (t < 0) t = 0; else if (t > last) t = last;
+        if (t != tprev) {
+            if (tprev < 0) {
+                ws.s1 = ws.s2 = ws.sl = 0.0;
+                for (int k = 0; k < w; ++k) {
+                    const double a = c[t + k];
+                    ws.s1 = __dadd_rn(ws.s1, a);
+                    ws.s2 = __dadd_rn(ws.s2, __dmul_rn(a, a));
+                    if (k < w - 1) ws.sl = __dadd_rn(ws.sl, __dmul_rn(a, c[t + k + 1]));
+                }
+            } else {
+                // slide tprev -> t (= tprev + 1), wls_backend.c:714-724
+                const double out_v = c[tprev], nx = c[tprev + w], lag_l = c[tprev + w - 1], lag_r = c[tprev + 1];
+                ws.s1 = __dadd_rn(__dsub_rn(ws.s1, out_v), nx);
+                ws.s2 = __dadd_rn(__dsub_rn(ws.s2, __dmul_rn(out_v, out_v)), __dmul_rn(nx, nx));
+                ws.sl = __dadd_rn(__dsub_rn(ws.sl, __dmul_rn(out_v, lag_r)), __dmul_rn(lag_l, nx));
+            }
+            cur = ar1_variance(ws, c[t], c[t + w - 1], wd, pairs);
+            tprev = t;
+        }
+        v[j] = fmax(cur, 1.0e-8);                          // wls_backend.c:869
+    }
+}
+
+// n < 5 (window 0) or n < 4: per-row robust scale^2 for both variance tracks (wls_backend.c:834-848)
+__global__ void k_robust_rows(const double *C, long long n, long long row_stride, double *row_const)
+{
+    const long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (row >= gridDim.x * (long long)blockDim.x) return;
+    double buf[4];
+    const int m = (int)n;                                  // n <= 4 here
+    for (int k = 0; k < m; ++k) buf[k] = C[row * row_stride + k];
+    auto med = [&](double *a, int len) {
+        for (int i = 1; i < len; ++i) { double key = a[i]; int q = i; while (q > 0 && a[q - 1] > key) { a[q] = a[q - 1]; --q; } a[q] = key; }
+        if (len == 1) return a[0];
+        return (len & 1) ? a[len / 2] : 0.5 * (a[len / 2 - 1] + a[len / 2]);
+    };
+    const double m0 = med(buf, m);
+    for (int k = 0; k < m; ++k) buf[k] = fabs(C[row * row_stride + k] - m0);
+    double mad = med(buf, m);
+    mad = __dmul_rn(mad, 1.4826);
+    double sc = (mad > 1.0e-6) ? mad : 1.0e-6;
+    row_const[row] = fmax(__dmul_rn(sc, sc), 1.0e-8);
+}
+
+// ------------------------------------------------------------------ trend knots from exact order statistics (sort-based)
+constexpr unsigned long long YBASE = 0x3E10000000000000ULL;   // bits of 2^-30
+
+__global__ void k_make_keys(const double *C, const double *V, long long n, unsigned long long *ky, unsigned long long *kx)
+{
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
+        ky[j] = (unsigned long long)__double_as_longlong(V[j]);           // V >= 1e-8 > 0: bit pattern is order preserving
+        kx[j] = (unsigned long long)__double_as_longlong(fabs(C[j]));
+    }
+}
+
+__device__ __forceinline__ int bin_of_rank(long long p, long long N, int B)
+{
+    int b = (int)((p * B) / N);
+    if (b >= B) b = B - 1;
+    while (b + 1 < B && ((long long)(b + 1) * N) / B <= p) ++b;
+    while (b > 0 && ((long long)b * N) / B > p) --b;
+    return b;
+}
+
+// after the lexicographic (x, y) sort: tag every y with its equal-count bin so one more sort groups y by bin
+__global__ void k_bin_keys(const unsigned long long *ysorted, long long N, int B, unsigned long long *out)
+{
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < N; p += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long yb = ysorted[p];
+        unsigned long long rel = yb > YBASE ? yb - YBASE : 0ULL;
+        if (rel >= (1ULL << 58)) rel = (1ULL << 58) - 1;
+        out[p] = ((unsigned long long)bin_of_rank(p, N, B) << 58) | rel;
+    }
+}
+
+struct Knots { double x[MAX_KNOTS]; double y[MAX_KNOTS]; int nk; int constant; double cval; };
+
+// one thread per row: bin medians -> PAVA -> de-duplicated knots (wls_backend.c:476-560)
+__global__ void k_knots_from_sorted(const unsigned long long *xsorted, const unsigned long long *ybinsorted, long long N, int B,
+                                    Knots *out)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double bx[MAX_KNOTS], by[MAX_KNOTS], bw[MAX_KNOTS], fit[MAX_KNOTS];
+    int used = 0;
+    for (int b = 0; b < B; ++b) {
+        const long long lo = ((long long)b * N) / B, hi = ((long long)(b + 1) * N) / B;
+        if (hi <= lo) continue;
+        const long long wdt = hi - lo;
+        auto xat = [&](long long p) { return __longlong_as_double((long long)xsorted[p]); };
+        auto yat = [&](long long p) { return __longlong_as_double((long long)((ybinsorted[p] & ((1ULL << 58) - 1)) + YBASE)); };
+        bx[used] = (wdt & 1) ? xat(lo + wdt / 2) : 0.5 * (xat(lo + wdt / 2 - 1) + xat(lo + wdt / 2));
+        by[used] = (wdt & 1) ? yat(lo + wdt / 2) : 0.5 * (yat(lo + wdt / 2 - 1) + yat(lo + wdt / 2));
+        if (wdt == 1) by[used] = yat(lo);
+        bw[used] = (double)wdt;
+        ++used;
+    }
+    Knots K;
+    K.nk = 0; K.constant = 0; K.cval = 1.0e-8;
+    if (used == 1) { K.constant = 1; K.cval = fmax(by[0], 1.0e-8); *out = K; return; }
+    // PAVA (wls_backend.c:262-338)
+    double pv[MAX_KNOTS], pw[MAX_KNOTS];
+    int pl[MAX_KNOTS], nb = 0;
+    for (int i = 0; i < used; ++i) {
+        pv[nb] = by[i]; pw[nb] = fmax(bw[i], 1.0e-8); pl[nb] = 1; ++nb;
+        while (nb >= 2 && pv[nb - 2] > pv[nb - 1]) {
+            const double tw = __dadd_rn(pw[nb - 2], pw[nb - 1]);
+            const double mv = __dadd_rn(__dmul_rn(pv[nb - 2], pw[nb - 2]), __dmul_rn(pv[nb - 1], pw[nb - 1])) / tw;
+            pv[nb - 2] = mv; pw[nb - 2] = tw; pl[nb - 2] += pl[nb - 1];
+            --nb;
+        }
+    }
+    int q = 0;
+    for (int b = 0; b < nb; ++b) for (int r = 0; r < pl[b]; ++r) fit[q++] = pv[b];
+    int nk = 0;
+    for (int b = 0; b < used; ++b) {
+        const double cx = bx[b], cy = fmax(fit[b], 1.0e-8);
+        if (nk > 0 && cx <= K.x[nk - 1]) { K.y[nk - 1] = fmax(K.y[nk - 1], cy); continue; }
+        K.x[nk] = cx; K.y[nk] = cy; ++nk;
+    }
+    K.nk = nk;
+    if (nk == 1) { K.constant = 1; K.cval = fmax(K.y[0], 1.0e-8); }
+    *out = K;
+}
+
+static int trend_knots_sorted(const double *d_C, const double *d_V, long long m, long long n, long long row_stride,
+                              Knots *d_knots, cudaStream_t st)
+{
+    const long long N = n;
+    const int B = (int)fmax(4.0, floor(1.0 + (log((double)N + 1.0) / log(2.0))));      // wls_backend.c:456
+    if (B > MAX_KNOTS) return ST_INVALID;
+    Arena ar(st);
+    unsigned long long *k0 = nullptr, *k1 = nullptr, *v0 = nullptr, *v1 = nullptr;
+    RB_TRY(ar.alloc(&k0, (size_t)n)); RB_TRY(ar.alloc(&k1, (size_t)n));
+    RB_TRY(ar.alloc(&v0, (size_t)n)); RB_TRY(ar.alloc(&v1, (size_t)n));
+    size_t tmp_bytes = 0, tb2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k0, k1, v0, v1, (int)n, 0, 63, st);
+    cub::DeviceRadixSort::SortKeys(nullptr, tb2, k0, k1, (int)n, 0, 64, st);
+    tmp_bytes = std::max(tmp_bytes, tb2);
+    char *tmp = nullptr;
+    RB_TRY(ar.alloc(&tmp, tmp_bytes));
+    const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 16);
+    for (long long r = 0; r < m; ++r) {
+        const double *c = d_C + r * row_stride, *v = d_V + r * row_stride;
+        k_make_keys<<<blocks, 256, 0, st>>>(c, v, n, k0, v0);                 // k0 = y bits, v0 = x bits
+        RB_LAUNCH_CHECK();
+        RB_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k0, k1, v0, v1, (int)n, 0, 63, st));   // by y
+        count_launch(8);
+        RB_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, v1, v0, k1, k0, (int)n, 0, 63, st));   // stable by x: v0 = x sorted, k0 = y
+        count_launch(8);
+        k_bin_keys<<<blocks, 256, 0, st>>>(k0, N, B, k1);
+        RB_LAUNCH_CHECK();
+        RB_CUDA(cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, k1, v1, (int)n, 0, 64, st));           // v1 = (bin, y) sorted
+        count_launch(8);
+        k_knots_from_sorted<<<1, 32, 0, st>>>(v0, v1, N, B, d_knots + r);
+        RB_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------ fused posterior + column reduction over samples
+struct CombineParams {
+    const double *C; const double *V; const Knots *knots; const double *row_const;
+    long long m, n, row_stride;
+    double ldf, pdf, tdf, pfr, lower_bound_z, min_effect;
+    int use_min_effect; int const_rows;
+    double *scores, *mean, *raw, *prior, *mod, *se;
+    int *bad;
+};
+
+__device__ __forceinline__ double interp_knots(const double *kx, const double *ky, int nk, double t)
+{
+    // wls_backend.c:341-391
+    if (nk == 0) return 1.0e-8;
+    if (nk == 1 || t <= kx[0]) return ky[0];
+    if (t >= kx[nk - 1]) return ky[nk - 1];
+    int lo = 0, hi = nk - 1;
+    while (hi - lo > 1) {
+        const int mid = lo + (hi - lo) / 2;
+        if (kx[mid] <= t) lo = mid; else hi = mid;
+    }
+    const double xl = kx[lo], xr = kx[hi];
+    if (xr <= xl) return fmax(ky[hi], ky[lo]);
+    const double wgt = __dsub_rn(t, xl) / __dsub_rn(xr, xl);
+    return __dadd_rn(ky[lo], __dmul_rn(wgt, __dsub_rn(ky[hi], ky[lo])));
+}
+
+constexpr int CB_THREADS = 256;
+constexpr int CB_ROWS_SMEM = 64;          // knot tables staged per batch of sample rows
+
+__global__ void __launch_bounds__(CB_THREADS) k_combine(CombineParams P)
+{
+    __shared__ double s_kx[CB_ROWS_SMEM][32], s_ky[CB_ROWS_SMEM][32];
+    __shared__ int s_nk[CB_ROWS_SMEM];
+    __shared__ double s_cv[CB_ROWS_SMEM];
+    const long long j = (long long)blockIdx.x * CB_THREADS + threadIdx.x;
+    const bool live = j < P.n;
+    double wsum = 0.0, psum = 0.0, rsum = 0.0, qsum = 0.0;
+    for (long long r0 = 0; r0 < P.m; r0 += CB_ROWS_SMEM) {
+        const int nr = (int)min((long long)CB_ROWS_SMEM, P.m - r0);
+        __syncthreads();
+        if (!P.const_rows) {
+            for (int e = threadIdx.x; e < nr * 32; e += CB_THREADS) {
+                const int rr = e >> 5, k = e & 31;
+                const Knots &K = P.knots[r0 + rr];
+                s_kx[rr][k] = (k < K.nk) ? K.x[k] : INFINITY;
+                s_ky[rr][k] = (k < K.nk) ? K.y[k] : 0.0;
+                if (k == 0) { s_nk[rr] = K.constant ? -1 : K.nk; s_cv[rr] = K.cval; }
+            }
+        }
+        __syncthreads();
+        if (live) {
+            for (int rr = 0; rr < nr; ++rr) {
+                const long long idx = (r0 + rr) * P.row_stride + j;
+                const double y = P.C[idx];
+                double ov, pv;
+                if (P.const_rows) { ov = pv = P.row_const[r0 + rr]; }
+                else {
+                    ov = fmax(P.V[idx], 1.0e-8);
+                    pv = (s_nk[rr] < 0) ? s_cv[rr] : fmax(interp_knots(s_kx[rr], s_ky[rr], s_nk[rr], fabs(y)), 1.0e-8);
+                    pv = fmax(pv, 1.0e-8);
+                }
+                // wls_backend.c:889-911
+                double post = __dadd_rn(__dmul_rn(P.ldf, ov), __dmul_rn(P.pdf, pv)) / fmax(P.tdf, 1.0);
+                const double flo = __dmul_rn(P.pfr, pv);
+                if (post < flo) post = flo;
+                post = fmax(post, 1.0e-8);
+                const double prec = 1.0 / post;
+                rsum = __dadd_rn(rsum, 1.0 / ov);
+                qsum = __dadd_rn(qsum, 1.0 / pv);
+                psum = __dadd_rn(psum, prec);
+                wsum = __dadd_rn(wsum, __dmul_rn(prec, y));
+            }
+        }
+    }
+    if (!live) return;
+    // wls_backend.c:915-937
+    const double Pj = fmax(psum, 1.0e-8);
+    const double mean = wsum / Pj;
+    const double md = (double)P.m;
+    const double se = sqrt(1.0 / Pj);
+    const double z = mean / fmax(se, 1.0e-8);
+    const double sc = P.use_min_effect ? __dsub_rn(mean, fmax(P.min_effect, 0.0)) / fmax(se, 1.0e-8) : __dsub_rn(z, P.lower_bound_z);
+    const double rawv = md / fmax(rsum, 1.0e-8), priv = md / fmax(qsum, 1.0e-8), modv = md / Pj;
+    if (!(isfinite(sc) && isfinite(mean) && isfinite(rawv) && isfinite(priv) && isfinite(modv) && isfinite(se) && isfinite(z)))
+        *P.bad = 1;
+    if (P.scores) P.scores[j] = sc;
+    if (P.mean) P.mean[j] = mean;
+    if (P.raw) P.raw[j] = rawv;
+    if (P.prior) P.prior[j] = priv;
+    if (P.mod) P.mod[j] = modv;
+    if (P.se) P.se[j] = se;
+}
+
+int centered_wls(const double *d_centered, long long m, long long n, const rocco_b200_score_params &prm,
+                 rocco_b200_score_outputs *out, cudaStream_t st)
+{
+    if (!d_centered || !out || m <= 0 || n <= 0) return ST_INVALID;
+    const double pdf = fmax(prm.prior_df, 0.0), pfr = fmax(prm.precision_floor_ratio, 0.0);
+    const int w = resolve_spatial_window(n, prm.spatial_window);
+    const double ldf = w > 0 ? fmax(4.0, (double)w - 3.0) : 1.0;
+    const double tdf = ldf + pdf;
+    out->total_df = tdf;
+    out->resolved_spatial_window = w;
+
+    Arena ar(st);
+    int *d_bad = nullptr;
+    RB_TRY(ar.alloc(&d_bad, 1));
+    RB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+    CombineParams P{};
+    P.C = d_centered; P.m = m; P.n = n; P.row_stride = n;
+    P.ldf = ldf; P.pdf = pdf; P.tdf = tdf; P.pfr = pfr; P.lower_bound_z = prm.lower_bound_z;
+    P.min_effect = prm.min_effect; P.use_min_effect = prm.use_min_effect;
+    P.scores = out->scores; P.mean = out->mean; P.raw = out->raw_variance; P.prior = out->prior_variance;
+    P.mod = out->moderated_variance; P.se = out->standard_error; P.bad = d_bad;
+
+    double *d_V = nullptr, *d_rc = nullptr;
+    Knots *d_knots = nullptr;
+    if (w == 0 || n < 4) {
+        RB_TRY(ar.alloc(&d_rc, (size_t)m));
+        k_robust_rows<<<(unsigned)m, 1, 0, st>>>(d_centered, n, n, d_rc);
+        RB_LAUNCH_CHECK();
+        P.const_rows = 1; P.row_const = d_rc;
+    } else {
+        RB_TRY(ar.alloc(&d_V, (size_t)m * n));
+        RB_TRY(ar.alloc(&d_knots, (size_t)m));
+        dim3 grid((unsigned)((n + 256LL * RV_ITEMS - 1) / (256LL * RV_ITEMS)), (unsigned)m);
+        k_rollvar<<<grid, 256, 0, st>>>(d_centered, n, n, w, d_V);
+        RB_LAUNCH_CHECK();
+        RB_TRY(trend_knots_sorted(d_centered, d_V, m, n, n, d_knots, st));
+        P.const_rows = 0; P.V = d_V; P.knots = d_knots;
+    }
+    k_combine<<<(unsigned)((n + CB_THREADS - 1) / CB_THREADS), CB_THREADS, 0, st>>>(P);
+    RB_LAUNCH_CHECK();
+    int bad = 0;
+    RB_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    RB_CUDA(cudaStreamSynchronize(st));
+    if (bad) return ST_NONFINITE;
+    return 0;
+}
+
+// ------------------------------------------------------------------ the full chain (inference.py:302-379)
+static int score_loci_dev(const void *d_matrix, int dtype, long long m, long long n, const rocco_b200_score_params *params,
+                          rocco_b200_score_outputs *out, cudaStream_t st)
+{
+    if (!d_matrix || !out || m <= 0 || n <= 0 || (dtype != 0 && dtype != 1)) return ST_INVALID;
+    rocco_b200_score_params prm;
+    if (params) prm = *params; else rocco_b200_default_score_params(&prm);
+    RB_TRY(ensure_device());
+    Arena ar(st);
+    double *d_pilot = nullptr, *d_cent = nullptr;
+    int *d_bad = nullptr;
+    RB_TRY(ar.alloc(&d_pilot, (size_t)m));
+    RB_TRY(ar.alloc(&d_bad, 1));
+    RB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+    const bool own_centered = out->centered_matrix == nullptr;
+    if (own_centered) RB_TRY(ar.alloc(&d_cent, (size_t)m * n)); else d_cent = out->centered_matrix;
+    RB_TRY(pilot_offsets(d_matrix, dtype, m, n, n, d_pilot, st));
+    const int bw = resolve_baseline_window(n, prm.baseline_window > 0 ? prm.baseline_window : 101);
+    const double lam = bw > 0 ? whittaker_lambda(bw) : 0.0;
+    out->baseline_window = bw;
+    out->baseline_lambda = lam;
+    RB_TRY(whittaker_rows(d_matrix, dtype, 1, d_pilot, m, n, n, lam, 0, d_cent, d_bad, st));
+    int bad = 0;
+    RB_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    RB_CUDA(cudaStreamSynchronize(st));
+    if (bad) return ST_NONFINITE;
+    return centered_wls(d_cent, m, n, prm, out, st);
+}
+
+}  // namespace score
+}  // namespace rb
+
+// ====================================================================== C-ABI
+using namespace rb;
+#define RB_API extern "C" __attribute__((visibility("default")))
+
+RB_API void rocco_b200_default_score_params(rocco_b200_score_params *p)
+{
+    if (!p) return;
+    p->lower_bound_z = 1.0; p->prior_df = 5.0; p->min_effect = 0.0; p->use_min_effect = 0;
+    p->spatial_window = 31; p->precision_floor_ratio = 0.01; p->baseline_window = 101; p->reserved = 0;
+}
+
+RB_API int rocco_b200_score_loci_wls_dev(const void *d_matrix, int dtype, size_t m, size_t n,
+                                         const rocco_b200_score_params *params, rocco_b200_score_outputs *out, void *cuda_stream)
+{
+    return score::score_loci_dev(d_matrix, dtype, (long long)m, (long long)n, params, out, (cudaStream_t)cuda_stream);
+}
+
+RB_API int rocco_b200_crossfit_baseline_dev(const double *d_rows, size_t m, size_t n, double penalty_lambda,
+                                            double *d_out, void *cuda_stream)
+{
+    if (!d_rows || !d_out) return ST_NOMEM;                  // baseline_backend.c:313-316 returns -1 on NULL
+    if (m == 0 || n == 0) return 0;
+    RB_TRY(ensure_device());
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    Arena ar(st);
+    int *d_bad = nullptr;
+    RB_TRY(ar.alloc(&d_bad, 1));
+    RB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+    RB_TRY(score::whittaker_rows(d_rows, 0, 0, nullptr, (long long)m, (long long)n, (long long)n, penalty_lambda, 1, d_out, d_bad, st));
+    RB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+RB_API int rocco_b200_score_centered_wls_dev(const double *d_centered, size_t m, size_t n,
+                                             const rocco_b200_score_params *params, rocco_b200_score_outputs *out,
+                                             void *cuda_stream)
+{
+    if (!d_centered || !out || m == 0 || n == 0) return ST_INVALID;
+    rocco_b200_score_params prm;
+    if (params) prm = *params; else rocco_b200_default_score_params(&prm);
+    RB_TRY(ensure_device());
+    return score::centered_wls(d_centered, (long long)m, (long long)n, prm, out, (cudaStream_t)cuda_stream);
+}
+
+// ---- host-pointer entries (H2D / D2H inside)
+namespace {
+struct HostOuts {
+    double *dev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double *host[6];
+};
+}
+
+static int run_host_outputs(Arena &ar, size_t n, rocco_b200_score_outputs &host_out, rocco_b200_score_outputs &dev_out, HostOuts &ho)
+{
+    double **hp[6] = {&host_out.scores, &host_out.mean, &host_out.raw_variance, &host_out.prior_variance,
+                      &host_out.moderated_variance, &host_out.standard_error};
+    double **dp[6] = {&dev_out.scores, &dev_out.mean, &dev_out.raw_variance, &dev_out.prior_variance,
+                      &dev_out.moderated_variance, &dev_out.standard_error};
+    for (int k = 0; k < 6; ++k) {
+        ho.host[k] = *hp[k];
+        *dp[k] = nullptr;
+        if (*hp[k]) { RB_TRY(ar.alloc(&ho.dev[k], n)); *dp[k] = ho.dev[k]; }
+    }
+    return 0;
+}
+
+static int copy_back(size_t n, HostOuts &ho, cudaStream_t st)
+{
+    for (int k = 0; k < 6; ++k)
+        if (ho.host[k]) RB_CUDA(cudaMemcpyAsync(ho.host[k], ho.dev[k], n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    RB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+static int score_loci_host(const void *matrix, int dtype, size_t m, size_t n, const rocco_b200_score_params *params,
+                           rocco_b200_score_outputs *out)
+{
+    if (!matrix || !out || m == 0 || n == 0) return ST_INVALID;
+    RB_TRY(ensure_device());
+    cudaStream_t st = 0;
+    Arena ar(st);
+    const size_t esz = dtype ? sizeof(float) : sizeof(double);
+    char *d_x = nullptr;
+    RB_TRY(ar.alloc(&d_x, m * n * esz));
+    RB_CUDA(cudaMemcpyAsync(d_x, matrix, m * n * esz, cudaMemcpyHostToDevice, st));
+    rocco_b200_score_outputs dev = *out;
+    HostOuts ho;
+    RB_TRY(run_host_outputs(ar, n, *out, dev, ho));
+    double *d_cent = nullptr;
+    if (out->centered_matrix) { RB_TRY(ar.alloc(&d_cent, m * n)); }
+    dev.centered_matrix = d_cent;
+    int s = score::score_loci_dev(d_x, dtype, (long long)m, (long long)n, params, &dev, st);
+    if (s != 0) return s;
+    out->total_df = dev.total_df; out->resolved_spatial_window = dev.resolved_spatial_window;
+    out->baseline_window = dev.baseline_window; out->baseline_lambda = dev.baseline_lambda;
+    if (out->centered_matrix)
+        RB_CUDA(cudaMemcpyAsync(out->centered_matrix, d_cent, m * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    return copy_back(n, ho, st);
+}
+
+RB_API int rocco_score_loci_wls_f64(const double *matrix, size_t m, size_t n, const rocco_b200_score_params *params,
+                                    rocco_b200_score_outputs *out)
+{
+    return score_loci_host(matrix, 0, m, n, params, out);
+}
+
+RB_API int rocco_score_loci_wls_f32(const float *matrix, size_t m, size_t n, const rocco_b200_score_params *params,
+                                    rocco_b200_score_outputs *out)
+{
+    return score_loci_host(matrix, 1, m, n, params, out);
+}
+
+RB_API int rocco_crossfit_whittaker_baseline_matrix_f64(const double *matrix_values, size_t row_count, size_t column_count,
+                                                        double penalty_lambda, double *baseline_out)
+{
+    if (!matrix_values || !baseline_out) return ST_NOMEM;
+    if (row_count == 0 || column_count == 0) return 0;
+    RB_TRY(ensure_device());
+    cudaStream_t st = 0;
+    Arena ar(st);
+    double *d_in = nullptr, *d_out = nullptr;
+    const size_t total = row_count * column_count;
+    RB_TRY(ar.alloc(&d_in, total));
+    RB_TRY(ar.alloc(&d_out, total));
+    RB_CUDA(cudaMemcpyAsync(d_in, matrix_values, total * sizeof(double), cudaMemcpyHostToDevice, st));
+    RB_TRY(rocco_b200_crossfit_baseline_dev(d_in, row_count, column_count, penalty_lambda, d_out, st));
+    RB_CUDA(cudaMemcpyAsync(baseline_out, d_out, total * sizeof(double), cudaMemcpyDeviceToHost, st));
+    RB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+RB_API int rocco_crossfit_whittaker_baseline_f64(const double *y_values, size_t value_count, double penalty_lambda,
+                                                 double *baseline_out)
+{
+    return rocco_crossfit_whittaker_baseline_matrix_f64(y_values, 1, value_count, penalty_lambda, baseline_out);
+}
+
+RB_API int rocco_score_centered_wls_f64(
+    const double *centered_matrix, size_t sample_count, size_t locus_count, double lower_bound_z, double prior_df,
+    double min_effect, int use_min_effect, int spatial_window, double precision_floor_ratio, double *mean_out,
+    double *raw_variance_out, double *prior_variance_out, double *moderated_variance_out, double *standard_error_out,
+    double *scores_out, double *degrees_of_freedom_out, int *resolved_window_out)
+{
+    // argument checks and status codes of wls_backend.c:779-788
+    if (!centered_matrix || !mean_out || !raw_variance_out || !prior_variance_out || !moderated_variance_out ||
+        !standard_error_out || !scores_out)
+        return ST_INVALID;
+    if (sample_count == 0 || locus_count == 0) return ST_INVALID;
+    RB_TRY(ensure_device());
+    cudaStream_t st = 0;
+    Arena ar(st);
+    double *d_c = nullptr;
+    const size_t total = sample_count * locus_count;
+    RB_TRY(ar.alloc(&d_c, total));
+    RB_CUDA(cudaMemcpyAsync(d_c, centered_matrix, total * sizeof(double), cudaMemcpyHostToDevice, st));
+    rocco_b200_score_params prm;
+    rocco_b200_default_score_params(&prm);
+    prm.lower_bound_z = lower_bound_z; prm.prior_df = prior_df; prm.min_effect = min_effect;
+    prm.use_min_effect = use_min_effect; prm.spatial_window = spatial_window; prm.precision_floor_ratio = precision_floor_ratio;
+    rocco_b200_score_outputs host{}, dev{};
+    host.scores = scores_out; host.mean = mean_out; host.raw_variance = raw_variance_out;
+    host.prior_variance = prior_variance_out; host.moderated_variance = moderated_variance_out;
+    host.standard_error = standard_error_out;
+    HostOuts ho;
+    RB_TRY(run_host_outputs(ar, locus_count, host, dev, ho));
+    int s = score::centered_wls(d_c, (long long)sample_count, (long long)locus_count, prm, &dev, st);
+    if (s != 0) return s;
+    if (degrees_of_freedom_out) *degrees_of_freedom_out = dev.total_df;
+    if (resolved_window_out) *resolved_window_out = dev.resolved_spatial_window;
+    return copy_back(locus_count, ho, st);
+}
