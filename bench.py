@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""Benchmark of the consensus-selection hot path (BASELINE.json metric: genome bins/s, score+solve+budget).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path, all host cores
+
+Workload (config.workload): synthetic hg38, 50 bp bins (61,765,409 bins, 24 chromosomes) x 100 samples,
+float64, per-chromosome (budget, gamma) from the reference's hg_params.csv, chromosomes LPT-packed
+over the ranks (strong scaling: the genome is fixed).  One step = every chromosome of the genome
+scored (log2p1 -> baseline -> WLS), budget-searched, solved and emitted as merged BED text.
+`value` times that with the count matrices resident in HBM; `e2e` times the reference-facing host
+API (NumPy in / NumPy + BED files out) with host<->device copies inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+from rocco_b200.synth import HG38_SIZES, HG_PARAMS, chrom_bins, chrom_matrix_numpy, chrom_seed  # noqa: E402
+
+METRIC = "genome_bins_per_sec"
+UNIT = "bins/s"
+PRIOR_DF = 6.0          # the reference CLI default (rocco.py:569-574)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--samples", type=int, default=100)
+    ap.add_argument("--step-bp", type=int, default=50)
+    ap.add_argument("--chroms", default="all", help="comma list (debug); default = all 24 hg38 chromosomes")
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"], help="dtype of the resident count matrices")
+    ap.add_argument("--e2e-steps", type=int, default=-1, help="-1: min(steps, 2); 0 disables the e2e leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-bins", type=int, default=250_000)
+    ap.add_argument("--levels", type=int, default=0, help="bisection levels per launch (0 = library default)")
+    return ap.parse_args()
+
+
+def workload(args):
+    names = list(HG38_SIZES) if args.chroms == "all" else args.chroms.split(",")
+    bins = [chrom_bins(c, args.step_bp) for c in names]
+    return names, bins
+
+
+def workload_name(args, names):
+    g = "hg38" if len(names) == 24 else "+".join(names)
+    return f"synthetic {g} @ {args.step_bp} bp x {args.samples} samples, {args.dtype}, hg_params budgets/gammas"
+
+
+# ---------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines: list[str] = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------- reference arm
+def _ref_worker(task):
+    """One worker = the reference's own kernels (oracle/_ref, else the oracle port) on one slice."""
+    m, n, seed, budget, gamma, kind = task
+    from oracle import oracle as orc
+    x = chrom_matrix_numpy(m, n, seed=seed)
+    t0 = time.perf_counter()
+    scores = orc.score_loci_wls(x, prior_df=PRIOR_DF, kind=kind)
+    sol, obj = orc.solve_chrom_exact(scores, budget=budget, gamma=gamma, kind=kind)
+    recs = orc.solution_to_records("chr21", np.arange(0, 50 * n, 50), sol)
+    return n, time.perf_counter() - t0, len(recs)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    names, bins = workload(args)
+    kind = "reference" if orc.reference_available() else "port"
+    cores = os.cpu_count() or 1
+    import multiprocessing as mp
+    # per-step sample: one slice per core, sized for ~4-6 s of single-core work each
+    n_slice = max(2_000, int(4.5 / (4.5e-7 * args.samples)))
+    budget, gamma = HG_PARAMS["chr21"]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        def step(k):
+            tasks = [(args.samples, n_slice, 1000 * k + w, budget, gamma, kind) for w in range(cores)]
+            t0 = time.perf_counter()
+            res = pool.map(_ref_worker, tasks)
+            return sum(r[0] for r in res), time.perf_counter() - t0
+        for k in range(args.warmup):
+            step(k)
+        tot_bins, tot_t = 0, 0.0
+        for k in range(args.steps):
+            b, t = step(100 + k)
+            tot_bins += b
+            tot_t += t
+    value = tot_bins / tot_t
+    sample = (f"{cores} slices/step of {n_slice} bins x {args.samples} samples (chr21 generator, budget {budget}, gamma {gamma}): "
+              f"score_loci_wls + solve_chrom_exact + BED records, one process per core")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args, names), "genome_bins": int(sum(bins)), "bounded_sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------- our arm
+def cpu_baseline_single_core(args):
+    from oracle import oracle as orc
+    kind = "reference" if orc.reference_available() else "port"
+    n = int(args.cpu_sample_bins * min(1.0, 100.0 / max(args.samples, 1)))
+    budget, gamma = HG_PARAMS["chr21"]
+    n_done, dt, _ = _ref_worker((args.samples, n, chrom_seed("chr21"), budget, gamma, kind))
+    return {"value": n_done / dt, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": f"first {n} bins of synthetic chr21 x {args.samples} samples: score_loci_wls + solve_chrom_exact "
+                      f"(budget {budget}, gamma {gamma}) + BED records, {dt:.1f} s on one core"}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import rocco_b200
+    from rocco_b200 import _lib, pipeline
+    from rocco_b200.synth import chrom_matrix_torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    names, bins = workload(args)
+    parts = pipeline.lpt_partition(bins, world)
+    mine = parts[rank]
+    my_names = [names[i] for i in mine]
+    my_bins = [bins[i] for i in mine]
+    budgets = [HG_PARAMS[c][0] for c in my_names]
+    gammas = [HG_PARAMS[c][1] for c in my_names]
+    tdtype = torch.float64 if args.dtype == "f64" else torch.float32
+    esz = 8 if args.dtype == "f64" else 4
+    d_mats = [chrom_matrix_torch(args.samples, n, chrom_seed(c), dev, tdtype) for c, n in zip(my_names, my_bins)]
+    params = pipeline.score_params(prior_df=PRIOR_DF)
+    genome_bins = int(sum(bins))
+    tmpdir = tempfile.mkdtemp(prefix=f"rocco_b200_bench_r{rank}_")
+    count_buf = torch.zeros(2, dtype=torch.int64, device=dev)
+
+    def step():
+        if not mine:
+            return None
+        shard = pipeline.run_shard(d_mats, budgets, gammas, params=params, levels_per_round=args.levels)
+        text = pipeline.runs_to_bed_text(my_names, shard["runs"], args.step_bp)
+        with open(os.path.join(tmpdir, "shard.bed"), "w") as fh:
+            fh.write(text)
+        # the one cross-GPU exchange of the path: genome-wide selected-bin count (reporting only)
+        count_buf[0] = sum(r["selected_count"] for r in shard["results"])
+        count_buf[1] = sum(my_bins)
+        if world > 1:
+            dist.all_reduce(count_buf)
+        return shard
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    _lib.profile_enable(True)
+    _lib.profile_report()
+    launches0 = _lib.kernel_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    last = None
+    for _ in range(args.steps):
+        last = step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = _lib.kernel_launches() - launches0
+    prof = _lib.profile_report()
+    _lib.profile_enable(False)
+    clocks = sampler.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lt)
+    ms = float(t.item())
+    value = genome_bins * args.steps / (ms / 1e3)
+    selected_total = int(count_buf[0].item())
+
+    # ---- end-to-end through the reference-facing host API (NumPy in, BED files out)
+    e2e = None
+    e2e_steps = min(args.steps, 2) if args.e2e_steps < 0 else args.e2e_steps
+    if e2e_steps > 0:
+        host = []
+        pinned = True
+        for x in d_mats:
+            try:
+                h = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
+            except RuntimeError:
+                h = torch.empty(x.shape, dtype=x.dtype)
+                pinned = False
+            h.copy_(x)
+            host.append(h.numpy())
+        del d_mats
+        torch.cuda.empty_cache()
+        cwd = os.getcwd()
+        os.chdir(tmpdir)
+
+        def e2e_step():
+            files = []
+            for c, n, x, b, g in zip(my_names, my_bins, host, budgets, gammas):
+                scores = rocco_b200.score_loci_wls(x, prior_df=PRIOR_DF)
+                sol, obj = rocco_b200.solve_chrom_exact(scores, budget=b, gamma=g)
+                files.append(rocco_b200.chrom_solution_to_bed(c, np.arange(0, args.step_bp * n, args.step_bp), sol, ID="bench"))
+            if files:
+                rocco_b200.combine_chrom_results(files, f"combined_r{rank}.bed")
+
+        e2e_step()                                      # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        os.chdir(cwd)
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        h2d = sum(args.samples * n * esz + n * 8 + n for n in my_bins)       # matrix + scores (solve) + mask (BED)
+        d2h = sum(n * 8 + n for n in my_bins)                                # scores + mask
+        bb = torch.tensor([h2d, d2h], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(bb)
+        e2e = {"value": genome_bins * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(bb[0].item()),
+               "d2h_bytes_per_step": int(bb[1].item()), "steps": e2e_steps, "pinned_host": pinned,
+               "api": "score_loci_wls + solve_chrom_exact + chrom_solution_to_bed + combine_chrom_results (NumPy in, BED files out)"}
+
+    if rank == 0:
+        peaks_path = os.path.join(REPO, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        # dominant kernel = the scope with the largest share of device time on rank 0
+        roof = None
+        if prof:
+            total_ms = sum(v[0] for v in prof.values())
+            dom = max(prof, key=lambda k: prof[k][0])
+            d_ms, d_cnt, d_bytes = prof[dom]
+            achieved = (d_bytes / 1e9) / (d_ms / 1e3) if d_ms > 0 else 0.0
+            roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "launches": d_cnt, "avg_launch_ms": d_ms / max(d_cnt, 1), "share_of_profiled_time": d_ms / total_ms,
+                    "all_scopes": {k: {"ms": round(v[0], 3), "launch_sets": v[1],
+                                       "GBps_algorithmic": round((v[2] / 1e9) / (v[0] / 1e3), 1) if v[0] > 0 else 0.0}
+                                   for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_baseline_single_core(args)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": workload_name(args, names), "genome_bins": genome_bins, "samples": args.samples,
+                       "chromosomes": len(names), "sharding": f"chromosomes LPT-packed over {world} rank(s)",
+                       "l2_policy": "inputs larger than L2 (per-chromosome matrices 0.7-4 GB vs 126 MB L2)",
+                       "selected_bins": selected_total, "collective": "one NCCL all-reduce of [selected, bins] per step"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(lt.item()), "roofline": roof, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -48,6 +48,11 @@ int rocco_b200_set_device(int device);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 unsigned long long rocco_b200_kernel_launches(void);
 
+/* Per-kernel timing with CUDA events on the launching stream (off by default).  report() synchronises,
+ * writes "<scope> <total_ms> <launch_sets> <algorithmic_bytes>" lines into buf and clears the log. */
+int rocco_b200_profile_enable(int on);
+int rocco_b200_profile_report(char *buf, size_t capacity);
+
 /* ------------------------------------------------------------------ reference-named host entries */
 int rocco_crossfit_whittaker_baseline_f64(
     const double *y_values, size_t value_count, double penalty_lambda, double *baseline_out);

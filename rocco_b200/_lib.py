@@ -62,6 +62,8 @@ def _declare(lib):
         "rocco_b200_device_count": (c_int, []),
         "rocco_b200_set_device": (c_int, [c_int]),
         "rocco_b200_kernel_launches": (c_ulonglong, []),
+        "rocco_b200_profile_enable": (c_int, [c_int]),
+        "rocco_b200_profile_report": (c_int, [c_char_p, c_size_t]),
         "rocco_b200_numpy_sum_f64": (c_double, [c_void_p, c_size_t]),
         "rocco_b200_numpy_sum_const_f64": (c_double, [c_double, c_size_t]),
         "rocco_solve_penalized_chain_f64": (c_int, [c_void_p, c_void_p, c_size_t, c_double, c_void_p, dp, llp]),
@@ -149,3 +151,18 @@ def kernel_launches() -> int:
 def numpy_sum_const(value: float, n: int) -> float:
     """numpy.sum(numpy.full(n, value)) without materialising the vector (dp.py:110-111 bracket)."""
     return float(load().rocco_b200_numpy_sum_const_f64(float(value), int(n)))
+
+
+def profile_enable(on: bool) -> bool:
+    return bool(load().rocco_b200_profile_enable(1 if on else 0))
+
+
+def profile_report() -> dict:
+    """{scope: (total_ms, launch_sets, algorithmic_bytes)} since the last report; synchronises the device."""
+    buf = ctypes.create_string_buffer(1 << 16)
+    load().rocco_b200_profile_report(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, ms, cnt, nbytes = line.split()
+        out[name] = (float(ms), int(cnt), float(nbytes))
+    return out

@@ -153,6 +153,7 @@ int runs_batch(const uint8_t *d_mask, const Seg *segs, int nseg, std::vector<lon
     RB_TRY(ar.alloc(&d_oe, ntiles));
     RB_TRY(ar.alloc(&d_tot, 2));
     RB_CUDA(cudaMemcpyAsync(d_last, last.data(), sizeof(long long) * nseg, cudaMemcpyHostToDevice, st));
+    RB_PROF("mask_to_runs", st, 2.0 * (double)total);
     k_runs<false><<<ntiles, THREADS, 0, st>>>(d_mask, total, d_last, nseg, d_cnt, nullptr, nullptr, nullptr, nullptr);
     RB_LAUNCH_CHECK();
     k_scan_tiles<<<1, 1024, 0, st>>>(d_cnt, ntiles, d_os, d_oe, d_tot);

@@ -758,6 +758,9 @@ static int launch_round(Params P, bool vec, int nslots_max, int &epoch, bool any
 {
     P.ngroups = (nslots_max + P.slots_per_block - 1) / P.slots_per_block;
     const int blocks = P.ntiles * P.ngroups;
+    // algorithmic bytes of a search round: every score read once (8 B/bin) whatever the number of multipliers;
+    // the emitting round also writes one mask byte per bin
+    RB_PROF(EMIT ? "chain_emit_round" : "chain_search_round", st, (double)P.ntiles * TILE * (EMIT ? 9.0 : 8.0));
     for (int lex = 0; lex < 2; ++lex) {
         P.lex_pass = lex;
         P.epoch = ++epoch;
@@ -930,9 +933,12 @@ static int solve_batch(const double *d_scores, const double *d_costs, const rocc
 
     // final solve at the chosen multiplier, mask emitted
     RB_TRY((launch_round<true>(P, vec, 1, epoch, any_seq, st)));
-    if (vec) k_chain_finalize<true><<<ntiles, THREADS, 0, st>>>(P, w.d_parts);
-    else k_chain_finalize<false><<<ntiles, THREADS, 0, st>>>(P, w.d_parts);
-    RB_LAUNCH_CHECK();
+    {
+        RB_PROF("k_chain_finalize", st, (double)ntiles * TILE * 9.0);
+        if (vec) k_chain_finalize<true><<<ntiles, THREADS, 0, st>>>(P, w.d_parts);
+        else k_chain_finalize<false><<<ntiles, THREADS, 0, st>>>(P, w.d_parts);
+        RB_LAUNCH_CHECK();
+    }
     k_chain_results<<<ntask, 32, 0, st>>>(P, w.d_parts, w.d_results, vec ? 1 : 0);
     RB_LAUNCH_CHECK();
     RB_CUDA(cudaMemcpyAsync(results, w.d_results, sizeof(rocco_b200_chain_result) * ntask, cudaMemcpyDeviceToHost, st));

@@ -94,6 +94,18 @@ template <typename T> class Pinned {
     void *p_ = nullptr;
 };
 
+// Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg).
+// Disabled by default: a scope then costs one relaxed atomic load.
+class ProfScope {
+  public:
+    ProfScope(const char *name, cudaStream_t st, double bytes = 0.0);
+    ~ProfScope();
+  private:
+    int idx_;
+    cudaStream_t st_;
+};
+#define RB_PROF(name, st, bytes) ::rb::ProfScope _prof_scope_##__LINE__(name, st, bytes)
+
 int ensure_device();     // returns 0 or ST_CUDA when no usable device
 int sm_count();
 

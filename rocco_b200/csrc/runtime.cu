@@ -4,6 +4,7 @@
 #include <stdarg.h>
 
 #include <map>
+#include <mutex>
 
 namespace rb {
 
@@ -43,6 +44,31 @@ int sm_count()
             cached = 148;
     }
     return cached;
+}
+
+// ---------------------------------------------------------------- event profiler
+struct ProfEntry { std::string name; cudaEvent_t a, b; double bytes; };
+static std::atomic<int> g_prof_on{0};
+static std::mutex g_prof_mu;
+static std::vector<ProfEntry> g_prof;
+
+ProfScope::ProfScope(const char *name, cudaStream_t st, double bytes) : idx_(-1), st_(st)
+{
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    ProfEntry e;
+    e.name = name; e.bytes = bytes;
+    if (cudaEventCreate(&e.a) != cudaSuccess || cudaEventCreate(&e.b) != cudaSuccess) return;
+    cudaEventRecord(e.a, st);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back(e);
+    idx_ = (int)g_prof.size() - 1;
+}
+
+ProfScope::~ProfScope()
+{
+    if (idx_ < 0) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (idx_ < (int)g_prof.size()) cudaEventRecord(g_prof[idx_].b, st_);
 }
 
 // numpy/_core/src/umath/loops_utils.h.src  DOUBLE_pairwise_sum, restated
@@ -120,6 +146,39 @@ RB_API int rocco_b200_set_device(int device)
 }
 
 RB_API unsigned long long rocco_b200_kernel_launches(void) { return rb::g_launches.load(); }
+
+RB_API int rocco_b200_profile_enable(int on)
+{
+    return rb::g_prof_on.exchange(on ? 1 : 0);
+}
+
+/* Writes one line per scope name: "<name> <total_ms> <count> <total_bytes>\n"; clears the log. */
+RB_API int rocco_b200_profile_report(char *buf, size_t cap)
+{
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lk(rb::g_prof_mu);
+    std::map<std::string, std::pair<double, std::pair<long long, double>>> agg;
+    for (auto &e : rb::g_prof) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) {
+            auto &a = agg[e.name];
+            a.first += ms; a.second.first += 1; a.second.second += e.bytes;
+        }
+        cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+    }
+    (void)cudaGetLastError();
+    rb::g_prof.clear();
+    size_t off = 0;
+    for (auto &kv : agg) {
+        int w = snprintf(buf ? buf + off : nullptr, buf && cap > off ? cap - off : 0, "%s %.6f %lld %.0f\n",
+                         kv.first.c_str(), kv.second.first, kv.second.second.first, kv.second.second.second);
+        if (w < 0) break;
+        off += (size_t)w;
+        if (buf && off >= cap) { off = cap ? cap - 1 : 0; break; }
+    }
+    if (buf && cap) buf[off < cap ? off : cap - 1] = 0;
+    return (int)off;
+}
 
 RB_API double rocco_b200_numpy_sum_f64(const double *a, size_t n) { return rb::numpy_sum_f64(a, n); }
 RB_API double rocco_b200_numpy_sum_const_f64(double value, size_t n) { return rb::numpy_sum_const_f64(value, n); }

@@ -577,6 +577,9 @@ int whittaker_rows(const void *d_x, int in_f32, int log_transform, const double 
         Q.span_tiles = sp.t1 - sp.t0;
         const long long blocks = rows * (long long)Q.span_tiles;
         if (blocks > 0x7fffffffLL) return ST_INVALID;
+        // algorithmic bytes of this launch: read the input once, write the centered matrix once
+        const double span_bins = (double)std::min<long long>(n, (long long)sp.t1 * WT_OUT) - (double)sp.t0 * WT_OUT;
+        RB_PROF(sp.steady ? "k_whittaker_steady" : "k_whittaker_edge", st, (double)rows * span_bins * ((in_f32 ? 4.0 : 8.0) + 8.0));
         if (sp.steady) k_whittaker<true><<<(unsigned)blocks, WT_THREADS, sm_steady, st>>>(Q);
         else k_whittaker<false><<<(unsigned)blocks, WT_THREADS, sm_general, st>>>(Q);
         RB_LAUNCH_CHECK();

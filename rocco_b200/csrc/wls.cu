@@ -438,13 +438,22 @@ int centered_wls(const double *d_centered, long long m, long long n, const rocco
         RB_TRY(ar.alloc(&d_V, (size_t)m * n));
         RB_TRY(ar.alloc(&d_knots, (size_t)m));
         dim3 grid((unsigned)((n + 256LL * RV_ITEMS - 1) / (256LL * RV_ITEMS)), (unsigned)m);
-        k_rollvar<<<grid, 256, 0, st>>>(d_centered, n, n, w, d_V);
-        RB_LAUNCH_CHECK();
-        RB_TRY(trend_knots_sorted(d_centered, d_V, m, n, n, d_knots, st));
+        {
+            RB_PROF("k_rollvar", st, (double)m * (double)n * 16.0);
+            k_rollvar<<<grid, 256, 0, st>>>(d_centered, n, n, w, d_V);
+            RB_LAUNCH_CHECK();
+        }
+        {
+            RB_PROF("trend_knots", st, (double)m * (double)n * 16.0);
+            RB_TRY(trend_knots_sorted(d_centered, d_V, m, n, n, d_knots, st));
+        }
         P.const_rows = 0; P.V = d_V; P.knots = d_knots;
     }
-    k_combine<<<(unsigned)((n + CB_THREADS - 1) / CB_THREADS), CB_THREADS, 0, st>>>(P);
-    RB_LAUNCH_CHECK();
+    {
+        RB_PROF("k_combine", st, (double)m * (double)n * (P.const_rows ? 8.0 : 16.0) + 48.0 * (double)n);
+        k_combine<<<(unsigned)((n + CB_THREADS - 1) / CB_THREADS), CB_THREADS, 0, st>>>(P);
+        RB_LAUNCH_CHECK();
+    }
     int bad = 0;
     RB_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
     RB_CUDA(cudaStreamSynchronize(st));
@@ -468,7 +477,10 @@ static int score_loci_dev(const void *d_matrix, int dtype, long long m, long lon
     RB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
     const bool own_centered = out->centered_matrix == nullptr;
     if (own_centered) RB_TRY(ar.alloc(&d_cent, (size_t)m * n)); else d_cent = out->centered_matrix;
-    RB_TRY(pilot_offsets(d_matrix, dtype, m, n, n, d_pilot, st));
+    {
+        RB_PROF("k_pilot", st, 0.0);
+        RB_TRY(pilot_offsets(d_matrix, dtype, m, n, n, d_pilot, st));
+    }
     const int bw = resolve_baseline_window(n, prm.baseline_window > 0 ? prm.baseline_window : 101);
     const double lam = bw > 0 ? whittaker_lambda(bw) : 0.0;
     out->baseline_window = bw;

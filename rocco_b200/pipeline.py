@@ -150,3 +150,105 @@ def masks_to_runs(d_masks, offsets, lengths):
     if k < 0:
         _lib.check(int(k), "mask_to_runs")
     return chrom[:k].copy(), starts[:k].copy(), ends[:k].copy()
+
+
+# ---------------------------------------------------------------------------------------------
+# scoring on device-resident matrices
+# ---------------------------------------------------------------------------------------------
+def score_params(lower_bound_z=1.0, prior_df=5.0, min_effect=None, precision_floor_ratio=0.01,
+                 spatial_window=31, baseline_window=101):
+    lib = _lib.load()
+    prm = _lib.ScoreParams()
+    lib.rocco_b200_default_score_params(ctypes.byref(prm))
+    prm.lower_bound_z = float(lower_bound_z)
+    prm.prior_df = float(prior_df)
+    prm.use_min_effect = 0 if min_effect is None else 1
+    prm.min_effect = 0.0 if min_effect is None else max(float(min_effect), 0.0)
+    prm.precision_floor_ratio = float(max(precision_floor_ratio, 0.0))
+    prm.spatial_window = int(spatial_window)
+    prm.baseline_window = int(baseline_window)
+    return prm
+
+
+def score_loci_wls_device(d_matrix, out_scores=None, params=None, details: bool = False):
+    """score_loci_wls on a CUDA tensor [samples, bins] (float64 or float32, C-contiguous).
+
+    Writes the scores into ``out_scores`` (a float64 CUDA tensor/view of length bins) or a new
+    tensor; with ``details`` also returns the per-locus detail tensors.  Nothing leaves the device."""
+    torch = _torch()
+    lib = _lib.load()
+    if d_matrix.dim() != 2 or not d_matrix.is_cuda or not d_matrix.is_contiguous():
+        raise ValueError("`d_matrix` must be a contiguous two-dimensional CUDA tensor")
+    if d_matrix.dtype not in (torch.float64, torch.float32):
+        raise ValueError("`d_matrix` must be float64 or float32")
+    m, n = d_matrix.shape
+    if m == 0 or n == 0:
+        raise ValueError("`chrom_matrix` must be non-empty")
+    dev = d_matrix.device
+    if out_scores is None:
+        out_scores = torch.empty(n, dtype=torch.float64, device=dev)
+    out = _lib.ScoreOutputs()
+    out.scores = out_scores.data_ptr()
+    extra = {}
+    if details:
+        for k in ("mean", "raw_variance", "prior_variance", "moderated_variance", "standard_error"):
+            extra[k] = torch.empty(n, dtype=torch.float64, device=dev)
+            setattr(out, k, extra[k].data_ptr())
+        extra["centered_matrix"] = torch.empty((m, n), dtype=torch.float64, device=dev)
+        out.centered_matrix = extra["centered_matrix"].data_ptr()
+    prm = params if params is not None else score_params()
+    with torch.cuda.device(dev):
+        st = lib.rocco_b200_score_loci_wls_dev(
+            ctypes.c_void_p(d_matrix.data_ptr()), 1 if d_matrix.dtype == torch.float32 else 0, m, n,
+            ctypes.byref(prm), ctypes.byref(out), ctypes.c_void_p(_stream_ptr(dev)))
+    if st == _lib.ST_NONFINITE:
+        raise ValueError("Locus scoring produced non-finite values (or `chrom_matrix` contains non-finite values)")
+    _lib.check(st, "score_loci_wls")
+    if not details:
+        return out_scores
+    extra["total_df"] = float(out.total_df)
+    extra["prior_spatial_window"] = int(out.resolved_spatial_window)
+    extra["local_baseline_window"] = int(out.baseline_window)
+    extra["local_baseline_lambda"] = float(out.baseline_lambda)
+    return out_scores, extra
+
+
+def lpt_partition(weights: Sequence[int], parts: int) -> list[list[int]]:
+    """Longest-processing-time greedy packing of chromosomes onto ranks by bin count."""
+    order = sorted(range(len(weights)), key=lambda i: (-int(weights[i]), i))
+    loads = [0] * parts
+    out: list[list[int]] = [[] for _ in range(parts)]
+    for i in order:
+        r = min(range(parts), key=lambda k: (loads[k], k))
+        out[r].append(i)
+        loads[r] += int(weights[i])
+    for r in range(parts):
+        out[r].sort()
+    return out
+
+
+def run_shard(d_matrices, budgets, gammas, params=None, levels_per_round: int = 0, want_runs: bool = True):
+    """The hot path for one rank's chromosomes, device-resident end to end:
+    score every chromosome -> one batched budget search + solve -> one batched mask->runs pass.
+
+    Returns dict(d_scores, d_masks, offsets, lengths, results, runs)."""
+    torch = _torch()
+    lengths = [int(x.shape[1]) for x in d_matrices]
+    offsets, total = layout_offsets(lengths)
+    dev = d_matrices[0].device
+    d_scores = torch.zeros(total, dtype=torch.float64, device=dev)
+    for x, off, n in zip(d_matrices, offsets, lengths):
+        score_loci_wls_device(x, out_scores=d_scores[off:off + n], params=params)
+    d_masks, results = solve_packed(d_scores, offsets, lengths, budgets, gammas, levels_per_round=levels_per_round)
+    runs = masks_to_runs(d_masks, offsets, lengths) if want_runs else None
+    return {"d_scores": d_scores, "d_masks": d_masks, "offsets": offsets, "lengths": lengths,
+            "results": results, "runs": runs}
+
+
+def runs_to_bed_text(chrom_names, runs, step: int, first_start: int = 0) -> str:
+    """BED3 text of all runs (per chromosome in the given order; coordinates = first_start + bin*step)."""
+    chrom, starts, ends = runs
+    s = first_start + starts * step
+    e = first_start + ends * step
+    names = np.asarray(chrom_names, dtype=object)[chrom]
+    return "".join(f"{c}\t{a}\t{b}\n" for c, a, b in zip(names.tolist(), s.tolist(), e.tolist()))
