@@ -1,0 +1,523 @@
+// Exact order statistics for the monotone variance trend WITHOUT sorting the row.
+//
+// The reference sorts the n (|signal|, variance) pairs of every sample row lexicographically
+// (wls_backend.c:454), cuts them into B = max(4, floor(1 + log2(n+1))) equal-count bins and takes, per bin,
+// the median |signal| by rank and the median variance (wls_backend.c:476-505).  Only ~3B order statistics
+// per row are ever used, so the sort is replaced by a histogram multi-select:
+//
+//   T1  k_xhist      stream |C|: 16384 order-preserving buckets (1024 per octave of the bit pattern) per row
+//   T2  k_xplan      per row: prefix sums -> bucket + in-bucket rank of every wanted x-rank; buckets holding a
+//                    bin boundary or a median rank become "slots"
+//   T3  k_xcollect   stream (|C|, V): pairs in slot buckets are collected; every other pair has a definite bin
+//                    (its bucket lies inside one bin) and is counted in that bin's variance histogram
+//   T4  k_xresolve   per (row, slot): sort the ~1e3 collected pairs lexicographically -> exact x medians; pairs of
+//                    boundary buckets get their exact bin from their rank and join the variance histograms
+//   T5  k_yplan      per row, per bin: locate the variance bucket(s) of the bin's median rank(s)
+//   T6  k_ycollect   stream (|C|, V) once more: collect the variances of those buckets (plus boundary-slot pairs)
+//   T7  k_yresolve   per row: sort the few collected variances per bin -> exact medians -> PAVA -> knots
+//
+// Any bucket larger than its capacity (massive ties, e.g. an all-zero matrix) flags the ROW, and flagged rows
+// take the sort-based path in wls.cu, which is exact for any input.  Results are identical either way.
+#include "common.cuh"
+#include "score.cuh"
+#include "trend.cuh"
+
+#include <math.h>
+
+namespace rb {
+namespace score {
+
+constexpr int NBX = 16384;              // |signal| buckets: bits >> 42 (exponent + 10 mantissa bits), 2^-8 .. 2^8
+constexpr int XSHIFT = 42;
+constexpr unsigned XB0 = (unsigned)(0x3F70000000000000ULL >> XSHIFT);   // bucket index of 2^-8
+constexpr int NBY = 1024;               // variance buckets: bits >> 47 (exponent + 5 mantissa bits), 2^-27 .. 2^5
+constexpr int YSHIFT = 47;
+constexpr unsigned YB0 = (unsigned)(0x3E40000000000000ULL >> YSHIFT);   // bucket index of 2^-27
+constexpr int MAXB = 32;                // bins per row (n < 2^31)
+constexpr int MAXSLOT = 3 * MAXB;
+constexpr int CAPX = 8192;              // pairs per x slot
+constexpr int CAPY = 4096;              // variances per (bin, k) slot
+constexpr int CHUNK = 131072;           // elements streamed per CTA
+constexpr int ST_THREADS = 512;
+
+__device__ __forceinline__ int xbucket(double x)
+{
+    const unsigned u = (unsigned)((unsigned long long)__double_as_longlong(x) >> XSHIFT);
+    const int b = (int)u - (int)XB0;
+    return b < 0 ? 0 : (b >= NBX ? NBX - 1 : b);
+}
+__device__ __forceinline__ int ybucket(double y)
+{
+    const unsigned u = (unsigned)((unsigned long long)__double_as_longlong(y) >> YSHIFT);
+    const int b = (int)u - (int)YB0;
+    return b < 0 ? 0 : (b >= NBY ? NBY - 1 : b);
+}
+__device__ __forceinline__ int bin_of_rank(long long p, long long N, int B)
+{
+    int b = (int)((p * B) / N);
+    if (b >= B) b = B - 1;
+    while (b + 1 < B && ((long long)(b + 1) * N) / B <= p) ++b;
+    while (b > 0 && ((long long)b * N) / B > p) --b;
+    return b;
+}
+
+struct RowPlan {
+    int nslot;
+    int fallback;
+    int slot_bucket[MAXSLOT];
+    int slot_prefix[MAXSLOT];          // rank of the first pair of the bucket
+    int slot_count[MAXSLOT];
+    int slot_boundary[MAXSLOT];        // bucket contains a bin boundary
+    // x medians: per bin up to two ranks -> (slot, rank inside slot)
+    int xm_slot[MAXB][2];
+    int xm_rank[MAXB][2];
+    double xm_val[MAXB][2];
+    // y medians: per bin up to two ranks -> (variance bucket, rank inside bucket)
+    int ym_bucket[MAXB][2];
+    int ym_rank[MAXB][2];
+    int ym_count[MAXB][2];
+    double ym_val[MAXB][2];
+};
+
+struct TrendBuffers {
+    int *xhist;            // [m][NBX]
+    unsigned char *lut;    // [m][NBX]  slot id or 0xFF
+    unsigned char *binlo;  // [m][NBX]  bin of the bucket (valid when the bucket holds no boundary)
+    RowPlan *plan;         // [m]
+    double2 *cand;         // [m][MAXSLOT][CAPX]
+    int *cand_cnt;         // [m][MAXSLOT]
+    int *yhist;            // [m][MAXB][NBY]
+    double *ycand;         // [m][MAXB][2][CAPY]
+    int *ycand_cnt;        // [m][MAXB][2]
+};
+
+// ------------------------------------------------------------------ T1
+__global__ void __launch_bounds__(ST_THREADS) k_xhist(const double *__restrict__ C, long long n, long long row_stride, int *xhist)
+{
+    extern __shared__ int s_h[];
+    const long long row = blockIdx.y;
+    const long long c0 = (long long)blockIdx.x * CHUNK, c1 = min(n, c0 + CHUNK);
+    for (int k = threadIdx.x; k < NBX; k += ST_THREADS) s_h[k] = 0;
+    __syncthreads();
+    const double *c = C + row * row_stride;
+    for (long long j = c0 + threadIdx.x; j < c1; j += ST_THREADS) atomicAdd(&s_h[xbucket(fabs(c[j]))], 1);
+    __syncthreads();
+    int *g = xhist + row * NBX;
+    for (int k = threadIdx.x; k < NBX; k += ST_THREADS) {
+        const int v = s_h[k];
+        if (v) atomicAdd(&g[k], v);
+    }
+}
+
+// ------------------------------------------------------------------ T2
+__global__ void __launch_bounds__(256) k_xplan(TrendBuffers T, long long n, int B)
+{
+    extern __shared__ int s_plan[];
+    int *s_pre = s_plan;                 // NBX + 1
+    int *s_part = s_plan + NBX + 1;      // 256
+    const long long row = blockIdx.x;
+    const int *h = T.xhist + row * NBX;
+    // exclusive prefix over NBX buckets: 64 consecutive buckets per thread
+    const int per = NBX / 256;
+    int loc = 0;
+    for (int k = 0; k < per; ++k) loc += h[threadIdx.x * per + k];
+    s_part[threadIdx.x] = loc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int t = 0; t < 256; ++t) { const int v = s_part[t]; s_part[t] = acc; acc += v; }
+    }
+    __syncthreads();
+    {
+        int acc = s_part[threadIdx.x];
+        for (int k = 0; k < per; ++k) { s_pre[threadIdx.x * per + k] = acc; acc += h[threadIdx.x * per + k]; }
+        if (threadIdx.x == 255) s_pre[NBX] = acc;
+    }
+    __syncthreads();
+    unsigned char *lut = T.lut + row * NBX, *binlo = T.binlo + row * NBX;
+    for (int k = threadIdx.x; k < NBX; k += 256) {
+        lut[k] = 0xFF;
+        binlo[k] = (unsigned char)bin_of_rank(min((long long)s_pre[k], n - 1), n, B);
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    RowPlan &P = T.plan[row];
+    P.nslot = 0; P.fallback = 0;
+    auto bucket_of = [&](long long r) {                 // largest b with pre[b] <= r
+        int lo = 0, hi = NBX;
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if ((long long)s_pre[mid] <= r) lo = mid; else hi = mid; }
+        return lo;
+    };
+    auto slot_for = [&](int b, int boundary) {
+        int s = lut[b];
+        if (s == 0xFF) {
+            s = P.nslot++;
+            lut[b] = (unsigned char)s;
+            P.slot_bucket[s] = b; P.slot_prefix[s] = s_pre[b]; P.slot_count[s] = s_pre[b + 1] - s_pre[b];
+            P.slot_boundary[s] = 0;
+            if (P.slot_count[s] > CAPX) P.fallback = 1;
+        }
+        if (boundary) P.slot_boundary[s] = 1;
+        return s;
+    };
+    for (int b = 0; b < B; ++b) {
+        const long long lo = ((long long)b * n) / B, hi = ((long long)(b + 1) * n) / B;
+        const long long w = hi - lo;
+        for (int k = 0; k < 2; ++k) { P.xm_slot[b][k] = -1; P.xm_rank[b][k] = 0; P.ym_bucket[b][k] = -1; }
+        if (w <= 0) continue;
+        if (b > 0) slot_for(bucket_of(lo), 1);
+        const long long r1 = lo + w / 2;
+        const int b1 = bucket_of(r1);
+        P.xm_slot[b][1] = slot_for(b1, 0); P.xm_rank[b][1] = (int)(r1 - s_pre[b1]);
+        if ((w & 1) == 0) {
+            const long long r0 = r1 - 1;
+            const int b0 = bucket_of(r0);
+            P.xm_slot[b][0] = slot_for(b0, 0); P.xm_rank[b][0] = (int)(r0 - s_pre[b0]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ T3
+__global__ void __launch_bounds__(ST_THREADS) k_xcollect(const double *__restrict__ C, const double *__restrict__ V, long long n,
+                                                         long long row_stride, TrendBuffers T, int B)
+{
+    extern __shared__ int s_raw[];
+    int *s_yh = s_raw;                                              // [B][NBY]
+    unsigned char *s_lut = reinterpret_cast<unsigned char *>(s_raw + B * NBY);
+    unsigned char *s_bin = s_lut + NBX;
+    const long long row = blockIdx.y;
+    if (T.plan[row].fallback) return;
+    const long long c0 = (long long)blockIdx.x * CHUNK, c1 = min(n, c0 + CHUNK);
+    for (int k = threadIdx.x; k < B * NBY; k += ST_THREADS) s_yh[k] = 0;
+    for (int k = threadIdx.x; k < NBX / 4; k += ST_THREADS) {
+        reinterpret_cast<unsigned *>(s_lut)[k] = reinterpret_cast<const unsigned *>(T.lut + row * NBX)[k];
+        reinterpret_cast<unsigned *>(s_bin)[k] = reinterpret_cast<const unsigned *>(T.binlo + row * NBX)[k];
+    }
+    __syncthreads();
+    const double *c = C + row * row_stride, *v = V + row * row_stride;
+    double2 *cand = T.cand + (size_t)row * MAXSLOT * CAPX;
+    int *ccnt = T.cand_cnt + row * MAXSLOT;
+    const RowPlan &P = T.plan[row];
+    for (long long j = c0 + threadIdx.x; j < c1; j += ST_THREADS) {
+        const double x = fabs(c[j]);
+        const int b = xbucket(x);
+        const int s = s_lut[b];
+        const double y = v[j];
+        bool boundary = false;
+        if (s != 0xFF) {
+            const int pos = atomicAdd(&ccnt[s], 1);
+            if (pos < CAPX) cand[(size_t)s * CAPX + pos] = make_double2(x, y);
+            boundary = P.slot_boundary[s] != 0;
+        }
+        if (!boundary) atomicAdd(&s_yh[(int)s_bin[b] * NBY + ybucket(y)], 1);
+    }
+    __syncthreads();
+    int *g = T.yhist + (size_t)row * MAXB * NBY;
+    for (int k = threadIdx.x; k < B * NBY; k += ST_THREADS) {
+        const int val = s_yh[k];
+        if (val) atomicAdd(&g[k], val);
+    }
+}
+
+// ------------------------------------------------------------------ T4
+__device__ __forceinline__ bool pair_gt(const double2 &a, const double2 &b) { return a.x > b.x || (a.x == b.x && a.y > b.y); }
+
+__global__ void __launch_bounds__(ST_THREADS) k_xresolve(TrendBuffers T, long long n, int B)
+{
+    extern __shared__ double2 s_p[];
+    const long long row = blockIdx.y;
+    const int s = blockIdx.x;
+    RowPlan &P = T.plan[row];
+    if (P.fallback || s >= P.nslot) return;
+    const int cnt = min(T.cand_cnt[row * MAXSLOT + s], CAPX);
+    if (cnt != P.slot_count[s]) { if (threadIdx.x == 0) P.fallback = 1; return; }
+    int len = 1;
+    while (len < cnt) len <<= 1;
+    double2 *cand = T.cand + ((size_t)row * MAXSLOT + s) * CAPX;
+    for (int k = threadIdx.x; k < len; k += ST_THREADS) s_p[k] = (k < cnt) ? cand[k] : make_double2(INFINITY, INFINITY);
+    __syncthreads();
+    for (int k = 2; k <= len; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < len; i += ST_THREADS) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const double2 a = s_p[i], b = s_p[ixj];
+                    const bool up = ((i & k) == 0);
+                    if (pair_gt(a, b) == up) { s_p[i] = b; s_p[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // x medians living in this slot
+    for (int q = threadIdx.x; q < 2 * B; q += ST_THREADS) {
+        const int b = q >> 1, k = q & 1;
+        if (P.xm_slot[b][k] == s) P.xm_val[b][k] = s_p[P.xm_rank[b][k]].x;
+    }
+    if (P.slot_boundary[s]) {
+        // exact bin of every pair from its rank; their variances join the bins' histograms; keep them sorted for T6
+        int *g = T.yhist + (size_t)row * MAXB * NBY;
+        const long long pre = P.slot_prefix[s];
+        for (int k = threadIdx.x; k < cnt; k += ST_THREADS) {
+            const double2 pr = s_p[k];
+            cand[k] = pr;
+            atomicAdd(&g[bin_of_rank(pre + k, n, B) * NBY + ybucket(pr.y)], 1);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ T5
+__global__ void __launch_bounds__(256) k_yplan(TrendBuffers T, long long n, int B)
+{
+    __shared__ int s_pre[NBY + 1];
+    const long long row = blockIdx.y;
+    const int b = blockIdx.x;
+    RowPlan &P = T.plan[row];
+    if (P.fallback) return;
+    const long long lo = ((long long)b * n) / B, hi = ((long long)(b + 1) * n) / B;
+    const long long w = hi - lo;
+    if (w <= 0) return;
+    const int *h = T.yhist + ((size_t)row * MAXB + b) * NBY;
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int k = 0; k < NBY; ++k) { s_pre[k] = acc; acc += h[k]; }
+        s_pre[NBY] = acc;
+        if (acc != (int)w) { P.fallback = 1; }
+        else {
+            auto bucket_of = [&](long long r) {
+                int l = 0, hgh = NBY;
+                while (hgh - l > 1) { const int mid = (l + hgh) >> 1; if ((long long)s_pre[mid] <= r) l = mid; else hgh = mid; }
+                return l;
+            };
+            const long long r1 = w / 2;
+            const int b1 = bucket_of(r1);
+            P.ym_bucket[b][1] = b1; P.ym_rank[b][1] = (int)(r1 - s_pre[b1]); P.ym_count[b][1] = s_pre[b1 + 1] - s_pre[b1];
+            P.ym_bucket[b][0] = -1; P.ym_count[b][0] = 0;
+            if ((w & 1) == 0) {
+                const long long r0 = r1 - 1;
+                const int b0 = bucket_of(r0);
+                P.ym_bucket[b][0] = b0; P.ym_rank[b][0] = (int)(r0 - s_pre[b0]); P.ym_count[b][0] = s_pre[b0 + 1] - s_pre[b0];
+            }
+            if (P.ym_count[b][1] > CAPY || P.ym_count[b][0] > CAPY) P.fallback = 1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ T6
+__device__ __forceinline__ void ycollect_one(TrendBuffers &T, long long row, const int (*s_yb)[2], int bin, double y)
+{
+    const int yb = ybucket(y);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        if (s_yb[bin][k] == yb && (k == 1 || s_yb[bin][1] != yb)) {
+            const int pos = atomicAdd(&T.ycand_cnt[(row * MAXB + bin) * 2 + k], 1);
+            if (pos < CAPY) T.ycand[(((size_t)row * MAXB + bin) * 2 + k) * CAPY + pos] = y;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(ST_THREADS) k_ycollect(const double *__restrict__ C, const double *__restrict__ V, long long n,
+                                                         long long row_stride, TrendBuffers T, int B)
+{
+    __shared__ unsigned char s_lut[NBX];
+    __shared__ unsigned char s_bin[NBX];
+    __shared__ int s_yb[MAXB][2];
+    __shared__ unsigned char s_bnd[MAXSLOT];
+    const long long row = blockIdx.y;
+    const RowPlan &P = T.plan[row];
+    if (P.fallback) return;
+    for (int k = threadIdx.x; k < NBX / 4; k += ST_THREADS) {
+        reinterpret_cast<unsigned *>(s_lut)[k] = reinterpret_cast<const unsigned *>(T.lut + row * NBX)[k];
+        reinterpret_cast<unsigned *>(s_bin)[k] = reinterpret_cast<const unsigned *>(T.binlo + row * NBX)[k];
+    }
+    for (int k = threadIdx.x; k < MAXB * 2; k += ST_THREADS) s_yb[k >> 1][k & 1] = (k >> 1) < B ? P.ym_bucket[k >> 1][k & 1] : -1;
+    for (int k = threadIdx.x; k < MAXSLOT; k += ST_THREADS) s_bnd[k] = (k < P.nslot && P.slot_boundary[k]) ? 1 : 0;
+    __syncthreads();
+    const long long c0 = (long long)blockIdx.x * CHUNK, c1 = min(n, c0 + CHUNK);
+    const double *c = C + row * row_stride, *v = V + row * row_stride;
+    for (long long j = c0 + threadIdx.x; j < c1; j += ST_THREADS) {
+        const int b = xbucket(fabs(c[j]));
+        const int s = s_lut[b];
+        if (s != 0xFF && s_bnd[s]) continue;                        // boundary buckets: handled from the sorted slot below
+        ycollect_one(T, row, s_yb, (int)s_bin[b], v[j]);
+    }
+    if (blockIdx.x == 0) {
+        for (int s = 0; s < P.nslot; ++s) {
+            if (!s_bnd[s]) continue;
+            const double2 *cand = T.cand + ((size_t)row * MAXSLOT + s) * CAPX;
+            const long long pre = P.slot_prefix[s];
+            for (int k = threadIdx.x; k < P.slot_count[s]; k += ST_THREADS)
+                ycollect_one(T, row, s_yb, bin_of_rank(pre + k, n, B), cand[k].y);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ T7
+__device__ void knots_from_bins(const double *bx, const double *by, const double *bw, int used, Knots *out);
+
+__global__ void __launch_bounds__(256) k_yresolve(TrendBuffers T, long long n, int B, Knots *knots, int *row_fallback)
+{
+    __shared__ double s_v[CAPY];
+    __shared__ double s_bx[MAXB], s_by[MAXB], s_bw[MAXB];
+    __shared__ int s_fail;
+    const long long row = blockIdx.x;
+    RowPlan &P = T.plan[row];
+    if (threadIdx.x == 0) s_fail = P.fallback;
+    __syncthreads();
+    if (s_fail) { if (threadIdx.x == 0) row_fallback[row] = 1; return; }
+    int used = 0;
+    for (int b = 0; b < B; ++b) {
+        const long long lo = ((long long)b * n) / B, hi = ((long long)(b + 1) * n) / B;
+        const long long w = hi - lo;
+        if (w <= 0) continue;
+        double ym[2] = {0.0, 0.0};
+        for (int k = 0; k < 2; ++k) {
+            if (P.ym_bucket[b][k] < 0) continue;
+            if (k == 0 && P.ym_bucket[b][0] == P.ym_bucket[b][1]) continue;       // same bucket: resolved with k = 1
+            const int cnt = T.ycand_cnt[(row * MAXB + b) * 2 + k];
+            if (cnt != P.ym_count[b][k]) { if (threadIdx.x == 0) s_fail = 1; }
+            __syncthreads();
+            if (s_fail) break;
+            int len = 1;
+            while (len < cnt) len <<= 1;
+            const double *src = T.ycand + (((size_t)row * MAXB + b) * 2 + k) * CAPY;
+            for (int q = threadIdx.x; q < len; q += 256) s_v[q] = q < cnt ? src[q] : INFINITY;
+            __syncthreads();
+            for (int kk = 2; kk <= len; kk <<= 1)
+                for (int j = kk >> 1; j > 0; j >>= 1) {
+                    for (int i = threadIdx.x; i < len; i += 256) {
+                        const int ixj = i ^ j;
+                        if (ixj > i) {
+                            const double a = s_v[i], c = s_v[ixj];
+                            const bool up = ((i & kk) == 0);
+                            if ((a > c) == up) { s_v[i] = c; s_v[ixj] = a; }
+                        }
+                    }
+                    __syncthreads();
+                }
+            ym[k] = s_v[P.ym_rank[b][k]];
+            if (k == 1 && P.ym_bucket[b][0] == P.ym_bucket[b][1]) ym[0] = s_v[P.ym_rank[b][0]];
+            __syncthreads();
+        }
+        if (s_fail) break;
+        if (threadIdx.x == 0) {
+            s_bx[used] = (w & 1) ? P.xm_val[b][1] : 0.5 * (P.xm_val[b][0] + P.xm_val[b][1]);
+            s_by[used] = (w & 1) ? ym[1] : 0.5 * (ym[0] + ym[1]);
+            s_bw[used] = (double)w;
+        }
+        ++used;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_fail) { row_fallback[row] = 1; }
+        else { row_fallback[row] = 0; knots_from_bins(s_bx, s_by, s_bw, used, knots + row); }
+    }
+}
+
+// bin medians -> PAVA -> de-duplicated knots (wls_backend.c:507-560, 262-338)
+__device__ void knots_from_bins(const double *bx, const double *by, const double *bw, int used, Knots *out)
+{
+    Knots K;
+    K.nk = 0; K.constant = 0; K.cval = 1.0e-8;
+    if (used == 1) { K.constant = 1; K.cval = fmax(by[0], 1.0e-8); *out = K; return; }
+    double pv[MAX_KNOTS], pw[MAX_KNOTS], fit[MAX_KNOTS];
+    int pl[MAX_KNOTS], nb = 0;
+    for (int i = 0; i < used; ++i) {
+        pv[nb] = by[i]; pw[nb] = fmax(bw[i], 1.0e-8); pl[nb] = 1; ++nb;
+        while (nb >= 2 && pv[nb - 2] > pv[nb - 1]) {
+            const double tw = __dadd_rn(pw[nb - 2], pw[nb - 1]);
+            const double mv = __dadd_rn(__dmul_rn(pv[nb - 2], pw[nb - 2]), __dmul_rn(pv[nb - 1], pw[nb - 1])) / tw;
+            pv[nb - 2] = mv; pw[nb - 2] = tw; pl[nb - 2] += pl[nb - 1];
+            --nb;
+        }
+    }
+    int q = 0;
+    for (int b = 0; b < nb; ++b) for (int r = 0; r < pl[b]; ++r) fit[q++] = pv[b];
+    int nk = 0;
+    for (int b = 0; b < used; ++b) {
+        const double cx = bx[b], cy = fmax(fit[b], 1.0e-8);
+        if (nk > 0 && cx <= K.x[nk - 1]) { K.y[nk - 1] = fmax(K.y[nk - 1], cy); continue; }
+        K.x[nk] = cx; K.y[nk] = cy; ++nk;
+    }
+    K.nk = nk;
+    if (nk == 1) { K.constant = 1; K.cval = fmax(K.y[0], 1.0e-8); }
+    *out = K;
+}
+
+__global__ void k_knots_serial(const double *bx, const double *by, const double *bw, int used, Knots *out)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) knots_from_bins(bx, by, bw, used, out);
+}
+
+// ------------------------------------------------------------------ host driver
+int trend_knots_select(const double *d_C, const double *d_V, long long m, long long n, long long row_stride, Knots *d_knots,
+                       int *d_row_fallback, cudaStream_t st)
+{
+    const int B = (int)fmax(4.0, floor(1.0 + (log((double)n + 1.0) / log(2.0))));      // wls_backend.c:456
+    if (B > MAXB) return ST_INVALID;
+    Arena ar(st);
+    TrendBuffers T{};
+    RB_TRY(ar.alloc(&T.xhist, (size_t)m * NBX));
+    RB_TRY(ar.alloc(&T.lut, (size_t)m * NBX));
+    RB_TRY(ar.alloc(&T.binlo, (size_t)m * NBX));
+    RB_TRY(ar.alloc(&T.plan, (size_t)m));
+    RB_TRY(ar.alloc(&T.cand, (size_t)m * MAXSLOT * CAPX));
+    RB_TRY(ar.alloc(&T.cand_cnt, (size_t)m * MAXSLOT));
+    RB_TRY(ar.alloc(&T.yhist, (size_t)m * MAXB * NBY));
+    RB_TRY(ar.alloc(&T.ycand, (size_t)m * MAXB * 2 * CAPY));
+    RB_TRY(ar.alloc(&T.ycand_cnt, (size_t)m * MAXB * 2));
+    RB_CUDA(cudaMemsetAsync(T.xhist, 0, sizeof(int) * (size_t)m * NBX, st));
+    RB_CUDA(cudaMemsetAsync(T.cand_cnt, 0, sizeof(int) * (size_t)m * MAXSLOT, st));
+    RB_CUDA(cudaMemsetAsync(T.yhist, 0, sizeof(int) * (size_t)m * MAXB * NBY, st));
+    RB_CUDA(cudaMemsetAsync(T.ycand_cnt, 0, sizeof(int) * (size_t)m * MAXB * 2, st));
+
+    static bool attr = false;
+    const size_t sm_xhist = sizeof(int) * NBX;
+    const size_t sm_collect = sizeof(int) * (size_t)B * NBY + 2 * NBX;
+    const size_t sm_resolve = sizeof(double2) * CAPX;
+    if (!attr) {
+        RB_CUDA(cudaFuncSetAttribute(k_xhist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_xhist));
+        RB_CUDA(cudaFuncSetAttribute(k_xcollect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(int) * MAXB * NBY + 2 * NBX)));
+        RB_CUDA(cudaFuncSetAttribute(k_xresolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_resolve));
+        RB_CUDA(cudaFuncSetAttribute(k_xplan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(int) * (NBX + 1 + 256))));
+        attr = true;
+    }
+    const unsigned chunks = (unsigned)((n + CHUNK - 1) / CHUNK);
+    const dim3 gstream(chunks, (unsigned)m);
+    {
+        RB_PROF("trend_xhist", st, (double)m * n * 8.0);
+        k_xhist<<<gstream, ST_THREADS, sm_xhist, st>>>(d_C, n, row_stride, T.xhist);
+        RB_LAUNCH_CHECK();
+    }
+    {
+        RB_PROF("trend_plan_resolve", st, 0.0);
+        k_xplan<<<(unsigned)m, 256, sizeof(int) * (NBX + 1 + 256), st>>>(T, n, B);
+        RB_LAUNCH_CHECK();
+    }
+    {
+        RB_PROF("trend_xcollect", st, (double)m * n * 16.0);
+        k_xcollect<<<gstream, ST_THREADS, sm_collect, st>>>(d_C, d_V, n, row_stride, T, B);
+        RB_LAUNCH_CHECK();
+    }
+    {
+        RB_PROF("trend_plan_resolve", st, 0.0);
+        k_xresolve<<<dim3(MAXSLOT, (unsigned)m), ST_THREADS, sm_resolve, st>>>(T, n, B);
+        RB_LAUNCH_CHECK();
+        k_yplan<<<dim3((unsigned)B, (unsigned)m), 256, 0, st>>>(T, n, B);
+        RB_LAUNCH_CHECK();
+    }
+    {
+        RB_PROF("trend_ycollect", st, (double)m * n * 16.0);
+        k_ycollect<<<gstream, ST_THREADS, 0, st>>>(d_C, d_V, n, row_stride, T, B);
+        RB_LAUNCH_CHECK();
+    }
+    {
+        RB_PROF("trend_plan_resolve", st, 0.0);
+        k_yresolve<<<(unsigned)m, 256, 0, st>>>(T, n, B, d_knots, d_row_fallback);
+        RB_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+}  // namespace score
+}  // namespace rb

@@ -1,0 +1,20 @@
+// Trend-knot interfaces shared by trend.cu (histogram multi-select) and wls.cu (sort-based path, combine).
+#pragma once
+#include "common.cuh"
+
+namespace rb {
+namespace score {
+
+constexpr int MAX_KNOTS = 64;
+
+struct Knots { double x[MAX_KNOTS]; double y[MAX_KNOTS]; int nk; int constant; double cval; };
+
+// bin medians -> PAVA -> de-duplicated knots (wls_backend.c:507-560, 262-338); single thread
+__device__ void knots_from_bins(const double *bx, const double *by, const double *bw, int used, Knots *out);
+
+// Histogram multi-select for all m rows; rows it cannot handle (a bucket over capacity) get row_fallback = 1.
+int trend_knots_select(const double *d_C, const double *d_V, long long m, long long n, long long row_stride, Knots *d_knots,
+                       int *d_row_fallback, cudaStream_t st);
+
+}  // namespace score
+}  // namespace rb

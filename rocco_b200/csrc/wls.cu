@@ -7,6 +7,7 @@
 // and the Python driver inference.py:302-379.
 #include "common.cuh"
 #include "score.cuh"
+#include "trend.cuh"
 
 #include <cub/cub.cuh>
 #include <math.h>
@@ -15,8 +16,6 @@
 
 namespace rb {
 namespace score {
-
-constexpr int MAX_KNOTS = 64;
 
 int resolve_spatial_window(long long n, int requested)          // wls_backend.c:232-260
 {
@@ -227,14 +226,12 @@ __global__ void k_bin_keys(const unsigned long long *ysorted, long long N, int B
     }
 }
 
-struct Knots { double x[MAX_KNOTS]; double y[MAX_KNOTS]; int nk; int constant; double cval; };
-
 // one thread per row: bin medians -> PAVA -> de-duplicated knots (wls_backend.c:476-560)
 __global__ void k_knots_from_sorted(const unsigned long long *xsorted, const unsigned long long *ybinsorted, long long N, int B,
                                     Knots *out)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    double bx[MAX_KNOTS], by[MAX_KNOTS], bw[MAX_KNOTS], fit[MAX_KNOTS];
+    double bx[MAX_KNOTS], by[MAX_KNOTS], bw[MAX_KNOTS];
     int used = 0;
     for (int b = 0; b < B; ++b) {
         const long long lo = ((long long)b * N) / B, hi = ((long long)(b + 1) * N) / B;
@@ -248,36 +245,11 @@ __global__ void k_knots_from_sorted(const unsigned long long *xsorted, const uns
         bw[used] = (double)wdt;
         ++used;
     }
-    Knots K;
-    K.nk = 0; K.constant = 0; K.cval = 1.0e-8;
-    if (used == 1) { K.constant = 1; K.cval = fmax(by[0], 1.0e-8); *out = K; return; }
-    // PAVA (wls_backend.c:262-338)
-    double pv[MAX_KNOTS], pw[MAX_KNOTS];
-    int pl[MAX_KNOTS], nb = 0;
-    for (int i = 0; i < used; ++i) {
-        pv[nb] = by[i]; pw[nb] = fmax(bw[i], 1.0e-8); pl[nb] = 1; ++nb;
-        while (nb >= 2 && pv[nb - 2] > pv[nb - 1]) {
-            const double tw = __dadd_rn(pw[nb - 2], pw[nb - 1]);
-            const double mv = __dadd_rn(__dmul_rn(pv[nb - 2], pw[nb - 2]), __dmul_rn(pv[nb - 1], pw[nb - 1])) / tw;
-            pv[nb - 2] = mv; pw[nb - 2] = tw; pl[nb - 2] += pl[nb - 1];
-            --nb;
-        }
-    }
-    int q = 0;
-    for (int b = 0; b < nb; ++b) for (int r = 0; r < pl[b]; ++r) fit[q++] = pv[b];
-    int nk = 0;
-    for (int b = 0; b < used; ++b) {
-        const double cx = bx[b], cy = fmax(fit[b], 1.0e-8);
-        if (nk > 0 && cx <= K.x[nk - 1]) { K.y[nk - 1] = fmax(K.y[nk - 1], cy); continue; }
-        K.x[nk] = cx; K.y[nk] = cy; ++nk;
-    }
-    K.nk = nk;
-    if (nk == 1) { K.constant = 1; K.cval = fmax(K.y[0], 1.0e-8); }
-    *out = K;
+    knots_from_bins(bx, by, bw, used, out);
 }
 
-static int trend_knots_sorted(const double *d_C, const double *d_V, long long m, long long n, long long row_stride,
-                              Knots *d_knots, cudaStream_t st)
+static int trend_knots_sorted(const double *d_C, const double *d_V, const std::vector<long long> &rows, long long n,
+                              long long row_stride, Knots *d_knots, cudaStream_t st)
 {
     const long long N = n;
     const int B = (int)fmax(4.0, floor(1.0 + (log((double)N + 1.0) / log(2.0))));      // wls_backend.c:456
@@ -293,7 +265,7 @@ static int trend_knots_sorted(const double *d_C, const double *d_V, long long m,
     char *tmp = nullptr;
     RB_TRY(ar.alloc(&tmp, tmp_bytes));
     const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 16);
-    for (long long r = 0; r < m; ++r) {
+    for (long long r : rows) {
         const double *c = d_C + r * row_stride, *v = d_V + r * row_stride;
         k_make_keys<<<blocks, 256, 0, st>>>(c, v, n, k0, v0);                 // k0 = y bits, v0 = x bits
         RB_LAUNCH_CHECK();
@@ -310,6 +282,10 @@ static int trend_knots_sorted(const double *d_C, const double *d_V, long long m,
     }
     return 0;
 }
+
+// 0: histogram multi-select with sort fallback (default); 1: force the sort-based path (tests)
+static std::atomic<int> g_trend_mode{0};
+static std::atomic<long long> g_trend_fallback_rows{0};
 
 // ------------------------------------------------------------------ fused posterior + column reduction over samples
 struct CombineParams {
@@ -444,8 +420,25 @@ int centered_wls(const double *d_centered, long long m, long long n, const rocco
             RB_LAUNCH_CHECK();
         }
         {
-            RB_PROF("trend_knots", st, (double)m * (double)n * 16.0);
-            RB_TRY(trend_knots_sorted(d_centered, d_V, m, n, n, d_knots, st));
+            // exact order statistics by histogram multi-select; rows it flags (a bucket over capacity: massive ties)
+            // fall back to the sort-based path, which is exact for any input
+            int *d_fb = nullptr;
+            RB_TRY(ar.alloc(&d_fb, (size_t)m));
+            std::vector<long long> rows;
+            if (g_trend_mode.load() == 1) {
+                for (long long r = 0; r < m; ++r) rows.push_back(r);
+            } else {
+                RB_TRY(trend_knots_select(d_centered, d_V, m, n, n, d_knots, d_fb, st));
+                std::vector<int> fb((size_t)m);
+                RB_CUDA(cudaMemcpyAsync(fb.data(), d_fb, sizeof(int) * (size_t)m, cudaMemcpyDeviceToHost, st));
+                RB_CUDA(cudaStreamSynchronize(st));
+                for (long long r = 0; r < m; ++r) if (fb[(size_t)r]) rows.push_back(r);
+            }
+            if (!rows.empty()) {
+                g_trend_fallback_rows.fetch_add((long long)rows.size());
+                RB_PROF("trend_sort_fallback", st, (double)rows.size() * (double)n * 16.0);
+                RB_TRY(trend_knots_sorted(d_centered, d_V, rows, n, n, d_knots, st));
+            }
         }
         P.const_rows = 0; P.V = d_V; P.knots = d_knots;
     }
@@ -499,6 +492,12 @@ static int score_loci_dev(const void *d_matrix, int dtype, long long m, long lon
 // ====================================================================== C-ABI
 using namespace rb;
 #define RB_API extern "C" __attribute__((visibility("default")))
+
+RB_API int rocco_b200_trend_set_mode(int mode)
+{
+    return score::g_trend_mode.exchange(mode ? 1 : 0);
+}
+RB_API long long rocco_b200_trend_fallback_rows(void) { return score::g_trend_fallback_rows.load(); }
 
 RB_API void rocco_b200_default_score_params(rocco_b200_score_params *p)
 {

@@ -200,6 +200,43 @@ def test_spatial_windows_match_oracle(rb, oracle, window):
     _check_details(got, want)
 
 
+# ------------------------------------------------------------------ order statistics: multi-select == sort path
+@pytest.mark.parametrize("m,n,seed,ties", [(3, 5, 1, True), (2, 37, 2, True), (4, 999, 3, True), (3, 20_000, 4, True),
+                                           (3, 20_000, 6, False), (6, 300_000, 5, False)])
+def test_trend_multiselect_equals_sort_path_bitwise(rb, m, n, seed, ties):
+    """both paths compute exact order statistics, so every output must agree bit for bit"""
+    from rocco_b200 import _lib, inference
+    lib = _lib.load()
+    rng = np.random.default_rng(seed)
+    c = rng.normal(size=(m, n)) * (0.2 + np.abs(np.sin(np.arange(n) / 150.0)))
+    if ties:
+        c[:, : n // 3] = np.round(c[:, : n // 3], 2)          # ties in |signal|
+    prev = lib.rocco_b200_trend_set_mode(1)
+    try:
+        want_s, want = inference._score_centered_wls_matrix(c, prior_df=6.0)
+    finally:
+        lib.rocco_b200_trend_set_mode(0)
+    fb0 = lib.rocco_b200_trend_fallback_rows()
+    got_s, got = inference._score_centered_wls_matrix(c, prior_df=6.0)
+    lib.rocco_b200_trend_set_mode(prev)
+    assert np.array_equal(got_s, want_s)
+    for k in DETAIL_KEYS:
+        assert np.array_equal(got[k], want[k]), k
+    if not ties:
+        assert lib.rocco_b200_trend_fallback_rows() == fb0       # the fast path really ran
+
+
+def test_trend_fallback_on_massive_ties(rb):
+    from rocco_b200 import _lib, inference
+    lib = _lib.load()
+    fb0 = lib.rocco_b200_trend_fallback_rows()
+    c = np.zeros((2, 50_000))
+    c[1, ::7] = 0.5
+    sc, det = inference._score_centered_wls_matrix(c)
+    assert lib.rocco_b200_trend_fallback_rows() > fb0            # over-capacity buckets -> sort path
+    assert np.all(np.isfinite(sc))
+
+
 # ------------------------------------------------------------------ end-to-end at benchmark-like shapes
 @pytest.mark.parametrize("m,n,seed", [(10, 60_000, 21), (4, 250_000, 19), (25, 30_011, 5)])
 def test_score_loci_wls_matches_oracle(rb, oracle, m, n, seed):
