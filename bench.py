@@ -14,6 +14,7 @@ API (NumPy in / NumPy + BED files out) with host<->device copies inside the time
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -243,6 +244,7 @@ def main():
     _lib.profile_enable(True)
     _lib.profile_report()
     launches0 = _lib.kernel_launches()
+    fb_rows0 = int(_lib.load().rocco_b200_trend_fallback_rows())
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
@@ -253,6 +255,9 @@ def main():
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = _lib.kernel_launches() - launches0
+    fb_rows = int(_lib.load().rocco_b200_trend_fallback_rows()) - fb_rows0
+    reasons = (ctypes.c_longlong * 8)()
+    _lib.load().rocco_b200_trend_fallback_reasons(reasons)
     prof = _lib.profile_report()
     _lib.profile_enable(False)
     clocks = sampler.stop()
@@ -343,7 +348,8 @@ def main():
             "config": {"workload": workload_name(args, names), "genome_bins": genome_bins, "samples": args.samples,
                        "chromosomes": len(names), "sharding": f"chromosomes LPT-packed over {world} rank(s)",
                        "l2_policy": "inputs larger than L2 (per-chromosome matrices 0.7-4 GB vs 126 MB L2)",
-                       "selected_bins": selected_total, "collective": "one NCCL all-reduce of [selected, bins] per step"},
+                       "selected_bins": selected_total, "trend_sort_fallback_rows": fb_rows,
+                       "trend_fallback_reason_counts": list(reasons)[:5], "collective": "one NCCL all-reduce of [selected, bins] per step"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(lt.item()), "roofline": roof, "cpu_baseline": cpu,
         }
         print(json.dumps(line))

@@ -29,6 +29,19 @@ int ensure_device()
         (void)cudaGetLastError();
         return ST_CUDA;
     }
+    // keep stream-ordered scratch cached in the pool between calls (default threshold 0 hands every
+    // buffer back to the driver at each synchronisation, which costs more than the kernels)
+    static std::atomic<unsigned> tuned{0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev < 32 && !(tuned.load() & (1u << dev))) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long thr = ~0ULL;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+        tuned.fetch_or(1u << dev);
+        (void)cudaGetLastError();
+    }
     return 0;
 }
 

@@ -30,13 +30,13 @@ namespace score {
 constexpr int NBX = 16384;              // |signal| buckets: bits >> 42 (exponent + 10 mantissa bits), 2^-8 .. 2^8
 constexpr int XSHIFT = 42;
 constexpr unsigned XB0 = (unsigned)(0x3F70000000000000ULL >> XSHIFT);   // bucket index of 2^-8
-constexpr int NBY = 1024;               // variance buckets: bits >> 47 (exponent + 5 mantissa bits), 2^-27 .. 2^5
-constexpr int YSHIFT = 47;
-constexpr unsigned YB0 = (unsigned)(0x3E40000000000000ULL >> YSHIFT);   // bucket index of 2^-27
+constexpr int NBY = 1024;               // variance buckets: bits >> 46 (exponent + 6 mantissa bits): 64 per octave,
+constexpr int YSHIFT = 46;              // 16 octaves centred on the row's sampled median variance
+constexpr int YSAMPLE = 2048;
 constexpr int MAXB = 32;                // bins per row (n < 2^31)
 constexpr int MAXSLOT = 3 * MAXB;
 constexpr int CAPX = 8192;              // pairs per x slot
-constexpr int CAPY = 4096;              // variances per (bin, k) slot
+constexpr int CAPY = 8192;              // variances per (bin, k) slot
 constexpr int CHUNK = 131072;           // elements streamed per CTA
 constexpr int ST_THREADS = 512;
 
@@ -46,10 +46,10 @@ __device__ __forceinline__ int xbucket(double x)
     const int b = (int)u - (int)XB0;
     return b < 0 ? 0 : (b >= NBX ? NBX - 1 : b);
 }
-__device__ __forceinline__ int ybucket(double y)
+__device__ __forceinline__ int ybucket(double y, int yb0)
 {
-    const unsigned u = (unsigned)((unsigned long long)__double_as_longlong(y) >> YSHIFT);
-    const int b = (int)u - (int)YB0;
+    const int u = (int)((unsigned long long)__double_as_longlong(y) >> YSHIFT);
+    const int b = u - yb0;
     return b < 0 ? 0 : (b >= NBY ? NBY - 1 : b);
 }
 __device__ __forceinline__ int bin_of_rank(long long p, long long N, int B)
@@ -61,9 +61,12 @@ __device__ __forceinline__ int bin_of_rank(long long p, long long N, int B)
     return b;
 }
 
+enum FallbackReason { FB_XSLOT = 1, FB_XCOUNT = 2, FB_YTOTAL = 4, FB_YSLOT = 8, FB_YCOUNT = 16 };
+
 struct RowPlan {
     int nslot;
-    int fallback;
+    int fallback;                      // bit mask of FallbackReason
+    int yb0;                           // variance bucket offset of this row
     int slot_bucket[MAXSLOT];
     int slot_prefix[MAXSLOT];          // rank of the first pair of the bucket
     int slot_count[MAXSLOT];
@@ -110,7 +113,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_xhist(const double *__restrict__
 }
 
 // ------------------------------------------------------------------ T2
-__global__ void __launch_bounds__(256) k_xplan(TrendBuffers T, long long n, int B)
+__global__ void __launch_bounds__(256) k_xplan(TrendBuffers T, const double *__restrict__ V, long long row_stride, long long n, int B)
 {
     extern __shared__ int s_plan[];
     int *s_pre = s_plan;                 // NBX + 1
@@ -140,6 +143,38 @@ __global__ void __launch_bounds__(256) k_xplan(TrendBuffers T, long long n, int 
         binlo[k] = (unsigned char)bin_of_rank(min((long long)s_pre[k], n - 1), n, B);
     }
     __syncthreads();
+    // centre the variance buckets on the median of a strided sample of this row's variances
+    {
+        double *s_smp = reinterpret_cast<double *>(s_plan + NBX + 1 + 256 + 1);   // 8-byte aligned: NBX+258 ints
+        const int take = (int)min((long long)YSAMPLE, n);
+        int len = 1;
+        while (len < take) len <<= 1;
+        for (int k = threadIdx.x; k < len; k += 256) {
+            double v = INFINITY;
+            if (k < take) {
+                const long long i = (n <= YSAMPLE) ? k : (long long)(((double)k + 0.5) * ((double)n / (double)YSAMPLE));
+                v = V[row * row_stride + min(i, n - 1)];
+            }
+            s_smp[k] = v;
+        }
+        __syncthreads();
+        for (int kk = 2; kk <= len; kk <<= 1)
+            for (int j = kk >> 1; j > 0; j >>= 1) {
+                for (int i = threadIdx.x; i < len; i += 256) {
+                    const int ixj = i ^ j;
+                    if (ixj > i) {
+                        const double a = s_smp[i], c = s_smp[ixj];
+                        const bool up = ((i & kk) == 0);
+                        if ((a > c) == up) { s_smp[i] = c; s_smp[ixj] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+        if (threadIdx.x == 0) {
+            const double med = s_smp[take / 2];
+            T.plan[row].yb0 = (int)((unsigned long long)__double_as_longlong(med) >> YSHIFT) - NBY / 2;
+        }
+    }
     if (threadIdx.x != 0) return;
     RowPlan &P = T.plan[row];
     P.nslot = 0; P.fallback = 0;
@@ -155,7 +190,7 @@ __global__ void __launch_bounds__(256) k_xplan(TrendBuffers T, long long n, int 
             lut[b] = (unsigned char)s;
             P.slot_bucket[s] = b; P.slot_prefix[s] = s_pre[b]; P.slot_count[s] = s_pre[b + 1] - s_pre[b];
             P.slot_boundary[s] = 0;
-            if (P.slot_count[s] > CAPX) P.fallback = 1;
+            if (P.slot_count[s] > CAPX) P.fallback |= FB_XSLOT;
         }
         if (boundary) P.slot_boundary[s] = 1;
         return s;
@@ -198,6 +233,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_xcollect(const double *__restric
     double2 *cand = T.cand + (size_t)row * MAXSLOT * CAPX;
     int *ccnt = T.cand_cnt + row * MAXSLOT;
     const RowPlan &P = T.plan[row];
+    const int yb0 = P.yb0;
     for (long long j = c0 + threadIdx.x; j < c1; j += ST_THREADS) {
         const double x = fabs(c[j]);
         const int b = xbucket(x);
@@ -209,7 +245,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_xcollect(const double *__restric
             if (pos < CAPX) cand[(size_t)s * CAPX + pos] = make_double2(x, y);
             boundary = P.slot_boundary[s] != 0;
         }
-        if (!boundary) atomicAdd(&s_yh[(int)s_bin[b] * NBY + ybucket(y)], 1);
+        if (!boundary) atomicAdd(&s_yh[(int)s_bin[b] * NBY + ybucket(y, yb0)], 1);
     }
     __syncthreads();
     int *g = T.yhist + (size_t)row * MAXB * NBY;
@@ -230,7 +266,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_xresolve(TrendBuffers T, long lo
     RowPlan &P = T.plan[row];
     if (P.fallback || s >= P.nslot) return;
     const int cnt = min(T.cand_cnt[row * MAXSLOT + s], CAPX);
-    if (cnt != P.slot_count[s]) { if (threadIdx.x == 0) P.fallback = 1; return; }
+    if (cnt != P.slot_count[s]) { if (threadIdx.x == 0) atomicOr(&P.fallback, FB_XCOUNT); return; }
     int len = 1;
     while (len < cnt) len <<= 1;
     double2 *cand = T.cand + ((size_t)row * MAXSLOT + s) * CAPX;
@@ -261,7 +297,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_xresolve(TrendBuffers T, long lo
         for (int k = threadIdx.x; k < cnt; k += ST_THREADS) {
             const double2 pr = s_p[k];
             cand[k] = pr;
-            atomicAdd(&g[bin_of_rank(pre + k, n, B) * NBY + ybucket(pr.y)], 1);
+            atomicAdd(&g[bin_of_rank(pre + k, n, B) * NBY + ybucket(pr.y, P.yb0)], 1);
         }
     }
 }
@@ -282,7 +318,7 @@ __global__ void __launch_bounds__(256) k_yplan(TrendBuffers T, long long n, int 
         int acc = 0;
         for (int k = 0; k < NBY; ++k) { s_pre[k] = acc; acc += h[k]; }
         s_pre[NBY] = acc;
-        if (acc != (int)w) { P.fallback = 1; }
+        if (acc != (int)w) { atomicOr(&P.fallback, FB_YTOTAL); }
         else {
             auto bucket_of = [&](long long r) {
                 int l = 0, hgh = NBY;
@@ -298,15 +334,15 @@ __global__ void __launch_bounds__(256) k_yplan(TrendBuffers T, long long n, int 
                 const int b0 = bucket_of(r0);
                 P.ym_bucket[b][0] = b0; P.ym_rank[b][0] = (int)(r0 - s_pre[b0]); P.ym_count[b][0] = s_pre[b0 + 1] - s_pre[b0];
             }
-            if (P.ym_count[b][1] > CAPY || P.ym_count[b][0] > CAPY) P.fallback = 1;
+            if (P.ym_count[b][1] > CAPY || P.ym_count[b][0] > CAPY) atomicOr(&P.fallback, FB_YSLOT);
         }
     }
 }
 
 // ------------------------------------------------------------------ T6
-__device__ __forceinline__ void ycollect_one(TrendBuffers &T, long long row, const int (*s_yb)[2], int bin, double y)
+__device__ __forceinline__ void ycollect_one(TrendBuffers &T, long long row, const int (*s_yb)[2], int bin, double y, int yb0)
 {
-    const int yb = ybucket(y);
+    const int yb = ybucket(y, yb0);
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         if (s_yb[bin][k] == yb && (k == 1 || s_yb[bin][1] != yb)) {
@@ -339,7 +375,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_ycollect(const double *__restric
         const int b = xbucket(fabs(c[j]));
         const int s = s_lut[b];
         if (s != 0xFF && s_bnd[s]) continue;                        // boundary buckets: handled from the sorted slot below
-        ycollect_one(T, row, s_yb, (int)s_bin[b], v[j]);
+        ycollect_one(T, row, s_yb, (int)s_bin[b], v[j], P.yb0);
     }
     if (blockIdx.x == 0) {
         for (int s = 0; s < P.nslot; ++s) {
@@ -347,7 +383,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_ycollect(const double *__restric
             const double2 *cand = T.cand + ((size_t)row * MAXSLOT + s) * CAPX;
             const long long pre = P.slot_prefix[s];
             for (int k = threadIdx.x; k < P.slot_count[s]; k += ST_THREADS)
-                ycollect_one(T, row, s_yb, bin_of_rank(pre + k, n, B), cand[k].y);
+                ycollect_one(T, row, s_yb, bin_of_rank(pre + k, n, B), cand[k].y, P.yb0);
         }
     }
 }
@@ -357,14 +393,14 @@ __device__ void knots_from_bins(const double *bx, const double *by, const double
 
 __global__ void __launch_bounds__(256) k_yresolve(TrendBuffers T, long long n, int B, Knots *knots, int *row_fallback)
 {
-    __shared__ double s_v[CAPY];
+    extern __shared__ double s_v[];              // CAPY
     __shared__ double s_bx[MAXB], s_by[MAXB], s_bw[MAXB];
     __shared__ int s_fail;
     const long long row = blockIdx.x;
     RowPlan &P = T.plan[row];
     if (threadIdx.x == 0) s_fail = P.fallback;
     __syncthreads();
-    if (s_fail) { if (threadIdx.x == 0) row_fallback[row] = 1; return; }
+    if (s_fail) { if (threadIdx.x == 0) row_fallback[row] = s_fail; return; }
     int used = 0;
     for (int b = 0; b < B; ++b) {
         const long long lo = ((long long)b * n) / B, hi = ((long long)(b + 1) * n) / B;
@@ -375,7 +411,7 @@ __global__ void __launch_bounds__(256) k_yresolve(TrendBuffers T, long long n, i
             if (P.ym_bucket[b][k] < 0) continue;
             if (k == 0 && P.ym_bucket[b][0] == P.ym_bucket[b][1]) continue;       // same bucket: resolved with k = 1
             const int cnt = T.ycand_cnt[(row * MAXB + b) * 2 + k];
-            if (cnt != P.ym_count[b][k]) { if (threadIdx.x == 0) s_fail = 1; }
+            if (cnt != P.ym_count[b][k]) { if (threadIdx.x == 0) s_fail = FB_YCOUNT; }
             __syncthreads();
             if (s_fail) break;
             int len = 1;
@@ -409,7 +445,7 @@ __global__ void __launch_bounds__(256) k_yresolve(TrendBuffers T, long long n, i
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        if (s_fail) { row_fallback[row] = 1; }
+        if (s_fail) { row_fallback[row] = s_fail; }
         else { row_fallback[row] = 0; knots_from_bins(s_bx, s_by, s_bw, used, knots + row); }
     }
 }
@@ -475,11 +511,13 @@ int trend_knots_select(const double *d_C, const double *d_V, long long m, long l
     const size_t sm_xhist = sizeof(int) * NBX;
     const size_t sm_collect = sizeof(int) * (size_t)B * NBY + 2 * NBX;
     const size_t sm_resolve = sizeof(double2) * CAPX;
+    const size_t sm_plan = sizeof(int) * (NBX + 258) + sizeof(double) * YSAMPLE;
     if (!attr) {
         RB_CUDA(cudaFuncSetAttribute(k_xhist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_xhist));
         RB_CUDA(cudaFuncSetAttribute(k_xcollect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(int) * MAXB * NBY + 2 * NBX)));
         RB_CUDA(cudaFuncSetAttribute(k_xresolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_resolve));
-        RB_CUDA(cudaFuncSetAttribute(k_xplan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(int) * (NBX + 1 + 256))));
+        RB_CUDA(cudaFuncSetAttribute(k_xplan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_plan));
+        RB_CUDA(cudaFuncSetAttribute(k_yresolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * CAPY)));
         attr = true;
     }
     const unsigned chunks = (unsigned)((n + CHUNK - 1) / CHUNK);
@@ -491,7 +529,7 @@ int trend_knots_select(const double *d_C, const double *d_V, long long m, long l
     }
     {
         RB_PROF("trend_plan_resolve", st, 0.0);
-        k_xplan<<<(unsigned)m, 256, sizeof(int) * (NBX + 1 + 256), st>>>(T, n, B);
+        k_xplan<<<(unsigned)m, 256, sm_plan, st>>>(T, d_V, row_stride, n, B);
         RB_LAUNCH_CHECK();
     }
     {
@@ -513,7 +551,7 @@ int trend_knots_select(const double *d_C, const double *d_V, long long m, long l
     }
     {
         RB_PROF("trend_plan_resolve", st, 0.0);
-        k_yresolve<<<(unsigned)m, 256, 0, st>>>(T, n, B, d_knots, d_row_fallback);
+        k_yresolve<<<(unsigned)m, 256, sizeof(double) * CAPY, st>>>(T, n, B, d_knots, d_row_fallback);
         RB_LAUNCH_CHECK();
     }
     return 0;

@@ -286,6 +286,7 @@ static int trend_knots_sorted(const double *d_C, const double *d_V, const std::v
 // 0: histogram multi-select with sort fallback (default); 1: force the sort-based path (tests)
 static std::atomic<int> g_trend_mode{0};
 static std::atomic<long long> g_trend_fallback_rows{0};
+static std::atomic<long long> g_trend_fb_reason[8];
 
 // ------------------------------------------------------------------ fused posterior + column reduction over samples
 struct CombineParams {
@@ -432,7 +433,8 @@ int centered_wls(const double *d_centered, long long m, long long n, const rocco
                 std::vector<int> fb((size_t)m);
                 RB_CUDA(cudaMemcpyAsync(fb.data(), d_fb, sizeof(int) * (size_t)m, cudaMemcpyDeviceToHost, st));
                 RB_CUDA(cudaStreamSynchronize(st));
-                for (long long r = 0; r < m; ++r) if (fb[(size_t)r]) rows.push_back(r);
+                for (long long r = 0; r < m; ++r)
+                    if (fb[(size_t)r]) { rows.push_back(r); for (int k = 0; k < 8; ++k) if (fb[(size_t)r] & (1 << k)) g_trend_fb_reason[k].fetch_add(1); }
             }
             if (!rows.empty()) {
                 g_trend_fallback_rows.fetch_add((long long)rows.size());
@@ -498,6 +500,7 @@ RB_API int rocco_b200_trend_set_mode(int mode)
     return score::g_trend_mode.exchange(mode ? 1 : 0);
 }
 RB_API long long rocco_b200_trend_fallback_rows(void) { return score::g_trend_fallback_rows.load(); }
+RB_API void rocco_b200_trend_fallback_reasons(long long *out8) { for (int k = 0; k < 8; ++k) out8[k] = score::g_trend_fb_reason[k].load(); }
 
 RB_API void rocco_b200_default_score_params(rocco_b200_score_params *p)
 {
