@@ -8,10 +8,11 @@ from ._version import __version__
 from .dp import (build_switch_costs, calibrate_selection_penalty, objective_value, solve_chrom_exact,
                  solve_penalized_chain)
 from .inference import score_loci_wls
-from .rocco import chrom_solution_to_bed, combine_chrom_results
+from .rocco import (chrom_solution_to_bed, combine_chrom_results, score_central_tendency_chrom,
+                    score_dispersion_chrom)
 
 __all__ = [
     "__version__", "build_switch_costs", "calibrate_selection_penalty", "objective_value",
     "solve_chrom_exact", "solve_penalized_chain", "chrom_solution_to_bed", "combine_chrom_results",
-    "score_loci_wls",
+    "score_loci_wls", "score_central_tendency_chrom", "score_dispersion_chrom",
 ]

@@ -124,6 +124,8 @@ struct SearchDev {
 };
 
 struct TileOut { int cnt; int pend; int head; int ties; };   // head: 0/1 value, 2 = whole tile undecided
+// multiplier sweep only: objective pieces of the tile (resolved = bins up to the tile's last decided bin)
+struct TileSweep { double ssz; double spend; int sw; int zp; };
 
 struct Params {
     const double *scores;
@@ -142,6 +144,9 @@ struct Params {
     uint8_t *mask;              // EMIT only
     int *zin;                   // [tile]  EMIT: value flowing into the tile from the right
     long long *near_ties;       // [nchrom] EMIT only
+    TileSweep *tsweep;          // [slot][tile]  (nullptr unless sweeping)
+    double *sweep_ssz;          // [nchrom][MAX_SLOTS] sum s*z
+    long long *sweep_sw;        // [nchrom][MAX_SLOTS] switches
     uint8_t *bt;                // [ntiles * TILE] back-pointers of the sequential kernel (EMIT only)
     double *seq_value;          // [nchrom] DP best value of the sequential kernel (EMIT only)
     int ntiles;
@@ -164,6 +169,9 @@ __global__ void __launch_bounds__(THREADS) k_chain_tiles(Params P)
     __shared__ int s_ticket;
     __shared__ int s_whas[WARPS], s_whead[WARPS];
     __shared__ int s_red[WARPS][4];
+    __shared__ double s_sw_d[WARPS][2];
+    __shared__ int s_sw_i[WARPS][2];
+    __shared__ int s_firstz[WARPS];
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) s_ticket = atomicAdd(P.ticket, 1);
@@ -356,6 +364,33 @@ __global__ void __launch_bounds__(THREADS) k_chain_tiles(Params P)
         }
         if (lane == 0) { s_red[wid][0] = r_cnt; s_red[wid][1] = r_pend; s_red[wid][2] = r_ties; s_red[wid][3] = r_near; }
 
+        if (P.tsweep) {
+            const unsigned rm = vm & ~pm;                          // resolved items of this thread
+            double ssz = 0.0, spend = 0.0;
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j) {
+                if ((z >> j) & (rm >> j) & 1u) ssz += sc[j];
+                if ((pm >> j) & 1u) spend += sc[j];
+            }
+            int sw = __popc((z ^ (z >> 1)) & rm & (rm >> 1) & ((1u << (ITEMS - 1)) - 1u));
+            // pair (last item of this thread, first item of the next thread)
+            const unsigned firstinfo = (rm & 1u) | ((z & 1u) << 1);
+            unsigned nxt = __shfl_down_sync(0xffffffffu, firstinfo, 1);
+            if (lane == 0) s_firstz[wid] = (int)firstinfo;
+            __syncthreads();
+            if (lane == 31) nxt = (wid + 1 < WARPS) ? (unsigned)s_firstz[wid + 1] : 0u;
+            if (cnt == ITEMS && ((rm >> (ITEMS - 1)) & 1u) && (nxt & 1u))
+                sw += (int)(((z >> (ITEMS - 1)) & 1u) ^ ((nxt >> 1) & 1u));
+            int pkey = has ? (((base + 31 - __clz(dec)) << 1) | (int)((val >> (31 - __clz(dec))) & 1u)) : -1;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                ssz += __shfl_xor_sync(0xffffffffu, ssz, d);
+                spend += __shfl_xor_sync(0xffffffffu, spend, d);
+                sw += __shfl_xor_sync(0xffffffffu, sw, d);
+                pkey = max(pkey, __shfl_xor_sync(0xffffffffu, pkey, d));
+            }
+            if (lane == 0) { s_sw_d[wid][0] = ssz; s_sw_d[wid][1] = spend; s_sw_i[wid][0] = sw; s_sw_i[wid][1] = pkey; }
+        }
         if (EMIT) {
             uint8_t *gm = P.mask + cd.offset + s0 + base;
             if (cnt == ITEMS && ((reinterpret_cast<uintptr_t>(gm) & 15) == 0)) {
@@ -377,6 +412,13 @@ __global__ void __launch_bounds__(THREADS) k_chain_tiles(Params P)
             }
             o.head = any ? (int)(z & 1u) : 2;
             P.tout[sidx] = o;
+            if (P.tsweep) {
+                TileSweep ts{0.0, 0.0, 0, 0};
+                int pk = -1;
+                for (int w = 0; w < WARPS; ++w) { ts.ssz += s_sw_d[w][0]; ts.spend += s_sw_d[w][1]; ts.sw += s_sw_i[w][0]; pk = max(pk, s_sw_i[w][1]); }
+                ts.zp = pk < 0 ? 2 : (pk & 1);
+                P.tsweep[sidx] = ts;
+            }
             if (EMIT && nr) atomicAdd(reinterpret_cast<unsigned long long *>(P.near_ties + c), (unsigned long long)nr);
         }
         __syncthreads();
@@ -480,6 +522,9 @@ __global__ void __launch_bounds__(256) k_chain_finish(Params P, int emit)
         long long total = 0;
         int ties = 0;
         int carry = 0;                                   // value flowing in from the right of the chunk
+        const TileSweep *tsw = P.tsweep ? P.tsweep + (size_t)slot * P.ntiles + cd.tile0 : nullptr;
+        double sw_ssz = 0.0;
+        long long sw_cnt = 0;
         for (int hi = cd.ntiles; hi > 0; hi -= 32) {     // chunks of 32 tiles, right to left
             const int t = hi - 32 + lane;                // this lane's tile (may be < 0)
             int h = 2, pend = 0, cnt = 0, tt = 0;
@@ -496,6 +541,12 @@ __global__ void __launch_bounds__(256) k_chain_finish(Params P, int emit)
                 total += cnt + (zin ? pend : 0);
                 ties += tt;
                 if (emit && slot == 0) P.zin[cd.tile0 + t] = zin;
+                if (tsw) {
+                    const TileSweep ts = tsw[t];
+                    sw_ssz += ts.ssz + (zin ? ts.spend : 0.0);
+                    sw_cnt += ts.sw;
+                    if (t + 1 < cd.ntiles && ts.zp != 2 && ts.zp != zin) sw_cnt += 1;   // boundary after the last decided bin
+                }
             }
             carry = __shfl_sync(0xffffffffu, zin, 0);
         }
@@ -503,7 +554,10 @@ __global__ void __launch_bounds__(256) k_chain_finish(Params P, int emit)
         for (int d = 16; d > 0; d >>= 1) {
             total += __shfl_xor_sync(0xffffffffu, total, d);
             ties += __shfl_xor_sync(0xffffffffu, ties, d);
+            sw_ssz += __shfl_xor_sync(0xffffffffu, sw_ssz, d);
+            sw_cnt += __shfl_xor_sync(0xffffffffu, sw_cnt, d);
         }
+        if (lane == 0 && tsw) { P.sweep_ssz[(size_t)c * MAX_SLOTS + slot] = sw_ssz; P.sweep_sw[(size_t)c * MAX_SLOTS + slot] = sw_cnt; }
         if (lane == 0) {
             P.counts[(size_t)c * MAX_SLOTS + slot] = total;
             P.tiecnt[(size_t)c * MAX_SLOTS + slot] = ties;
@@ -948,6 +1002,59 @@ static int solve_batch(const double *d_scores, const double *d_costs, const rocc
     return 0;
 }
 
+// Multiplier sweep: counts and objectives of one chromosome for up to MAX_SLOTS multipliers per launch set.
+static int sweep(const double *d_scores, size_t n, double gamma, const double *lambdas, int K, long long *count_out,
+                 double *pen_out, double *obj_out, cudaStream_t st)
+{
+    if (!d_scores || !lambdas || n == 0 || K <= 0 || !(gamma >= 0.0)) return ST_INVALID;
+    RB_TRY(ensure_device());
+    const int ntiles = (int)((n + TILE - 1) / TILE);
+    Arena ar(st);
+    ChromDev cd{};
+    cd.offset = 0; cd.n = (long long)n; cd.gamma = gamma; cd.tile0 = 0; cd.ntiles = ntiles; cd.mode = 0; cd.seq = 0;
+    ChromDev *d_cd = nullptr; SearchDev *d_sd = nullptr; int *d_tc = nullptr, *d_flags = nullptr, *d_ticket = nullptr, *d_zin = nullptr;
+    double *d_lam = nullptr, *d_ssz = nullptr; long long *d_cnt = nullptr, *d_tie = nullptr, *d_near = nullptr, *d_sw = nullptr;
+    char *agg = nullptr, *incl = nullptr; TileOut *d_to = nullptr; TileSweep *d_ts = nullptr;
+    const int batch = std::min(K, MAX_SLOTS);
+    RB_TRY(ar.alloc(&d_cd, 1)); RB_TRY(ar.alloc(&d_sd, 1)); RB_TRY(ar.alloc(&d_tc, ntiles));
+    RB_TRY(ar.alloc(&d_lam, MAX_SLOTS)); RB_TRY(ar.alloc(&d_cnt, MAX_SLOTS)); RB_TRY(ar.alloc(&d_tie, MAX_SLOTS));
+    RB_TRY(ar.alloc(&d_near, 1)); RB_TRY(ar.alloc(&d_ssz, MAX_SLOTS)); RB_TRY(ar.alloc(&d_sw, MAX_SLOTS));
+    RB_TRY(ar.alloc(&d_flags, (size_t)batch * ntiles)); RB_TRY(ar.alloc(&agg, (size_t)batch * ntiles * sizeof(Map<VL>)));
+    RB_TRY(ar.alloc(&incl, (size_t)batch * ntiles * sizeof(VL))); RB_TRY(ar.alloc(&d_to, (size_t)batch * ntiles));
+    RB_TRY(ar.alloc(&d_ts, (size_t)batch * ntiles)); RB_TRY(ar.alloc(&d_ticket, 1)); RB_TRY(ar.alloc(&d_zin, ntiles));
+    RB_CUDA(cudaMemcpyAsync(d_cd, &cd, sizeof(cd), cudaMemcpyHostToDevice, st));
+    RB_CUDA(cudaMemsetAsync(d_tc, 0, sizeof(int) * ntiles, st));
+    RB_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int) * (size_t)batch * ntiles, st));
+    RB_CUDA(cudaMemsetAsync(d_ticket, 0, sizeof(int), st));
+    Params P{};
+    P.scores = d_scores; P.costs = nullptr; P.chroms = d_cd; P.search = d_sd; P.tile_chrom = d_tc; P.lam = d_lam;
+    P.counts = d_cnt; P.tiecnt = d_tie; P.flags = d_flags; P.agg = agg; P.incl = incl; P.tout = d_to; P.ticket = d_ticket;
+    P.mask = nullptr; P.zin = d_zin; P.near_ties = d_near; P.ntiles = ntiles; P.nchrom = 1; P.slots_per_block = 8;
+    P.tsweep = d_ts; P.sweep_ssz = d_ssz; P.sweep_sw = d_sw;
+    int epoch = 0;
+    std::vector<double> ssz(MAX_SLOTS);
+    std::vector<long long> cnt(MAX_SLOTS), sw(MAX_SLOTS);
+    for (int k0 = 0; k0 < K; k0 += batch) {
+        const int kb = std::min(batch, K - k0);
+        SearchDev sd{};
+        sd.phase = PH_MANUAL; sd.nslots = kb; sd.need_lex = 0;
+        RB_CUDA(cudaMemcpyAsync(d_sd, &sd, sizeof(sd), cudaMemcpyHostToDevice, st));
+        RB_CUDA(cudaMemcpyAsync(d_lam, lambdas + k0, sizeof(double) * kb, cudaMemcpyHostToDevice, st));
+        RB_TRY((launch_round<false>(P, false, kb, epoch, false, st)));
+        RB_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt, sizeof(long long) * kb, cudaMemcpyDeviceToHost, st));
+        RB_CUDA(cudaMemcpyAsync(ssz.data(), d_ssz, sizeof(double) * kb, cudaMemcpyDeviceToHost, st));
+        RB_CUDA(cudaMemcpyAsync(sw.data(), d_sw, sizeof(long long) * kb, cudaMemcpyDeviceToHost, st));
+        RB_CUDA(cudaStreamSynchronize(st));
+        for (int k = 0; k < kb; ++k) {
+            const double tv = gamma * (double)sw[k];
+            if (count_out) count_out[k0 + k] = cnt[k];
+            if (pen_out) pen_out[k0 + k] = ssz[k] - lambdas[k0 + k] * (double)cnt[k] - tv;
+            if (obj_out) obj_out[k0 + k] = -ssz[k] + tv;
+        }
+    }
+    return 0;
+}
+
 }  // namespace chain
 }  // namespace rb
 
@@ -967,6 +1074,14 @@ extern "C" __attribute__((visibility("default"))) int rocco_b200_chain_solve_bat
 {
     return chain::solve_batch(d_scores, d_switch_costs, tasks, task_count, d_masks_out, results_out,
                               levels_per_round, (cudaStream_t)cuda_stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int rocco_b200_chain_sweep_dev(
+    const double *d_scores, size_t n, double gamma, const double *lambdas, int lambda_count, long long *selected_count_out,
+    double *penalized_objective_out, double *objective_out, void *cuda_stream)
+{
+    return chain::sweep(d_scores, n, gamma, lambdas, lambda_count, selected_count_out, penalized_objective_out, objective_out,
+                        (cudaStream_t)cuda_stream);
 }
 
 static int host_chain(const double *scores, const double *costs, size_t n, int mode, double lam, long long target,

@@ -1,0 +1,227 @@
+// Column-wise statistics over the sample axis of a [samples, bins] matrix.
+//
+// Replaces /root/reference/rocco/rocco.py:243-304 (score_central_tendency_chrom: np.median /
+// np.quantile(method="nearest") / scipy.stats.tmean in a Python loop over bins / np.mean) and
+// rocco.py:307-355 (score_dispersion_chrom: scipy median_abs_deviation / iqr / np.std / tstd).
+//
+// One thread per bin.  Loads are coalesced along the bin axis (thread j reads X[i, j] for every sample i);
+// the column is kept in shared memory as [sample][thread] (conflict-free) and insertion-sorted there, so all
+// order statistics are exact.  Sums follow NumPy's own association order -- sequential over rows for axis-0
+// reductions of a C-contiguous matrix, pairwise (8 accumulators, blocks of 128) for the 1-D reductions that
+// scipy's tmean/tstd perform per column -- so means and standard deviations reproduce the reference's bits.
+#include "common.cuh"
+
+#include <math.h>
+
+#include <algorithm>
+
+namespace rb {
+namespace colstats {
+
+struct Params {
+    const void *x; double *out;
+    long long m, n;
+    int in_f32, stat;
+    double arg0, arg1, power;
+    int tb;
+};
+
+__device__ __forceinline__ double ldx(const Params &P, long long i, long long j)
+{
+    return P.in_f32 ? (double)reinterpret_cast<const float *>(P.x)[i * P.n + j]
+                    : reinterpret_cast<const double *>(P.x)[i * P.n + j];
+}
+
+// np.around: round half to even
+__device__ __forceinline__ long long round_half_even(double v) { return (long long)rint(v); }
+
+// numpy pairwise sum of f(i) for i in [0, m) (DOUBLE_pairwise_sum: n<8 serial, <=128 eight accumulators, else halves)
+template <typename F> __device__ double np_pairwise(F f, long long lo, long long cnt)
+{
+    if (cnt < 8) {
+        double r = 0.0;
+        for (long long i = 0; i < cnt; ++i) r = __dadd_rn(r, f(lo + i));
+        return r;
+    }
+    if (cnt <= 128) {
+        double r[8];
+        for (int k = 0; k < 8; ++k) r[k] = f(lo + k);
+        long long i = 8;
+        for (; i < cnt - (cnt % 8); i += 8)
+            for (int k = 0; k < 8; ++k) r[k] = __dadd_rn(r[k], f(lo + i + k));
+        double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                               __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+        for (; i < cnt; ++i) res = __dadd_rn(res, f(lo + i));
+        return res;
+    }
+    long long n2 = cnt / 2;
+    n2 -= n2 % 8;
+    return __dadd_rn(np_pairwise(f, lo, n2), np_pairwise(f, lo + n2, cnt - n2));
+}
+
+__device__ __forceinline__ double lerp_np(double a, double b, double t)
+{
+    const double d = __dsub_rn(b, a);
+    return (t >= 0.5) ? __dsub_rn(b, __dmul_rn(d, __dsub_rn(1.0, t))) : __dadd_rn(a, __dmul_rn(d, t));
+}
+
+__global__ void k_colstat(Params P)
+{
+    extern __shared__ double s_col[];                 // [m][tb]
+    const int tb = P.tb;
+    const long long j = (long long)blockIdx.x * tb + threadIdx.x;
+    if (j >= P.n) return;
+    const long long m = P.m;
+    double *col = s_col + threadIdx.x;
+    auto S = [&](long long i) -> double & { return col[i * tb]; };
+
+    double result = 0.0;
+    const int stat = P.stat;
+    if (stat == ROCCO_STAT_MEAN || stat == ROCCO_STAT_STD) {
+        // axis-0 reduction of a C-contiguous matrix: rows are added one after the other
+        double sum = ldx(P, 0, j);
+        for (long long i = 1; i < m; ++i) sum = __dadd_rn(sum, ldx(P, i, j));
+        const double mean = sum / (double)m;
+        if (stat == ROCCO_STAT_MEAN) result = mean;
+        else {
+            double d0 = __dsub_rn(ldx(P, 0, j), mean);
+            double ss = __dmul_rn(d0, d0);
+            for (long long i = 1; i < m; ++i) { const double d = __dsub_rn(ldx(P, i, j), mean); ss = __dadd_rn(ss, __dmul_rn(d, d)); }
+            result = sqrt(ss / (double)m);
+        }
+    } else {
+        // insertion sort of the column in shared memory
+        for (long long i = 0; i < m; ++i) {
+            const double v = ldx(P, i, j);
+            long long q = i;
+            while (q > 0 && S(q - 1) > v) { S(q) = S(q - 1); --q; }
+            S(q) = v;
+        }
+        auto median_sorted = [&]() { return (m & 1) ? S(m / 2) : __dadd_rn(S(m / 2 - 1), S(m / 2)) / 2.0; };
+        if (stat == ROCCO_STAT_MEDIAN) {
+            result = median_sorted();
+        } else if (stat == ROCCO_STAT_QUANTILE) {
+            long long k = round_half_even((double)(m - 1) * P.arg0);
+            k = k < 0 ? 0 : (k >= m ? m - 1 : k);
+            result = S(k);
+        } else if (stat == ROCCO_STAT_MAD) {
+            const double med = median_sorted();
+            // |x - med| of a sorted column is V-shaped: merge the two monotone halves to reach the middle ranks
+            long long lo = 0;                                   // first index with S >= med
+            while (lo < m && S(lo) < med) ++lo;
+            long long a = lo - 1, b = lo;                       // a walks down (values below med), b walks up
+            double prev = 0.0, cur = 0.0;
+            const long long need = m / 2;                       // 0-based rank of the upper middle
+            for (long long r = 0; r <= need; ++r) {
+                const double da = (a >= 0) ? __dsub_rn(med, S(a)) : INFINITY;
+                const double db = (b < m) ? __dsub_rn(S(b), med) : INFINITY;
+                prev = cur;
+                if (da <= db) { cur = da; --a; } else { cur = db; ++b; }
+            }
+            result = (m & 1) ? cur : __dadd_rn(prev, cur) / 2.0;
+        } else if (stat == ROCCO_STAT_IQR) {
+            double pv[2];
+            for (int k = 0; k < 2; ++k) {
+                const double q = (k == 0 ? P.arg0 : P.arg1) / 100.0;
+                const double vi = (double)(m - 1) * q;
+                double prev = floor(vi);
+                long long ip = (long long)prev, in = ip + 1;
+                if (vi >= (double)(m - 1)) { ip = m - 1; in = m - 1; }
+                if (vi < 0) { ip = 0; in = 0; }
+                const double gamma = __dsub_rn(vi, prev);
+                pv[k] = lerp_np(S(ip), S(in), gamma);
+            }
+            result = __dsub_rn(pv[1], pv[0]);
+        } else {                                               // TMEAN / TSTD: nearest-rank limits, inclusive
+            long long kl = round_half_even((double)(m - 1) * P.arg0);
+            long long kh = round_half_even((double)(m - 1) * (1.0 - P.arg0));
+            kl = kl < 0 ? 0 : (kl >= m ? m - 1 : kl);
+            kh = kh < 0 ? 0 : (kh >= m ? m - 1 : kh);
+            const double lim_lo = S(kl), lim_hi = S(kh);
+            long long cnt = 0;
+            for (long long i = 0; i < m; ++i) { const double v = ldx(P, i, j); cnt += (v >= lim_lo && v <= lim_hi); }
+            if (stat == ROCCO_STAT_TMEAN) {
+                // scipy.stats.tmean -> np.nanmean over the column in row order with outsiders zeroed
+                auto f = [&](long long i) { const double v = ldx(P, i, j); return (v >= lim_lo && v <= lim_hi) ? v : 0.0; };
+                result = cnt > 0 ? np_pairwise(f, 0, m) / (double)cnt : NAN;
+            } else {
+                // sample standard deviation (ddof 1) of the kept values, np.std on the compressed 1-D vector:
+                // kept values in row order are gathered into the (now free) shared column
+                long long k = 0;
+                for (long long i = 0; i < m; ++i) { const double v = ldx(P, i, j); if (v >= lim_lo && v <= lim_hi) S(k++) = v; }
+                auto f1 = [&](long long i) { return S(i); };
+                const double mean = np_pairwise(f1, 0, cnt) / (double)cnt;
+                auto f2 = [&](long long i) { const double d = __dsub_rn(S(i), mean); return __dmul_rn(d, d); };
+                result = cnt > 1 ? sqrt(np_pairwise(f2, 0, cnt) / (double)(cnt - 1)) : NAN;
+            }
+        }
+    }
+    if (P.power != 1.0) result = pow(result, P.power);
+    P.out[j] = result;
+}
+
+__global__ void k_single_row(Params P)
+{
+    // m == 1: central tendency = row ** power; dispersion = zeros ** power (rocco.py:254-255, 318-319)
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P.n) return;
+    const bool dispersion = P.stat >= ROCCO_STAT_MAD;
+    const double v = dispersion ? 0.0 : ldx(P, 0, j);
+    P.out[j] = pow(v, P.power);
+}
+
+static int run(const void *d_x, int dtype, size_t m, size_t n, int stat, double arg0, double arg1, double power,
+               double *d_out, cudaStream_t st)
+{
+    if (!d_x || !d_out || m == 0 || n == 0) return ST_INVALID;
+    if (stat < ROCCO_STAT_MEDIAN || stat > ROCCO_STAT_TSTD || (dtype != 0 && dtype != 1)) return ST_INVALID;
+    RB_TRY(ensure_device());
+    Params P{};
+    P.x = d_x; P.out = d_out; P.m = (long long)m; P.n = (long long)n; P.in_f32 = dtype; P.stat = stat;
+    P.arg0 = arg0; P.arg1 = arg1; P.power = power;
+    if (m == 1) {
+        k_single_row<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P);
+        RB_LAUNCH_CHECK();
+        return 0;
+    }
+    const size_t budget = 192 * 1024;
+    int tb = (int)std::min<size_t>(128, budget / (8 * m));
+    tb = (tb / 32) * 32;
+    if (tb < 32) { set_error("column statistics support at most %zu samples", budget / (8 * 32)); return ST_INVALID; }
+    P.tb = tb;
+    const size_t smem = (size_t)tb * m * sizeof(double);
+    RB_CUDA(cudaFuncSetAttribute(k_colstat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+    RB_PROF("k_colstat", st, (double)m * n * (dtype ? 4.0 : 8.0) + 8.0 * n);
+    k_colstat<<<(unsigned)((n + tb - 1) / tb), tb, smem, st>>>(P);
+    RB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace colstats
+}  // namespace rb
+
+using namespace rb;
+#define RB_API extern "C" __attribute__((visibility("default")))
+
+RB_API int rocco_b200_column_stat_dev(const void *d_matrix, int dtype, size_t m, size_t n, int stat, double arg0, double arg1,
+                                      double power, double *d_out, void *cuda_stream)
+{
+    return colstats::run(d_matrix, dtype, m, n, stat, arg0, arg1, power, d_out, (cudaStream_t)cuda_stream);
+}
+
+RB_API int rocco_column_stat_f64(const double *matrix, size_t m, size_t n, int stat, double arg0, double arg1, double power,
+                                 double *out)
+{
+    if (!matrix || !out || m == 0 || n == 0) return ST_INVALID;
+    RB_TRY(ensure_device());
+    cudaStream_t st = 0;
+    Arena ar(st);
+    double *d_x = nullptr, *d_o = nullptr;
+    RB_TRY(ar.alloc(&d_x, m * n));
+    RB_TRY(ar.alloc(&d_o, n));
+    RB_CUDA(cudaMemcpyAsync(d_x, matrix, m * n * sizeof(double), cudaMemcpyHostToDevice, st));
+    RB_TRY(colstats::run(d_x, 0, m, n, stat, arg0, arg1, power, d_o, st));
+    RB_CUDA(cudaMemcpyAsync(out, d_o, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    RB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}

@@ -252,3 +252,31 @@ def runs_to_bed_text(chrom_names, runs, step: int, first_start: int = 0) -> str:
     e = first_start + ends * step
     names = np.asarray(chrom_names, dtype=object)[chrom]
     return "".join(f"{c}\t{a}\t{b}\n" for c, a, b in zip(names.tolist(), s.tolist(), e.tolist()))
+
+
+def sweep_multipliers(scores, gamma: float, lambdas):
+    """Selected count, penalized objective and objective of one chromosome for MANY multipliers
+    (BASELINE.json config 5: a 256-multiplier budget sweep) -- up to 256 per launch set, the scores
+    read once per tile whatever the number of multipliers.  Returns three NumPy arrays."""
+    torch = _torch()
+    lib = _lib.load()
+    _lib.require_device()
+    if isinstance(scores, torch.Tensor):
+        d_scores = scores.to(dtype=torch.float64).contiguous()
+        if not d_scores.is_cuda:
+            d_scores = d_scores.cuda()
+    else:
+        d_scores = torch.from_numpy(np.ascontiguousarray(scores, dtype=np.float64)).cuda()
+    if d_scores.dim() != 1 or d_scores.shape[0] == 0:
+        raise ValueError("`scores` must be a non-empty one-dimensional array")
+    lam = np.ascontiguousarray(lambdas, dtype=np.float64)
+    k = lam.shape[0]
+    counts = np.zeros(k, dtype=np.int64)
+    pen = np.zeros(k, dtype=np.float64)
+    obj = np.zeros(k, dtype=np.float64)
+    with torch.cuda.device(d_scores.device):
+        st = lib.rocco_b200_chain_sweep_dev(
+            ctypes.c_void_p(d_scores.data_ptr()), int(d_scores.shape[0]), float(gamma), _lib.np_ptr(lam), int(k),
+            _lib.np_ptr(counts), _lib.np_ptr(pen), _lib.np_ptr(obj), ctypes.c_void_p(_stream_ptr(d_scores.device)))
+    _lib.check(st, "sweep_multipliers")
+    return counts, pen, obj

@@ -133,3 +133,68 @@ def combine_chrom_results(chrom_bed_files: list, output_file: str, name_features
         combined_records.extend(chrom_records)
     merged_records = _merge_bed_records(combined_records)
     return _write_bed_records(merged_records, output_file, name_features=name_features)
+
+
+# ------------------------------------------------------------------------------------------------
+# column-wise statistics over the sample axis (rocco.py:243-355)
+# ------------------------------------------------------------------------------------------------
+_STAT = {"median": 0, "quantile": 1, "tmean": 2, "mean": 3, "mad": 4, "iqr": 5, "std": 6, "tstd": 7}
+
+
+def _column_stat(chrom_matrix: np.ndarray, stat: str, arg0: float = 0.0, arg1: float = 0.0, power: float = 1.0) -> np.ndarray:
+    x = np.ascontiguousarray(chrom_matrix, dtype=np.float64)
+    m, n = x.shape
+    out = np.zeros(n, dtype=np.float64)
+    if n == 0:
+        return out
+    lib = _lib.load()
+    _lib.require_device()
+    st = lib.rocco_column_stat_f64(_lib.np_ptr(x), m, n, _STAT[stat], float(arg0), float(arg1), float(power), _lib.np_ptr(out))
+    _lib.check(st, "column statistic")
+    return out
+
+
+def score_central_tendency_chrom(chrom_matrix, method="quantile", quantile=0.50, tprop=0.05, power=1.0) -> np.ndarray:
+    r"""Return a column-wise location summary across samples (rocco.py:243-304)."""
+    chrom_matrix = np.asarray(chrom_matrix, dtype=float)
+    if chrom_matrix.ndim != 2:
+        raise ValueError("`chrom_matrix` must be a 2D array.")
+    method_ = str(method).strip().lower().replace("-", "").replace("_", "")
+    if chrom_matrix.shape[0] == 1:
+        return _column_stat(chrom_matrix, "mean", power=power)
+    if method_ == "quantile":
+        if not 0.0 <= quantile <= 1.0:
+            logger.warning("`quantile` must be in [0, 1]. Using the median instead.")
+            quantile = 0.50
+        if quantile == 0.50:
+            return _column_stat(chrom_matrix, "median", power=power)
+        return _column_stat(chrom_matrix, "quantile", arg0=quantile, power=power)
+    if method_ == "tmean":
+        return _column_stat(chrom_matrix, "tmean", arg0=tprop, power=power)
+    if method_ == "mean":
+        return _column_stat(chrom_matrix, "mean", power=power)
+    raise ValueError(f"Central tendency method not recognized: {method}")
+
+
+def score_dispersion_chrom(chrom_matrix: np.ndarray, method: str = "mad", rng: Tuple[int, int] = (25, 75),
+                           tprop: float = 0.05, power: float = 1.0) -> np.ndarray:
+    r"""Return a column-wise dispersion summary across samples (rocco.py:307-355).
+
+    ``tstd`` computes the evident per-column intent -- sample standard deviation (ddof 1) of the values
+    inside the inclusive nearest-rank limits; the reference itself raises for that method under current
+    SciPy."""
+    chrom_matrix = np.asarray(chrom_matrix, dtype=float)
+    if chrom_matrix.ndim != 2:
+        raise ValueError("`chrom_matrix` must be a 2D array.")
+    method_ = str(method).strip().lower().replace("-", "").replace("_", "")
+    if chrom_matrix.shape[0] == 1:
+        return _column_stat(chrom_matrix, "mad", power=power)
+    if method_ == "mad":
+        return _column_stat(chrom_matrix, "mad", power=power)
+    if method_ == "iqr":
+        return _column_stat(chrom_matrix, "iqr", arg0=rng[0], arg1=rng[1], power=power)
+    if method_ == "std":
+        return _column_stat(chrom_matrix, "std", power=power)
+    if method_ == "tstd":
+        return _column_stat(chrom_matrix, "tstd", arg0=tprop, power=power)
+    raise ValueError(f"Dispersion method not recognized or could not execute: {method}")

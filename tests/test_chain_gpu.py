@@ -226,3 +226,35 @@ def test_combine_reproduces_reference_combined_bed(rb, bed_fixtures, tmp_path):
         files.append(str(p))
     out = rb.combine_chrom_results(files, str(tmp_path / "combined.bed"))
     assert open(out, "rb").read() == bed_fixtures["combined_ref"].tobytes()
+
+
+# ------------------------------------------------------------------ multiplier sweep (BASELINE.json config 5)
+@pytest.mark.parametrize("n,gamma,seed", [(5000, 1.0, 0), (70_001, 1.0, 1), (200_000, 6.86, 2), (33_000, 0.0, 3)])
+def test_multiplier_sweep_matches_oracle(rb, oracle, n, gamma, seed):
+    from rocco_b200 import _lib
+    from rocco_b200.pipeline import sweep_multipliers
+    prev = _lib.load().rocco_b200_chain_set_seq_max(0)
+    try:
+        s = _scores(n, seed)
+        lams = np.concatenate([np.linspace(np.quantile(s, 0.5), np.quantile(s, 0.999), 61), [-3.0, 0.0, 50.0]])
+        counts, pen, obj = sweep_multipliers(s, gamma, lams)
+        c = oracle.build_switch_costs(s, gamma)
+        for k, lam in enumerate(lams):
+            sol, val, cnt = oracle.solve_penalized_chain(s, c, lam)
+            assert counts[k] == cnt, (k, lam)
+            assert abs(pen[k] - val) <= 1e-6 * max(1.0, abs(val))
+            want_obj = oracle.objective_value(sol, s, c)
+            assert abs(obj[k] - want_obj) <= 1e-6 * max(1.0, abs(want_obj))
+        assert np.all(np.diff(counts[:61]) <= 0)                   # count(lambda) is non-increasing
+    finally:
+        _lib.load().rocco_b200_chain_set_seq_max(prev)
+
+
+def test_multiplier_sweep_256_in_one_launch_set(rb, oracle):
+    from rocco_b200.pipeline import sweep_multipliers
+    s = _scores(120_000, 42)
+    lams = np.linspace(np.quantile(s, 0.5), np.quantile(s, 0.999), 256)
+    counts, pen, obj = sweep_multipliers(s, 1.0, lams)
+    c = oracle.build_switch_costs(s, 1.0)
+    for k in (0, 17, 128, 255):
+        assert counts[k] == oracle.solve_penalized_chain(s, c, lams[k])[2]
