@@ -76,8 +76,8 @@ typedef struct rocco_b200_chain_result {
     long long switch_count;       /* number of 0/1 boundaries in the mask                        */
     long long exact_tie_bins;     /* decisions that needed the (value, fewer-count) tie-break    */
     long long near_tie_bins;      /* decisions within 1e-9*(1+|c|) of a threshold (documented)   */
-    int dp_passes;                /* DP evaluations spent (reference: 62 per budget search)      */
-    int search_rounds;            /* batched launches spent                                      */
+    int dp_passes;                /* DP passes the reference spends on this search (62 by default) */
+    int search_rounds;            /* batched launch sets actually used (each evaluates 2^L-1 multipliers) */
     int status;                   /* 0, or -2 / -4 for this chromosome                           */
     int reserved;
 } rocco_b200_chain_result;

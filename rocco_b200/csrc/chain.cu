@@ -575,7 +575,8 @@ __global__ void __launch_bounds__(256) k_chain_finish(Params P, int emit)
     }
     sd.need_lex = 0;
     if (!emit) {                                        // the final mask-emitting solve re-evaluates `upper`
-        sd.passes += sd.nslots;
+        // reference-equivalent pass count (dp.py: 2 bracket solves + one per bisection level)
+        sd.passes += (sd.phase == PH_BISECT) ? sd.levels : sd.nslots;
         sd.rounds += 1;
     }
     const long long *cnt = P.counts + (size_t)c * MAX_SLOTS;

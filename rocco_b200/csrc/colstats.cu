@@ -35,28 +35,61 @@ __device__ __forceinline__ double ldx(const Params &P, long long i, long long j)
 // np.around: round half to even
 __device__ __forceinline__ long long round_half_even(double v) { return (long long)rint(v); }
 
-// numpy pairwise sum of f(i) for i in [0, m) (DOUBLE_pairwise_sum: n<8 serial, <=128 eight accumulators, else halves)
-template <typename F> __device__ double np_pairwise(F f, long long lo, long long cnt)
+// numpy pairwise sum (DOUBLE_pairwise_sum: n < 8 serial, <= 128 eight accumulators, else split in halves rounded to
+// a multiple of 8) of the strided vector v[0], v[stride], ...; `sq_mean` != nullptr sums (v - *sq_mean)^2 instead.
+__device__ double np_pairwise_block(const double *v, int stride, long long cnt, const double *sq_mean)
 {
+    auto at = [&](long long i) {
+        const double x = v[i * stride];
+        if (!sq_mean) return x;
+        const double d = __dsub_rn(x, *sq_mean);
+        return __dmul_rn(d, d);
+    };
     if (cnt < 8) {
         double r = 0.0;
-        for (long long i = 0; i < cnt; ++i) r = __dadd_rn(r, f(lo + i));
+        for (long long i = 0; i < cnt; ++i) r = __dadd_rn(r, at(i));
         return r;
     }
-    if (cnt <= 128) {
-        double r[8];
-        for (int k = 0; k < 8; ++k) r[k] = f(lo + k);
-        long long i = 8;
-        for (; i < cnt - (cnt % 8); i += 8)
-            for (int k = 0; k < 8; ++k) r[k] = __dadd_rn(r[k], f(lo + i + k));
-        double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                               __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-        for (; i < cnt; ++i) res = __dadd_rn(res, f(lo + i));
-        return res;
+    double r[8];
+    for (int k = 0; k < 8; ++k) r[k] = at(k);
+    long long i = 8;
+    for (; i < cnt - (cnt % 8); i += 8)
+        for (int k = 0; k < 8; ++k) r[k] = __dadd_rn(r[k], at(i + k));
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    for (; i < cnt; ++i) res = __dadd_rn(res, at(i));
+    return res;
+}
+
+__device__ double np_pairwise(const double *v, int stride, long long cnt, const double *sq_mean)
+{
+    // explicit post-order walk of numpy's recursion (depth <= 8 for any supported sample count)
+    struct Frame { long long lo, cnt; int state; double left; };
+    Frame st[12];
+    int sp = 0;
+    st[0] = Frame{0, cnt, 0, 0.0};
+    double ret = 0.0;
+    while (sp >= 0) {
+        Frame &f = st[sp];
+        if (f.cnt <= 128) { ret = np_pairwise_block(v + f.lo * stride, stride, f.cnt, sq_mean); --sp; continue; }
+        long long n2 = f.cnt / 2;
+        n2 -= n2 % 8;
+        if (f.state == 0) { f.state = 1; st[sp + 1] = Frame{f.lo, n2, 0, 0.0}; ++sp; }
+        else if (f.state == 1) { f.left = ret; f.state = 2; st[sp + 1] = Frame{f.lo + n2, f.cnt - n2, 0, 0.0}; ++sp; }
+        else { ret = __dadd_rn(f.left, ret); --sp; }
     }
-    long long n2 = cnt / 2;
-    n2 -= n2 % 8;
-    return __dadd_rn(np_pairwise(f, lo, n2), np_pairwise(f, lo + n2, cnt - n2));
+    return ret;
+}
+
+// np.power(x, scalar): NumPy's scalar fast paths (square, sqrt, reciprocal) are exact; libm pow otherwise
+__device__ __forceinline__ double np_power(double x, double p)
+{
+    if (p == 1.0) return x;
+    if (p == 2.0) return __dmul_rn(x, x);
+    if (p == 0.5) return sqrt(x);
+    if (p == -1.0) return 1.0 / x;
+    if (p == 0.0) return 1.0;
+    return pow(x, p);
 }
 
 __device__ __forceinline__ double lerp_np(double a, double b, double t)
@@ -141,23 +174,20 @@ __global__ void k_colstat(Params P)
             long long cnt = 0;
             for (long long i = 0; i < m; ++i) { const double v = ldx(P, i, j); cnt += (v >= lim_lo && v <= lim_hi); }
             if (stat == ROCCO_STAT_TMEAN) {
-                // scipy.stats.tmean -> np.nanmean over the column in row order with outsiders zeroed
-                auto f = [&](long long i) { const double v = ldx(P, i, j); return (v >= lim_lo && v <= lim_hi) ? v : 0.0; };
-                result = cnt > 0 ? np_pairwise(f, 0, m) / (double)cnt : NAN;
+                // scipy.stats.tmean: sum over the column in row order with outsiders replaced by 0, / count
+                for (long long i = 0; i < m; ++i) { const double v = ldx(P, i, j); S(i) = (v >= lim_lo && v <= lim_hi) ? v : 0.0; }
+                result = cnt > 0 ? np_pairwise(col, tb, m, nullptr) / (double)cnt : NAN;
             } else {
-                // sample standard deviation (ddof 1) of the kept values, np.std on the compressed 1-D vector:
-                // kept values in row order are gathered into the (now free) shared column
+                // sample standard deviation (ddof 1) of the kept values (np.std on the compressed 1-D vector):
+                // kept values are gathered in row order into the (now free) shared column
                 long long k = 0;
                 for (long long i = 0; i < m; ++i) { const double v = ldx(P, i, j); if (v >= lim_lo && v <= lim_hi) S(k++) = v; }
-                auto f1 = [&](long long i) { return S(i); };
-                const double mean = np_pairwise(f1, 0, cnt) / (double)cnt;
-                auto f2 = [&](long long i) { const double d = __dsub_rn(S(i), mean); return __dmul_rn(d, d); };
-                result = cnt > 1 ? sqrt(np_pairwise(f2, 0, cnt) / (double)(cnt - 1)) : NAN;
+                const double mean = np_pairwise(col, tb, cnt, nullptr) / (double)cnt;
+                result = cnt > 1 ? sqrt(np_pairwise(col, tb, cnt, &mean) / (double)(cnt - 1)) : NAN;
             }
         }
     }
-    if (P.power != 1.0) result = pow(result, P.power);
-    P.out[j] = result;
+    P.out[j] = np_power(result, P.power);
 }
 
 __global__ void k_single_row(Params P)
@@ -167,7 +197,7 @@ __global__ void k_single_row(Params P)
     if (j >= P.n) return;
     const bool dispersion = P.stat >= ROCCO_STAT_MAD;
     const double v = dispersion ? 0.0 : ldx(P, 0, j);
-    P.out[j] = pow(v, P.power);
+    P.out[j] = np_power(v, P.power);
 }
 
 static int run(const void *d_x, int dtype, size_t m, size_t n, int stat, double arg0, double arg1, double power,
