@@ -270,6 +270,11 @@ def main():
     ms = float(t.item())
     value = genome_bins * args.steps / (ms / 1e3)
     selected_total = int(count_buf[0].item())
+    by_chrom = {c: (r["selected_count"], r["selection_penalty"]) for c, r in zip(my_names, last["results"])} if last else {}
+    if world > 1:
+        parts_ = [None] * world
+        dist.all_gather_object(parts_, by_chrom)
+        by_chrom = {k: v for p_ in parts_ for k, v in p_.items()}
 
     # ---- end-to-end through the reference-facing host API (NumPy in, BED files out)
     e2e = None
@@ -349,7 +354,9 @@ def main():
             "config": {"workload": workload_name(args, names), "genome_bins": genome_bins, "samples": args.samples,
                        "chromosomes": len(names), "sharding": f"chromosomes LPT-packed over {world} rank(s)",
                        "l2_policy": "inputs larger than L2 (per-chromosome matrices 0.7-4 GB vs 126 MB L2)",
-                       "selected_bins": selected_total, "trend_sort_fallback_rows": fb_rows,
+                       "selected_bins": selected_total,
+                       "selected_by_chrom": {c: by_chrom[c][0] for c in names if c in by_chrom},
+                       "lambda_by_chrom": {c: by_chrom[c][1] for c in names if c in by_chrom}, "trend_sort_fallback_rows": fb_rows,
                        "trend_fallback_reason_counts": list(reasons)[:5], "collective": "one NCCL all-reduce of [selected, bins] per step"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(lt.item()), "roofline": roof, "cpu_baseline": cpu,
         }
