@@ -842,7 +842,7 @@ static int solve_batch(const double *d_scores, const double *d_costs, const rocc
 {
     if (ntask <= 0) return 0;
     if (!d_scores || !tasks || !d_masks || !results) return ST_INVALID;
-    if (levels <= 0) levels = 3;
+    if (levels <= 0) levels = 2;      // measured on B200: 1 GPU, hg38 x 100: L=2 49 ms, L=3 57 ms, L=4 84 ms per genome search
     levels = std::min(levels, MAX_LEVELS);
     RB_TRY(ensure_device());
 

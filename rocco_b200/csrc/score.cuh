@@ -19,6 +19,41 @@ int pilot_offsets(const void *d_x, int in_f32, long long rows, long long n, long
 int centered_wls(const double *d_centered, long long m, long long n, const rocco_b200_score_params &prm,
                  rocco_b200_score_outputs *out, cudaStream_t st);
 
+// a / b from a correctly rounded reciprocal rb = RN(1/b): Markstein's final step (q = RN(a*rb), r = a - q*b exactly by
+// FMA, RN(q + r*rb)) gives the correctly rounded quotient for operands in the normal range without the generic
+// division's special-case slow path (~3 issue slots instead of ~30).
+__device__ __forceinline__ double div_rcp(double a, double b, double rb)
+{
+    const double q = __dmul_rn(a, rb);
+    const double r = __fma_rn(-q, b, a);
+    return __fma_rn(r, rb, q);
+}
+
+// AR(1) innovation variance of one window from its three sums (wls_backend.c:665-712), same association order;
+// intrinsics keep nvcc from contracting the products into FMAs.  rwd = RN(1/wd), shrink = 1/(wd+1).
+__device__ __forceinline__ double ar1_window_variance(double s1, double s2, double sl, double first, double last, double wd,
+                                                      double rwd, double pairs, double shrink)
+{
+    const double sum_head = __dsub_rn(s1, last);
+    const double sum_tail = __dsub_rn(s1, first);
+    const double mu = div_rcp(s1, wd, rwd);
+    double g0 = __dsub_rn(s2, __dmul_rn(__dmul_rn(wd, mu), mu));
+    if (g0 < 0.0) g0 = 0.0;
+    double g1 = __dsub_rn(sl, __dmul_rn(mu, sum_head));
+    g1 = __dsub_rn(g1, __dmul_rn(mu, sum_tail));
+    g1 = __dadd_rn(g1, __dmul_rn(__dmul_rn(pairs, mu), mu));
+    const double flo = __dmul_rn(1.0e-4, __dadd_rn(g0, 1.0));
+    const double den = __dadd_rn(__dmul_rn(g0, __dadd_rn(1.0, shrink)), flo);
+    const double eps = __dmul_rn(1.0e-12, __dadd_rn(g0, 1.0));
+    double beta = 0.0;
+    if (den > eps) beta = div_rcp(g1, den, __drcp_rn(den));
+    if (beta > 0.99) beta = 0.99; else if (beta < 0.0) beta = 0.0;
+    const double gam0 = div_rcp(g0, wd, rwd);
+    double omb = __dsub_rn(1.0, __dmul_rn(beta, beta));
+    if (omb < 0.0) omb = 0.0;
+    return fmax(__dmul_rn(gam0, omb), 0.0);
+}
+
 int resolve_spatial_window(long long n, int requested);
 int resolve_baseline_window(long long n, int target);
 double whittaker_lambda(int block);

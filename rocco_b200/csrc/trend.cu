@@ -39,6 +39,7 @@ constexpr int CAPX = 8192;              // pairs per x slot
 constexpr int CAPY = 8192;              // variances per (bin, k) slot
 constexpr int CHUNK = 131072;           // elements streamed per CTA
 constexpr int ST_THREADS = 512;
+int trend_fused_max_window() { return 2049; }
 
 __device__ __forceinline__ int xbucket(double x)
 {
@@ -92,6 +93,7 @@ struct TrendBuffers {
     int *yhist;            // [m][MAXB][NBY]
     double *ycand;         // [m][MAXB][2][CAPY]
     int *ycand_cnt;        // [m][MAXB][2]
+    long long rows;
 };
 
 // ------------------------------------------------------------------ T1
@@ -109,6 +111,92 @@ __global__ void __launch_bounds__(ST_THREADS) k_xhist(const double *__restrict__
     for (int k = threadIdx.x; k < NBX; k += ST_THREADS) {
         const int v = s_h[k];
         if (v) atomicAdd(&g[k], v);
+    }
+}
+
+// ------------------------------------------------------------------ T1 fused with the rolling AR(1) variance
+// One CTA streams a CHUNK of one row in tiles of RV_T bins: the tile (+ w-1 halo) is staged in shared memory in a
+// padded layout (position i + i/8, so that 8-bin-per-thread accesses are bank-conflict free), every thread
+// produces 8 consecutive variances (direct 31-term window sums for the first, sliding updates for the next 7 --
+// far less drift than the reference's whole-row slide), results go back through shared memory for coalesced
+// stores, and the same pass feeds the |C| histogram.  Replaces wls_backend.c:610-742 + the T1 pass.
+constexpr int RV_T = 2048;
+constexpr int RV_K = 8;
+constexpr int RV_THREADS = RV_T / RV_K;      // 256
+constexpr int RV_MAXW = 2049;
+
+__host__ __device__ __forceinline__ int padpos(int i) { return i + (i >> 3); }
+
+__global__ void __launch_bounds__(RV_THREADS) k_rollvar_xhist(const double *__restrict__ C, long long n, long long row_stride, int w,
+                                                               double *__restrict__ V, int *xhist)
+{
+    extern __shared__ int s_dyn[];
+    int *s_h = s_dyn;                                              // NBX
+    double *s_in = reinterpret_cast<double *>(s_dyn + NBX);        // padpos(RV_T + w)
+    double *s_out = s_in + padpos(RV_T + w) + 8;                   // padpos(RV_T)
+    const long long row = blockIdx.y;
+    const double *c = C + row * row_stride;
+    double *v = V + row * row_stride;
+    const long long c0 = (long long)blockIdx.x * CHUNK, c1 = min(n, c0 + CHUNK);
+    const long long half = w / 2, last = n - w;
+    const double wd = (double)w, pairs = (double)(w - 1), rwd = 1.0 / wd, shrink = 1.0 / (wd + 1.0);
+    for (int k = threadIdx.x; k < NBX; k += RV_THREADS) s_h[k] = 0;
+    __syncthreads();
+    for (long long j0 = c0; j0 < c1; j0 += RV_T) {
+        const long long j1 = min(c1, j0 + RV_T);
+        long long tlo = j0 - half; if (tlo < 0) tlo = 0; else if (tlo > last) tlo = last;
+        long long thi = (j1 - 1) - half; if (thi < 0) thi = 0; else if (thi > last) thi = last;
+        const int span = (int)(thi - tlo) + w;                     // bins staged: [tlo, tlo + span)
+        for (int e = threadIdx.x; e < span; e += RV_THREADS) {
+            const long long g = tlo + e;
+            const double val = c[g];
+            s_in[padpos(e)] = val;
+            if (g >= j0 && g < j1) atomicAdd(&s_h[xbucket(fabs(val))], 1);
+        }
+        __syncthreads();
+        {
+            const long long jt = j0 + (long long)threadIdx.x * RV_K;
+            double s1 = 0.0, s2 = 0.0, sl = 0.0, cur = 0.0;
+            long long tprev = -1;
+#pragma unroll 1
+            for (int k = 0; k < RV_K; ++k) {
+                const long long j = jt + k;
+                if (j >= j1) break;
+                long long t = j - half;
+                if (t < 0) t = 0; else if (t > last) t = last;
+                const int r = (int)(t - tlo);
+                if (t != tprev) {
+                    if (tprev < 0) {
+                        s1 = s2 = sl = 0.0;
+                        double a = s_in[padpos(r)];
+                        for (int q = 0; q < w; ++q) {
+                            const double nx = (q + 1 < w) ? s_in[padpos(r + q + 1)] : 0.0;
+                            s1 = __dadd_rn(s1, a);
+                            s2 = __dadd_rn(s2, __dmul_rn(a, a));
+                            if (q + 1 < w) sl = __dadd_rn(sl, __dmul_rn(a, nx));
+                            a = nx;
+                        }
+                    } else {
+                        const double out_v = s_in[padpos(r - 1)], nx = s_in[padpos(r - 1 + w)];
+                        const double lag_l = s_in[padpos(r - 1 + w - 1)], lag_r = s_in[padpos(r)];
+                        s1 = __dadd_rn(__dsub_rn(s1, out_v), nx);
+                        s2 = __dadd_rn(__dsub_rn(s2, __dmul_rn(out_v, out_v)), __dmul_rn(nx, nx));
+                        sl = __dadd_rn(__dsub_rn(sl, __dmul_rn(out_v, lag_r)), __dmul_rn(lag_l, nx));
+                    }
+                    cur = ar1_window_variance(s1, s2, sl, s_in[padpos(r)], s_in[padpos(r + w - 1)], wd, rwd, pairs, shrink);
+                    tprev = t;
+                }
+                s_out[padpos(threadIdx.x * RV_K + k)] = fmax(cur, 1.0e-8);        // wls_backend.c:869
+            }
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < (int)(j1 - j0); e += RV_THREADS) v[j0 + e] = s_out[padpos(e)];
+        __syncthreads();
+    }
+    int *g = xhist + row * NBX;
+    for (int k = threadIdx.x; k < NBX; k += RV_THREADS) {
+        const int val = s_h[k];
+        if (val) atomicAdd(&g[k], val);
     }
 }
 
@@ -234,18 +322,29 @@ __global__ void __launch_bounds__(ST_THREADS) k_xcollect(const double *__restric
     int *ccnt = T.cand_cnt + row * MAXSLOT;
     const RowPlan &P = T.plan[row];
     const int yb0 = P.yb0;
-    for (long long j = c0 + threadIdx.x; j < c1; j += ST_THREADS) {
-        const double x = fabs(c[j]);
-        const int b = xbucket(x);
-        const int s = s_lut[b];
-        const double y = v[j];
-        bool boundary = false;
-        if (s != 0xFF) {
-            const int pos = atomicAdd(&ccnt[s], 1);
-            if (pos < CAPX) cand[(size_t)s * CAPX + pos] = make_double2(x, y);
-            boundary = P.slot_boundary[s] != 0;
+    // four independent loads in flight per thread before the dependent LUT / atomic chain
+    for (long long jb = c0; jb < c1; jb += 4 * ST_THREADS) {
+        double xs[4], ys[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long j = jb + u * ST_THREADS + threadIdx.x;
+            xs[u] = (j < c1) ? fabs(c[j]) : -1.0;
+            ys[u] = (j < c1) ? v[j] : 0.0;
         }
-        if (!boundary) atomicAdd(&s_yh[(int)s_bin[b] * NBY + ybucket(y, yb0)], 1);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (xs[u] < 0.0) continue;
+            const double x = xs[u], y = ys[u];
+            const int b = xbucket(x);
+            const int s = s_lut[b];
+            bool boundary = false;
+            if (s != 0xFF) {
+                const int pos = atomicAdd(&ccnt[s], 1);
+                if (pos < CAPX) cand[(size_t)s * CAPX + pos] = make_double2(x, y);
+                boundary = P.slot_boundary[s] != 0;
+            }
+            if (!boundary) atomicAdd(&s_yh[(int)s_bin[b] * NBY + ybucket(y, yb0)], 1);
+        }
     }
     __syncthreads();
     int *g = T.yhist + (size_t)row * MAXB * NBY;
@@ -371,11 +470,23 @@ __global__ void __launch_bounds__(ST_THREADS) k_ycollect(const double *__restric
     __syncthreads();
     const long long c0 = (long long)blockIdx.x * CHUNK, c1 = min(n, c0 + CHUNK);
     const double *c = C + row * row_stride, *v = V + row * row_stride;
-    for (long long j = c0 + threadIdx.x; j < c1; j += ST_THREADS) {
-        const int b = xbucket(fabs(c[j]));
-        const int s = s_lut[b];
-        if (s != 0xFF && s_bnd[s]) continue;                        // boundary buckets: handled from the sorted slot below
-        ycollect_one(T, row, s_yb, (int)s_bin[b], v[j], P.yb0);
+    const int yb0 = P.yb0;
+    for (long long jb = c0; jb < c1; jb += 4 * ST_THREADS) {
+        double xs[4], ys[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long j = jb + u * ST_THREADS + threadIdx.x;
+            xs[u] = (j < c1) ? fabs(c[j]) : -1.0;
+            ys[u] = (j < c1) ? v[j] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (xs[u] < 0.0) continue;
+            const int b = xbucket(xs[u]);
+            const int s = s_lut[b];
+            if (s != 0xFF && s_bnd[s]) continue;                    // boundary buckets: handled from the sorted slot below
+            ycollect_one(T, row, s_yb, (int)s_bin[b], ys[u], yb0);
+        }
     }
     if (blockIdx.x == 0) {
         for (int s = 0; s < P.nslot; ++s) {
@@ -389,65 +500,76 @@ __global__ void __launch_bounds__(ST_THREADS) k_ycollect(const double *__restric
 }
 
 // ------------------------------------------------------------------ T7
+
+__global__ void __launch_bounds__(256) k_yresolve(TrendBuffers T, long long n, int B)
+{
+    // one CTA per (bin, row): sort the collected variances of the bin's target bucket(s), pick the median rank(s)
+    extern __shared__ double s_v[];              // CAPY
+    __shared__ int s_fail;
+    const long long row = blockIdx.y;
+    const int b = blockIdx.x;
+    RowPlan &P = T.plan[row];
+    if (P.fallback) return;
+    const long long lo = ((long long)b * n) / B, hi = ((long long)(b + 1) * n) / B;
+    if (hi <= lo) return;
+    if (threadIdx.x == 0) s_fail = 0;
+    __syncthreads();
+    double ym[2] = {0.0, 0.0};
+    for (int k = 0; k < 2; ++k) {
+        if (P.ym_bucket[b][k] < 0) continue;
+        if (k == 0 && P.ym_bucket[b][0] == P.ym_bucket[b][1]) continue;       // same bucket: resolved with k = 1
+        const int cnt = T.ycand_cnt[(row * MAXB + b) * 2 + k];
+        if (cnt != P.ym_count[b][k]) { if (threadIdx.x == 0) s_fail = FB_YCOUNT; }
+        __syncthreads();
+        if (s_fail) break;
+        int len = 1;
+        while (len < cnt) len <<= 1;
+        const double *src = T.ycand + (((size_t)row * MAXB + b) * 2 + k) * CAPY;
+        for (int q = threadIdx.x; q < len; q += 256) s_v[q] = q < cnt ? src[q] : INFINITY;
+        __syncthreads();
+        for (int kk = 2; kk <= len; kk <<= 1)
+            for (int j = kk >> 1; j > 0; j >>= 1) {
+                for (int i = threadIdx.x; i < len; i += 256) {
+                    const int ixj = i ^ j;
+                    if (ixj > i) {
+                        const double a = s_v[i], c = s_v[ixj];
+                        const bool up = ((i & kk) == 0);
+                        if ((a > c) == up) { s_v[i] = c; s_v[ixj] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+        ym[k] = s_v[P.ym_rank[b][k]];
+        if (k == 1 && P.ym_bucket[b][0] == P.ym_bucket[b][1]) ym[0] = s_v[P.ym_rank[b][0]];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (s_fail) atomicOr(&P.fallback, s_fail);
+        else { P.ym_val[b][0] = ym[0]; P.ym_val[b][1] = ym[1]; }
+    }
+}
+
 __device__ void knots_from_bins(const double *bx, const double *by, const double *bw, int used, Knots *out);
 
-__global__ void __launch_bounds__(256) k_yresolve(TrendBuffers T, long long n, int B, Knots *knots, int *row_fallback)
+__global__ void k_row_knots(TrendBuffers T, long long n, int B, Knots *knots, int *row_fallback)
 {
-    extern __shared__ double s_v[];              // CAPY
-    __shared__ double s_bx[MAXB], s_by[MAXB], s_bw[MAXB];
-    __shared__ int s_fail;
-    const long long row = blockIdx.x;
-    RowPlan &P = T.plan[row];
-    if (threadIdx.x == 0) s_fail = P.fallback;
-    __syncthreads();
-    if (s_fail) { if (threadIdx.x == 0) row_fallback[row] = s_fail; return; }
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= T.rows) return;
+    const RowPlan &P = T.plan[row];
+    if (P.fallback) { row_fallback[row] = P.fallback; return; }
+    double bx[MAXB], by[MAXB], bw[MAXB];
     int used = 0;
     for (int b = 0; b < B; ++b) {
         const long long lo = ((long long)b * n) / B, hi = ((long long)(b + 1) * n) / B;
         const long long w = hi - lo;
         if (w <= 0) continue;
-        double ym[2] = {0.0, 0.0};
-        for (int k = 0; k < 2; ++k) {
-            if (P.ym_bucket[b][k] < 0) continue;
-            if (k == 0 && P.ym_bucket[b][0] == P.ym_bucket[b][1]) continue;       // same bucket: resolved with k = 1
-            const int cnt = T.ycand_cnt[(row * MAXB + b) * 2 + k];
-            if (cnt != P.ym_count[b][k]) { if (threadIdx.x == 0) s_fail = FB_YCOUNT; }
-            __syncthreads();
-            if (s_fail) break;
-            int len = 1;
-            while (len < cnt) len <<= 1;
-            const double *src = T.ycand + (((size_t)row * MAXB + b) * 2 + k) * CAPY;
-            for (int q = threadIdx.x; q < len; q += 256) s_v[q] = q < cnt ? src[q] : INFINITY;
-            __syncthreads();
-            for (int kk = 2; kk <= len; kk <<= 1)
-                for (int j = kk >> 1; j > 0; j >>= 1) {
-                    for (int i = threadIdx.x; i < len; i += 256) {
-                        const int ixj = i ^ j;
-                        if (ixj > i) {
-                            const double a = s_v[i], c = s_v[ixj];
-                            const bool up = ((i & kk) == 0);
-                            if ((a > c) == up) { s_v[i] = c; s_v[ixj] = a; }
-                        }
-                    }
-                    __syncthreads();
-                }
-            ym[k] = s_v[P.ym_rank[b][k]];
-            if (k == 1 && P.ym_bucket[b][0] == P.ym_bucket[b][1]) ym[0] = s_v[P.ym_rank[b][0]];
-            __syncthreads();
-        }
-        if (s_fail) break;
-        if (threadIdx.x == 0) {
-            s_bx[used] = (w & 1) ? P.xm_val[b][1] : 0.5 * (P.xm_val[b][0] + P.xm_val[b][1]);
-            s_by[used] = (w & 1) ? ym[1] : 0.5 * (ym[0] + ym[1]);
-            s_bw[used] = (double)w;
-        }
+        bx[used] = (w & 1) ? P.xm_val[b][1] : 0.5 * (P.xm_val[b][0] + P.xm_val[b][1]);
+        by[used] = (w & 1) ? P.ym_val[b][1] : 0.5 * (P.ym_val[b][0] + P.ym_val[b][1]);
+        bw[used] = (double)w;
         ++used;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (s_fail) { row_fallback[row] = s_fail; }
-        else { row_fallback[row] = 0; knots_from_bins(s_bx, s_by, s_bw, used, knots + row); }
-    }
+    row_fallback[row] = 0;
+    knots_from_bins(bx, by, bw, used, knots + row);
 }
 
 // bin medians -> PAVA -> de-duplicated knots (wls_backend.c:507-560, 262-338)
@@ -486,13 +608,15 @@ __global__ void k_knots_serial(const double *bx, const double *by, const double 
 }
 
 // ------------------------------------------------------------------ host driver
-int trend_knots_select(const double *d_C, const double *d_V, long long m, long long n, long long row_stride, Knots *d_knots,
-                       int *d_row_fallback, cudaStream_t st)
+int trend_knots_select(const double *d_C, double *d_V, long long m, long long n, long long row_stride, Knots *d_knots,
+                       int *d_row_fallback, int fused_window, cudaStream_t st)
 {
+    // fused_window > 0: V is not computed yet -- the first pass produces it together with the |C| histogram
     const int B = (int)fmax(4.0, floor(1.0 + (log((double)n + 1.0) / log(2.0))));      // wls_backend.c:456
     if (B > MAXB) return ST_INVALID;
     Arena ar(st);
     TrendBuffers T{};
+    T.rows = m;
     RB_TRY(ar.alloc(&T.xhist, (size_t)m * NBX));
     RB_TRY(ar.alloc(&T.lut, (size_t)m * NBX));
     RB_TRY(ar.alloc(&T.binlo, (size_t)m * NBX));
@@ -522,7 +646,18 @@ int trend_knots_select(const double *d_C, const double *d_V, long long m, long l
     }
     const unsigned chunks = (unsigned)((n + CHUNK - 1) / CHUNK);
     const dim3 gstream(chunks, (unsigned)m);
-    {
+    if (fused_window > 0) {
+        const size_t sm_fused = sizeof(int) * NBX + sizeof(double) * (padpos(RV_T + fused_window) + 8 + padpos(RV_T) + 8);
+        static bool attr2 = false;
+        if (!attr2) {
+            RB_CUDA(cudaFuncSetAttribute(k_rollvar_xhist, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(sizeof(int) * NBX + sizeof(double) * (padpos(RV_T + RV_MAXW) + 8 + padpos(RV_T) + 8))));
+            attr2 = true;
+        }
+        RB_PROF("k_rollvar_xhist", st, (double)m * n * 16.0);
+        k_rollvar_xhist<<<gstream, RV_THREADS, sm_fused, st>>>(d_C, n, row_stride, fused_window, d_V, T.xhist);
+        RB_LAUNCH_CHECK();
+    } else {
         RB_PROF("trend_xhist", st, (double)m * n * 8.0);
         k_xhist<<<gstream, ST_THREADS, sm_xhist, st>>>(d_C, n, row_stride, T.xhist);
         RB_LAUNCH_CHECK();
@@ -551,7 +686,9 @@ int trend_knots_select(const double *d_C, const double *d_V, long long m, long l
     }
     {
         RB_PROF("trend_plan_resolve", st, 0.0);
-        k_yresolve<<<(unsigned)m, 256, sizeof(double) * CAPY, st>>>(T, n, B, d_knots, d_row_fallback);
+        k_yresolve<<<dim3((unsigned)B, (unsigned)m), 256, sizeof(double) * CAPY, st>>>(T, n, B);
+        RB_LAUNCH_CHECK();
+        k_row_knots<<<(unsigned)((m + 63) / 64), 64, 0, st>>>(T, n, B, d_knots, d_row_fallback);
         RB_LAUNCH_CHECK();
     }
     return 0;

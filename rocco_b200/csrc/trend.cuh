@@ -13,8 +13,11 @@ struct Knots { double x[MAX_KNOTS]; double y[MAX_KNOTS]; int nk; int constant; d
 __device__ void knots_from_bins(const double *bx, const double *by, const double *bw, int used, Knots *out);
 
 // Histogram multi-select for all m rows; rows it cannot handle (a bucket over capacity) get row_fallback = 1.
-int trend_knots_select(const double *d_C, const double *d_V, long long m, long long n, long long row_stride, Knots *d_knots,
-                       int *d_row_fallback, cudaStream_t st);
+// fused_window > 0: d_V is an OUTPUT -- the rolling AR(1) variance (window `fused_window`, already resolved) is
+// computed in the same pass as the first histogram; fused_window == 0: d_V is an input.
+int trend_knots_select(const double *d_C, double *d_V, long long m, long long n, long long row_stride, Knots *d_knots,
+                       int *d_row_fallback, int fused_window, cudaStream_t st);
+int trend_fused_max_window();
 
 }  // namespace score
 }  // namespace rb

@@ -288,11 +288,15 @@ __global__ void __launch_bounds__(WT_THREADS, 1) k_whittaker(WhitParams P)
 
     // ---- stage rhs (masked y) for both parities, coalesced
     int bad = 0;
+    const bool keep_y = !P.write_baseline;
     for (int e = tid; e < WT_REGION; e += WT_THREADS) {
         double y = 0.0;
         if (e < rlen) {
             y = load_y(P, row, r0 + e);
             bad |= !isfinite(y);
+            // park y of the tile's own bins in the output buffer: the epilogue needs it again and a second
+            // fp64 log2 per bin costs more issue slots than an L2 round trip
+            if (keep_y && r0 + e >= out0 && r0 + e < out1) P.out[row * P.row_stride + r0 + e] = y;
         }
         const int a = e + e / WT_ITEMS;
         const bool even = (((r0 + e) & 1) == 0);
@@ -465,7 +469,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) k_whittaker(WhitParams P)
     for (int e = o_begin + tid; e < o_end; e += WT_THREADS) {
         const double b = s_f0[e + e / WT_ITEMS];
         double v = b;
-        if (!P.write_baseline) v = load_y(P, row, r0 + e) - b;
+        if (!P.write_baseline) v = __ldcg(P.out + row * P.row_stride + r0 + e) - b;
         bad2 |= !isfinite(v);
         P.out[row * P.row_stride + r0 + e] = v;
     }

@@ -108,30 +108,6 @@ constexpr int RV_ITEMS = 8;
 
 struct WinSums { double s1, s2, sl; };
 
-__device__ __forceinline__ double ar1_variance(const WinSums &ws, double first, double last, double wd, double pairs)
-{
-    // wls_backend.c:665-712, same association order (intrinsics keep nvcc from contracting into FMAs)
-    const double sum_head = __dsub_rn(ws.s1, last);
-    const double sum_tail = __dsub_rn(ws.s1, first);
-    const double mu = ws.s1 / wd;
-    double g0 = __dsub_rn(ws.s2, __dmul_rn(__dmul_rn(wd, mu), mu));
-    const double shrink = 1.0 / (wd + 1.0);
-    if (g0 < 0.0) g0 = 0.0;
-    double g1 = __dsub_rn(ws.sl, __dmul_rn(mu, sum_head));
-    g1 = __dsub_rn(g1, __dmul_rn(mu, sum_tail));
-    g1 = __dadd_rn(g1, __dmul_rn(__dmul_rn(pairs, mu), mu));
-    const double flo = __dmul_rn(1.0e-4, __dadd_rn(g0, 1.0));
-    const double den = __dadd_rn(__dmul_rn(g0, __dadd_rn(1.0, shrink)), flo);
-    const double eps = __dmul_rn(1.0e-12, __dadd_rn(g0, 1.0));
-    double beta = 0.0;
-    if (den > eps) beta = g1 / den;
-    if (beta > 0.99) beta = 0.99; else if (beta < 0.0) beta = 0.0;
-    const double gam0 = g0 / wd;
-    double omb = __dsub_rn(1.0, __dmul_rn(beta, beta));
-    if (omb < 0.0) omb = 0.0;
-    return fmax(__dmul_rn(gam0, omb), 0.0);
-}
-
 __global__ void __launch_bounds__(256) k_rollvar(const double *__restrict__ C, long long n, long long row_stride, int w,
                                                  double *__restrict__ V)
 {
@@ -141,7 +117,7 @@ __global__ void __launch_bounds__(256) k_rollvar(const double *__restrict__ C, l
     const long long j0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * RV_ITEMS;
     if (j0 >= n) return;
     const long long half = w / 2, last = n - w;
-    const double wd = (double)w, pairs = (double)(w - 1);
+    const double wd = (double)w, pairs = (double)(w - 1), rwd = 1.0 / wd, shrink = 1.0 / (wd + 1.0);
     WinSums ws{0.0, 0.0, 0.0};
     long long tprev = -1;
     double cur = 0.0;
@@ -167,7 +143,7 @@ __global__ void __launch_bounds__(256) k_rollvar(const double *__restrict__ C, l
                 ws.s2 = __dadd_rn(__dsub_rn(ws.s2, __dmul_rn(out_v, out_v)), __dmul_rn(nx, nx));
                 ws.sl = __dadd_rn(__dsub_rn(ws.sl, __dmul_rn(out_v, lag_r)), __dmul_rn(lag_l, nx));
             }
-            cur = ar1_variance(ws, c[t], c[t + w - 1], wd, pairs);
+            cur = ar1_window_variance(ws.s1, ws.s2, ws.sl, c[t], c[t + w - 1], wd, rwd, pairs, shrink);
             tprev = t;
         }
         v[j] = fmax(cur, 1.0e-8);                          // wls_backend.c:869
@@ -298,7 +274,7 @@ struct CombineParams {
     int *bad;
 };
 
-__device__ __forceinline__ double interp_knots(const double *kx, const double *ky, int nk, double t)
+__device__ __forceinline__ double interp_knots(const double *kx, const double *ky, const double *krw, int nk, double t)
 {
     // wls_backend.c:341-391
     if (nk == 0) return 1.0e-8;
@@ -311,21 +287,22 @@ __device__ __forceinline__ double interp_knots(const double *kx, const double *k
     }
     const double xl = kx[lo], xr = kx[hi];
     if (xr <= xl) return fmax(ky[hi], ky[lo]);
-    const double wgt = __dsub_rn(t, xl) / __dsub_rn(xr, xl);
+    const double wgt = div_rcp(__dsub_rn(t, xl), __dsub_rn(xr, xl), krw[lo]);      // krw[lo] = RN(1 / (kx[lo+1] - kx[lo]))
     return __dadd_rn(ky[lo], __dmul_rn(wgt, __dsub_rn(ky[hi], ky[lo])));
 }
 
 constexpr int CB_THREADS = 256;
-constexpr int CB_ROWS_SMEM = 64;          // knot tables staged per batch of sample rows
+constexpr int CB_ROWS_SMEM = 48;          // knot tables staged per batch of sample rows
 
 __global__ void __launch_bounds__(CB_THREADS) k_combine(CombineParams P)
 {
-    __shared__ double s_kx[CB_ROWS_SMEM][32], s_ky[CB_ROWS_SMEM][32];
+    __shared__ double s_kx[CB_ROWS_SMEM][32], s_ky[CB_ROWS_SMEM][32], s_kr[CB_ROWS_SMEM][32];
     __shared__ int s_nk[CB_ROWS_SMEM];
     __shared__ double s_cv[CB_ROWS_SMEM];
     const long long j = (long long)blockIdx.x * CB_THREADS + threadIdx.x;
     const bool live = j < P.n;
     double wsum = 0.0, psum = 0.0, rsum = 0.0, qsum = 0.0;
+    const double tdf1 = fmax(P.tdf, 1.0), rtdf1 = 1.0 / tdf1;
     for (long long r0 = 0; r0 < P.m; r0 += CB_ROWS_SMEM) {
         const int nr = (int)min((long long)CB_ROWS_SMEM, P.m - r0);
         __syncthreads();
@@ -335,6 +312,7 @@ __global__ void __launch_bounds__(CB_THREADS) k_combine(CombineParams P)
                 const Knots &K = P.knots[r0 + rr];
                 s_kx[rr][k] = (k < K.nk) ? K.x[k] : INFINITY;
                 s_ky[rr][k] = (k < K.nk) ? K.y[k] : 0.0;
+                s_kr[rr][k] = (k + 1 < K.nk && K.x[k + 1] > K.x[k]) ? __drcp_rn(__dsub_rn(K.x[k + 1], K.x[k])) : 0.0;
                 if (k == 0) { s_nk[rr] = K.constant ? -1 : K.nk; s_cv[rr] = K.cval; }
             }
         }
@@ -347,17 +325,17 @@ __global__ void __launch_bounds__(CB_THREADS) k_combine(CombineParams P)
                 if (P.const_rows) { ov = pv = P.row_const[r0 + rr]; }
                 else {
                     ov = fmax(P.V[idx], 1.0e-8);
-                    pv = (s_nk[rr] < 0) ? s_cv[rr] : fmax(interp_knots(s_kx[rr], s_ky[rr], s_nk[rr], fabs(y)), 1.0e-8);
+                    pv = (s_nk[rr] < 0) ? s_cv[rr] : fmax(interp_knots(s_kx[rr], s_ky[rr], s_kr[rr], s_nk[rr], fabs(y)), 1.0e-8);
                     pv = fmax(pv, 1.0e-8);
                 }
                 // wls_backend.c:889-911
-                double post = __dadd_rn(__dmul_rn(P.ldf, ov), __dmul_rn(P.pdf, pv)) / fmax(P.tdf, 1.0);
+                double post = div_rcp(__dadd_rn(__dmul_rn(P.ldf, ov), __dmul_rn(P.pdf, pv)), tdf1, rtdf1);
                 const double flo = __dmul_rn(P.pfr, pv);
                 if (post < flo) post = flo;
                 post = fmax(post, 1.0e-8);
-                const double prec = 1.0 / post;
-                rsum = __dadd_rn(rsum, 1.0 / ov);
-                qsum = __dadd_rn(qsum, 1.0 / pv);
+                const double prec = __drcp_rn(post);        // == 1.0 / post (correctly rounded), without the division slow path
+                rsum = __dadd_rn(rsum, __drcp_rn(ov));
+                qsum = __dadd_rn(qsum, __drcp_rn(pv));
                 psum = __dadd_rn(psum, prec);
                 wsum = __dadd_rn(wsum, __dmul_rn(prec, y));
             }
@@ -414,8 +392,9 @@ int centered_wls(const double *d_centered, long long m, long long n, const rocco
     } else {
         RB_TRY(ar.alloc(&d_V, (size_t)m * n));
         RB_TRY(ar.alloc(&d_knots, (size_t)m));
-        dim3 grid((unsigned)((n + 256LL * RV_ITEMS - 1) / (256LL * RV_ITEMS)), (unsigned)m);
-        {
+        const bool fused = (g_trend_mode.load() == 0) && (w <= trend_fused_max_window());
+        if (!fused) {
+            dim3 grid((unsigned)((n + 256LL * RV_ITEMS - 1) / (256LL * RV_ITEMS)), (unsigned)m);
             RB_PROF("k_rollvar", st, (double)m * (double)n * 16.0);
             k_rollvar<<<grid, 256, 0, st>>>(d_centered, n, n, w, d_V);
             RB_LAUNCH_CHECK();
@@ -429,7 +408,7 @@ int centered_wls(const double *d_centered, long long m, long long n, const rocco
             if (g_trend_mode.load() == 1) {
                 for (long long r = 0; r < m; ++r) rows.push_back(r);
             } else {
-                RB_TRY(trend_knots_select(d_centered, d_V, m, n, n, d_knots, d_fb, st));
+                RB_TRY(trend_knots_select(d_centered, d_V, m, n, n, d_knots, d_fb, fused ? w : 0, st));
                 std::vector<int> fb((size_t)m);
                 RB_CUDA(cudaMemcpyAsync(fb.data(), d_fb, sizeof(int) * (size_t)m, cudaMemcpyDeviceToHost, st));
                 RB_CUDA(cudaStreamSynchronize(st));
