@@ -127,10 +127,13 @@ constexpr int RV_MAXW = 2049;
 
 __host__ __device__ __forceinline__ int padpos(int i) { return i + (i >> 3); }
 
-__global__ void __launch_bounds__(RV_THREADS) k_rollvar_xhist(const double *__restrict__ C, long long n, long long row_stride, int w,
+// W > 0: compile-time window (31 = the reference default): interior tiles run fully unrolled from registers.
+template <int W>
+__global__ void __launch_bounds__(RV_THREADS) k_rollvar_xhist(const double *__restrict__ C, long long n, long long row_stride, int w_rt,
                                                                double *__restrict__ V, int *xhist)
 {
     extern __shared__ int s_dyn[];
+    const int w = W > 0 ? W : w_rt;
     int *s_h = s_dyn;                                              // NBX
     double *s_in = reinterpret_cast<double *>(s_dyn + NBX);        // padpos(RV_T + w)
     double *s_out = s_in + padpos(RV_T + w) + 8;                   // padpos(RV_T)
@@ -140,22 +143,50 @@ __global__ void __launch_bounds__(RV_THREADS) k_rollvar_xhist(const double *__re
     const long long c0 = (long long)blockIdx.x * CHUNK, c1 = min(n, c0 + CHUNK);
     const long long half = w / 2, last = n - w;
     const double wd = (double)w, pairs = (double)(w - 1), rwd = 1.0 / wd, shrink = 1.0 / (wd + 1.0);
-    for (int k = threadIdx.x; k < NBX; k += RV_THREADS) s_h[k] = 0;
+    const int tid = threadIdx.x;
+    for (int k = tid; k < NBX; k += RV_THREADS) s_h[k] = 0;
     __syncthreads();
     for (long long j0 = c0; j0 < c1; j0 += RV_T) {
         const long long j1 = min(c1, j0 + RV_T);
         long long tlo = j0 - half; if (tlo < 0) tlo = 0; else if (tlo > last) tlo = last;
         long long thi = (j1 - 1) - half; if (thi < 0) thi = 0; else if (thi > last) thi = last;
         const int span = (int)(thi - tlo) + w;                     // bins staged: [tlo, tlo + span)
-        for (int e = threadIdx.x; e < span; e += RV_THREADS) {
-            const long long g = tlo + e;
-            const double val = c[g];
+        const int own0 = (int)(j0 - tlo), own1 = (int)(j1 - tlo);  // staged positions of the tile's own bins
+        const double *src = c + tlo;
+        for (int e = tid; e < span; e += RV_THREADS) {
+            const double val = src[e];
             s_in[padpos(e)] = val;
-            if (g >= j0 && g < j1) atomicAdd(&s_h[xbucket(fabs(val))], 1);
+            if (e >= own0 && e < own1) atomicAdd(&s_h[xbucket(fabs(val))], 1);
         }
         __syncthreads();
-        {
-            const long long jt = j0 + (long long)threadIdx.x * RV_K;
+        const bool interior = (j0 - half >= 0) && ((j1 - 1) - half <= last) && (j1 - j0 == RV_T);
+        if (W > 0 && interior) {
+            // window of output k starts at staged position tid*8 + k; padded address = tid*9 + q + (q >> 3)
+            const double *base = s_in + tid * 9;
+            double y[W + RV_K - 1];
+#pragma unroll
+            for (int q = 0; q < W + RV_K - 1; ++q) y[q] = base[q + (q >> 3)];
+            double s1 = 0.0, s2 = 0.0, sl = 0.0;
+#pragma unroll
+            for (int q = 0; q < W; ++q) {
+                s1 = __dadd_rn(s1, y[q]);
+                s2 = __fma_rn(y[q], y[q], s2);
+                if (q + 1 < W) sl = __fma_rn(y[q], y[q + 1], sl);
+            }
+            double *ob = s_out + tid * 9;
+#pragma unroll
+            for (int k = 0; k < RV_K; ++k) {
+                if (k > 0) {
+                    const double out_v = y[k - 1], nx = y[k - 1 + W];
+                    s1 = __dadd_rn(__dsub_rn(s1, out_v), nx);
+                    s2 = __fma_rn(nx, nx, __fma_rn(-out_v, out_v, s2));
+                    sl = __fma_rn(y[k - 2 + W], nx, __fma_rn(-out_v, y[k], sl));
+                }
+                const double cur = ar1_window_variance(s1, s2, sl, y[k], y[k + W - 1], wd, rwd, pairs, shrink);
+                ob[k] = fmax(cur, 1.0e-8);                                         // wls_backend.c:869
+            }
+        } else {
+            const long long jt = j0 + (long long)tid * RV_K;
             double s1 = 0.0, s2 = 0.0, sl = 0.0, cur = 0.0;
             long long tprev = -1;
 #pragma unroll 1
@@ -172,29 +203,30 @@ __global__ void __launch_bounds__(RV_THREADS) k_rollvar_xhist(const double *__re
                         for (int q = 0; q < w; ++q) {
                             const double nx = (q + 1 < w) ? s_in[padpos(r + q + 1)] : 0.0;
                             s1 = __dadd_rn(s1, a);
-                            s2 = __dadd_rn(s2, __dmul_rn(a, a));
-                            if (q + 1 < w) sl = __dadd_rn(sl, __dmul_rn(a, nx));
+                            s2 = __fma_rn(a, a, s2);
+                            if (q + 1 < w) sl = __fma_rn(a, nx, sl);
                             a = nx;
                         }
                     } else {
                         const double out_v = s_in[padpos(r - 1)], nx = s_in[padpos(r - 1 + w)];
                         const double lag_l = s_in[padpos(r - 1 + w - 1)], lag_r = s_in[padpos(r)];
                         s1 = __dadd_rn(__dsub_rn(s1, out_v), nx);
-                        s2 = __dadd_rn(__dsub_rn(s2, __dmul_rn(out_v, out_v)), __dmul_rn(nx, nx));
-                        sl = __dadd_rn(__dsub_rn(sl, __dmul_rn(out_v, lag_r)), __dmul_rn(lag_l, nx));
+                        s2 = __fma_rn(nx, nx, __fma_rn(-out_v, out_v, s2));
+                        sl = __fma_rn(lag_l, nx, __fma_rn(-out_v, lag_r, sl));
                     }
                     cur = ar1_window_variance(s1, s2, sl, s_in[padpos(r)], s_in[padpos(r + w - 1)], wd, rwd, pairs, shrink);
                     tprev = t;
                 }
-                s_out[padpos(threadIdx.x * RV_K + k)] = fmax(cur, 1.0e-8);        // wls_backend.c:869
+                s_out[padpos(tid * RV_K + k)] = fmax(cur, 1.0e-8);
             }
         }
         __syncthreads();
-        for (int e = threadIdx.x; e < (int)(j1 - j0); e += RV_THREADS) v[j0 + e] = s_out[padpos(e)];
+        double *dst = v + j0;
+        for (int e = tid; e < (int)(j1 - j0); e += RV_THREADS) dst[e] = s_out[padpos(e)];
         __syncthreads();
     }
     int *g = xhist + row * NBX;
-    for (int k = threadIdx.x; k < NBX; k += RV_THREADS) {
+    for (int k = tid; k < NBX; k += RV_THREADS) {
         const int val = s_h[k];
         if (val) atomicAdd(&g[k], val);
     }
@@ -650,12 +682,14 @@ int trend_knots_select(const double *d_C, double *d_V, long long m, long long n,
         const size_t sm_fused = sizeof(int) * NBX + sizeof(double) * (padpos(RV_T + fused_window) + 8 + padpos(RV_T) + 8);
         static bool attr2 = false;
         if (!attr2) {
-            RB_CUDA(cudaFuncSetAttribute(k_rollvar_xhist, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(sizeof(int) * NBX + sizeof(double) * (padpos(RV_T + RV_MAXW) + 8 + padpos(RV_T) + 8))));
+            const int mx = (int)(sizeof(int) * NBX + sizeof(double) * (padpos(RV_T + RV_MAXW) + 8 + padpos(RV_T) + 8));
+            RB_CUDA(cudaFuncSetAttribute(k_rollvar_xhist<31>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+            RB_CUDA(cudaFuncSetAttribute(k_rollvar_xhist<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
             attr2 = true;
         }
         RB_PROF("k_rollvar_xhist", st, (double)m * n * 16.0);
-        k_rollvar_xhist<<<gstream, RV_THREADS, sm_fused, st>>>(d_C, n, row_stride, fused_window, d_V, T.xhist);
+        if (fused_window == 31) k_rollvar_xhist<31><<<gstream, RV_THREADS, sm_fused, st>>>(d_C, n, row_stride, fused_window, d_V, T.xhist);
+        else k_rollvar_xhist<0><<<gstream, RV_THREADS, sm_fused, st>>>(d_C, n, row_stride, fused_window, d_V, T.xhist);
         RB_LAUNCH_CHECK();
     } else {
         RB_PROF("trend_xhist", st, (double)m * n * 8.0);

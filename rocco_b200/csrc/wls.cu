@@ -133,15 +133,15 @@ __global__ void __launch_bounds__(256) k_rollvar(const double *__restrict__ C, l
                 for (int k = 0; k < w; ++k) {
                     const double a = c[t + k];
                     ws.s1 = __dadd_rn(ws.s1, a);
-                    ws.s2 = __dadd_rn(ws.s2, __dmul_rn(a, a));
-                    if (k < w - 1) ws.sl = __dadd_rn(ws.sl, __dmul_rn(a, c[t + k + 1]));
+                    ws.s2 = __fma_rn(a, a, ws.s2);
+                    if (k < w - 1) ws.sl = __fma_rn(a, c[t + k + 1], ws.sl);
                 }
             } else {
                 // slide tprev -> t (= tprev + 1), wls_backend.c:714-724
                 const double out_v = c[tprev], nx = c[tprev + w], lag_l = c[tprev + w - 1], lag_r = c[tprev + 1];
                 ws.s1 = __dadd_rn(__dsub_rn(ws.s1, out_v), nx);
-                ws.s2 = __dadd_rn(__dsub_rn(ws.s2, __dmul_rn(out_v, out_v)), __dmul_rn(nx, nx));
-                ws.sl = __dadd_rn(__dsub_rn(ws.sl, __dmul_rn(out_v, lag_r)), __dmul_rn(lag_l, nx));
+                ws.s2 = __fma_rn(nx, nx, __fma_rn(-out_v, out_v, ws.s2));
+                ws.sl = __fma_rn(lag_l, nx, __fma_rn(-out_v, lag_r, ws.sl));
             }
             cur = ar1_window_variance(ws.s1, ws.s2, ws.sl, c[t], c[t + w - 1], wd, rwd, pairs, shrink);
             tprev = t;
@@ -280,11 +280,11 @@ __device__ __forceinline__ double interp_knots(const double *kx, const double *k
     if (nk == 0) return 1.0e-8;
     if (nk == 1 || t <= kx[0]) return ky[0];
     if (t >= kx[nk - 1]) return ky[nk - 1];
-    int lo = 0, hi = nk - 1;
-    while (hi - lo > 1) {
-        const int mid = lo + (hi - lo) / 2;
-        if (kx[mid] <= t) lo = mid; else hi = mid;
-    }
+    // kx is padded with +inf up to 32 entries: five branch-free steps find the last knot <= t
+    int lo = 0;
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) lo += (kx[lo + step] <= t) ? step : 0;
+    const int hi = lo + 1;
     const double xl = kx[lo], xr = kx[hi];
     if (xr <= xl) return fmax(ky[hi], ky[lo]);
     const double wgt = div_rcp(__dsub_rn(t, xl), __dsub_rn(xr, xl), krw[lo]);      // krw[lo] = RN(1 / (kx[lo+1] - kx[lo]))
@@ -303,6 +303,7 @@ __global__ void __launch_bounds__(CB_THREADS) k_combine(CombineParams P)
     const bool live = j < P.n;
     double wsum = 0.0, psum = 0.0, rsum = 0.0, qsum = 0.0;
     const double tdf1 = fmax(P.tdf, 1.0), rtdf1 = 1.0 / tdf1;
+    const bool want_rq = (P.raw != nullptr) || (P.prior != nullptr);
     for (long long r0 = 0; r0 < P.m; r0 += CB_ROWS_SMEM) {
         const int nr = (int)min((long long)CB_ROWS_SMEM, P.m - r0);
         __syncthreads();
@@ -318,13 +319,15 @@ __global__ void __launch_bounds__(CB_THREADS) k_combine(CombineParams P)
         }
         __syncthreads();
         if (live) {
+            const double *pc = P.C + r0 * P.row_stride + j;
+            const double *pv_ = P.const_rows ? nullptr : P.V + r0 * P.row_stride + j;
+#pragma unroll 4
             for (int rr = 0; rr < nr; ++rr) {
-                const long long idx = (r0 + rr) * P.row_stride + j;
-                const double y = P.C[idx];
+                const double y = pc[(long long)rr * P.row_stride];
                 double ov, pv;
                 if (P.const_rows) { ov = pv = P.row_const[r0 + rr]; }
                 else {
-                    ov = fmax(P.V[idx], 1.0e-8);
+                    ov = fmax(pv_[(long long)rr * P.row_stride], 1.0e-8);
                     pv = (s_nk[rr] < 0) ? s_cv[rr] : fmax(interp_knots(s_kx[rr], s_ky[rr], s_kr[rr], s_nk[rr], fabs(y)), 1.0e-8);
                     pv = fmax(pv, 1.0e-8);
                 }
@@ -334,8 +337,10 @@ __global__ void __launch_bounds__(CB_THREADS) k_combine(CombineParams P)
                 if (post < flo) post = flo;
                 post = fmax(post, 1.0e-8);
                 const double prec = __drcp_rn(post);        // == 1.0 / post (correctly rounded), without the division slow path
-                rsum = __dadd_rn(rsum, __drcp_rn(ov));
-                qsum = __dadd_rn(qsum, __drcp_rn(pv));
+                if (want_rq) {                              // only when raw / prior variance outputs are requested
+                    rsum = __dadd_rn(rsum, __drcp_rn(ov));
+                    qsum = __dadd_rn(qsum, __drcp_rn(pv));
+                }
                 psum = __dadd_rn(psum, prec);
                 wsum = __dadd_rn(wsum, __dmul_rn(prec, y));
             }
