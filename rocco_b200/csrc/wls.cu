@@ -365,68 +365,96 @@ __global__ void __launch_bounds__(CB_THREADS) k_combine(CombineParams P)
     if (P.se) P.se[j] = se;
 }
 
-int centered_wls(const double *d_centered, long long m, long long n, const rocco_b200_score_params &prm,
-                 rocco_b200_score_outputs *out, cudaStream_t st)
-{
-    if (!d_centered || !out || m <= 0 || n <= 0) return ST_INVALID;
-    const double pdf = fmax(prm.prior_df, 0.0), pfr = fmax(prm.precision_floor_ratio, 0.0);
-    const int w = resolve_spatial_window(n, prm.spatial_window);
-    const double ldf = w > 0 ? fmax(4.0, (double)w - 3.0) : 1.0;
-    const double tdf = ldf + pdf;
-    out->total_df = tdf;
-    out->resolved_spatial_window = w;
-
-    Arena ar(st);
-    int *d_bad = nullptr;
-    RB_TRY(ar.alloc(&d_bad, 1));
-    RB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
-    CombineParams P{};
-    P.C = d_centered; P.m = m; P.n = n; P.row_stride = n;
-    P.ldf = ldf; P.pdf = pdf; P.tdf = tdf; P.pfr = pfr; P.lower_bound_z = prm.lower_bound_z;
-    P.min_effect = prm.min_effect; P.use_min_effect = prm.use_min_effect;
-    P.scores = out->scores; P.mean = out->mean; P.raw = out->raw_variance; P.prior = out->prior_variance;
-    P.mod = out->moderated_variance; P.se = out->standard_error; P.bad = d_bad;
-
+// ---- the per-row stages (rolling variance + trend knots) and the cross-sample finish, split so that the host
+// ---- entry can pipeline row groups behind their host->device copies
+struct WlsRun {
+    long long m = 0, n = 0;
+    int w = 0;
+    double ldf = 0, pdf = 0, tdf = 0, pfr = 0;
+    bool const_rows = false, fused = false, sort_all = false;
     double *d_V = nullptr, *d_rc = nullptr;
     Knots *d_knots = nullptr;
-    if (w == 0 || n < 4) {
-        RB_TRY(ar.alloc(&d_rc, (size_t)m));
-        k_robust_rows<<<(unsigned)m, 1, 0, st>>>(d_centered, n, n, d_rc);
-        RB_LAUNCH_CHECK();
-        P.const_rows = 1; P.row_const = d_rc;
+    int *d_fb = nullptr, *d_bad = nullptr;
+};
+
+static int wls_prepare(Arena &ar, long long m, long long n, const rocco_b200_score_params &prm, rocco_b200_score_outputs *out,
+                       WlsRun &R, cudaStream_t st)
+{
+    R.m = m; R.n = n;
+    R.pdf = fmax(prm.prior_df, 0.0); R.pfr = fmax(prm.precision_floor_ratio, 0.0);
+    R.w = resolve_spatial_window(n, prm.spatial_window);
+    R.ldf = R.w > 0 ? fmax(4.0, (double)R.w - 3.0) : 1.0;
+    R.tdf = R.ldf + R.pdf;
+    out->total_df = R.tdf;
+    out->resolved_spatial_window = R.w;
+    RB_TRY(ar.alloc(&R.d_bad, 1));
+    RB_CUDA(cudaMemsetAsync(R.d_bad, 0, sizeof(int), st));
+    R.const_rows = (R.w == 0 || n < 4);
+    if (R.const_rows) {
+        RB_TRY(ar.alloc(&R.d_rc, (size_t)m));
     } else {
-        RB_TRY(ar.alloc(&d_V, (size_t)m * n));
-        RB_TRY(ar.alloc(&d_knots, (size_t)m));
-        const bool fused = (g_trend_mode.load() == 0) && (w <= trend_fused_max_window());
-        if (!fused) {
-            dim3 grid((unsigned)((n + 256LL * RV_ITEMS - 1) / (256LL * RV_ITEMS)), (unsigned)m);
-            RB_PROF("k_rollvar", st, (double)m * (double)n * 16.0);
-            k_rollvar<<<grid, 256, 0, st>>>(d_centered, n, n, w, d_V);
-            RB_LAUNCH_CHECK();
+        RB_TRY(ar.alloc(&R.d_V, (size_t)m * n));
+        RB_TRY(ar.alloc(&R.d_knots, (size_t)m));
+        RB_TRY(ar.alloc(&R.d_fb, (size_t)m));
+        R.sort_all = g_trend_mode.load() == 1;
+        R.fused = !R.sort_all && (R.w <= trend_fused_max_window());
+    }
+    return 0;
+}
+
+// rows [r0, r1): variance track and trend knots (everything that needs one sample row only)
+static int wls_rows(const double *d_centered, WlsRun &R, long long r0, long long r1, cudaStream_t st)
+{
+    const long long g = r1 - r0, n = R.n;
+    const double *c = d_centered + r0 * n;
+    if (R.const_rows) {
+        k_robust_rows<<<(unsigned)g, 1, 0, st>>>(c, n, n, R.d_rc + r0);
+        RB_LAUNCH_CHECK();
+        return 0;
+    }
+    double *v = R.d_V + r0 * n;
+    if (!R.fused) {
+        dim3 grid((unsigned)((n + 256LL * RV_ITEMS - 1) / (256LL * RV_ITEMS)), (unsigned)g);
+        RB_PROF("k_rollvar", st, (double)g * (double)n * 16.0);
+        k_rollvar<<<grid, 256, 0, st>>>(c, n, n, R.w, v);
+        RB_LAUNCH_CHECK();
+    }
+    if (!R.sort_all) RB_TRY(trend_knots_select(c, v, g, n, n, R.d_knots + r0, R.d_fb + r0, R.fused ? R.w : 0, st));
+    return 0;
+}
+
+// after every row went through wls_rows: sort-path for flagged rows, then the fused column reduction
+static int wls_finish(const double *d_centered, WlsRun &R, const rocco_b200_score_params &prm, rocco_b200_score_outputs *out,
+                      cudaStream_t st)
+{
+    const long long m = R.m, n = R.n;
+    CombineParams P{};
+    P.C = d_centered; P.m = m; P.n = n; P.row_stride = n;
+    P.ldf = R.ldf; P.pdf = R.pdf; P.tdf = R.tdf; P.pfr = R.pfr; P.lower_bound_z = prm.lower_bound_z;
+    P.min_effect = prm.min_effect; P.use_min_effect = prm.use_min_effect;
+    P.scores = out->scores; P.mean = out->mean; P.raw = out->raw_variance; P.prior = out->prior_variance;
+    P.mod = out->moderated_variance; P.se = out->standard_error; P.bad = R.d_bad;
+    if (R.const_rows) {
+        P.const_rows = 1; P.row_const = R.d_rc;
+    } else {
+        // exact order statistics by histogram multi-select; rows it flags (a bucket over capacity: massive ties)
+        // fall back to the sort-based path, which is exact for any input
+        std::vector<long long> rows;
+        if (R.sort_all) {
+            for (long long r = 0; r < m; ++r) rows.push_back(r);
+        } else {
+            std::vector<int> fb((size_t)m);
+            RB_CUDA(cudaMemcpyAsync(fb.data(), R.d_fb, sizeof(int) * (size_t)m, cudaMemcpyDeviceToHost, st));
+            RB_CUDA(cudaStreamSynchronize(st));
+            for (long long r = 0; r < m; ++r)
+                if (fb[(size_t)r]) { rows.push_back(r); for (int k = 0; k < 8; ++k) if (fb[(size_t)r] & (1 << k)) g_trend_fb_reason[k].fetch_add(1); }
         }
-        {
-            // exact order statistics by histogram multi-select; rows it flags (a bucket over capacity: massive ties)
-            // fall back to the sort-based path, which is exact for any input
-            int *d_fb = nullptr;
-            RB_TRY(ar.alloc(&d_fb, (size_t)m));
-            std::vector<long long> rows;
-            if (g_trend_mode.load() == 1) {
-                for (long long r = 0; r < m; ++r) rows.push_back(r);
-            } else {
-                RB_TRY(trend_knots_select(d_centered, d_V, m, n, n, d_knots, d_fb, fused ? w : 0, st));
-                std::vector<int> fb((size_t)m);
-                RB_CUDA(cudaMemcpyAsync(fb.data(), d_fb, sizeof(int) * (size_t)m, cudaMemcpyDeviceToHost, st));
-                RB_CUDA(cudaStreamSynchronize(st));
-                for (long long r = 0; r < m; ++r)
-                    if (fb[(size_t)r]) { rows.push_back(r); for (int k = 0; k < 8; ++k) if (fb[(size_t)r] & (1 << k)) g_trend_fb_reason[k].fetch_add(1); }
-            }
-            if (!rows.empty()) {
-                g_trend_fallback_rows.fetch_add((long long)rows.size());
-                RB_PROF("trend_sort_fallback", st, (double)rows.size() * (double)n * 16.0);
-                RB_TRY(trend_knots_sorted(d_centered, d_V, rows, n, n, d_knots, st));
-            }
+        if (!rows.empty()) {
+            g_trend_fallback_rows.fetch_add((long long)rows.size());
+            RB_PROF("trend_sort_fallback", st, (double)rows.size() * (double)n * 16.0);
+            RB_TRY(trend_knots_sorted(d_centered, R.d_V, rows, n, n, R.d_knots, st));
         }
-        P.const_rows = 0; P.V = d_V; P.knots = d_knots;
+        P.const_rows = 0; P.V = R.d_V; P.knots = R.d_knots;
     }
     {
         RB_PROF("k_combine", st, (double)m * (double)n * (P.const_rows ? 8.0 : 16.0) + 48.0 * (double)n);
@@ -434,42 +462,107 @@ int centered_wls(const double *d_centered, long long m, long long n, const rocco
         RB_LAUNCH_CHECK();
     }
     int bad = 0;
-    RB_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    RB_CUDA(cudaMemcpyAsync(&bad, R.d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
     RB_CUDA(cudaStreamSynchronize(st));
     if (bad) return ST_NONFINITE;
     return 0;
 }
 
-// ------------------------------------------------------------------ the full chain (inference.py:302-379)
-static int score_loci_dev(const void *d_matrix, int dtype, long long m, long long n, const rocco_b200_score_params *params,
-                          rocco_b200_score_outputs *out, cudaStream_t st)
+int centered_wls(const double *d_centered, long long m, long long n, const rocco_b200_score_params &prm,
+                 rocco_b200_score_outputs *out, cudaStream_t st)
 {
-    if (!d_matrix || !out || m <= 0 || n <= 0 || (dtype != 0 && dtype != 1)) return ST_INVALID;
+    if (!d_centered || !out || m <= 0 || n <= 0) return ST_INVALID;
+    Arena ar(st);
+    WlsRun R;
+    RB_TRY(wls_prepare(ar, m, n, prm, out, R, st));
+    RB_TRY(wls_rows(d_centered, R, 0, m, st));
+    return wls_finish(d_centered, R, prm, out, st);
+}
+
+// ------------------------------------------------------------------ the full chain (inference.py:302-379)
+// `h_matrix` != nullptr: the matrix lives on the host; row groups are copied on a second stream and every
+// per-row stage of a group starts as soon as its rows have landed (copy of group g+1 overlaps compute of g).
+static cudaStream_t copy_stream()
+{
+    static cudaStream_t cs[32] = {nullptr};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 31;
+    if (!cs[dev]) cudaStreamCreateWithFlags(&cs[dev], cudaStreamNonBlocking);
+    return cs[dev];
+}
+
+static int score_loci_core(const void *d_matrix_in, const void *h_matrix, int dtype, long long m, long long n,
+                           const rocco_b200_score_params *params, rocco_b200_score_outputs *out, cudaStream_t st)
+{
+    if ((!d_matrix_in && !h_matrix) || !out || m <= 0 || n <= 0 || (dtype != 0 && dtype != 1)) return ST_INVALID;
     rocco_b200_score_params prm;
     if (params) prm = *params; else rocco_b200_default_score_params(&prm);
     RB_TRY(ensure_device());
     Arena ar(st);
+    const size_t esz = dtype ? sizeof(float) : sizeof(double);
     double *d_pilot = nullptr, *d_cent = nullptr;
     int *d_bad = nullptr;
+    char *d_x = nullptr;
     RB_TRY(ar.alloc(&d_pilot, (size_t)m));
     RB_TRY(ar.alloc(&d_bad, 1));
     RB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
-    const bool own_centered = out->centered_matrix == nullptr;
-    if (own_centered) RB_TRY(ar.alloc(&d_cent, (size_t)m * n)); else d_cent = out->centered_matrix;
-    {
-        RB_PROF("k_pilot", st, 0.0);
-        RB_TRY(pilot_offsets(d_matrix, dtype, m, n, n, d_pilot, st));
+    if (out->centered_matrix == nullptr) RB_TRY(ar.alloc(&d_cent, (size_t)m * n)); else d_cent = out->centered_matrix;
+    const void *d_matrix = d_matrix_in;
+    // row groups of ~256 MB
+    long long group = std::max<long long>(1, std::min<long long>(m, (256LL << 20) / std::max<long long>(1, n * (long long)esz)));
+    if (!h_matrix) group = m;
+    const int ngroups = (int)((m + group - 1) / group);
+    std::vector<cudaEvent_t> ev;
+    if (h_matrix) {
+        RB_TRY(ar.alloc(&d_x, (size_t)m * n * esz));
+        d_matrix = d_x;
+        cudaStream_t cs = copy_stream();
+        cudaEvent_t ready;
+        RB_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+        RB_CUDA(cudaEventRecord(ready, st));                       // the stream-ordered allocation is valid from here on
+        RB_CUDA(cudaStreamWaitEvent(cs, ready, 0));
+        cudaEventDestroy(ready);
+        ev.resize(ngroups);
+        for (int g = 0; g < ngroups; ++g) {
+            const long long r0 = g * group, r1 = std::min(m, r0 + group);
+            RB_CUDA(cudaMemcpyAsync(d_x + (size_t)r0 * n * esz, (const char *)h_matrix + (size_t)r0 * n * esz,
+                                    (size_t)(r1 - r0) * n * esz, cudaMemcpyHostToDevice, cs));
+            RB_CUDA(cudaEventCreateWithFlags(&ev[g], cudaEventDisableTiming));
+            RB_CUDA(cudaEventRecord(ev[g], cs));
+        }
     }
     const int bw = resolve_baseline_window(n, prm.baseline_window > 0 ? prm.baseline_window : 101);
     const double lam = bw > 0 ? whittaker_lambda(bw) : 0.0;
     out->baseline_window = bw;
     out->baseline_lambda = lam;
-    RB_TRY(whittaker_rows(d_matrix, dtype, 1, d_pilot, m, n, n, lam, 0, d_cent, d_bad, st));
+    WlsRun R;
+    RB_TRY(wls_prepare(ar, m, n, prm, out, R, st));
+    int status = 0;
+    for (int g = 0; g < ngroups && status == 0; ++g) {
+        const long long r0 = g * group, r1 = std::min(m, r0 + group);
+        if (h_matrix) { cudaStreamWaitEvent(st, ev[g], 0); }
+        const char *xg = (const char *)d_matrix + (size_t)r0 * n * esz;
+        {
+            RB_PROF("k_pilot", st, 0.0);
+            status = pilot_offsets(xg, dtype, r1 - r0, n, n, d_pilot + r0, st);
+        }
+        if (status == 0) status = whittaker_rows(xg, dtype, 1, d_pilot + r0, r1 - r0, n, n, lam, 0, d_cent + r0 * n, d_bad, st);
+        if (status == 0) status = wls_rows(d_cent, R, r0, r1, st);
+    }
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    if (status != 0) { cudaStreamSynchronize(st); return status; }
     int bad = 0;
     RB_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
     RB_CUDA(cudaStreamSynchronize(st));
     if (bad) return ST_NONFINITE;
-    return centered_wls(d_cent, m, n, prm, out, st);
+    return wls_finish(d_cent, R, prm, out, st);
+}
+
+static int score_loci_dev(const void *d_matrix, int dtype, long long m, long long n, const rocco_b200_score_params *params,
+                          rocco_b200_score_outputs *out, cudaStream_t st)
+{
+    return score_loci_core(d_matrix, nullptr, dtype, m, n, params, out, st);
 }
 
 }  // namespace score
@@ -563,17 +656,13 @@ static int score_loci_host(const void *matrix, int dtype, size_t m, size_t n, co
     RB_TRY(ensure_device());
     cudaStream_t st = 0;
     Arena ar(st);
-    const size_t esz = dtype ? sizeof(float) : sizeof(double);
-    char *d_x = nullptr;
-    RB_TRY(ar.alloc(&d_x, m * n * esz));
-    RB_CUDA(cudaMemcpyAsync(d_x, matrix, m * n * esz, cudaMemcpyHostToDevice, st));
     rocco_b200_score_outputs dev = *out;
     HostOuts ho;
     RB_TRY(run_host_outputs(ar, n, *out, dev, ho));
     double *d_cent = nullptr;
     if (out->centered_matrix) { RB_TRY(ar.alloc(&d_cent, m * n)); }
     dev.centered_matrix = d_cent;
-    int s = score::score_loci_dev(d_x, dtype, (long long)m, (long long)n, params, &dev, st);
+    int s = score::score_loci_core(nullptr, matrix, dtype, (long long)m, (long long)n, params, &dev, st);
     if (s != 0) return s;
     out->total_df = dev.total_df; out->resolved_spatial_window = dev.resolved_spatial_window;
     out->baseline_window = dev.baseline_window; out->baseline_lambda = dev.baseline_lambda;

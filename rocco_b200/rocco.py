@@ -91,10 +91,10 @@ def chrom_solution_to_bed(chromosome, intervals, solution, ID=None, check_gaps_i
         raise ValueError(
             f"Intervals and solution must have the same length at the pre-merge stage: {len(intervals)} != {len(solution)}")
     intervals_ = np.asarray(intervals)
-    if check_gaps_intervals:
-        gaps = np.unique(np.diff(intervals_))
-        if len(gaps) > 1:
-            raise ValueError(f"Intervals must be contiguous: {set(gaps.tolist())}")
+    if check_gaps_intervals and len(intervals_) > 1:
+        gaps = np.diff(intervals_)
+        if gaps.min() != gaps.max():          # same test as len(set(np.diff(intervals))) > 1, without the sort
+            raise ValueError(f"Intervals must be contiguous: {set(np.unique(gaps).tolist())}")
     step_ = intervals_[1] - intervals_[0]  # noqa: F841  (kept: the reference evaluates it, so len < 2 raises)
     output_file = f"rocco_{chromosome}.bed" if ID is None else f"rocco_{ID}_{chromosome}.bed"
     first, last = solution_runs(solution)
