@@ -201,6 +201,14 @@ int rocco_score_loci_wls_f32(const float *matrix, size_t m, size_t n,
 int rocco_b200_score_loci_wls_dev(const void *d_matrix, int dtype, size_t m, size_t n,
                                   const rocco_b200_score_params *params,
                                   rocco_b200_score_outputs *out, void *cuda_stream);
+/* Sample-sharded scoring (BASELINE.json config 5): each rank runs the per-sample stages on
+ * its own rows and writes the four per-bin sums d_acc[4][n] = {sum y/post, sum 1/post, sum 1/obs, sum 1/prior}
+ * (wls_backend.c:889-911); the caller sums d_acc over ranks (one NCCL all-reduce, 32 B/bin) and finalises with
+ * the TOTAL sample count (wls_backend.c:915-937). */
+int rocco_b200_score_partial_dev(const void *d_matrix, int dtype, size_t m_local, size_t n,
+                                 const rocco_b200_score_params *params, double *d_acc, void *cuda_stream);
+int rocco_b200_score_finalize_dev(const double *d_acc, size_t m_total, size_t n, const rocco_b200_score_params *params,
+                                  rocco_b200_score_outputs *out, void *cuda_stream);
 int rocco_b200_crossfit_baseline_dev(const double *d_rows, size_t m, size_t n, double penalty_lambda,
                                      double *d_out, void *cuda_stream);
 int rocco_b200_score_centered_wls_dev(const double *d_centered, size_t m, size_t n,

@@ -93,6 +93,8 @@ def _declare(lib):
         "rocco_score_loci_wls_f32": (c_int, [c_void_p, c_size_t, c_size_t, POINTER(ScoreParams), POINTER(ScoreOutputs)]),
         "rocco_b200_score_loci_wls_dev": (
             c_int, [c_void_p, c_int, c_size_t, c_size_t, POINTER(ScoreParams), POINTER(ScoreOutputs), c_void_p]),
+        "rocco_b200_score_partial_dev": (c_int, [c_void_p, c_int, c_size_t, c_size_t, POINTER(ScoreParams), c_void_p, c_void_p]),
+        "rocco_b200_score_finalize_dev": (c_int, [c_void_p, c_size_t, c_size_t, POINTER(ScoreParams), POINTER(ScoreOutputs), c_void_p]),
         "rocco_b200_crossfit_baseline_dev": (c_int, [c_void_p, c_size_t, c_size_t, c_double, c_void_p, c_void_p]),
         "rocco_b200_score_centered_wls_dev": (
             c_int, [c_void_p, c_size_t, c_size_t, POINTER(ScoreParams), POINTER(ScoreOutputs), c_void_p]),

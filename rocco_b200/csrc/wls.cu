@@ -271,6 +271,7 @@ struct CombineParams {
     double ldf, pdf, tdf, pfr, lower_bound_z, min_effect;
     int use_min_effect; int const_rows;
     double *scores, *mean, *raw, *prior, *mod, *se;
+    double *acc;          // != nullptr: sample-sharded mode, write the four per-bin sums [4][n] and stop
     int *bad;
 };
 
@@ -303,7 +304,7 @@ __global__ void __launch_bounds__(CB_THREADS) k_combine(CombineParams P)
     const bool live = j < P.n;
     double wsum = 0.0, psum = 0.0, rsum = 0.0, qsum = 0.0;
     const double tdf1 = fmax(P.tdf, 1.0), rtdf1 = 1.0 / tdf1;
-    const bool want_rq = (P.raw != nullptr) || (P.prior != nullptr);
+    const bool want_rq = (P.raw != nullptr) || (P.prior != nullptr) || (P.acc != nullptr);
     for (long long r0 = 0; r0 < P.m; r0 += CB_ROWS_SMEM) {
         const int nr = (int)min((long long)CB_ROWS_SMEM, P.m - r0);
         __syncthreads();
@@ -347,6 +348,10 @@ __global__ void __launch_bounds__(CB_THREADS) k_combine(CombineParams P)
         }
     }
     if (!live) return;
+    if (P.acc) {                                   // partial sums of this rank's samples (summed across ranks by the caller)
+        P.acc[j] = wsum; P.acc[P.n + j] = psum; P.acc[2 * P.n + j] = rsum; P.acc[3 * P.n + j] = qsum;
+        return;
+    }
     // wls_backend.c:915-937
     const double Pj = fmax(psum, 1.0e-8);
     const double mean = wsum / Pj;
@@ -363,6 +368,29 @@ __global__ void __launch_bounds__(CB_THREADS) k_combine(CombineParams P)
     if (P.prior) P.prior[j] = priv;
     if (P.mod) P.mod[j] = modv;
     if (P.se) P.se[j] = se;
+}
+
+// finalisation of summed accumulators (sample-sharded scoring): wls_backend.c:915-937 on [4][n] sums
+__global__ void __launch_bounds__(256) k_finalize_acc(const double *acc, long long n, double m_total, double lower_bound_z,
+                                                      double min_effect, int use_min_effect, double *scores, double *mean_o,
+                                                      double *raw, double *prior, double *mod, double *se_o, int *bad)
+{
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const double wsum = acc[j], psum = acc[n + j], rsum = acc[2 * n + j], qsum = acc[3 * n + j];
+    const double Pj = fmax(psum, 1.0e-8);
+    const double mean = wsum / Pj;
+    const double se = sqrt(1.0 / Pj);
+    const double z = mean / fmax(se, 1.0e-8);
+    const double sc = use_min_effect ? __dsub_rn(mean, fmax(min_effect, 0.0)) / fmax(se, 1.0e-8) : __dsub_rn(z, lower_bound_z);
+    const double rawv = m_total / fmax(rsum, 1.0e-8), priv = m_total / fmax(qsum, 1.0e-8), modv = m_total / Pj;
+    if (!(isfinite(sc) && isfinite(mean) && isfinite(rawv) && isfinite(priv) && isfinite(modv) && isfinite(se))) *bad = 1;
+    if (scores) scores[j] = sc;
+    if (mean_o) mean_o[j] = mean;
+    if (raw) raw[j] = rawv;
+    if (prior) prior[j] = priv;
+    if (mod) mod[j] = modv;
+    if (se_o) se_o[j] = se;
 }
 
 // ---- the per-row stages (rolling variance + trend knots) and the cross-sample finish, split so that the host
@@ -425,7 +453,7 @@ static int wls_rows(const double *d_centered, WlsRun &R, long long r0, long long
 
 // after every row went through wls_rows: sort-path for flagged rows, then the fused column reduction
 static int wls_finish(const double *d_centered, WlsRun &R, const rocco_b200_score_params &prm, rocco_b200_score_outputs *out,
-                      cudaStream_t st)
+                      cudaStream_t st, double *d_acc = nullptr)
 {
     const long long m = R.m, n = R.n;
     CombineParams P{};
@@ -433,7 +461,7 @@ static int wls_finish(const double *d_centered, WlsRun &R, const rocco_b200_scor
     P.ldf = R.ldf; P.pdf = R.pdf; P.tdf = R.tdf; P.pfr = R.pfr; P.lower_bound_z = prm.lower_bound_z;
     P.min_effect = prm.min_effect; P.use_min_effect = prm.use_min_effect;
     P.scores = out->scores; P.mean = out->mean; P.raw = out->raw_variance; P.prior = out->prior_variance;
-    P.mod = out->moderated_variance; P.se = out->standard_error; P.bad = R.d_bad;
+    P.mod = out->moderated_variance; P.se = out->standard_error; P.bad = R.d_bad; P.acc = d_acc;
     if (R.const_rows) {
         P.const_rows = 1; P.row_const = R.d_rc;
     } else {
@@ -493,7 +521,8 @@ static cudaStream_t copy_stream()
 }
 
 static int score_loci_core(const void *d_matrix_in, const void *h_matrix, int dtype, long long m, long long n,
-                           const rocco_b200_score_params *params, rocco_b200_score_outputs *out, cudaStream_t st)
+                           const rocco_b200_score_params *params, rocco_b200_score_outputs *out, cudaStream_t st,
+                           double *d_acc = nullptr)
 {
     if ((!d_matrix_in && !h_matrix) || !out || m <= 0 || n <= 0 || (dtype != 0 && dtype != 1)) return ST_INVALID;
     rocco_b200_score_params prm;
@@ -556,7 +585,7 @@ static int score_loci_core(const void *d_matrix_in, const void *h_matrix, int dt
     RB_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
     RB_CUDA(cudaStreamSynchronize(st));
     if (bad) return ST_NONFINITE;
-    return wls_finish(d_cent, R, prm, out, st);
+    return wls_finish(d_cent, R, prm, out, st, d_acc);
 }
 
 static int score_loci_dev(const void *d_matrix, int dtype, long long m, long long n, const rocco_b200_score_params *params,
@@ -590,6 +619,40 @@ RB_API int rocco_b200_score_loci_wls_dev(const void *d_matrix, int dtype, size_t
                                          const rocco_b200_score_params *params, rocco_b200_score_outputs *out, void *cuda_stream)
 {
     return score::score_loci_dev(d_matrix, dtype, (long long)m, (long long)n, params, out, (cudaStream_t)cuda_stream);
+}
+
+/* Sample-sharded scoring: this rank's rows -> four per-bin sums [4][n]; sum them over ranks, then finalise. */
+RB_API int rocco_b200_score_partial_dev(const void *d_matrix, int dtype, size_t m_local, size_t n,
+                                        const rocco_b200_score_params *params, double *d_acc, void *cuda_stream)
+{
+    if (!d_acc) return ST_INVALID;
+    rocco_b200_score_outputs out{};
+    return score::score_loci_core(d_matrix, nullptr, dtype, (long long)m_local, (long long)n, params, &out, (cudaStream_t)cuda_stream, d_acc);
+}
+
+RB_API int rocco_b200_score_finalize_dev(const double *d_acc, size_t m_total, size_t n, const rocco_b200_score_params *params,
+                                         rocco_b200_score_outputs *out, void *cuda_stream)
+{
+    if (!d_acc || !out || m_total == 0 || n == 0) return ST_INVALID;
+    rocco_b200_score_params prm;
+    if (params) prm = *params; else rocco_b200_default_score_params(&prm);
+    RB_TRY(ensure_device());
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    Arena ar(st);
+    int *d_bad = nullptr;
+    RB_TRY(ar.alloc(&d_bad, 1));
+    RB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+    score::k_finalize_acc<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_acc, (long long)n, (double)m_total, prm.lower_bound_z, prm.min_effect,
+                                                                      prm.use_min_effect, out->scores, out->mean, out->raw_variance,
+                                                                      out->prior_variance, out->moderated_variance, out->standard_error, d_bad);
+    RB_LAUNCH_CHECK();
+    const int w = score::resolve_spatial_window((long long)n, prm.spatial_window);
+    out->resolved_spatial_window = w;
+    out->total_df = (w > 0 ? fmax(4.0, (double)w - 3.0) : 1.0) + fmax(prm.prior_df, 0.0);
+    int bad = 0;
+    RB_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    RB_CUDA(cudaStreamSynchronize(st));
+    return bad ? ST_NONFINITE : 0;
 }
 
 RB_API int rocco_b200_crossfit_baseline_dev(const double *d_rows, size_t m, size_t n, double penalty_lambda,

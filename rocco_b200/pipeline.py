@@ -280,3 +280,54 @@ def sweep_multipliers(scores, gamma: float, lambdas):
             _lib.np_ptr(counts), _lib.np_ptr(pen), _lib.np_ptr(obj), ctypes.c_void_p(_stream_ptr(d_scores.device)))
     _lib.check(st, "sweep_multipliers")
     return counts, pen, obj
+
+
+def score_partial_device(d_matrix_local, params=None):
+    """Per-sample stages of this rank's rows -> the four per-bin accumulators, a [4, bins] float64 CUDA tensor."""
+    torch = _torch()
+    lib = _lib.load()
+    if d_matrix_local.dim() != 2 or not d_matrix_local.is_cuda or not d_matrix_local.is_contiguous():
+        raise ValueError("`d_matrix_local` must be a contiguous two-dimensional CUDA tensor")
+    m, n = d_matrix_local.shape
+    acc = torch.empty((4, n), dtype=torch.float64, device=d_matrix_local.device)
+    prm = params if params is not None else score_params()
+    with torch.cuda.device(d_matrix_local.device):
+        st = lib.rocco_b200_score_partial_dev(
+            ctypes.c_void_p(d_matrix_local.data_ptr()), 1 if d_matrix_local.dtype == torch.float32 else 0, m, n,
+            ctypes.byref(prm), ctypes.c_void_p(acc.data_ptr()), ctypes.c_void_p(_stream_ptr(d_matrix_local.device)))
+    if st == _lib.ST_NONFINITE:
+        raise ValueError("Locus scoring produced non-finite values (or `chrom_matrix` contains non-finite values)")
+    _lib.check(st, "score_partial")
+    return acc
+
+
+def score_finalize_device(acc, m_total: int, params=None, details: bool = False):
+    torch = _torch()
+    lib = _lib.load()
+    n = acc.shape[1]
+    out = _lib.ScoreOutputs()
+    res = {"scores": torch.empty(n, dtype=torch.float64, device=acc.device)}
+    if details:
+        for k in ("mean", "raw_variance", "prior_variance", "moderated_variance", "standard_error"):
+            res[k] = torch.empty(n, dtype=torch.float64, device=acc.device)
+    for k, v in res.items():
+        setattr(out, k, v.data_ptr())
+    prm = params if params is not None else score_params()
+    with torch.cuda.device(acc.device):
+        st = lib.rocco_b200_score_finalize_dev(ctypes.c_void_p(acc.data_ptr()), int(m_total), n, ctypes.byref(prm),
+                                               ctypes.byref(out), ctypes.c_void_p(_stream_ptr(acc.device)))
+    if st == _lib.ST_NONFINITE:
+        raise ValueError("Locus scoring produced non-finite values")
+    _lib.check(st, "score_finalize")
+    return res if details else res["scores"]
+
+
+def score_loci_wls_sample_sharded(d_matrix_local, m_total: int, params=None, group=None, details: bool = False):
+    """score_loci_wls with the SAMPLES sharded over ranks (every rank holds [m_local, bins] of the same bins):
+    per-sample stages stay local; one all-reduce(sum, float64) of the [4, bins] accumulators; every rank then
+    finishes the per-bin combine."""
+    import torch.distributed as dist
+    acc = score_partial_device(d_matrix_local, params)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(acc, group=group)
+    return score_finalize_device(acc, m_total, params, details=details)

@@ -261,3 +261,24 @@ def test_score_then_solve_gives_reference_mask(rb, oracle):
     assert got["selected_count"] == want["selected_count"]
     assert abs(got_obj - want_obj) <= 1e-6 * abs(want_obj)
     assert abs(got["selection_penalty"] - want["selection_penalty"]) <= 1e-6
+
+
+def test_sample_sharded_scoring_matches_unsharded(rb, oracle):
+    """per-sample stages on each shard, sum of the [4, bins] accumulators (the all-reduce, emulated
+    here by adding the two shards' tensors on one GPU), then the per-bin finalisation."""
+    import torch
+    from rocco_b200 import pipeline
+    x = chrom_matrix_numpy(12, 50_000, seed=77)
+    prm = pipeline.score_params(prior_df=6.0)
+    d = torch.from_numpy(x).cuda()
+    acc = pipeline.score_partial_device(d[:5].contiguous(), prm) + pipeline.score_partial_device(d[5:].contiguous(), prm)
+    got = pipeline.score_finalize_device(acc, 12, prm, details=True)
+    want_s, want = oracle.score_loci_wls(x, prior_df=6.0, return_details=True)
+    assert rel_err(got["scores"].cpu().numpy(), want_s) <= TIGHT
+    for k in ("mean", "raw_variance", "prior_variance", "moderated_variance", "standard_error"):
+        assert rel_err(got[k].cpu().numpy(), want[k]) <= TIGHT, k
+    whole = pipeline.score_loci_wls_device(d, params=prm).cpu().numpy()
+    assert np.max(np.abs(got["scores"].cpu().numpy() - whole)) <= 1e-12 * max(1.0, float(np.max(np.abs(whole))))
+    # world size 1: the sharded entry is the unsharded computation
+    one = pipeline.score_loci_wls_sample_sharded(d, 12, prm).cpu().numpy()
+    assert np.max(np.abs(one - whole)) <= 1e-12 * max(1.0, float(np.max(np.abs(whole))))
