@@ -229,7 +229,8 @@ extern "C" __attribute__((visibility("default"))) long long rocco_mask_to_interv
 {
     if (!mask || n == 0) return ST_INVALID;
     RB_TRY(ensure_device());
-    cudaStream_t st = 0;
+    HostScope lease;
+    cudaStream_t st = lease.stream();
     Arena ar(st);
     uint8_t *d_m = nullptr;
     RB_TRY(ar.alloc(&d_m, n));

@@ -1091,7 +1091,8 @@ static int host_chain(const double *scores, const double *costs, size_t n, int m
     if (!scores || !mask_out || n == 0) return ST_INVALID;
     if (n > 1 && !costs) return ST_INVALID;
     RB_TRY(ensure_device());
-    cudaStream_t st = 0;
+    HostScope lease;
+    cudaStream_t st = lease.stream();
     Arena ar(st);
     double *d_s = nullptr, *d_c = nullptr;
     uint8_t *d_m = nullptr;

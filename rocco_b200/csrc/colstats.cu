@@ -244,7 +244,8 @@ RB_API int rocco_column_stat_f64(const double *matrix, size_t m, size_t n, int s
 {
     if (!matrix || !out || m == 0 || n == 0) return ST_INVALID;
     RB_TRY(ensure_device());
-    cudaStream_t st = 0;
+    HostScope lease;
+    cudaStream_t st = lease.stream();
     Arena ar(st);
     double *d_x = nullptr, *d_o = nullptr;
     RB_TRY(ar.alloc(&d_x, m * n));

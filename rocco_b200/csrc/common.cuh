@@ -41,9 +41,14 @@ inline void count_launch(int k = 1) { g_launches.fetch_add((unsigned long long)k
     } while (0)
 
 // Stream-ordered scratch: every buffer is freed (stream-ordered) when the arena dies.
+// Memory pool private to host_stream() of the calling thread (nullptr for any other stream: default pool).  A private
+// pool keeps a thread's scratch from being recycled into another thread's stream, which would chain the two
+// streams together through the allocator's internal dependencies.
+cudaMemPool_t pool_for_stream(cudaStream_t s);
+
 class Arena {
   public:
-    explicit Arena(cudaStream_t s) : stream_(s) {}
+    explicit Arena(cudaStream_t s) : stream_(s), pool_(pool_for_stream(s)) {}
     ~Arena() { release(); }
     Arena(const Arena &) = delete;
     Arena &operator=(const Arena &) = delete;
@@ -51,7 +56,7 @@ class Arena {
         void *p = nullptr;
         size_t bytes = count * sizeof(T);
         if (bytes == 0) bytes = 16;
-        cudaError_t e = cudaMallocAsync(&p, bytes, stream_);
+        cudaError_t e = pool_ ? cudaMallocFromPoolAsync(&p, bytes, pool_, stream_) : cudaMallocAsync(&p, bytes, stream_);
         if (e != cudaSuccess) {
             set_error("cudaMallocAsync(%zu bytes) -> %s", bytes, cudaGetErrorString(e));
             (void)cudaGetLastError();
@@ -69,6 +74,7 @@ class Arena {
 
   private:
     cudaStream_t stream_;
+    cudaMemPool_t pool_;
     std::vector<void *> ptrs_;
 };
 
@@ -107,6 +113,23 @@ class ProfScope {
 #define RB_PROF(name, st, bytes) ::rb::ProfScope _prof_scope_##__LINE__(name, st, bytes)
 
 int ensure_device();     // returns 0 or ST_CUDA when no usable device
+// Stream used by the host-pointer entries: one non-blocking stream per host thread and device, so that two host
+// threads driving different chromosomes overlap (one's H2D copy with the other's kernels) instead of queueing
+// behind each other on the legacy default stream.
+cudaStream_t host_stream();
+// RAII lease of a (non-blocking stream, private memory pool) pair for one host-pointer call.  Pairs are recycled
+// through a global free list, so the number that exist equals the highest concurrency seen, whatever the threads do.
+class HostScope {
+  public:
+    HostScope();
+    ~HostScope();
+    HostScope(const HostScope &) = delete;
+    HostScope &operator=(const HostScope &) = delete;
+    cudaStream_t stream() const { return st_; }
+  private:
+    int slot_;
+    cudaStream_t st_;
+};
 int sm_count();
 
 // ---------------------------------------------------------------- device helpers

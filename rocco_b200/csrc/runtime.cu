@@ -45,6 +45,51 @@ int ensure_device()
     return 0;
 }
 
+struct HostCtx { int dev; cudaStream_t st; cudaMemPool_t pool; bool busy; };
+static std::mutex g_ctx_mu;
+static std::vector<HostCtx> g_ctx;
+
+HostScope::HostScope() : slot_(-1), st_(nullptr)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    for (size_t k = 0; k < g_ctx.size(); ++k)
+        if (!g_ctx[k].busy && g_ctx[k].dev == dev) { g_ctx[k].busy = true; slot_ = (int)k; st_ = g_ctx[k].st; return; }
+    HostCtx c{dev, nullptr, nullptr, true};
+    if (cudaStreamCreateWithFlags(&c.st, cudaStreamNonBlocking) != cudaSuccess) { (void)cudaGetLastError(); return; }
+    cudaMemPoolProps props{};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    if (cudaMemPoolCreate(&c.pool, &props) == cudaSuccess) {
+        unsigned long long thr = ~0ULL;
+        cudaMemPoolSetAttribute(c.pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    } else { (void)cudaGetLastError(); c.pool = nullptr; }
+    g_ctx.push_back(c);
+    slot_ = (int)g_ctx.size() - 1;
+    st_ = c.st;
+}
+
+HostScope::~HostScope()
+{
+    if (slot_ < 0) return;
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    g_ctx[slot_].busy = false;
+}
+
+cudaStream_t host_stream() { return nullptr; }      // legacy default stream (kept for callers without a lease)
+
+cudaMemPool_t pool_for_stream(cudaStream_t s)
+{
+    if (s == nullptr) return nullptr;
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    for (const HostCtx &c : g_ctx)
+        if (c.st == s) return c.pool;
+    return nullptr;
+}
+
 int sm_count()
 {
     static int cached = 0;

@@ -717,7 +717,8 @@ static int score_loci_host(const void *matrix, int dtype, size_t m, size_t n, co
 {
     if (!matrix || !out || m == 0 || n == 0) return ST_INVALID;
     RB_TRY(ensure_device());
-    cudaStream_t st = 0;
+    HostScope lease;
+    cudaStream_t st = lease.stream();
     Arena ar(st);
     rocco_b200_score_outputs dev = *out;
     HostOuts ho;
@@ -752,7 +753,8 @@ RB_API int rocco_crossfit_whittaker_baseline_matrix_f64(const double *matrix_val
     if (!matrix_values || !baseline_out) return ST_NOMEM;
     if (row_count == 0 || column_count == 0) return 0;
     RB_TRY(ensure_device());
-    cudaStream_t st = 0;
+    HostScope lease;
+    cudaStream_t st = lease.stream();
     Arena ar(st);
     double *d_in = nullptr, *d_out = nullptr;
     const size_t total = row_count * column_count;
@@ -783,7 +785,8 @@ RB_API int rocco_score_centered_wls_f64(
         return ST_INVALID;
     if (sample_count == 0 || locus_count == 0) return ST_INVALID;
     RB_TRY(ensure_device());
-    cudaStream_t st = 0;
+    HostScope lease;
+    cudaStream_t st = lease.stream();
     Arena ar(st);
     double *d_c = nullptr;
     const size_t total = sample_count * locus_count;

@@ -108,9 +108,32 @@ def chrom_solution_to_bed(chromosome, intervals, solution, ID=None, check_gaps_i
     return _write_bed_records(records, output_file)
 
 
+def _merge_bed_arrays(chrom: np.ndarray, start: np.ndarray, end: np.ndarray):
+    """Vectorised restatement of _merge_bed_records: sort by (chromosome string, start, end) and merge records with
+    start <= running end.  Returns (chrom, start, end) arrays of the merged records."""
+    if len(start) == 0:
+        return chrom, start, end
+    names, inv = np.unique(chrom, return_inverse=True)             # np.unique sorts strings like Python's sorted()
+    order = np.lexsort((end, start, inv))
+    inv, start, end = inv[order], start[order], end[order]
+    out_c, out_s, out_e = [], [], []
+    bounds = np.flatnonzero(np.diff(inv)) + 1
+    for lo, hi in zip(np.concatenate(([0], bounds)), np.concatenate((bounds, [len(inv)]))):
+        s_, e_ = start[lo:hi], end[lo:hi]
+        run_end = np.maximum.accumulate(e_)
+        new_grp = np.concatenate(([True], s_[1:] > run_end[:-1]))   # a record starts a new interval iff start > previous end
+        first = np.flatnonzero(new_grp)
+        last = np.concatenate((first[1:] - 1, [len(s_) - 1]))
+        out_s.append(s_[first]); out_e.append(run_end[last])
+        out_c.append(np.full(len(first), names[inv[lo]], dtype=object))
+    return np.concatenate(out_c), np.concatenate(out_s), np.concatenate(out_e)
+
+
 def combine_chrom_results(chrom_bed_files: list, output_file: str, name_features: bool = False) -> str:
     r"""Concatenate per-chromosome BED files, sort by (chrom string, start, end), merge, write
-    (rocco.py:194-240)."""
+    (rocco.py:194-240).  Same records as the reference; parsing, sorting and merging are vectorised."""
+    import pandas as pd
+
     printed_colct_msg = False
     if os.path.exists(output_file):
         logger.info(f"Removing existing output file: {output_file}")
@@ -118,21 +141,39 @@ def combine_chrom_results(chrom_bed_files: list, output_file: str, name_features
             os.remove(output_file)
         except OSError:
             logger.info(f"Could not remove existing output file: {output_file}.")
-    combined_records: list[tuple[str, int, int]] = []
+    frames = []
     for chrom_bed_file in chrom_bed_files:
         if not os.path.exists(chrom_bed_file):
             raise FileNotFoundError(f"File does not exist: {chrom_bed_file}")
+        if os.path.getsize(chrom_bed_file) == 0:
+            continue
         try:
-            chrom_records, saw_extra_columns = _read_bed_records(chrom_bed_file)
+            df = pd.read_csv(chrom_bed_file, sep="\t", header=None, dtype=str, keep_default_na=False, skip_blank_lines=True)
+        except pd.errors.EmptyDataError:
+            continue
         except Exception as e:
             logger.info(f"Could not read BED file: {chrom_bed_file}\n{e}\n")
             raise
-        if saw_extra_columns and not printed_colct_msg:
+        if df.shape[1] < 3 or (df.iloc[:, 2] == "").any():
+            bad = int(np.flatnonzero((df.iloc[:, 2] == "").to_numpy())[0]) + 1 if df.shape[1] >= 3 else 1
+            raise ValueError(f"BED row {bad} in {chrom_bed_file} has fewer than 3 columns.")
+        if df.shape[1] > 3 and not printed_colct_msg:
             logger.info("More than 3 columns detected in the input BED files. Extra columns will be ignored.")
             printed_colct_msg = True
-        combined_records.extend(chrom_records)
-    merged_records = _merge_bed_records(combined_records)
-    return _write_bed_records(merged_records, output_file, name_features=name_features)
+        frames.append(df.iloc[:, :3])
+    if frames:
+        allrec = pd.concat(frames, ignore_index=True)
+        chrom = allrec.iloc[:, 0].to_numpy(dtype=object)
+        start = allrec.iloc[:, 1].astype(np.int64).to_numpy()
+        end = allrec.iloc[:, 2].astype(np.int64).to_numpy()
+        chrom, start, end = _merge_bed_arrays(chrom, start, end)
+    else:
+        chrom, start, end = np.zeros(0, dtype=object), np.zeros(0, np.int64), np.zeros(0, np.int64)
+    out = pd.DataFrame({"c": chrom, "s": start, "e": end})
+    if name_features:
+        out["n"] = out["c"].astype(str) + "_" + out["s"].astype(str) + "_" + out["e"].astype(str)
+    out.to_csv(output_file, sep="\t", header=False, index=False, lineterminator="\n")
+    return output_file
 
 
 # ------------------------------------------------------------------------------------------------

@@ -61,3 +61,33 @@ def test_merge_sorts_chromosomes_lexicographically(oracle):
     want = oracle.merge_bed_records(recs)
     assert _merge_bed_records(recs) == want == [("chr1", 50, 80), ("chr10", 0, 7), ("chr2", 5, 10)]
     assert _merge_bed_records(recs, min_length_bp=10) == oracle.merge_bed_records(recs, 10)
+
+
+def test_combine_chrom_results_matches_oracle_on_messy_input(oracle, tmp_path):
+    """vectorised combine == the reference's sort/merge semantics (rocco.py:74-95, 194-240): unsorted, overlapping,
+    touching and nested records, extra columns, blank lines, lexicographic chromosome order, feature names"""
+    from rocco_b200.rocco import combine_chrom_results
+    rng = np.random.default_rng(0)
+    files = []
+    for k, chrom in enumerate(["chr2", "chr10", "chr1", "chrX"]):
+        starts = rng.integers(0, 50_000, size=3000) * 10
+        lens = rng.integers(1, 40, size=3000) * 10
+        p = tmp_path / f"in{k}.bed"
+        with open(p, "w") as fh:
+            for i, (s, l) in enumerate(zip(starts, lens)):
+                extra = "\tname\t0" if (k == 1 and i % 3 == 0) else ""
+                fh.write(f"{chrom}\t{s}\t{s + l}{extra}\n")
+                if i % 500 == 0:
+                    fh.write("\n")
+        files.append(str(p))
+    (tmp_path / "empty.bed").write_text("")
+    files.append(str(tmp_path / "empty.bed"))
+    for names in (False, True):
+        a = combine_chrom_results(files, str(tmp_path / "a.bed"), name_features=names)
+        b = oracle.combine_chrom_results(files, str(tmp_path / "b.bed"), name_features=names)
+        assert open(a).read() == open(b).read()
+    with pytest.raises(FileNotFoundError):
+        combine_chrom_results([str(tmp_path / "missing.bed")], str(tmp_path / "c.bed"))
+    (tmp_path / "bad.bed").write_text("chr1\t5\n")
+    with pytest.raises(ValueError):
+        combine_chrom_results([str(tmp_path / "bad.bed")], str(tmp_path / "c.bed"))
