@@ -153,6 +153,7 @@ long long rocco_b200_mask_to_runs_batch_dev(
 
 /* numpy.sum of a float64 vector / of n copies of one value, restated bit-exactly (host helpers:
  * dp.py:110-111 builds the search bracket from numpy.sum(switch_costs)). */
+int rocco_b200_uniform_step_i64(const long long *values, size_t n);   /* 1 iff all consecutive differences are equal */
 double rocco_b200_numpy_sum_f64(const double *values, size_t n);
 double rocco_b200_numpy_sum_const_f64(double value, size_t n);
 

@@ -64,6 +64,7 @@ def _declare(lib):
         "rocco_b200_kernel_launches": (c_ulonglong, []),
         "rocco_b200_profile_enable": (c_int, [c_int]),
         "rocco_b200_profile_report": (c_int, [c_char_p, c_size_t]),
+        "rocco_b200_uniform_step_i64": (c_int, [c_void_p, c_size_t]),
         "rocco_b200_numpy_sum_f64": (c_double, [c_void_p, c_size_t]),
         "rocco_b200_numpy_sum_const_f64": (c_double, [c_double, c_size_t]),
         "rocco_solve_penalized_chain_f64": (c_int, [c_void_p, c_void_p, c_size_t, c_double, c_void_p, dp, llp]),

@@ -238,6 +238,17 @@ RB_API int rocco_b200_profile_report(char *buf, size_t cap)
     return (int)off;
 }
 
+/* 1 when v[i+1]-v[i] is the same for all i (the reference's `len(set(np.diff(intervals))) > 1` test, rocco.py:170-172,
+ * without materialising the differences); host helper. */
+RB_API int rocco_b200_uniform_step_i64(const long long *v, size_t n)
+{
+    if (!v || n < 3) return 1;
+    const long long step = v[1] - v[0];
+    int ok = 1;
+    for (size_t i = 2; i < n; ++i) ok &= ((v[i] - v[i - 1]) == step);
+    return ok;
+}
+
 RB_API double rocco_b200_numpy_sum_f64(const double *a, size_t n) { return rb::numpy_sum_f64(a, n); }
 RB_API double rocco_b200_numpy_sum_const_f64(double value, size_t n) { return rb::numpy_sum_const_f64(value, n); }
 }

@@ -91,10 +91,15 @@ def chrom_solution_to_bed(chromosome, intervals, solution, ID=None, check_gaps_i
         raise ValueError(
             f"Intervals and solution must have the same length at the pre-merge stage: {len(intervals)} != {len(solution)}")
     intervals_ = np.asarray(intervals)
-    if check_gaps_intervals and len(intervals_) > 1:
-        gaps = np.diff(intervals_)
-        if gaps.min() != gaps.max():          # same test as len(set(np.diff(intervals))) > 1, without the sort
-            raise ValueError(f"Intervals must be contiguous: {set(np.unique(gaps).tolist())}")
+    if check_gaps_intervals and len(intervals_) > 2:
+        # same test as len(set(np.diff(intervals))) > 1 (rocco.py:170-172) without materialising / sorting the differences
+        if intervals_.dtype == np.int64 and intervals_.flags.c_contiguous:
+            uniform = bool(_lib.load().rocco_b200_uniform_step_i64(_lib.np_ptr(intervals_), len(intervals_)))
+        else:
+            gaps = np.diff(intervals_)
+            uniform = bool(gaps.min() == gaps.max())
+        if not uniform:
+            raise ValueError(f"Intervals must be contiguous: {set(np.unique(np.diff(intervals_)).tolist())}")
     step_ = intervals_[1] - intervals_[0]  # noqa: F841  (kept: the reference evaluates it, so len < 2 raises)
     output_file = f"rocco_{chromosome}.bed" if ID is None else f"rocco_{ID}_{chromosome}.bed"
     first, last = solution_runs(solution)
@@ -108,25 +113,38 @@ def chrom_solution_to_bed(chromosome, intervals, solution, ID=None, check_gaps_i
     return _write_bed_records(records, output_file)
 
 
-def _merge_bed_arrays(chrom: np.ndarray, start: np.ndarray, end: np.ndarray):
-    """Vectorised restatement of _merge_bed_records: sort by (chromosome string, start, end) and merge records with
-    start <= running end.  Returns (chrom, start, end) arrays of the merged records."""
+def _merge_bed_arrays(chrom_rank: np.ndarray, start: np.ndarray, end: np.ndarray):
+    """Vectorised restatement of _merge_bed_records on (chromosome rank, start, end) arrays: sort lexicographically
+    and merge records with start <= running end.  Returns the merged (rank, start, end)."""
     if len(start) == 0:
-        return chrom, start, end
-    names, inv = np.unique(chrom, return_inverse=True)             # np.unique sorts strings like Python's sorted()
-    order = np.lexsort((end, start, inv))
-    inv, start, end = inv[order], start[order], end[order]
-    out_c, out_s, out_e = [], [], []
-    bounds = np.flatnonzero(np.diff(inv)) + 1
-    for lo, hi in zip(np.concatenate(([0], bounds)), np.concatenate((bounds, [len(inv)]))):
-        s_, e_ = start[lo:hi], end[lo:hi]
-        run_end = np.maximum.accumulate(e_)
-        new_grp = np.concatenate(([True], s_[1:] > run_end[:-1]))   # a record starts a new interval iff start > previous end
-        first = np.flatnonzero(new_grp)
-        last = np.concatenate((first[1:] - 1, [len(s_) - 1]))
-        out_s.append(s_[first]); out_e.append(run_end[last])
-        out_c.append(np.full(len(first), names[inv[lo]], dtype=object))
-    return np.concatenate(out_c), np.concatenate(out_s), np.concatenate(out_e)
+        return chrom_rank, start, end
+    order = np.lexsort((end, start, chrom_rank))
+    rk, start, end = chrom_rank[order], start[order], end[order]
+    # running maximum of `end` restarted at every chromosome change: offset each chromosome by a stride larger than any coordinate
+    stride = np.int64(max(int(end.max()), 0) + 1)
+    shifted_end = end + rk.astype(np.int64) * stride
+    run_end = np.maximum.accumulate(shifted_end)
+    shifted_start = start + rk.astype(np.int64) * stride
+    new_grp = np.concatenate(([True], (shifted_start[1:] > run_end[:-1]) | (rk[1:] != rk[:-1])))
+    first = np.flatnonzero(new_grp)
+    last = np.concatenate((first[1:] - 1, [len(start) - 1]))
+    return rk[first], start[first], run_end[last] - rk[last].astype(np.int64) * stride
+
+
+def _read_bed_fast(bed_file: str):
+    """(chrom object array, start int64, end int64, saw_extra_columns) via the C parser; None when the file needs the
+    line-by-line reader (ragged rows, non-integer coordinates, ...)."""
+    import pandas as pd
+    try:
+        df = pd.read_csv(bed_file, sep="\t", header=None, dtype={0: str}, keep_default_na=False, na_values=[""],
+                         skip_blank_lines=True)
+    except pd.errors.EmptyDataError:
+        return np.zeros(0, dtype=object), np.zeros(0, np.int64), np.zeros(0, np.int64), False
+    except Exception:
+        return None
+    if df.shape[1] < 3 or df[1].dtype != np.int64 or df[2].dtype != np.int64:
+        return None
+    return df[0].to_numpy(dtype=object), df[1].to_numpy(), df[2].to_numpy(), df.shape[1] > 3
 
 
 def combine_chrom_results(chrom_bed_files: list, output_file: str, name_features: bool = False) -> str:
@@ -141,34 +159,36 @@ def combine_chrom_results(chrom_bed_files: list, output_file: str, name_features
             os.remove(output_file)
         except OSError:
             logger.info(f"Could not remove existing output file: {output_file}.")
-    frames = []
+    chroms, starts, ends = [], [], []
     for chrom_bed_file in chrom_bed_files:
         if not os.path.exists(chrom_bed_file):
             raise FileNotFoundError(f"File does not exist: {chrom_bed_file}")
-        if os.path.getsize(chrom_bed_file) == 0:
-            continue
-        try:
-            df = pd.read_csv(chrom_bed_file, sep="\t", header=None, dtype=str, keep_default_na=False, skip_blank_lines=True)
-        except pd.errors.EmptyDataError:
-            continue
-        except Exception as e:
-            logger.info(f"Could not read BED file: {chrom_bed_file}\n{e}\n")
-            raise
-        if df.shape[1] < 3 or (df.iloc[:, 2] == "").any():
-            bad = int(np.flatnonzero((df.iloc[:, 2] == "").to_numpy())[0]) + 1 if df.shape[1] >= 3 else 1
-            raise ValueError(f"BED row {bad} in {chrom_bed_file} has fewer than 3 columns.")
-        if df.shape[1] > 3 and not printed_colct_msg:
+        fast = _read_bed_fast(chrom_bed_file)
+        if fast is None:
+            try:
+                recs, saw_extra_columns = _read_bed_records(chrom_bed_file)      # the reference's reader (and its errors)
+            except Exception as e:
+                logger.info(f"Could not read BED file: {chrom_bed_file}\n{e}\n")
+                raise
+            c = np.array([r[0] for r in recs], dtype=object)
+            a = np.array([r[1] for r in recs], dtype=np.int64)
+            b = np.array([r[2] for r in recs], dtype=np.int64)
+        else:
+            c, a, b, saw_extra_columns = fast
+        if saw_extra_columns and not printed_colct_msg:
             logger.info("More than 3 columns detected in the input BED files. Extra columns will be ignored.")
             printed_colct_msg = True
-        frames.append(df.iloc[:, :3])
-    if frames:
-        allrec = pd.concat(frames, ignore_index=True)
-        chrom = allrec.iloc[:, 0].to_numpy(dtype=object)
-        start = allrec.iloc[:, 1].astype(np.int64).to_numpy()
-        end = allrec.iloc[:, 2].astype(np.int64).to_numpy()
-        chrom, start, end = _merge_bed_arrays(chrom, start, end)
-    else:
-        chrom, start, end = np.zeros(0, dtype=object), np.zeros(0, np.int64), np.zeros(0, np.int64)
+        chroms.append(c); starts.append(a); ends.append(b)
+    chrom = np.concatenate(chroms) if chroms else np.zeros(0, dtype=object)
+    start = np.concatenate(starts) if starts else np.zeros(0, np.int64)
+    end = np.concatenate(ends) if ends else np.zeros(0, np.int64)
+    if len(start):
+        codes, uniques = pd.factorize(chrom)
+        names = sorted(str(u) for u in uniques)                      # Python string order, as sorted() in the reference
+        rank_of = {nm: k for k, nm in enumerate(names)}
+        rank = np.array([rank_of[str(u)] for u in uniques], dtype=np.int64)[codes]
+        rk, start, end = _merge_bed_arrays(rank, start.astype(np.int64), end.astype(np.int64))
+        chrom = np.array(names, dtype=object)[rk]
     out = pd.DataFrame({"c": chrom, "s": start, "e": end})
     if name_features:
         out["n"] = out["c"].astype(str) + "_" + out["s"].astype(str) + "_" + out["e"].astype(str)
