@@ -39,7 +39,7 @@ constexpr int CAPX = 8192;              // pairs per x slot
 constexpr int CAPY = 8192;              // variances per (bin, k) slot
 constexpr int CHUNK = 131072;           // elements streamed per CTA
 constexpr int ST_THREADS = 512;
-int trend_fused_max_window() { return 2049; }
+int trend_fused_max_window() { return 1025; }
 
 __device__ __forceinline__ int xbucket(double x)
 {
@@ -120,10 +120,10 @@ __global__ void __launch_bounds__(ST_THREADS) k_xhist(const double *__restrict__
 // produces 8 consecutive variances (direct 31-term window sums for the first, sliding updates for the next 7 --
 // far less drift than the reference's whole-row slide), results go back through shared memory for coalesced
 // stores, and the same pass feeds the |C| histogram.  Replaces wls_backend.c:610-742 + the T1 pass.
-constexpr int RV_T = 2048;
+constexpr int RV_T = 8192;                   // bins per CTA iteration
 constexpr int RV_K = 8;
-constexpr int RV_THREADS = RV_T / RV_K;      // 256
-constexpr int RV_MAXW = 2049;
+constexpr int RV_THREADS = RV_T / RV_K;      // 1024: one CTA per SM, 32 warps (the 64 KB histogram is shared)
+constexpr int RV_MAXW = 1025;
 
 __host__ __device__ __forceinline__ int padpos(int i) { return i + (i >> 3); }
 

@@ -30,13 +30,14 @@
 namespace rb {
 namespace score {
 
-constexpr int WT_THREADS = 512;
-constexpr int WT_ITEMS = 24;                       // even: every thread chunk starts on the same index parity
-constexpr int WT_REGION = WT_THREADS * WT_ITEMS;   // 12288 bins solved per CTA
+constexpr int WT_REGION = 12288;                   // bins solved per CTA
 constexpr int WT_HALO = 1280;
 constexpr int WT_OUT = WT_REGION - 2 * WT_HALO;    // 9728 bins written per CTA
-constexpr int WT_PAD = WT_ITEMS + 1;
-constexpr int WT_LEVELS = 9;                       // log2(WT_THREADS)
+// two thread geometries over the same region: steady (interior) tiles use 1024 threads x 12 bins (32 warps per SM to
+// hide the FP64 dependency chains), edge tiles 512 x 24 (the general carry scan needs the extra shared memory)
+constexpr int WT_THREADS_S = 1024, WT_ITEMS_S = 12;
+constexpr int WT_THREADS_G = 512, WT_ITEMS_G = 24;
+constexpr int WT_LEVELS = 10;                      // log2(max threads)
 constexpr int HEAD_LEN = 4096;
 
 // ------------------------------------------------------------------ host: factor tables
@@ -75,7 +76,8 @@ struct FactorHost {
     std::vector<double> head[2][3];      // [parity][dinv,l1,l2][head_len]
     double steady[2][3][2];              // [parity][coef][index parity]
     double tail[2][3][4];                // rows n-4 .. n-1
-    double trans[2][2][WT_LEVELS + 1][4];  // [parity][fwd/bwd][level] 2x2 transition over ITEMS * 2^level bins
+    double trans[2][2][WT_LEVELS + 1][4];  // [parity][fwd/bwd][level] 2x2 transition over WT_ITEMS_S * 2^level bins
+    double lanepow[2][2][32][4];           // [parity][fwd/bwd][k] transition over (k+1) chunks: T^(k+1)
 };
 
 static void mat2_mul(const double *a, const double *b, double *c)   // c = a*b (row-major 2x2)
@@ -129,13 +131,13 @@ static void build_factor(long long n, double lam, FactorHost &F)
         // backward state (x[i], x[i+1]): x[i] = -l1[i] x[i+1] - l2[i] x[i+2]
         // chunks start on an even index (region starts are even), so index parity == position parity
         double Tf[4] = {1, 0, 0, 1}, Tb[4] = {1, 0, 0, 1};
-        for (int j = 0; j < WT_ITEMS; ++j) {                  // forward: j = position in chunk, index parity j&1
+        for (int j = 0; j < WT_ITEMS_S; ++j) {                // forward: j = position in chunk, index parity j&1
             const double c1 = F.steady[p][1][(j + 1) & 1];    // l1[i-1]
             const double c2 = F.steady[p][2][j & 1];          // l2[i-2]
             const double S[4] = {-c1, -c2, 1.0, 0.0};
             mat2_mul(S, Tf, Tf);
         }
-        for (int j = WT_ITEMS - 1; j >= 0; --j) {             // backward
+        for (int j = WT_ITEMS_S - 1; j >= 0; --j) {           // backward
             const double c1 = F.steady[p][1][j & 1], c2 = F.steady[p][2][j & 1];
             const double S[4] = {-c1, -c2, 1.0, 0.0};
             mat2_mul(S, Tb, Tb);
@@ -144,6 +146,13 @@ static void build_factor(long long n, double lam, FactorHost &F)
         for (int l = 1; l <= WT_LEVELS; ++l) {
             mat2_mul(F.trans[p][0][l - 1], F.trans[p][0][l - 1], F.trans[p][0][l]);
             mat2_mul(F.trans[p][1][l - 1], F.trans[p][1][l - 1], F.trans[p][1][l]);
+        }
+        for (int dct = 0; dct < 2; ++dct) {
+            double acc[4] = {1, 0, 0, 1};
+            for (int k = 0; k < 32; ++k) {
+                mat2_mul(F.trans[p][dct][0], acc, acc);
+                for (int q = 0; q < 4; ++q) F.lanepow[p][dct][k][q] = acc[q];
+            }
         }
     }
 }
@@ -158,6 +167,7 @@ struct WhitParams {
     double steady[2][3][2];
     double tail[2][3][4];
     double trans[2][2][WT_LEVELS + 1][4];
+    const double *lanepow;      // device copy of FactorHost::lanepow, [parity][dir][32][4]
     long long n;
     long long row_stride;       // elements between rows of x / out
     int head_len;
@@ -189,58 +199,62 @@ __device__ __forceinline__ double coef(const WhitParams &P, int p, int k, long l
     return P.steady[p][k][i & 1];
 }
 
-// Kogge-Stone carry scan for the uniform (steady) case: state_t = r_{t-1} + T r_{t-2} + T^2 r_{t-3} + ...
+// Carry scan for the uniform (steady) case: state_t = r_t + T r_{t-1} + T^2 r_{t-2} + ...
 // `v` holds the chunk's zero-state end vector on entry, the inclusive carry on exit.
-__device__ __forceinline__ void carry_scan_uniform(double &v0, double &v1, const double (*T)[4], bool reverse,
-                                                   double2 *s_warp /* [16] */)
+//   1. Kogge-Stone inside each warp with T^(2^l);  2. warp 0 scans the warp totals with T^(32 * 2^l);
+//   3. every lane adds T^(lane+1) applied to the state entering its warp (table `lp`, staged in shared memory).
+template <int THREADS>
+__device__ __forceinline__ void carry_scan_uniform(double &v0, double &v1, const double (*T)[4], const double *lp /* [32][4] */,
+                                                   bool reverse, double2 *s_warp /* [THREADS/32] */)
 {
+    constexpr int NW = THREADS / 32;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int lpos = reverse ? 31 - lane : lane;
 #pragma unroll
     for (int l = 0; l < 5; ++l) {
         const int dlt = 1 << l;
-        double o0 = reverse ? __shfl_down_sync(0xffffffffu, v0, dlt) : __shfl_up_sync(0xffffffffu, v0, dlt);
-        double o1 = reverse ? __shfl_down_sync(0xffffffffu, v1, dlt) : __shfl_up_sync(0xffffffffu, v1, dlt);
+        const double o0 = reverse ? __shfl_down_sync(0xffffffffu, v0, dlt) : __shfl_up_sync(0xffffffffu, v0, dlt);
+        const double o1 = reverse ? __shfl_down_sync(0xffffffffu, v1, dlt) : __shfl_up_sync(0xffffffffu, v1, dlt);
         if (lpos >= dlt) {
             v0 += T[l][0] * o0 + T[l][1] * o1;
             v1 += T[l][2] * o0 + T[l][3] * o1;
         }
     }
-    // cross-warp: 16 warps, serial over warp totals with T^(32) = level 5
-    if (lpos == 31) s_warp[wid] = make_double2(v0, v1);
+    const int wpos = reverse ? NW - 1 - wid : wid;            // position of this warp in scan order
+    if (lpos == 31) s_warp[wpos] = make_double2(v0, v1);
     __syncthreads();
-    const int nw = WT_THREADS / 32;
-    const int wpos = reverse ? nw - 1 - wid : wid;
-    // prefix over previous warps (in scan order): acc = sum_k T32^(k) total_{prev k}
-    double a0 = 0.0, a1 = 0.0;
-    for (int k = 0; k < wpos; ++k) {                 // oldest first: acc = T32*acc + total_k
-        const int w = reverse ? nw - 1 - k : k;
-        const double2 t = s_warp[w];
-        const double n0 = T[5][0] * a0 + T[5][1] * a1 + t.x;
-        const double n1 = T[5][2] * a0 + T[5][3] * a1 + t.y;
-        a0 = n0; a1 = n1;
-    }
-    // carry into lane: T^(lpos+1 chunks) applied to acc: use binary decomposition of (lpos+1)
-    {
-        double b0 = a0, b1 = a1;
-        const int steps = lpos + 1;
+    if (wid == 0) {
+        double a0 = 0.0, a1 = 0.0;
+        if (lane < NW) { const double2 t = s_warp[lane]; a0 = t.x; a1 = t.y; }
 #pragma unroll
-        for (int l = 0; l < 6; ++l) {
-            if (steps & (1 << l)) {
-                const double n0 = T[l][0] * b0 + T[l][1] * b1;
-                const double n1 = T[l][2] * b0 + T[l][3] * b1;
-                b0 = n0; b1 = n1;
+        for (int l = 0; (1 << l) < NW; ++l) {
+            const int dlt = 1 << l;
+            const double o0 = __shfl_up_sync(0xffffffffu, a0, dlt), o1 = __shfl_up_sync(0xffffffffu, a1, dlt);
+            if (lane >= dlt) {
+                a0 += T[5 + l][0] * o0 + T[5 + l][1] * o1;
+                a1 += T[5 + l][2] * o0 + T[5 + l][3] * o1;
             }
         }
-        v0 += b0; v1 += b1;
+        // exclusive: the state entering warp w is the inclusive value of warp w-1
+        const double e0 = __shfl_up_sync(0xffffffffu, a0, 1), e1 = __shfl_up_sync(0xffffffffu, a1, 1);
+        if (lane < NW) s_warp[lane] = (lane == 0) ? make_double2(0.0, 0.0) : make_double2(e0, e1);
+    }
+    __syncthreads();
+    {
+        const double2 e = s_warp[wpos];
+        const double *m = lp + lpos * 4;
+        v0 += m[0] * e.x + m[1] * e.y;
+        v1 += m[2] * e.x + m[3] * e.y;
     }
     __syncthreads();
 }
 
 // General carry scan (chunks with their own transition matrices: first / last tile of a row).
+template <int THREADS>
 __device__ __forceinline__ void carry_scan_general(double &v0, double &v1, double m00, double m01, double m10, double m11,
-                                                   bool reverse, double *s_buf /* [6 * WT_THREADS] */)
+                                                   bool reverse, double *s_buf /* [6 * THREADS] */)
 {
+    constexpr int WT_THREADS = THREADS;
     // plain Hillis-Steele in shared memory over (M, v) affine maps; x -> M x + v
     const int t = threadIdx.x;
     const int pos = reverse ? WT_THREADS - 1 - t : t;
@@ -268,13 +282,18 @@ __device__ __forceinline__ void carry_scan_general(double &v0, double &v1, doubl
     }
 }
 
-template <bool STEADY>
+template <bool STEADY, int WT_THREADS, int WT_ITEMS>
 __global__ void __launch_bounds__(WT_THREADS, 1) k_whittaker(WhitParams P)
 {
+    constexpr int WT_PAD = WT_ITEMS + 1;
     extern __shared__ double smem[];
     double *s_f0 = smem;                             // WT_THREADS * WT_PAD
     double *s_f1 = smem + WT_THREADS * WT_PAD;
     __shared__ double2 s_warp[WT_THREADS / 32];
+    __shared__ double s_lp[STEADY ? 4 * 32 * 4 : 1];  // T^(k+1) tables: [parity][dir][32][4]
+    if (STEADY) {
+        for (int k = threadIdx.x; k < 4 * 32 * 4; k += WT_THREADS) s_lp[k] = P.lanepow[k];
+    }
 
     const int tid = threadIdx.x;
     const long long row = blockIdx.x / P.span_tiles;
@@ -353,12 +372,12 @@ __global__ void __launch_bounds__(WT_THREADS, 1) k_whittaker(WhitParams P)
     // carry: state entering chunk t = inclusive scan value of chunk t-1
     double in00, in01, in10, in11;
     if (STEADY) {
-        carry_scan_uniform(e00, e01, P.trans[0][0], false, s_warp);
-        carry_scan_uniform(e10, e11, P.trans[1][0], false, s_warp);
+        carry_scan_uniform<WT_THREADS>(e00, e01, P.trans[0][0], s_lp + (0 * 2 + 0) * 128, false, s_warp);
+        carry_scan_uniform<WT_THREADS>(e10, e11, P.trans[1][0], s_lp + (1 * 2 + 0) * 128, false, s_warp);
     } else {
         double *s_buf = reinterpret_cast<double *>(smem + 2 * WT_THREADS * WT_PAD);
-        carry_scan_general(e00, e01, ha[0][0], ha[0][1], ha[0][2], ha[0][3], false, s_buf);
-        carry_scan_general(e10, e11, ha[1][0], ha[1][1], ha[1][2], ha[1][3], false, s_buf);
+        carry_scan_general<WT_THREADS>(e00, e01, ha[0][0], ha[0][1], ha[0][2], ha[0][3], false, s_buf);
+        carry_scan_general<WT_THREADS>(e10, e11, ha[1][0], ha[1][1], ha[1][2], ha[1][3], false, s_buf);
     }
     in00 = __shfl_up_sync(0xffffffffu, e00, 1); in01 = __shfl_up_sync(0xffffffffu, e01, 1);
     in10 = __shfl_up_sync(0xffffffffu, e10, 1); in11 = __shfl_up_sync(0xffffffffu, e11, 1);
@@ -423,12 +442,12 @@ __global__ void __launch_bounds__(WT_THREADS, 1) k_whittaker(WhitParams P)
         e00 = a1; e01 = a2; e10 = b1; e11 = b2;
     }
     if (STEADY) {
-        carry_scan_uniform(e00, e01, P.trans[0][1], true, s_warp);
-        carry_scan_uniform(e10, e11, P.trans[1][1], true, s_warp);
+        carry_scan_uniform<WT_THREADS>(e00, e01, P.trans[0][1], s_lp + (0 * 2 + 1) * 128, true, s_warp);
+        carry_scan_uniform<WT_THREADS>(e10, e11, P.trans[1][1], s_lp + (1 * 2 + 1) * 128, true, s_warp);
     } else {
         double *s_buf = reinterpret_cast<double *>(smem + 2 * WT_THREADS * WT_PAD);
-        carry_scan_general(e00, e01, ha[0][0], ha[0][1], ha[0][2], ha[0][3], true, s_buf);
-        carry_scan_general(e10, e11, ha[1][0], ha[1][1], ha[1][2], ha[1][3], true, s_buf);
+        carry_scan_general<WT_THREADS>(e00, e01, ha[0][0], ha[0][1], ha[0][2], ha[0][3], true, s_buf);
+        carry_scan_general<WT_THREADS>(e10, e11, ha[1][0], ha[1][1], ha[1][2], ha[1][3], true, s_buf);
     }
     in00 = __shfl_down_sync(0xffffffffu, e00, 1); in01 = __shfl_down_sync(0xffffffffu, e01, 1);
     in10 = __shfl_down_sync(0xffffffffu, e10, 1); in11 = __shfl_down_sync(0xffffffffu, e11, 1);
@@ -494,6 +513,7 @@ __global__ void k_small_rows(WhitParams P)
 struct FactorDev {
     FactorHost host;
     double *d_head[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+    double *d_lanepow = nullptr;
 };
 static std::mutex g_fmutex;
 static std::map<std::pair<long long, double>, FactorDev *> g_fcache[16];
@@ -515,8 +535,10 @@ static int get_factor(long long n, double lam, FactorDev **out)
             RB_CUDA(cudaMalloc(&F->d_head[p][k], sizeof(double) * std::max(1, F->host.head_len)));
             RB_CUDA(cudaMemcpy(F->d_head[p][k], F->host.head[p][k].data(), sizeof(double) * F->host.head_len, cudaMemcpyHostToDevice));
         }
+    RB_CUDA(cudaMalloc(&F->d_lanepow, sizeof(F->host.lanepow)));
+    RB_CUDA(cudaMemcpy(F->d_lanepow, F->host.lanepow, sizeof(F->host.lanepow), cudaMemcpyHostToDevice));
     if (cache.size() > 256) {                        // bounded: drop everything (tables are tiny)
-        for (auto &kv : cache) { for (int p = 0; p < 2; ++p) for (int k = 0; k < 3; ++k) cudaFree(kv.second->d_head[p][k]); delete kv.second; }
+        for (auto &kv : cache) { for (int p = 0; p < 2; ++p) for (int k = 0; k < 3; ++k) cudaFree(kv.second->d_head[p][k]); cudaFree(kv.second->d_lanepow); delete kv.second; }
         cache.clear();
     }
     cache[key] = F;
@@ -546,15 +568,16 @@ int whittaker_rows(const void *d_x, int in_f32, int log_transform, const double 
     memcpy(P.steady, F->host.steady, sizeof(P.steady));
     memcpy(P.tail, F->host.tail, sizeof(P.tail));
     memcpy(P.trans, F->host.trans, sizeof(P.trans));
+    P.lanepow = F->d_lanepow;
     P.tiles_per_row = (int)((n + WT_OUT - 1) / WT_OUT);
     // Interior tiles (region inside [head_len, n-4)) take the steady instantiation; the first and last
     // tile(s) of each row take the general one.  Two launches over disjoint tile sets.
-    const size_t sm_steady = sizeof(double) * 2 * WT_THREADS * WT_PAD;
-    const size_t sm_general = sm_steady + sizeof(double) * 6 * WT_THREADS;
+    const size_t sm_steady = sizeof(double) * 2 * WT_THREADS_S * (WT_ITEMS_S + 1);
+    const size_t sm_general = sizeof(double) * 2 * WT_THREADS_G * (WT_ITEMS_G + 1) + sizeof(double) * 6 * WT_THREADS_G;
     static bool attr = false;
     if (!attr) {
-        RB_CUDA(cudaFuncSetAttribute(k_whittaker<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_steady));
-        RB_CUDA(cudaFuncSetAttribute(k_whittaker<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_general));
+        RB_CUDA(cudaFuncSetAttribute(k_whittaker<true, WT_THREADS_S, WT_ITEMS_S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_steady));
+        RB_CUDA(cudaFuncSetAttribute(k_whittaker<false, WT_THREADS_G, WT_ITEMS_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_general));
         attr = true;
     }
     // classify tiles
@@ -584,8 +607,8 @@ int whittaker_rows(const void *d_x, int in_f32, int log_transform, const double 
         // algorithmic bytes of this launch: read the input once, write the centered matrix once
         const double span_bins = (double)std::min<long long>(n, (long long)sp.t1 * WT_OUT) - (double)sp.t0 * WT_OUT;
         RB_PROF(sp.steady ? "k_whittaker_steady" : "k_whittaker_edge", st, (double)rows * span_bins * ((in_f32 ? 4.0 : 8.0) + 8.0));
-        if (sp.steady) k_whittaker<true><<<(unsigned)blocks, WT_THREADS, sm_steady, st>>>(Q);
-        else k_whittaker<false><<<(unsigned)blocks, WT_THREADS, sm_general, st>>>(Q);
+        if (sp.steady) k_whittaker<true, WT_THREADS_S, WT_ITEMS_S><<<(unsigned)blocks, WT_THREADS_S, sm_steady, st>>>(Q);
+        else k_whittaker<false, WT_THREADS_G, WT_ITEMS_G><<<(unsigned)blocks, WT_THREADS_G, sm_general, st>>>(Q);
         RB_LAUNCH_CHECK();
     }
     return 0;

@@ -293,9 +293,9 @@ __device__ __forceinline__ double interp_knots(const double *kx, const double *k
 }
 
 constexpr int CB_THREADS = 256;
-constexpr int CB_ROWS_SMEM = 48;          // knot tables staged per batch of sample rows
+constexpr int CB_ROWS_SMEM = 25;          // knot tables staged per batch of sample rows
 
-__global__ void __launch_bounds__(CB_THREADS) k_combine(CombineParams P)
+__global__ void __launch_bounds__(CB_THREADS, 4) k_combine(CombineParams P)
 {
     __shared__ double s_kx[CB_ROWS_SMEM][32], s_ky[CB_ROWS_SMEM][32], s_kr[CB_ROWS_SMEM][32];
     __shared__ int s_nk[CB_ROWS_SMEM];
