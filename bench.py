@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--chroms", default="all", help="comma list (debug); default = all 24 hg38 chromosomes")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"], help="dtype of the resident count matrices")
     ap.add_argument("--e2e-steps", type=int, default=-1, help="-1: min(steps, 2); 0 disables the e2e leg")
+    ap.add_argument("--score-streams", type=int, default=1, help="host threads / CUDA streams scoring chromosomes concurrently")
     ap.add_argument("--e2e-threads", type=int, default=2, help="host threads driving chromosomes through the public API")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-bins", type=int, default=250_000)
@@ -222,7 +223,8 @@ def main():
     def step():
         if not mine:
             return None
-        shard = pipeline.run_shard(d_mats, budgets, gammas, params=params, levels_per_round=args.levels)
+        shard = pipeline.run_shard(d_mats, budgets, gammas, params=params, levels_per_round=args.levels,
+                                   score_streams=args.score_streams)
         text = pipeline.runs_to_bed_text(my_names, shard["runs"], args.step_bp)
         with open(os.path.join(tmpdir, "shard.bed"), "w") as fh:
             fh.write(text)
@@ -362,7 +364,7 @@ def main():
             "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": workload_name(args, names), "genome_bins": genome_bins, "samples": args.samples,
-                       "chromosomes": len(names), "sharding": f"chromosomes LPT-packed over {world} rank(s)",
+                       "chromosomes": len(names), "sharding": f"chromosomes LPT-packed over {world} rank(s)", "score_streams": args.score_streams,
                        "l2_policy": "inputs larger than L2 (per-chromosome matrices 0.7-4 GB vs 126 MB L2)",
                        "selected_bins": selected_total,
                        "selected_by_chrom": {c: by_chrom[c][0] for c in names if c in by_chrom},

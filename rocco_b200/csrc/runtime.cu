@@ -81,13 +81,35 @@ HostScope::~HostScope()
 
 cudaStream_t host_stream() { return nullptr; }      // legacy default stream (kept for callers without a lease)
 
+// Every stream the library is called on gets its own memory pool (up to 16 caller streams; the legacy default
+// stream keeps the device's default pool): scratch freed on one stream is then never recycled into another
+// stream, which would chain the two streams together through the allocator's internal dependencies and
+// serialise callers that drive different chromosomes from different host threads.
+static std::vector<HostCtx> g_user_ctx;
+
 cudaMemPool_t pool_for_stream(cudaStream_t s)
 {
     if (s == nullptr) return nullptr;
+    int dev = 0;
+    cudaGetDevice(&dev);
     std::lock_guard<std::mutex> lk(g_ctx_mu);
     for (const HostCtx &c : g_ctx)
         if (c.st == s) return c.pool;
-    return nullptr;
+    for (const HostCtx &c : g_user_ctx)
+        if (c.st == s && c.dev == dev) return c.pool;
+    if (g_user_ctx.size() >= 16) return nullptr;
+    HostCtx c{dev, s, nullptr, true};
+    cudaMemPoolProps props{};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    if (cudaMemPoolCreate(&c.pool, &props) == cudaSuccess) {
+        unsigned long long thr = ~0ULL;
+        cudaMemPoolSetAttribute(c.pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    } else { (void)cudaGetLastError(); c.pool = nullptr; }
+    g_user_ctx.push_back(c);
+    return c.pool;
 }
 
 int sm_count()

@@ -24,6 +24,8 @@
 
 #include <math.h>
 
+#include <algorithm>
+
 namespace rb {
 namespace score {
 
@@ -389,14 +391,19 @@ __global__ void __launch_bounds__(ST_THREADS) k_xcollect(const double *__restric
 // ------------------------------------------------------------------ T4
 __device__ __forceinline__ bool pair_gt(const double2 &a, const double2 &b) { return a.x > b.x || (a.x == b.x && a.y > b.y); }
 
-__global__ void __launch_bounds__(ST_THREADS) k_xresolve(TrendBuffers T, long long n, int B)
+// Two tiers over the same slots: <256 threads, slots of <= 2048 pairs> (32 KB of shared memory, several CTAs per SM --
+// almost every slot) and <512 threads, up to CAPX pairs> for the rare large ones; a CTA exits if the slot is not its tier.
+template <int THREADS, int CAP_LO, int CAP_HI>
+__global__ void __launch_bounds__(THREADS, (THREADS == 256) ? 4 : 1) k_xresolve(TrendBuffers T, long long n, int B)
 {
+    constexpr int ST_THREADS = THREADS;
     extern __shared__ double2 s_p[];
     const long long row = blockIdx.y;
     const int s = blockIdx.x;
     RowPlan &P = T.plan[row];
     if (P.fallback || s >= P.nslot) return;
     const int cnt = min(T.cand_cnt[row * MAXSLOT + s], CAPX);
+    if (P.slot_count[s] <= CAP_LO || P.slot_count[s] > CAP_HI) return;          // not this tier
     if (cnt != P.slot_count[s]) { if (threadIdx.x == 0) atomicOr(&P.fallback, FB_XCOUNT); return; }
     int len = 1;
     while (len < cnt) len <<= 1;
@@ -671,7 +678,7 @@ int trend_knots_select(const double *d_C, double *d_V, long long m, long long n,
     if (!attr) {
         RB_CUDA(cudaFuncSetAttribute(k_xhist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_xhist));
         RB_CUDA(cudaFuncSetAttribute(k_xcollect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(int) * MAXB * NBY + 2 * NBX)));
-        RB_CUDA(cudaFuncSetAttribute(k_xresolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_resolve));
+        RB_CUDA(cudaFuncSetAttribute(k_xresolve<512, 2048, CAPX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_resolve));
         RB_CUDA(cudaFuncSetAttribute(k_xplan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_plan));
         RB_CUDA(cudaFuncSetAttribute(k_yresolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * CAPY)));
         attr = true;
@@ -708,7 +715,10 @@ int trend_knots_select(const double *d_C, double *d_V, long long m, long long n,
     }
     {
         RB_PROF("trend_plan_resolve", st, 0.0);
-        k_xresolve<<<dim3(MAXSLOT, (unsigned)m), ST_THREADS, sm_resolve, st>>>(T, n, B);
+        const unsigned nslot_max = (unsigned)std::min(MAXSLOT, 3 * B);
+        k_xresolve<256, -1, 2048><<<dim3(nslot_max, (unsigned)m), 256, sizeof(double2) * 2048, st>>>(T, n, B);
+        RB_LAUNCH_CHECK();
+        k_xresolve<512, 2048, CAPX><<<dim3(nslot_max, (unsigned)m), 512, sm_resolve, st>>>(T, n, B);
         RB_LAUNCH_CHECK();
         k_yplan<<<dim3((unsigned)B, (unsigned)m), 256, 0, st>>>(T, n, B);
         RB_LAUNCH_CHECK();

@@ -64,15 +64,18 @@ def chrom_matrix_torch(n_samples: int, n_bins: int, seed: int, device, dtype=Non
     g.manual_seed(int(seed))
     conc = torch.full((n_bins,), 0.6, device=device, dtype=torch.float32)
     rate = torch._standard_gamma(conc, generator=g)
+    # planted peaks: drawn and accumulated on the host (float atomics on the device would make the rates, and
+    # through them the Poisson draws, differ from run to run), then prefix-summed
     n_peaks = int(math.ceil(n_bins / 500))
-    starts = torch.randint(0, max(n_bins, 1), (n_peaks,), device=device, generator=g)
-    widths = torch.randint(4, 30, (n_peaks,), device=device, generator=g)
-    heights = torch.empty(n_peaks, device=device).uniform_(5.0, 40.0, generator=g)
-    # scatter +h at start, -h at start+width, prefix-sum -> planted peaks
-    delta = torch.zeros(n_bins + 32, device=device, dtype=torch.float32)
-    delta.index_add_(0, starts, heights)
-    delta.index_add_(0, starts + widths, -heights)
-    rate = rate + torch.cumsum(delta, 0)[:n_bins].clamp_(min=0.0)
+    prng = np.random.default_rng(int(seed) + 7919)
+    starts = prng.integers(0, max(n_bins, 1), size=n_peaks)
+    widths = prng.integers(4, 30, size=n_peaks)
+    heights = prng.uniform(5.0, 40.0, size=n_peaks)
+    delta_h = np.zeros(n_bins + 32, dtype=np.float64)
+    np.add.at(delta_h, starts, heights)
+    np.add.at(delta_h, starts + widths, -heights)
+    peaks = np.clip(np.cumsum(delta_h)[:n_bins], 0.0, None).astype(np.float32)
+    rate = rate + torch.from_numpy(peaks).to(device)
     depth = torch.empty((n_samples, 1), device=device).uniform_(0.5, 1.5, generator=g)
     norm = torch.empty((n_samples, 1), device=device).uniform_(0.2, 0.5, generator=g)
     out = torch.empty((n_samples, n_bins), device=device, dtype=dtype)
