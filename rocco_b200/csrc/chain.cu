@@ -159,7 +159,7 @@ struct Params {
 
 // ------------------------------------------------------------------ the tile kernel
 template <typename V, bool VEC_COST, bool EMIT>
-__global__ void __launch_bounds__(THREADS) k_chain_tiles(Params P)
+__global__ void __launch_bounds__(THREADS, 4) k_chain_tiles(Params P)
 {
     extern __shared__ double smem[];
     double *s_sc = smem;                               // TILE + THREADS (padded)

@@ -335,7 +335,8 @@ __global__ void __launch_bounds__(256) k_xplan(TrendBuffers T, const double *__r
 }
 
 // ------------------------------------------------------------------ T3
-__global__ void __launch_bounds__(ST_THREADS) k_xcollect(const double *__restrict__ C, const double *__restrict__ V, long long n,
+constexpr int XC_THREADS = 1024;          // one CTA per SM (160 KB of histograms + LUTs): 32 warps hide the LUT/atomic chain
+__global__ void __launch_bounds__(XC_THREADS) k_xcollect(const double *__restrict__ C, const double *__restrict__ V, long long n,
                                                          long long row_stride, TrendBuffers T, int B)
 {
     extern __shared__ int s_raw[];
@@ -345,8 +346,8 @@ __global__ void __launch_bounds__(ST_THREADS) k_xcollect(const double *__restric
     const long long row = blockIdx.y;
     if (T.plan[row].fallback) return;
     const long long c0 = (long long)blockIdx.x * CHUNK, c1 = min(n, c0 + CHUNK);
-    for (int k = threadIdx.x; k < B * NBY; k += ST_THREADS) s_yh[k] = 0;
-    for (int k = threadIdx.x; k < NBX / 4; k += ST_THREADS) {
+    for (int k = threadIdx.x; k < B * NBY; k += XC_THREADS) s_yh[k] = 0;
+    for (int k = threadIdx.x; k < NBX / 4; k += XC_THREADS) {
         reinterpret_cast<unsigned *>(s_lut)[k] = reinterpret_cast<const unsigned *>(T.lut + row * NBX)[k];
         reinterpret_cast<unsigned *>(s_bin)[k] = reinterpret_cast<const unsigned *>(T.binlo + row * NBX)[k];
     }
@@ -357,11 +358,11 @@ __global__ void __launch_bounds__(ST_THREADS) k_xcollect(const double *__restric
     const RowPlan &P = T.plan[row];
     const int yb0 = P.yb0;
     // four independent loads in flight per thread before the dependent LUT / atomic chain
-    for (long long jb = c0; jb < c1; jb += 4 * ST_THREADS) {
+    for (long long jb = c0; jb < c1; jb += 4 * XC_THREADS) {
         double xs[4], ys[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const long long j = jb + u * ST_THREADS + threadIdx.x;
+            const long long j = jb + u * XC_THREADS + threadIdx.x;
             xs[u] = (j < c1) ? fabs(c[j]) : -1.0;
             ys[u] = (j < c1) ? v[j] : 0.0;
         }
@@ -382,7 +383,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_xcollect(const double *__restric
     }
     __syncthreads();
     int *g = T.yhist + (size_t)row * MAXB * NBY;
-    for (int k = threadIdx.x; k < B * NBY; k += ST_THREADS) {
+    for (int k = threadIdx.x; k < B * NBY; k += XC_THREADS) {
         const int val = s_yh[k];
         if (val) atomicAdd(&g[k], val);
     }
@@ -710,7 +711,7 @@ int trend_knots_select(const double *d_C, double *d_V, long long m, long long n,
     }
     {
         RB_PROF("trend_xcollect", st, (double)m * n * 16.0);
-        k_xcollect<<<gstream, ST_THREADS, sm_collect, st>>>(d_C, d_V, n, row_stride, T, B);
+        k_xcollect<<<gstream, XC_THREADS, sm_collect, st>>>(d_C, d_V, n, row_stride, T, B);
         RB_LAUNCH_CHECK();
     }
     {
