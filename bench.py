@@ -225,9 +225,7 @@ def main():
             return None
         shard = pipeline.run_shard(d_mats, budgets, gammas, params=params, levels_per_round=args.levels,
                                    score_streams=args.score_streams)
-        text = pipeline.runs_to_bed_text(my_names, shard["runs"], args.step_bp)
-        with open(os.path.join(tmpdir, "shard.bed"), "w") as fh:
-            fh.write(text)
+        pipeline.runs_to_bed_file(os.path.join(tmpdir, "shard.bed"), my_names, shard["runs"], args.step_bp)
         # the one cross-GPU exchange of the path: genome-wide selected-bin count (reporting only)
         count_buf[0] = sum(r["selected_count"] for r in shard["results"])
         count_buf[1] = sum(my_bins)

@@ -153,6 +153,10 @@ long long rocco_b200_mask_to_runs_batch_dev(
 
 /* numpy.sum of a float64 vector / of n copies of one value, restated bit-exactly (host helpers:
  * dp.py:110-111 builds the search bracket from numpy.sum(switch_costs)). */
+/* Host helper: write n BED3 records (BED4 with chrom_start_end names when name_features != 0) to `path`
+ * (rocco.py:98-110 _write_bed_records).  Record i uses names[name_idx[i]] (name_idx == NULL: names[0]). */
+int rocco_b200_write_bed3(const char *path, const char *const *names, int n_names, const int *name_idx,
+                          const long long *starts, const long long *ends, size_t n, int name_features);
 int rocco_b200_uniform_step_i64(const long long *values, size_t n);   /* 1 iff all consecutive differences are equal */
 double rocco_b200_numpy_sum_f64(const double *values, size_t n);
 double rocco_b200_numpy_sum_const_f64(double value, size_t n);

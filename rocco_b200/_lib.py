@@ -65,6 +65,7 @@ def _declare(lib):
         "rocco_b200_profile_enable": (c_int, [c_int]),
         "rocco_b200_profile_report": (c_int, [c_char_p, c_size_t]),
         "rocco_b200_uniform_step_i64": (c_int, [c_void_p, c_size_t]),
+        "rocco_b200_write_bed3": (c_int, [c_char_p, POINTER(c_char_p), c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int]),
         "rocco_b200_numpy_sum_f64": (c_double, [c_void_p, c_size_t]),
         "rocco_b200_numpy_sum_const_f64": (c_double, [c_double, c_size_t]),
         "rocco_solve_penalized_chain_f64": (c_int, [c_void_p, c_void_p, c_size_t, c_double, c_void_p, dp, llp]),
@@ -172,3 +173,17 @@ def profile_report() -> dict:
         name, ms, cnt, nbytes = line.split()
         out[name] = (float(ms), int(cnt), float(nbytes))
     return out
+
+
+def write_bed_arrays(path: str, names, name_idx, starts: np.ndarray, ends: np.ndarray, name_features: bool = False) -> str:
+    """BED3/BED4 text of (names[name_idx[i]], starts[i], ends[i]) written by the native formatter."""
+    lib = load()
+    starts = np.ascontiguousarray(starts, dtype=np.int64)
+    ends = np.ascontiguousarray(ends, dtype=np.int64)
+    arr = (c_char_p * len(names))(*[str(x).encode("utf-8") for x in names])
+    idx = None if name_idx is None else np.ascontiguousarray(name_idx, dtype=np.int32)
+    st = lib.rocco_b200_write_bed3(str(path).encode("utf-8"), arr, len(names), None if idx is None else np_ptr(idx),
+                                   np_ptr(starts), np_ptr(ends), len(starts), 1 if name_features else 0)
+    if st != 0:
+        raise OSError(f"could not write BED file {path}: {last_error()}")
+    return path

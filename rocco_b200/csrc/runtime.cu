@@ -3,6 +3,7 @@
 
 #include <stdarg.h>
 
+#include <algorithm>
 #include <map>
 #include <mutex>
 
@@ -269,6 +270,54 @@ RB_API int rocco_b200_uniform_step_i64(const long long *v, size_t n)
     int ok = 1;
     for (size_t i = 2; i < n; ++i) ok &= ((v[i] - v[i - 1]) == step);
     return ok;
+}
+
+/* BED3 (or BED4 with chrom_start_end names) text of n records straight to a file: the host half of rocco.py:98-110
+ * (_write_bed_records) without a Python loop per record.  names[name_idx[i]] (name_idx == NULL: names[0]). */
+static inline char *put_ll(char *p, long long v)
+{
+    char tmp[24];
+    int k = 0;
+    unsigned long long u = v < 0 ? (unsigned long long)(-(v + 1)) + 1ULL : (unsigned long long)v;
+    if (v < 0) *p++ = '-';
+    do { tmp[k++] = (char)('0' + (u % 10)); u /= 10; } while (u);
+    while (k) *p++ = tmp[--k];
+    return p;
+}
+
+RB_API int rocco_b200_write_bed3(const char *path, const char *const *names, int n_names, const int *name_idx,
+                                 const long long *starts, const long long *ends, size_t n, int name_features)
+{
+    if (!path || !names || n_names <= 0 || (n && (!starts || !ends))) return rb::ST_INVALID;
+    FILE *fh = fopen(path, "wb");
+    if (!fh) { rb::set_error("cannot open %s for writing", path); return rb::ST_INVALID; }
+    std::vector<size_t> len((size_t)n_names);
+    size_t maxlen = 0;
+    for (int k = 0; k < n_names; ++k) { len[k] = strlen(names[k]); maxlen = std::max(maxlen, len[k]); }
+    const size_t per = 2 * maxlen + 4 * 21 + 8;
+    const size_t chunk = 1 << 16;
+    std::vector<char> buf(per * chunk);
+    for (size_t i0 = 0; i0 < n; i0 += chunk) {
+        char *p = buf.data();
+        const size_t i1 = std::min(n, i0 + chunk);
+        for (size_t i = i0; i < i1; ++i) {
+            const int c = name_idx ? name_idx[i] : 0;
+            if (c < 0 || c >= n_names) { fclose(fh); return rb::ST_INVALID; }
+            memcpy(p, names[c], len[c]); p += len[c];
+            *p++ = '\t'; p = put_ll(p, starts[i]);
+            *p++ = '\t'; p = put_ll(p, ends[i]);
+            if (name_features) {
+                *p++ = '\t';
+                memcpy(p, names[c], len[c]); p += len[c];
+                *p++ = '_'; p = put_ll(p, starts[i]);
+                *p++ = '_'; p = put_ll(p, ends[i]);
+            }
+            *p++ = '\n';
+        }
+        if (fwrite(buf.data(), 1, (size_t)(p - buf.data()), fh) != (size_t)(p - buf.data())) { fclose(fh); return rb::ST_INVALID; }
+    }
+    fclose(fh);
+    return 0;
 }
 
 RB_API double rocco_b200_numpy_sum_f64(const double *a, size_t n) { return rb::numpy_sum_f64(a, n); }

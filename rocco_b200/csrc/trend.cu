@@ -395,7 +395,7 @@ __device__ __forceinline__ bool pair_gt(const double2 &a, const double2 &b) { re
 // Two tiers over the same slots: <256 threads, slots of <= 2048 pairs> (32 KB of shared memory, several CTAs per SM --
 // almost every slot) and <512 threads, up to CAPX pairs> for the rare large ones; a CTA exits if the slot is not its tier.
 template <int THREADS, int CAP_LO, int CAP_HI>
-__global__ void __launch_bounds__(THREADS, (THREADS == 256) ? 4 : 1) k_xresolve(TrendBuffers T, long long n, int B)
+__global__ void __launch_bounds__(THREADS, (THREADS == 256) ? 4 : (CAP_HI <= 4096 ? 2 : 1)) k_xresolve(TrendBuffers T, long long n, int B)
 {
     constexpr int ST_THREADS = THREADS;
     extern __shared__ double2 s_p[];
@@ -679,7 +679,8 @@ int trend_knots_select(const double *d_C, double *d_V, long long m, long long n,
     if (!attr) {
         RB_CUDA(cudaFuncSetAttribute(k_xhist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_xhist));
         RB_CUDA(cudaFuncSetAttribute(k_xcollect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(int) * MAXB * NBY + 2 * NBX)));
-        RB_CUDA(cudaFuncSetAttribute(k_xresolve<512, 2048, CAPX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_resolve));
+        RB_CUDA(cudaFuncSetAttribute(k_xresolve<512, 4096, CAPX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_resolve));
+        RB_CUDA(cudaFuncSetAttribute(k_xresolve<512, 2048, 4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double2) * 4096)));
         RB_CUDA(cudaFuncSetAttribute(k_xplan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_plan));
         RB_CUDA(cudaFuncSetAttribute(k_yresolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * CAPY)));
         attr = true;
@@ -719,7 +720,9 @@ int trend_knots_select(const double *d_C, double *d_V, long long m, long long n,
         const unsigned nslot_max = (unsigned)std::min(MAXSLOT, 3 * B);
         k_xresolve<256, -1, 2048><<<dim3(nslot_max, (unsigned)m), 256, sizeof(double2) * 2048, st>>>(T, n, B);
         RB_LAUNCH_CHECK();
-        k_xresolve<512, 2048, CAPX><<<dim3(nslot_max, (unsigned)m), 512, sm_resolve, st>>>(T, n, B);
+        k_xresolve<512, 2048, 4096><<<dim3(nslot_max, (unsigned)m), 512, sizeof(double2) * 4096, st>>>(T, n, B);
+        RB_LAUNCH_CHECK();
+        k_xresolve<512, 4096, CAPX><<<dim3(nslot_max, (unsigned)m), 512, sm_resolve, st>>>(T, n, B);
         RB_LAUNCH_CHECK();
         k_yplan<<<dim3((unsigned)B, (unsigned)m), 256, 0, st>>>(T, n, B);
         RB_LAUNCH_CHECK();

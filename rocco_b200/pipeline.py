@@ -282,6 +282,13 @@ def run_shard(d_matrices, budgets, gammas, params=None, levels_per_round: int = 
             "results": results, "runs": runs}
 
 
+def runs_to_bed_file(path: str, chrom_names, runs, step: int, first_start: int = 0) -> str:
+    """Write all runs as BED3 (chromosomes in the given order; coordinates = first_start + bin*step) with the native
+    formatter -- no per-record Python work."""
+    chrom, starts, ends = runs
+    return _lib.write_bed_arrays(path, list(chrom_names), chrom, first_start + starts * step, first_start + ends * step)
+
+
 def runs_to_bed_text(chrom_names, runs, step: int, first_start: int = 0) -> str:
     """BED3 text of all runs (per chromosome in the given order; coordinates = first_start + bin*step)."""
     chrom, starts, ends = runs

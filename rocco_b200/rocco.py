@@ -103,14 +103,17 @@ def chrom_solution_to_bed(chromosome, intervals, solution, ID=None, check_gaps_i
     step_ = intervals_[1] - intervals_[0]  # noqa: F841  (kept: the reference evaluates it, so len < 2 raises)
     output_file = f"rocco_{chromosome}.bed" if ID is None else f"rocco_{ID}_{chromosome}.bed"
     first, last = solution_runs(solution)
-    starts = intervals_[first]
-    ends = intervals_[last]
-    records = [(str(chromosome), int(s), int(e)) for s, e in zip(starts.tolist(), ends.tolist())]
-    if len(records) > 1 and not np.all(starts[1:] > ends[:-1]):
-        records = _merge_bed_records(records)          # non-monotone interval tables: full reference merge
+    starts = np.asarray(intervals_[first], dtype=np.int64)
+    ends = np.asarray(intervals_[last], dtype=np.int64)
+    if len(starts) > 1 and not np.all(starts[1:] > ends[:-1]):
+        # non-monotone interval tables: full reference merge
+        records = _merge_bed_records([(str(chromosome), int(s), int(e)) for s, e in zip(starts.tolist(), ends.tolist())])
+        starts = np.array([r[1] for r in records], dtype=np.int64)
+        ends = np.array([r[2] for r in records], dtype=np.int64)
     if min_length_bp is not None:
-        records = [r for r in records if (r[2] - r[1]) >= int(min_length_bp)]
-    return _write_bed_records(records, output_file)
+        keep = (ends - starts) >= int(min_length_bp)
+        starts, ends = starts[keep], ends[keep]
+    return _lib.write_bed_arrays(output_file, [str(chromosome)], None, starts, ends)
 
 
 def _merge_bed_arrays(chrom_rank: np.ndarray, start: np.ndarray, end: np.ndarray):
@@ -188,11 +191,9 @@ def combine_chrom_results(chrom_bed_files: list, output_file: str, name_features
         rank_of = {nm: k for k, nm in enumerate(names)}
         rank = np.array([rank_of[str(u)] for u in uniques], dtype=np.int64)[codes]
         rk, start, end = _merge_bed_arrays(rank, start.astype(np.int64), end.astype(np.int64))
-        chrom = np.array(names, dtype=object)[rk]
-    out = pd.DataFrame({"c": chrom, "s": start, "e": end})
-    if name_features:
-        out["n"] = out["c"].astype(str) + "_" + out["s"].astype(str) + "_" + out["e"].astype(str)
-    out.to_csv(output_file, sep="\t", header=False, index=False, lineterminator="\n")
+    if len(start):
+        return _lib.write_bed_arrays(output_file, names, rk.astype(np.int32), start, end, name_features=name_features)
+    open(output_file, "w").close()
     return output_file
 
 
