@@ -157,6 +157,47 @@ static void build_factor(long long n, double lam, FactorHost &F)
     }
 }
 
+// ------------------------------------------------------------------ fast log2 for arguments >= 1
+// v = 2^e * m, m in [1,2); i = top 7 mantissa bits; r = m * inv[i] - 1 with inv[i] ~ 1/(1 + (i + 0.5)/128), |r| <= 2^-8;
+// log2(v) = e + (tab[i] + log2(1 + r)), tab[i] = -log2(inv[i]) for the ROUNDED inv[i], log2(1+r) by a degree-7 polynomial
+// (truncation < 2^-66).  Total error ~1 ulp of the result for v >= 2 and < 3e-19 absolute near 1: four orders of
+// magnitude below the solver's own noise floor, at ~25 issue slots instead of ~110 for the library log2.
+struct Log2Tables { double inv[128]; double tab[128]; };
+static Log2Tables g_log2_host;
+static bool g_log2_ready = false;
+
+static void build_log2_tables()
+{
+    if (g_log2_ready) return;
+    for (int i = 0; i < 128; ++i) {
+        const long double c = 1.0L + ((long double)i + 0.5L) / 128.0L;
+        const double inv = (double)(1.0L / c);
+        g_log2_host.inv[i] = inv;
+        g_log2_host.tab[i] = (double)(-log2l((long double)inv));
+    }
+    g_log2_ready = true;
+}
+
+__device__ __forceinline__ double fast_log2_ge1(double v, const double *s_inv, const double *s_tab)
+{
+    const long long bits = __double_as_longlong(v);
+    const long long mant = bits & 0x000FFFFFFFFFFFFFLL;
+    const int e = (int)(bits >> 52) - 1023;
+    if (mant == 0) return (double)e;                                 // exact powers of two (zero counts -> 0.0)
+    const int i = (int)(mant >> 45);
+    const double m = __longlong_as_double(mant | 0x3FF0000000000000LL);
+    const double r = __fma_rn(m, s_inv[i], -1.0);
+    // log2(1+r) = r/ln2 * (1 - r/2 + r^2/3 - ...)
+    double p = 0.20609929155656704;                                  //  1/(7 ln2)
+    p = __fma_rn(p, r, -0.24044917348266152);                        // -1/(6 ln2)
+    p = __fma_rn(p, r, 0.28853900817779268);                         //  1/(5 ln2)
+    p = __fma_rn(p, r, -0.36067376022224085);                        // -1/(4 ln2)
+    p = __fma_rn(p, r, 0.48089834696298783);                         //  1/(3 ln2)
+    p = __fma_rn(p, r, -0.72134752044448170);                        // -1/(2 ln2)
+    p = __fma_rn(p, r, 1.4426950408889634);                          //  1/ln2
+    return (double)e + __fma_rn(p, r, s_tab[i]);
+}
+
 // ------------------------------------------------------------------ device side
 struct WhitParams {
     const void *x;              // input matrix rows (f64 or f32) or already-transformed rows
@@ -168,6 +209,7 @@ struct WhitParams {
     double tail[2][3][4];
     double trans[2][2][WT_LEVELS + 1][4];
     const double *lanepow;      // device copy of FactorHost::lanepow, [parity][dir][32][4]
+    const double *log2tab;      // device copy of Log2Tables (inv[128], tab[128])
     long long n;
     long long row_stride;       // elements between rows of x / out
     int head_len;
@@ -180,13 +222,14 @@ struct WhitParams {
     int write_baseline;         // 1: out = baseline ; 0: out = y - baseline
 };
 
-__device__ __forceinline__ double load_y(const WhitParams &P, long long row, long long i)
+__device__ __forceinline__ double load_y(const WhitParams &P, long long row, long long i, const double *s_log = nullptr)
 {
     double v = P.in_f32 ? (double)reinterpret_cast<const float *>(P.x)[row * P.row_stride + i]
                         : reinterpret_cast<const double *>(P.x)[row * P.row_stride + i];
     if (P.log_transform) {
         if (!isfinite(v)) return NAN;            // inference.py:45-46 rejects non-finite input (fmax would swallow NaN / -inf)
-        v = log2(fmax(v, 0.0) + 1.0);
+        v = fmax(v, 0.0) + 1.0;
+        v = s_log ? fast_log2_ge1(v, s_log, s_log + 128) : log2(v);
         if (P.pilot) v -= P.pilot[row];
     }
     return v;
@@ -291,6 +334,9 @@ __global__ void __launch_bounds__(WT_THREADS, 1) k_whittaker(WhitParams P)
     double *s_f1 = smem + WT_THREADS * WT_PAD;
     __shared__ double2 s_warp[WT_THREADS / 32];
     __shared__ double s_lp[STEADY ? 4 * 32 * 4 : 1];  // T^(k+1) tables: [parity][dir][32][4]
+    __shared__ double s_log[256];                     // fast-log2 tables: inv[128], tab[128]
+    for (int k = threadIdx.x; k < 256; k += WT_THREADS) s_log[k] = P.log2tab[k];
+    __syncthreads();
     if (STEADY) {
         for (int k = threadIdx.x; k < 4 * 32 * 4; k += WT_THREADS) s_lp[k] = P.lanepow[k];
     }
@@ -311,7 +357,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) k_whittaker(WhitParams P)
     for (int e = tid; e < WT_REGION; e += WT_THREADS) {
         double y = 0.0;
         if (e < rlen) {
-            y = load_y(P, row, r0 + e);
+            y = load_y(P, row, r0 + e, P.log_transform ? s_log : nullptr);
             bad |= !isfinite(y);
             // park y of the tile's own bins in the output buffer: the epilogue needs it again and a second
             // fp64 log2 per bin costs more issue slots than an L2 round trip
@@ -514,6 +560,7 @@ struct FactorDev {
     FactorHost host;
     double *d_head[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     double *d_lanepow = nullptr;
+    double *d_log2 = nullptr;
 };
 static std::mutex g_fmutex;
 static std::map<std::pair<long long, double>, FactorDev *> g_fcache[16];
@@ -535,10 +582,13 @@ static int get_factor(long long n, double lam, FactorDev **out)
             RB_CUDA(cudaMalloc(&F->d_head[p][k], sizeof(double) * std::max(1, F->host.head_len)));
             RB_CUDA(cudaMemcpy(F->d_head[p][k], F->host.head[p][k].data(), sizeof(double) * F->host.head_len, cudaMemcpyHostToDevice));
         }
+    build_log2_tables();
+    RB_CUDA(cudaMalloc(&F->d_log2, sizeof(Log2Tables)));
+    RB_CUDA(cudaMemcpy(F->d_log2, &g_log2_host, sizeof(Log2Tables), cudaMemcpyHostToDevice));
     RB_CUDA(cudaMalloc(&F->d_lanepow, sizeof(F->host.lanepow)));
     RB_CUDA(cudaMemcpy(F->d_lanepow, F->host.lanepow, sizeof(F->host.lanepow), cudaMemcpyHostToDevice));
     if (cache.size() > 256) {                        // bounded: drop everything (tables are tiny)
-        for (auto &kv : cache) { for (int p = 0; p < 2; ++p) for (int k = 0; k < 3; ++k) cudaFree(kv.second->d_head[p][k]); cudaFree(kv.second->d_lanepow); delete kv.second; }
+        for (auto &kv : cache) { for (int p = 0; p < 2; ++p) for (int k = 0; k < 3; ++k) cudaFree(kv.second->d_head[p][k]); cudaFree(kv.second->d_lanepow); cudaFree(kv.second->d_log2); delete kv.second; }
         cache.clear();
     }
     cache[key] = F;
@@ -569,6 +619,7 @@ int whittaker_rows(const void *d_x, int in_f32, int log_transform, const double 
     memcpy(P.tail, F->host.tail, sizeof(P.tail));
     memcpy(P.trans, F->host.trans, sizeof(P.trans));
     P.lanepow = F->d_lanepow;
+    P.log2tab = F->d_log2;
     P.tiles_per_row = (int)((n + WT_OUT - 1) / WT_OUT);
     // Interior tiles (region inside [head_len, n-4)) take the steady instantiation; the first and last
     // tile(s) of each row take the general one.  Two launches over disjoint tile sets.
