@@ -133,14 +133,19 @@ static std::atomic<int> g_prof_on{0};
 static std::mutex g_prof_mu;
 static std::vector<ProfEntry> g_prof;
 
+static std::vector<cudaEvent_t> g_prof_pool;      // recycled events: creating them inside the timed region is not free
+
 ProfScope::ProfScope(const char *name, cudaStream_t st, double bytes) : idx_(-1), st_(st)
 {
     if (!g_prof_on.load(std::memory_order_relaxed)) return;
     ProfEntry e;
     e.name = name; e.bytes = bytes;
-    if (cudaEventCreate(&e.a) != cudaSuccess || cudaEventCreate(&e.b) != cudaSuccess) return;
-    cudaEventRecord(e.a, st);
     std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (cudaEvent_t *ev : {&e.a, &e.b}) {
+        if (!g_prof_pool.empty()) { *ev = g_prof_pool.back(); g_prof_pool.pop_back(); }
+        else if (cudaEventCreate(ev) != cudaSuccess) { (void)cudaGetLastError(); return; }
+    }
+    cudaEventRecord(e.a, st);
     g_prof.push_back(e);
     idx_ = (int)g_prof.size() - 1;
 }
@@ -245,7 +250,7 @@ RB_API int rocco_b200_profile_report(char *buf, size_t cap)
             auto &a = agg[e.name];
             a.first += ms; a.second.first += 1; a.second.second += e.bytes;
         }
-        cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+        rb::g_prof_pool.push_back(e.a); rb::g_prof_pool.push_back(e.b);
     }
     (void)cudaGetLastError();
     rb::g_prof.clear();

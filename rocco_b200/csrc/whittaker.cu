@@ -351,22 +351,45 @@ __global__ void __launch_bounds__(WT_THREADS, 1) k_whittaker(WhitParams P)
     const int rlen = (int)(r1 - r0);
     // STEADY instantiation is only launched for CTAs whose region lies in [head_len, n-4)
 
-    // ---- stage rhs (masked y) for both parities, coalesced
+    // ---- stage rhs (masked y) for both parities, coalesced; four loads in flight per thread before any arithmetic
     int bad = 0;
     const bool keep_y = !P.write_baseline;
-    for (int e = tid; e < WT_REGION; e += WT_THREADS) {
-        double y = 0.0;
-        if (e < rlen) {
-            y = load_y(P, row, r0 + e, P.log_transform ? s_log : nullptr);
-            bad |= !isfinite(y);
-            // park y of the tile's own bins in the output buffer: the epilogue needs it again and a second
-            // fp64 log2 per bin costs more issue slots than an L2 round trip
-            if (keep_y && r0 + e >= out0 && r0 + e < out1) P.out[row * P.row_stride + r0 + e] = y;
+    const int o_lo = (int)(out0 - r0), o_hi = (int)(out1 - r0);            // region positions of the tile's own bins
+    const long long rbase = row * P.row_stride + r0;
+    const float *xf = reinterpret_cast<const float *>(P.x) + rbase;
+    const double *xd = reinterpret_cast<const double *>(P.x) + rbase;
+    double *outp = P.out + rbase;
+    const double pil = (P.log_transform && P.pilot) ? P.pilot[row] : 0.0;
+    const bool par0 = ((r0 & 1) == 0);
+#pragma unroll 1
+    for (int e0 = tid; e0 < WT_REGION; e0 += 4 * WT_THREADS) {
+        double raw[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u * WT_THREADS;
+            raw[u] = (e < rlen) ? (P.in_f32 ? (double)xf[e] : xd[e]) : 0.0;
         }
-        const int a = e + e / WT_ITEMS;
-        const bool even = (((r0 + e) & 1) == 0);
-        s_f0[a] = even ? y : 0.0;
-        s_f1[a] = even ? 0.0 : y;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u * WT_THREADS;
+            if (e >= WT_REGION) break;
+            double y = 0.0;
+            if (e < rlen) {
+                y = raw[u];
+                if (P.log_transform) {
+                    // inference.py:45-46 rejects non-finite input (fmax would swallow NaN / -inf)
+                    y = isfinite(y) ? fast_log2_ge1(fmax(y, 0.0) + 1.0, s_log, s_log + 128) - pil : NAN;
+                }
+                bad |= !isfinite(y);
+                // park y of the tile's own bins in the output buffer: the epilogue needs it again and a second
+                // log2 per bin costs more issue slots than an L2 round trip
+                if (keep_y && e >= o_lo && e < o_hi) outp[e] = y;
+            }
+            const int a = e + e / WT_ITEMS;
+            const bool even = (((e & 1) == 0) == par0);
+            s_f0[a] = even ? y : 0.0;
+            s_f1[a] = even ? 0.0 : y;
+        }
     }
     if (bad) *P.bad = 1;
     __syncthreads();
@@ -528,15 +551,25 @@ __global__ void __launch_bounds__(WT_THREADS, 1) k_whittaker(WhitParams P)
     }
     __syncthreads();
 
-    // ---- write the tile (coalesced); y is re-derived from the input (an L2 hit)
-    const int o_begin = (int)(out0 - r0), o_end = (int)(out1 - r0);
+    // ---- write the tile (coalesced); y comes back from where the staging loop parked it (an L2 hit)
     int bad2 = 0;
-    for (int e = o_begin + tid; e < o_end; e += WT_THREADS) {
-        const double b = s_f0[e + e / WT_ITEMS];
-        double v = b;
-        if (!P.write_baseline) v = __ldcg(P.out + row * P.row_stride + r0 + e) - b;
-        bad2 |= !isfinite(v);
-        P.out[row * P.row_stride + r0 + e] = v;
+#pragma unroll 1
+    for (int e0 = o_lo + tid; e0 < o_hi; e0 += 4 * WT_THREADS) {
+        double yv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u * WT_THREADS;
+            yv[u] = (!P.write_baseline && e < o_hi) ? __ldcg(outp + e) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u * WT_THREADS;
+            if (e >= o_hi) break;
+            const double b = s_f0[e + e / WT_ITEMS];
+            const double v = P.write_baseline ? b : yv[u] - b;
+            bad2 |= !isfinite(v);
+            outp[e] = v;
+        }
     }
     if (bad2) *P.bad = 1;
 }
