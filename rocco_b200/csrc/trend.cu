@@ -155,10 +155,18 @@ __global__ void __launch_bounds__(RV_THREADS) k_rollvar_xhist(const double *__re
         const int span = (int)(thi - tlo) + w;                     // bins staged: [tlo, tlo + span)
         const int own0 = (int)(j0 - tlo), own1 = (int)(j1 - tlo);  // staged positions of the tile's own bins
         const double *src = c + tlo;
-        for (int e = tid; e < span; e += RV_THREADS) {
-            const double val = src[e];
-            s_in[padpos(e)] = val;
-            if (e >= own0 && e < own1) atomicAdd(&s_h[xbucket(fabs(val))], 1);
+#pragma unroll 1
+        for (int e0 = tid; e0 < span; e0 += 4 * RV_THREADS) {          // four loads in flight per thread
+            double val[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int e = e0 + u * RV_THREADS; val[u] = (e < span) ? src[e] : 0.0; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * RV_THREADS;
+                if (e >= span) break;
+                s_in[padpos(e)] = val[u];
+                if (e >= own0 && e < own1) atomicAdd(&s_h[xbucket(fabs(val[u]))], 1);
+            }
         }
         __syncthreads();
         const bool interior = (j0 - half >= 0) && ((j1 - 1) - half <= last) && (j1 - j0 == RV_T);

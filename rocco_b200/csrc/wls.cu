@@ -322,28 +322,40 @@ __global__ void __launch_bounds__(CB_THREADS, 4) k_combine(CombineParams P)
         if (live) {
             const double *pc = P.C + r0 * P.row_stride + j;
             const double *pv_ = P.const_rows ? nullptr : P.V + r0 * P.row_stride + j;
-#pragma unroll 4
-            for (int rr = 0; rr < nr; ++rr) {
-                const double y = pc[(long long)rr * P.row_stride];
-                double ov, pv;
-                if (P.const_rows) { ov = pv = P.row_const[r0 + rr]; }
-                else {
-                    ov = fmax(pv_[(long long)rr * P.row_stride], 1.0e-8);
-                    pv = (s_nk[rr] < 0) ? s_cv[rr] : fmax(interp_knots(s_kx[rr], s_ky[rr], s_kr[rr], s_nk[rr], fabs(y)), 1.0e-8);
-                    pv = fmax(pv, 1.0e-8);
+            // rows in groups of four: the eight loads of a group are issued before any of its arithmetic
+            for (int rb = 0; rb < nr; rb += 4) {
+                double ys[4], vs[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int rr = rb + u;
+                    ys[u] = (rr < nr) ? pc[(long long)rr * P.row_stride] : 0.0;
+                    vs[u] = (rr < nr && pv_) ? pv_[(long long)rr * P.row_stride] : 1.0;
                 }
-                // wls_backend.c:889-911
-                double post = div_rcp(__dadd_rn(__dmul_rn(P.ldf, ov), __dmul_rn(P.pdf, pv)), tdf1, rtdf1);
-                const double flo = __dmul_rn(P.pfr, pv);
-                if (post < flo) post = flo;
-                post = fmax(post, 1.0e-8);
-                const double prec = __drcp_rn(post);        // == 1.0 / post (correctly rounded), without the division slow path
-                if (want_rq) {                              // only when raw / prior variance outputs are requested
-                    rsum = __dadd_rn(rsum, __drcp_rn(ov));
-                    qsum = __dadd_rn(qsum, __drcp_rn(pv));
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int rr = rb + u;
+                    if (rr >= nr) break;
+                    const double y = ys[u];
+                    double ov, pv;
+                    if (P.const_rows) { ov = pv = P.row_const[r0 + rr]; }
+                    else {
+                        ov = fmax(vs[u], 1.0e-8);
+                        pv = (s_nk[rr] < 0) ? s_cv[rr] : fmax(interp_knots(s_kx[rr], s_ky[rr], s_kr[rr], s_nk[rr], fabs(y)), 1.0e-8);
+                        pv = fmax(pv, 1.0e-8);
+                    }
+                    // wls_backend.c:889-911
+                    double post = div_rcp(__dadd_rn(__dmul_rn(P.ldf, ov), __dmul_rn(P.pdf, pv)), tdf1, rtdf1);
+                    const double flo = __dmul_rn(P.pfr, pv);
+                    if (post < flo) post = flo;
+                    post = fmax(post, 1.0e-8);
+                    const double prec = __drcp_rn(post);        // == 1.0 / post (correctly rounded), without the division slow path
+                    if (want_rq) {                              // only when raw / prior variance outputs are requested
+                        rsum = __dadd_rn(rsum, __drcp_rn(ov));
+                        qsum = __dadd_rn(qsum, __drcp_rn(pv));
+                    }
+                    psum = __dadd_rn(psum, prec);
+                    wsum = __dadd_rn(wsum, __dmul_rn(prec, y));
                 }
-                psum = __dadd_rn(psum, prec);
-                wsum = __dadd_rn(wsum, __dmul_rn(prec, y));
             }
         }
     }
