@@ -47,7 +47,7 @@ def parse_args():
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"], help="dtype of the resident count matrices")
     ap.add_argument("--e2e-steps", type=int, default=-1, help="-1: min(steps, 2); 0 disables the e2e leg")
     ap.add_argument("--score-streams", type=int, default=1, help="host threads / CUDA streams scoring chromosomes concurrently")
-    ap.add_argument("--e2e-threads", type=int, default=2, help="host threads driving chromosomes through the public API")
+    ap.add_argument("--e2e-threads", type=int, default=3, help="host threads driving chromosomes through the public API")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-bins", type=int, default=250_000)
     ap.add_argument("--levels", type=int, default=0, help="bisection levels per launch (0 = library default)")

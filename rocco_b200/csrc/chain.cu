@@ -797,7 +797,10 @@ static size_t smem_bytes(bool vec) { return (size_t)(TILE + THREADS) * sizeof(do
 template <typename V, bool VEC, bool EMIT>
 static int launch_tiles(const Params &P, int blocks, cudaStream_t st)
 {
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {false};
+    int attr_set_d = 0;
+    cudaGetDevice(&attr_set_d);
+    bool &attr_set = attr_set_dev[attr_set_d & 63];
     const size_t sm = smem_bytes(VEC);
     if (!attr_set) {
         RB_CUDA(cudaFuncSetAttribute(k_chain_tiles<V, VEC, EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));

@@ -679,7 +679,10 @@ int trend_knots_select(const double *d_C, double *d_V, long long m, long long n,
     RB_CUDA(cudaMemsetAsync(T.yhist, 0, sizeof(int) * (size_t)m * MAXB * NBY, st));
     RB_CUDA(cudaMemsetAsync(T.ycand_cnt, 0, sizeof(int) * (size_t)m * MAXB * 2, st));
 
-    static bool attr = false;
+    static bool attr_dev[64] = {false};
+    int attr_d = 0;
+    cudaGetDevice(&attr_d);
+    bool &attr = attr_dev[attr_d & 63];
     const size_t sm_xhist = sizeof(int) * NBX;
     const size_t sm_collect = sizeof(int) * (size_t)B * NBY + 2 * NBX;
     const size_t sm_resolve = sizeof(double2) * CAPX;
@@ -697,7 +700,10 @@ int trend_knots_select(const double *d_C, double *d_V, long long m, long long n,
     const dim3 gstream(chunks, (unsigned)m);
     if (fused_window > 0) {
         const size_t sm_fused = sizeof(int) * NBX + sizeof(double) * (padpos(RV_T + fused_window) + 8 + padpos(RV_T) + 8);
-        static bool attr2 = false;
+        static bool attr2_dev[64] = {false};
+    int attr2_d = 0;
+    cudaGetDevice(&attr2_d);
+    bool &attr2 = attr2_dev[attr2_d & 63];
         if (!attr2) {
             const int mx = (int)(sizeof(int) * NBX + sizeof(double) * (padpos(RV_T + RV_MAXW) + 8 + padpos(RV_T) + 8));
             RB_CUDA(cudaFuncSetAttribute(k_rollvar_xhist<31>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));

@@ -658,7 +658,10 @@ int whittaker_rows(const void *d_x, int in_f32, int log_transform, const double 
     // tile(s) of each row take the general one.  Two launches over disjoint tile sets.
     const size_t sm_steady = sizeof(double) * 2 * WT_THREADS_S * (WT_ITEMS_S + 1);
     const size_t sm_general = sizeof(double) * 2 * WT_THREADS_G * (WT_ITEMS_G + 1) + sizeof(double) * 6 * WT_THREADS_G;
-    static bool attr = false;
+    static bool attr_dev[64] = {false};
+    int attr_d = 0;
+    cudaGetDevice(&attr_d);
+    bool &attr = attr_dev[attr_d & 63];
     if (!attr) {
         RB_CUDA(cudaFuncSetAttribute(k_whittaker<true, WT_THREADS_S, WT_ITEMS_S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_steady));
         RB_CUDA(cudaFuncSetAttribute(k_whittaker<false, WT_THREADS_G, WT_ITEMS_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_general));
