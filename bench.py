@@ -349,8 +349,17 @@ def main():
             dom = max(prof, key=lambda k: prof[k][0])
             d_ms, d_cnt, d_bytes = prof[dom]
             achieved = (d_bytes / 1e9) / (d_ms / 1e3) if d_ms > 0 else 0.0
+            traffic, traffic_src = None, None
+            tpath = os.path.join(REPO, "profiles", "r1_traffic.json")
+            if os.path.exists(tpath):
+                tj = json.load(open(tpath))
+                if dom in tj["kernels"]:
+                    # DRAM bytes per launch = this run's algorithmic bytes per launch x the ncu-measured DRAM/algorithmic ratio
+                    traffic = (d_bytes / max(d_cnt, 1)) * tj["kernels"][dom]["traffic_per_algorithmic_byte"]
+                    traffic_src = "dram__bytes_read+write per algorithmic byte from " + tj["source"]
             roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                    "algorithmic_bytes_per_launch": d_bytes / max(d_cnt, 1), "peak_source": peak_src,
                     "launches": d_cnt, "avg_launch_ms": d_ms / max(d_cnt, 1), "share_of_profiled_time": d_ms / total_ms,
                     "all_scopes": {k: {"ms": round(v[0], 3), "launch_sets": v[1],
                                        "GBps_algorithmic": round((v[2] / 1e9) / (v[0] / 1e3), 1) if v[0] > 0 else 0.0}
