@@ -157,6 +157,12 @@ long long rocco_b200_mask_to_runs_batch_dev(
  * (rocco.py:98-110 _write_bed_records).  Record i uses names[name_idx[i]] (name_idx == NULL: names[0]). */
 int rocco_b200_write_bed3(const char *path, const char *const *names, int n_names, const int *name_idx,
                           const long long *starts, const long long *ends, size_t n, int name_features);
+/* Host helper: combine_chrom_results (rocco.py:194-240) over canonical BED text -- read `n_paths` files, order the
+ * records by (chrom, start, end), merge overlapping/abutting records per chrom, write BED3 (BED4 when name_features).
+ * Returns the number of records written, or -1 when a file is not canonical BED (the caller falls back to the
+ * reference-faithful line reader); *saw_extra_columns = 1 when any row had more than three fields. */
+long long rocco_b200_combine_bed3(const char *const *paths, int n_paths, const char *out_path, int name_features,
+                                  int *saw_extra_columns);
 int rocco_b200_uniform_step_i64(const long long *values, size_t n);   /* 1 iff all consecutive differences are equal */
 double rocco_b200_numpy_sum_f64(const double *values, size_t n);
 double rocco_b200_numpy_sum_const_f64(double value, size_t n);

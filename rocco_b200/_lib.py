@@ -66,6 +66,7 @@ def _declare(lib):
         "rocco_b200_profile_report": (c_int, [c_char_p, c_size_t]),
         "rocco_b200_uniform_step_i64": (c_int, [c_void_p, c_size_t]),
         "rocco_b200_write_bed3": (c_int, [c_char_p, POINTER(c_char_p), c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int]),
+        "rocco_b200_combine_bed3": (ctypes.c_longlong, [POINTER(c_char_p), c_int, c_char_p, c_int, POINTER(c_int)]),
         "rocco_b200_numpy_sum_f64": (c_double, [c_void_p, c_size_t]),
         "rocco_b200_numpy_sum_const_f64": (c_double, [c_double, c_size_t]),
         "rocco_solve_penalized_chain_f64": (c_int, [c_void_p, c_void_p, c_size_t, c_double, c_void_p, dp, llp]),
@@ -187,3 +188,17 @@ def write_bed_arrays(path: str, names, name_idx, starts: np.ndarray, ends: np.nd
     if st != 0:
         raise OSError(f"could not write BED file {path}: {last_error()}")
     return path
+
+
+def combine_bed_files(paths, output_file: str, name_features: bool = False):
+    """Native combine of canonical BED files; returns (records_written, saw_extra_columns) or None when a file needs the
+    line-by-line reader."""
+    lib = load()
+    arr = (c_char_p * len(paths))(*[os.fsencode(str(x)) for x in paths])
+    extra = c_int(0)
+    n = lib.rocco_b200_combine_bed3(arr, len(paths), os.fsencode(str(output_file)), 1 if name_features else 0, ctypes.byref(extra))
+    if n == -1:
+        return None
+    if n < 0:
+        raise OSError(f"could not write BED file {output_file}: {last_error()}")
+    return int(n), bool(extra.value)

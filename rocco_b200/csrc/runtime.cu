@@ -5,6 +5,9 @@
 
 #include <algorithm>
 #include <map>
+#include <string>
+#include <vector>
+#include <cstring>
 #include <mutex>
 
 namespace rb {
@@ -323,6 +326,126 @@ RB_API int rocco_b200_write_bed3(const char *path, const char *const *names, int
     }
     fclose(fh);
     return 0;
+}
+
+/* combine_chrom_results (rocco.py:194-240) for canonical BED text, without a Python object per record: read every file,
+ * order records by (chrom bytes, start, end) -- bytewise order of UTF-8/ASCII names is Python's str order --, merge
+ * records with start <= previous end on the same chrom, write BED3/BED4.  Returns the number of records written, or
+ * -1 when any file is not canonical (the caller then takes the reference-faithful line-by-line reader, which owns the
+ * error behaviour): canonical = every non-empty line is  <chrom>\t<digits>\t<digits>[\t...]  with ASCII chrom, no
+ * leading/trailing whitespace, no carriage returns, at most 18 digits. */
+namespace {
+struct BedRec { int name; long long start, end; };
+static bool is_space_py(unsigned char c) { return c == ' ' || (c >= 9 && c <= 13) || (c >= 28 && c <= 31) || c == 0x85 || c == 0xA0; }
+static bool parse_digits(const char *&p, const char *end, long long *out)
+{
+    const char *q = p;
+    unsigned long long v = 0;
+    while (q < end && *q >= '0' && *q <= '9') { v = v * 10ULL + (unsigned long long)(*q - '0'); ++q; }
+    const size_t nd = (size_t)(q - p);
+    if (nd == 0 || nd > 18) return false;
+    *out = (long long)v;
+    p = q;
+    return true;
+}
+}  // namespace
+
+RB_API long long rocco_b200_combine_bed3(const char *const *paths, int n_paths, const char *out_path, int name_features,
+                                         int *saw_extra_columns)
+{
+    if (!paths || n_paths < 0 || !out_path) return rb::ST_INVALID;
+    std::vector<std::string> names;
+    std::map<std::string, int> name_id;
+    std::vector<BedRec> recs;
+    int extra = 0;
+    std::vector<char> buf;
+    for (int f = 0; f < n_paths; ++f) {
+        FILE *fh = fopen(paths[f], "rb");
+        if (!fh) return -1;
+        fseek(fh, 0, SEEK_END);
+        const long sz = ftell(fh);
+        fseek(fh, 0, SEEK_SET);
+        if (sz < 0) { fclose(fh); return -1; }
+        buf.resize((size_t)sz + 1);
+        if (sz && fread(buf.data(), 1, (size_t)sz, fh) != (size_t)sz) { fclose(fh); return -1; }
+        fclose(fh);
+        const char *p = buf.data(), *end = p + sz;
+        if (memchr(p, '\r', (size_t)sz)) return -1;
+        int last_id = -1;
+        const char *last_name = nullptr;
+        size_t last_len = 0;
+        while (p < end) {
+            const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
+            const char *le = nl ? nl : end;
+            if (le == p) { p = le + 1; continue; }                                  // empty line
+            if (is_space_py((unsigned char)*p) || is_space_py((unsigned char)le[-1]) || (unsigned char)le[-1] >= 0x80) return -1;
+            const char *t1 = (const char *)memchr(p, '\t', (size_t)(le - p));
+            if (!t1 || t1 == p) return -1;
+            for (const char *q = p; q < t1; ++q) if ((unsigned char)*q >= 0x80) return -1;
+            const char *q = t1 + 1;
+            BedRec r;
+            if (!parse_digits(q, le, &r.start) || q >= le || *q != '\t') return -1;
+            ++q;
+            if (!parse_digits(q, le, &r.end)) return -1;
+            if (q < le) { if (*q != '\t') return -1; extra = 1; }
+            const size_t nlen = (size_t)(t1 - p);
+            if (last_id >= 0 && nlen == last_len && memcmp(p, last_name, nlen) == 0) r.name = last_id;
+            else {
+                std::string nm(p, nlen);
+                auto it = name_id.find(nm);
+                if (it == name_id.end()) { it = name_id.emplace(nm, (int)names.size()).first; names.push_back(nm); }
+                r.name = it->second;
+                last_id = r.name; last_name = names[(size_t)r.name].data(); last_len = nlen;
+            }
+            recs.push_back(r);
+            p = le + 1;
+        }
+    }
+    if (saw_extra_columns) *saw_extra_columns = extra;
+    // rank of every name in sorted (bytewise) order; std::map iterates in that order
+    std::vector<int> rank(names.size());
+    std::vector<const std::string *> by_rank(names.size());
+    { int k = 0; for (auto &kv : name_id) { rank[(size_t)kv.second] = k; by_rank[(size_t)k] = &kv.first; ++k; } }
+    for (auto &r : recs) r.name = rank[(size_t)r.name];
+    auto less = [](const BedRec &a, const BedRec &b) {
+        if (a.name != b.name) return a.name < b.name;
+        if (a.start != b.start) return a.start < b.start;
+        return a.end < b.end;
+    };
+    if (!std::is_sorted(recs.begin(), recs.end(), less)) std::stable_sort(recs.begin(), recs.end(), less);
+    size_t w = 0;
+    for (size_t i = 0; i < recs.size(); ++i) {
+        if (w && recs[i].name == recs[w - 1].name && recs[i].start <= recs[w - 1].end) {
+            if (recs[i].end > recs[w - 1].end) recs[w - 1].end = recs[i].end;
+        } else recs[w++] = recs[i];
+    }
+    recs.resize(w);
+    FILE *fo = fopen(out_path, "wb");
+    if (!fo) { rb::set_error("cannot open %s for writing", out_path); return rb::ST_INVALID; }
+    size_t maxlen = 0;
+    for (auto &nm : names) maxlen = std::max(maxlen, nm.size());
+    const size_t per = 2 * maxlen + 4 * 21 + 8, chunk = 1 << 16;
+    std::vector<char> ob(per * chunk);
+    for (size_t i0 = 0; i0 < recs.size(); i0 += chunk) {
+        char *p = ob.data();
+        const size_t i1 = std::min(recs.size(), i0 + chunk);
+        for (size_t i = i0; i < i1; ++i) {
+            const std::string &nm = *by_rank[(size_t)recs[i].name];
+            memcpy(p, nm.data(), nm.size()); p += nm.size();
+            *p++ = '\t'; p = put_ll(p, recs[i].start);
+            *p++ = '\t'; p = put_ll(p, recs[i].end);
+            if (name_features) {
+                *p++ = '\t';
+                memcpy(p, nm.data(), nm.size()); p += nm.size();
+                *p++ = '_'; p = put_ll(p, recs[i].start);
+                *p++ = '_'; p = put_ll(p, recs[i].end);
+            }
+            *p++ = '\n';
+        }
+        if (fwrite(ob.data(), 1, (size_t)(p - ob.data()), fo) != (size_t)(p - ob.data())) { fclose(fo); return rb::ST_INVALID; }
+    }
+    fclose(fo);
+    return (long long)recs.size();
 }
 
 RB_API double rocco_b200_numpy_sum_f64(const double *a, size_t n) { return rb::numpy_sum_f64(a, n); }

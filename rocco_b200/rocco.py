@@ -166,6 +166,12 @@ def combine_chrom_results(chrom_bed_files: list, output_file: str, name_features
     for chrom_bed_file in chrom_bed_files:
         if not os.path.exists(chrom_bed_file):
             raise FileNotFoundError(f"File does not exist: {chrom_bed_file}")
+    native = _lib.combine_bed_files(list(chrom_bed_files), output_file, name_features) if len(chrom_bed_files) else None
+    if native is not None:                       # canonical BED text everywhere: read, sort, merge, write in one native pass
+        if native[1]:
+            logger.info("More than 3 columns detected in the input BED files. Extra columns will be ignored.")
+        return output_file
+    for chrom_bed_file in chrom_bed_files:
         fast = _read_bed_fast(chrom_bed_file)
         if fast is None:
             try:

@@ -91,3 +91,33 @@ def test_combine_chrom_results_matches_oracle_on_messy_input(oracle, tmp_path):
     (tmp_path / "bad.bed").write_text("chr1\t5\n")
     with pytest.raises(ValueError):
         combine_chrom_results([str(tmp_path / "bad.bed")], str(tmp_path / "c.bed"))
+
+
+def test_combine_native_and_fallback_paths_agree_with_oracle(oracle, tmp_path):
+    """The native one-pass combine takes canonical BED text only; anything else (CRLF, padded lines, signed or
+    underscore integers, whitespace-only lines) goes through the line reader -- both must give the oracle's file."""
+    from rocco_b200 import _lib
+    from rocco_b200.rocco import combine_chrom_results
+    canon = tmp_path / "canon.bed"
+    canon.write_text("chrB\t10\t20\nchrA\t5\t9\nchrA\t9\t12\n\nchrB\t15\t40\textra\nchr10\t007\t8\n")
+    assert _lib.combine_bed_files([str(canon)], str(tmp_path / "n.bed")) == (3, True)
+    assert open(tmp_path / "n.bed").read() == "chr10\t7\t8\nchrA\t5\t12\nchrB\t10\t40\n"
+    messy = {
+        "crlf.bed": "chr1\t1\t5\r\nchr1\t4\t9\r\n",
+        "padded.bed": "  chr1\t100\t200  \n\t\nchr1\t150\t250\n",
+        "signed.bed": "chr2\t+3\t1_0\nchr2\t-5\t2\n",
+        "spaces_only.bed": "chr3\t1\t2\n   \nchr3\t2\t3\n",
+    }
+    for name, text in messy.items():
+        p = tmp_path / name
+        with open(p, "w", newline="") as fh:
+            fh.write(text)
+        assert _lib.combine_bed_files([str(p)], str(tmp_path / "x.bed")) is None, name
+    files = [str(canon)] + [str(tmp_path / k) for k in messy]
+    a = combine_chrom_results(files, str(tmp_path / "a.bed"))
+    b = oracle.combine_chrom_results(files, str(tmp_path / "b.bed"))
+    assert open(a).read() == open(b).read()
+    a = combine_chrom_results([str(canon)], str(tmp_path / "a2.bed"), name_features=True)
+    b = oracle.combine_chrom_results([str(canon)], str(tmp_path / "b2.bed"), name_features=True)
+    assert open(a).read() == open(b).read()
+    assert open(combine_chrom_results([], str(tmp_path / "none.bed"))).read() == ""
