@@ -242,3 +242,56 @@ def test_combine_reproduces_reference_combined_bed(oracle, bed_fixtures, tmp_pat
     for name, bins in (("ref_chr21", 16675), ("ref_chr19", 52689), ("ref_chrX", 46805)):
         recs = oracle.read_bed_records(str(tmp_path / f"{name}.bed"))
         assert sum(e - s for _, s, e in recs) // 50 == bins
+
+
+# ------------------------------------------------------------------------------------------------
+# dependent-wild-bootstrap budget null + automatic gamma (oracle/budget.py)
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def budget_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_budget_v1_11_0.npz"))
+
+
+def _close(a, b, tol):
+    return abs(float(a) - float(b)) <= tol * max(1.0, abs(float(b)))
+
+
+def test_budget_building_blocks_match_reference(budget_golden):
+    from oracle import budget as ob
+    g = budget_golden
+    for b in (8, 101):
+        assert np.array_equal(ob.bartlett_kernel(b), g[f"kernel_b{b}"])
+    for n, h, bw, lag in g["bandwidth_rules"]:
+        hint = None if h < 0 else int(h)
+        assert ob.bootstrap_bandwidth(int(n), hint) == bw and ob.ess_max_lag(int(n), hint) == lag
+    taps = ob.bartlett_kernel(16)
+    w = ob.dependent_wild_weights(np.random.default_rng(77).standard_normal(4000 + taps.size - 1), taps)
+    assert np.max(np.abs(w - g["weights_n4000_b16"])) < 1e-12          # FFT vs direct correlation: rounding only
+    for key, vals, lag in (("ess_out", g["ess_values"], 404), ("ess_out_short", g["ess_values"][:40], 64)):
+        n_eff, tau, used = ob.effective_sample_size(vals, lag)
+        assert _close(n_eff, g[key][0], 1e-10) and _close(tau, g[key][1], 1e-10) and used == int(g[key][2])
+
+
+@pytest.mark.parametrize("tag", ["ref_test", "synth_a", "synth_b"])
+def test_budget_estimator_matches_reference(budget_golden, tag):
+    """Same PCG64 streams as the reference => every entry of the details dict is reproduced."""
+    import json
+    from oracle import budget as ob
+    g = budget_golden
+    kw = json.loads(str(g[f"{tag}_kwargs"]))
+    want = json.loads(str(g[f"{tag}_meta"]))
+    frac, meta = ob.estimate_budget_nonnull_fraction(g[f"{tag}_centered"], observed_scores=g[f"{tag}_scores"],
+                                                     return_details=True, **kw)
+    assert set(meta) == set(want)
+    for k, v in want.items():
+        if isinstance(v, (str, bool)):
+            assert meta[k] == v, k
+        else:
+            assert _close(meta[k], v, 1e-9), (k, meta[k], v)
+    assert _close(frac, float(g[f"{tag}_fraction"]), 1e-9)
+    gam, gmeta = ob.resolve_chrom_gamma(g[f"{tag}_scores"], meta["autocorrelation_time"])
+    wantg = json.loads(str(g[f"{tag}_gamma_meta"]))
+    assert _close(gam, float(g[f"{tag}_gamma"]), 1e-12)
+    for k, v in wantg.items():
+        assert (gmeta[k] == v) if isinstance(v, str) else _close(gmeta[k], v, 1e-10), k
