@@ -226,6 +226,62 @@ int rocco_b200_score_centered_wls_dev(const double *d_centered, size_t m, size_t
                                       const rocco_b200_score_params *params,
                                       rocco_b200_score_outputs *out, void *cuda_stream);
 
+/* ------------------------------------------------------------------ budget null
+ * Dependent-wild-bootstrap estimate of a chromosome's enriched fraction (inference.py:988-1148 on top of 446-985) and
+ * the inputs of the automatic gamma (rocco.py:751-789), device-resident: fit the null residual template, score it,
+ * take the null centre/scale, then re-score  template x W  for up to num_null_draws Bartlett-smoothed Gaussian
+ * multiplier fields W with the reference's adaptive stop.  Innovations: Philox4x32-10 keyed by random_seed (the
+ * reference uses NumPy PCG64 streams: statistical parity) unless d_innovations supplies them (bit-level replay). */
+typedef struct rocco_b200_budget_params {
+    rocco_b200_score_params score;  /* lower_bound_z, prior_df, min_effect, precision_floor_ratio as for the scores  */
+    int dependence_lag_hint;        /* <= 0: none (bandwidth round(n^(1/3)), ESS scale 101); rocco.py:1035 passes >= 25 */
+    int num_null_draws;             /* 25                                                                        */
+    int min_null_draws;             /* <= 0: 8 (inference.py:795-797)                                            */
+    int reserved;
+    double stability_abs_tol;       /* 5e-3                                                                      */
+    double stability_rel_tol;       /* 5e-2                                                                      */
+    unsigned long long random_seed;
+    const double *d_innovations;    /* optional DEVICE buffer [num_null_draws][m][n + 2*bandwidth] of iid N(0,1)  */
+} rocco_b200_budget_params;
+
+typedef struct rocco_b200_budget_result {
+    double nonnull_fraction, effective_count, effective_total_count, autocorrelation_time;
+    double null_center, null_scale, null_threshold;
+    double null_positive_mass, null_positive_units, null_positive_fraction;
+    double null_positive_units_sd, null_positive_units_stderr;
+    double null_tail_occupancy, null_tail_occupancy_sd, null_tail_occupancy_stderr;
+    double negative_fraction;
+    double observed_positive_fraction, observed_negative_fraction, observed_excess_mass, observed_excess_units;
+    double observed_tail_occupancy;
+    double null_reference_mean_positive_consensus, null_reference_max_positive_consensus;
+    double positive_score_median;   /* median of the observed scores > 0 (1.0 when none): rocco.py:762-769        */
+    long long negative_support_size, positive_score_count, num_loci;
+    int num_null_draws, max_null_draws, adaptive_stop, wild_bandwidth, ess_max_lag, ess_lags_used;
+} rocco_b200_budget_result;
+
+void rocco_b200_default_budget_params(rocco_b200_budget_params *p);
+int rocco_b200_budget_bandwidth(size_t n, int dependence_lag_hint);      /* inference.py:520-530 */
+int rocco_b200_budget_ess_max_lag(size_t n, int dependence_lag_hint);    /* inference.py:504-517 */
+/* d_observed_scores == NULL: the scores of the fit (inference.py:752-753). */
+int rocco_b200_budget_nonnull_fraction_dev(const double *d_centered, size_t m, size_t n, const double *d_observed_scores,
+                                           const rocco_b200_budget_params *params, rocco_b200_budget_result *result,
+                                           void *cuda_stream);
+/* Building block of one draw (inference.py:653-662): d_out = d_template x W, W the Bartlett multiplier field of
+ * (random_seed, draw_index), or of d_innovations [m][n + 2*bandwidth] when given.  d_out may not alias d_template. */
+int rocco_b200_wild_multiply_dev(const double *d_template, size_t m, size_t n, int bandwidth,
+                                 unsigned long long random_seed, unsigned draw_index, const double *d_innovations,
+                                 double *d_out, void *cuda_stream);
+/* Host buffers (H2D inside); `innovations` is an optional HOST buffer laid out like d_innovations. */
+int rocco_budget_nonnull_fraction_f64(const double *centered, size_t m, size_t n, const double *observed_scores,
+                                      const rocco_b200_budget_params *params, const double *innovations,
+                                      rocco_b200_budget_result *result);
+/* _estimate_effective_sample_size (inference.py:446-501) of a host series. */
+int rocco_effective_sample_size_f64(const double *values, size_t n, int max_lag, double *n_eff, double *tau_int,
+                                    int *lags_used);
+/* Median and count of the scores > 0 (rocco.py:762-769, the scale of the automatic gamma); NaNs sort last and would
+ * count as positive, so the caller rejects non-finite scores first, as rocco.py:1019-1020 does. */
+int rocco_positive_score_median_f64(const double *scores, size_t n, double *median, long long *count);
+
 /* ------------------------------------------------------------------ column statistics */
 enum {
     ROCCO_STAT_MEDIAN = 0,     /* np.median                                   (rocco.py:265)  */

@@ -51,6 +51,30 @@ class ScoreOutputs(Structure):
     ]
 
 
+class BudgetParams(Structure):
+    _fields_ = [
+        ("score", ScoreParams), ("dependence_lag_hint", c_int), ("num_null_draws", c_int), ("min_null_draws", c_int),
+        ("reserved", c_int), ("stability_abs_tol", c_double), ("stability_rel_tol", c_double),
+        ("random_seed", c_ulonglong), ("d_innovations", c_void_p),
+    ]
+
+
+_BUDGET_DOUBLES = (
+    "nonnull_fraction", "effective_count", "effective_total_count", "autocorrelation_time", "null_center", "null_scale",
+    "null_threshold", "null_positive_mass", "null_positive_units", "null_positive_fraction", "null_positive_units_sd",
+    "null_positive_units_stderr", "null_tail_occupancy", "null_tail_occupancy_sd", "null_tail_occupancy_stderr",
+    "negative_fraction", "observed_positive_fraction", "observed_negative_fraction", "observed_excess_mass",
+    "observed_excess_units", "observed_tail_occupancy", "null_reference_mean_positive_consensus",
+    "null_reference_max_positive_consensus", "positive_score_median")
+_BUDGET_LONGS = ("negative_support_size", "positive_score_count", "num_loci")
+_BUDGET_INTS = ("num_null_draws", "max_null_draws", "adaptive_stop", "wild_bandwidth", "ess_max_lag", "ess_lags_used")
+
+
+class BudgetResult(Structure):
+    _fields_ = ([(k, c_double) for k in _BUDGET_DOUBLES] + [(k, c_longlong) for k in _BUDGET_LONGS]
+                + [(k, c_int) for k in _BUDGET_INTS])
+
+
 _lib = None
 
 
@@ -67,6 +91,17 @@ def _declare(lib):
         "rocco_b200_uniform_step_i64": (c_int, [c_void_p, c_size_t]),
         "rocco_b200_write_bed3": (c_int, [c_char_p, POINTER(c_char_p), c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int]),
         "rocco_b200_combine_bed3": (ctypes.c_longlong, [POINTER(c_char_p), c_int, c_char_p, c_int, POINTER(c_int)]),
+        "rocco_b200_default_budget_params": (None, [POINTER(BudgetParams)]),
+        "rocco_b200_budget_bandwidth": (c_int, [c_size_t, c_int]),
+        "rocco_b200_budget_ess_max_lag": (c_int, [c_size_t, c_int]),
+        "rocco_b200_budget_nonnull_fraction_dev": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p, POINTER(BudgetParams),
+                                                           POINTER(BudgetResult), c_void_p]),
+        "rocco_budget_nonnull_fraction_f64": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p, POINTER(BudgetParams), c_void_p,
+                                                      POINTER(BudgetResult)]),
+        "rocco_b200_wild_multiply_dev": (c_int, [c_void_p, c_size_t, c_size_t, c_int, c_ulonglong, ctypes.c_uint, c_void_p, c_void_p,
+                                                 c_void_p]),
+        "rocco_effective_sample_size_f64": (c_int, [c_void_p, c_size_t, c_int, dp, dp, ip]),
+        "rocco_positive_score_median_f64": (c_int, [c_void_p, c_size_t, dp, llp]),
         "rocco_b200_numpy_sum_f64": (c_double, [c_void_p, c_size_t]),
         "rocco_b200_numpy_sum_const_f64": (c_double, [c_double, c_size_t]),
         "rocco_solve_penalized_chain_f64": (c_int, [c_void_p, c_void_p, c_size_t, c_double, c_void_p, dp, llp]),

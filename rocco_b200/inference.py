@@ -176,3 +176,155 @@ def score_loci_wls(chrom_matrix: np.ndarray, lower_bound_z: float = 1.0, prior_d
         "centered_matrix": centered.astype(np.float32 if low_memory else np.float64, copy=False),
     }
     return scores.astype(np.float64), details
+
+
+# ------------------------------------------------------------------------------------------------
+# Budget null: dependent wild residual bootstrap (inference.py:446-1148) -- SURVEY.md 8(f) rank 1
+# ------------------------------------------------------------------------------------------------
+def _resolve_budget_ess_max_lag(n_loci: int, dependence_lag_hint: int | None = None) -> int:
+    r"""ESS autocorrelation lag cap (inference.py:504-517)."""
+    return int(_lib.load().rocco_b200_budget_ess_max_lag(int(max(1, n_loci)), _hint(dependence_lag_hint)))
+
+
+def _resolve_budget_bootstrap_bandwidth(n_loci: int, dependence_lag_hint: int | None = None) -> int:
+    r"""Bartlett bandwidth of the multiplier field (inference.py:520-530)."""
+    return int(_lib.load().rocco_b200_budget_bandwidth(int(max(1, n_loci)), _hint(dependence_lag_hint)))
+
+
+def _hint(dependence_lag_hint) -> int:
+    # the C entries use "<= 0" for "no hint"; a non-positive hint means max(8, hint) = 8 bins / 4 * max(1, hint) = 4 in the
+    # reference, which the smallest positive hint reproduces
+    if dependence_lag_hint is None:
+        return 0
+    return max(1, int(dependence_lag_hint))
+
+
+def _build_budget_bootstrap_kernel(bandwidth: int) -> np.ndarray:
+    r"""Bartlett taps on [-b, b] with unit L2 norm (inference.py:533-541); host helper."""
+    b = int(max(1, bandwidth))
+    taps = np.maximum(1.0 - np.abs(np.arange(-b, b + 1, dtype=np.float64)) / float(b + 1), 0.0)
+    return taps / np.sqrt(np.sum(taps * taps))
+
+
+def _estimate_effective_sample_size(values: np.ndarray, max_lag: int) -> tuple[float, float, int]:
+    r"""ESS from the integrated autocorrelation time with Geyer's truncation (inference.py:446-501); the
+    autocovariances are direct lag products on the device instead of an FFT."""
+    values_ = np.ascontiguousarray(values, dtype=np.float64)
+    if values_.ndim != 1:
+        raise ValueError("`values` must be one-dimensional")
+    n_eff, tau, used = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
+    if values_.size >= 4:
+        _lib.require_device()
+    st = _lib.load().rocco_effective_sample_size_f64(_lib.np_ptr(values_), values_.size, int(max_lag), ctypes.byref(n_eff),
+                                                     ctypes.byref(tau), ctypes.byref(used))
+    if st == _lib.ST_NONFINITE:                       # non-finite series: the reference returns (n, 1, 0) (inference.py:470-471)
+        return float(values_.size), 1.0, 0
+    _lib.check(st, "effective sample size")
+    return float(n_eff.value), float(tau.value), int(used.value)
+
+
+def _budget_params(lower_bound_z, prior_df, min_effect, precision_floor_ratio, dependence_lag_hint, num_null_draws,
+                   random_seed, min_null_draws, stability_abs_tol, stability_rel_tol):
+    lib = _lib.load()
+    prm = _lib.BudgetParams()
+    lib.rocco_b200_default_budget_params(ctypes.byref(prm))
+    prm.score.lower_bound_z = float(lower_bound_z)
+    prm.score.prior_df = float(prior_df)
+    prm.score.use_min_effect = 0 if min_effect is None else 1
+    prm.score.min_effect = 0.0 if min_effect is None else max(float(min_effect), 0.0)
+    prm.score.precision_floor_ratio = float(max(precision_floor_ratio, 0.0))
+    prm.dependence_lag_hint = _hint(dependence_lag_hint)
+    prm.num_null_draws = int(max(1, num_null_draws))
+    prm.min_null_draws = 0 if min_null_draws is None else int(max(1, min_null_draws))
+    prm.stability_abs_tol = float(stability_abs_tol)
+    prm.stability_rel_tol = float(stability_rel_tol)
+    prm.random_seed = int(random_seed) & 0xFFFFFFFFFFFFFFFF
+    return prm
+
+
+def _budget_details(res: "_lib.BudgetResult") -> Dict[str, Any]:
+    d = {k: float(getattr(res, k)) for k in (
+        "observed_positive_fraction", "observed_negative_fraction", "null_positive_fraction", "observed_excess_mass",
+        "observed_excess_units", "null_threshold", "observed_tail_occupancy", "null_tail_occupancy",
+        "null_tail_occupancy_sd", "null_tail_occupancy_stderr", "null_center", "null_scale", "nonnull_fraction",
+        "effective_count", "effective_total_count", "autocorrelation_time", "negative_fraction",
+        "null_reference_mean_positive_consensus", "null_reference_max_positive_consensus")}
+    d.update({
+        "null_excess_mass": float(res.null_positive_mass), "null_excess_units": float(res.null_positive_units),
+        "null_excess_units_sd": float(res.null_positive_units_sd),
+        "null_excess_units_stderr": float(res.null_positive_units_stderr),
+        "ess_max_lag": float(res.ess_max_lag), "ess_lags_used": float(res.ess_lags_used), "num_loci": float(res.num_loci),
+        "negative_support_size": float(res.negative_support_size), "num_null_draws": float(res.num_null_draws),
+        "max_null_draws": float(res.max_null_draws), "adaptive_stop": bool(res.adaptive_stop),
+        "wild_bandwidth": float(res.wild_bandwidth), "wild_process": "bartlett_multiplier",
+        "null_method": "dependent_wild_residual_bootstrap",
+        # not in the reference's dict: inputs of rocco._resolve_chrom_gamma, computed while the scores are on the device
+        "positive_score_median": float(res.positive_score_median), "positive_score_count": int(res.positive_score_count),
+    })
+    return d
+
+
+def estimate_budget_nonnull_fraction_from_wild_bootstrap_null(
+        centered_matrix: np.ndarray, observed_scores: np.ndarray | None = None, lower_bound_z: float = 1.0,
+        prior_df: float = 5.0, min_effect: float | None = None, precision_floor_ratio: float = 0.01,
+        dependence_lag_hint: int | None = None, num_null_draws: int = 25, random_seed: int = 0,
+        progress_label: str | None = None, num_processes: int = 1, return_details: bool = False,
+        min_null_draws: int | None = None, stability_abs_tol: float = 5.0e-3, stability_rel_tol: float = 5.0e-2,
+        innovations: np.ndarray | None = None) -> float | Tuple[float, Dict[str, Any]]:
+    r"""Conservative enriched fraction from a dependent-wild-bootstrap null (inference.py:988-1148).
+
+    Same arguments, return value and details keys as the reference.  The whole estimator -- null template, fitted-null
+    score field, up to ``num_null_draws`` multiplier fields each re-scored by the WLS chain, the adaptive stop, the
+    observed-side summary and the ESS -- runs on the GPU in one native call; ``num_processes`` and ``progress_label``
+    are accepted and unused.  Random streams are Philox (keyed by ``random_seed``), not NumPy's PCG64: results agree
+    with the reference in distribution.  ``innovations`` (``[num_null_draws, n_samples, n_loci + 2*bandwidth]`` iid
+    N(0,1)) replaces the generator, e.g. to replay the reference's own streams.
+    """
+    centered = np.asarray(centered_matrix, dtype=np.float64)
+    if centered.ndim == 1:
+        centered = centered[np.newaxis, :]
+    if centered.ndim != 2:
+        raise ValueError("`centered_matrix` must be one- or two-dimensional")
+    m, n = centered.shape
+    if n <= 0:
+        raise ValueError("`centered_matrix` must contain at least one locus")
+    if m == 0:
+        raise ValueError("`centered_matrix` must be non-empty")
+    centered = np.ascontiguousarray(centered)
+    obs = None
+    if observed_scores is not None:
+        obs = np.ascontiguousarray(observed_scores, dtype=np.float64)
+        if obs.shape[0] != n:
+            raise ValueError("`observed_scores` must have the same number of loci as `centered_matrix`")
+    lib = _lib.load()
+    _lib.require_device()
+    prm = _budget_params(lower_bound_z, prior_df, min_effect, precision_floor_ratio, dependence_lag_hint, num_null_draws,
+                         random_seed, min_null_draws, stability_abs_tol, stability_rel_tol)
+    inn = None
+    if innovations is not None:
+        bw = _resolve_budget_bootstrap_bandwidth(n, dependence_lag_hint)
+        inn = np.ascontiguousarray(innovations, dtype=np.float64)
+        if inn.shape != (prm.num_null_draws, m, n + 2 * bw):
+            raise ValueError(f"`innovations` must have shape {(prm.num_null_draws, m, n + 2 * bw)}")
+    res = _lib.BudgetResult()
+    st = lib.rocco_budget_nonnull_fraction_f64(_lib.np_ptr(centered), m, n, None if obs is None else _lib.np_ptr(obs),
+                                               ctypes.byref(prm), None if inn is None else _lib.np_ptr(inn), ctypes.byref(res))
+    if st == _lib.ST_NONFINITE:
+        raise ValueError("Budget initialization produced non-finite values")
+    _lib.check(st, "budget null")
+    details = _budget_details(res)
+    if return_details:
+        return float(res.nonnull_fraction), details
+    return float(res.nonnull_fraction)
+
+
+def estimate_budget_nonnull_fraction_from_empirical_null(centered_matrix, observed_scores=None, lower_bound_z=1.0, prior_df=5.0,
+                                                         min_effect=None, precision_floor_ratio=0.01, dependence_lag_hint=None,
+                                                         num_null_draws=25, random_seed=0, progress_label=None,
+                                                         num_processes=1, return_details=False):
+    r"""Wrapper for the wild-bootstrap budget estimator (inference.py:1424-1452)."""
+    return estimate_budget_nonnull_fraction_from_wild_bootstrap_null(
+        centered_matrix, observed_scores=observed_scores, lower_bound_z=lower_bound_z, prior_df=prior_df,
+        min_effect=min_effect, precision_floor_ratio=precision_floor_ratio, dependence_lag_hint=dependence_lag_hint,
+        num_null_draws=num_null_draws, random_seed=random_seed, progress_label=progress_label,
+        num_processes=num_processes, return_details=return_details)

@@ -266,3 +266,42 @@ def score_dispersion_chrom(chrom_matrix: np.ndarray, method: str = "mad", rng: T
     if method_ == "tstd":
         return _column_stat(chrom_matrix, "tstd", arg0=tprop, power=power)
     raise ValueError(f"Dispersion method not recognized or could not execute: {method}")
+
+
+# ------------------------------------------------------------------------------------------------
+# automatic gamma (rocco.py:751-789) -- SURVEY.md 8(f) rank 2
+# ------------------------------------------------------------------------------------------------
+def _resolve_chrom_gamma(chrom: str, args: dict, chrom_scores: np.ndarray, budget_rate_meta: dict) -> tuple[float, dict | None]:
+    r"""gamma = clip(0.5 * ceil(tau_int) * median(scores > 0), 0.5, 10) unless ``args["gamma"]`` fixes it.
+
+    The median of the positive scores is taken on the GPU; when ``budget_rate_meta`` comes from this package's budget
+    estimator it already carries that number (computed while the scores were on the device) and nothing is re-read."""
+    if args["gamma"] is not None:
+        chrom_gamma = float(args["gamma"])
+        if not np.isfinite(chrom_gamma) or chrom_gamma < 0.0:
+            raise ValueError("`--gamma` must be finite and non-negative")
+        logger.info("%s fixed gamma value=%.6f", chrom, chrom_gamma)
+        return float(chrom_gamma), None
+    if "positive_score_median" in budget_rate_meta and "positive_score_count" in budget_rate_meta:
+        positive_scale = float(budget_rate_meta["positive_score_median"])
+        positive_count = int(budget_rate_meta["positive_score_count"])
+    else:
+        scores_ = np.ascontiguousarray(chrom_scores, dtype=np.float64)
+        med, cnt = ctypes.c_double(1.0), ctypes.c_longlong(0)
+        if scores_.size:
+            _lib.require_device()
+            _lib.check(_lib.load().rocco_positive_score_median_f64(_lib.np_ptr(scores_), scores_.size, ctypes.byref(med),
+                                                                   ctypes.byref(cnt)), "positive score median")
+        positive_scale, positive_count = float(med.value), int(cnt.value)
+    autocorrelation_time = max(1.0, float(budget_rate_meta.get("autocorrelation_time", 1.0)))
+    characteristic_run = int(np.ceil(autocorrelation_time))
+    gamma_raw = 0.5 * float(characteristic_run) * float(positive_scale)
+    chrom_gamma = float(np.clip(gamma_raw, 0.5, 10.0))
+    gamma_meta = {
+        "method": "auto_score_autocorr", "autocorrelation_time": float(autocorrelation_time),
+        "characteristic_run_length": int(characteristic_run), "positive_score_median": float(positive_scale),
+        "positive_score_count": int(positive_count), "gamma_raw": float(gamma_raw), "gamma_clipped": float(chrom_gamma),
+        "gamma_clip_min": 0.5, "gamma_clip_max": 10.0,
+    }
+    logger.info("%s auto gamma estimate: %s", chrom, gamma_meta)
+    return float(chrom_gamma), gamma_meta
