@@ -21,13 +21,14 @@ namespace rb {
 namespace budget {
 
 constexpr int FIR_THREADS = 512;
-constexpr int FIR_ITEMS = 8;
+constexpr int FIR_ITEMS = 16;
 constexpr int FIR_T = FIR_THREADS * FIR_ITEMS;        // outputs per CTA
 constexpr int MAX_BANDWIDTH = 2048;                   // taps = 2 b + 1 <= 4097 (n^(1/3) rule: 171 at 5 M bins)
 constexpr int AC_T = 4096, AC_THREADS = 256, AC_MAXLAG = 4096;
 constexpr int RED_BLOCKS = 1184, RED_THREADS = 256;   // 8 CTAs per SM x 148
 
-__host__ __device__ __forceinline__ int padpos(int i) { return i + (i >> 3); }
+// 16 bins per thread: position i lives at i + i/16 (thread stride 17 doubles: conflict-free 8-byte accesses)
+__host__ __device__ __forceinline__ int padpos(int i) { return i + (i >> 4); }
 
 // ------------------------------------------------------------------ Philox4x32-10 + Box-Muller
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k)
@@ -68,16 +69,20 @@ __global__ void __launch_bounds__(256) k_template(const double *__restrict__ C, 
 }
 
 // ------------------------------------------------------------------ multiplier field: FIR of the innovations
-// raw[i][j] = sum_k taps[k] * z[i][j + k],  k = 0 .. K-1  (valid-mode correlation; the taps are symmetric, so this is
-// the reference's fftconvolve(..., mode="valid")).  One CTA per (tile of FIR_T outputs, sample); the z span of the
-// tile is staged in shared memory (generated in place when no innovations are supplied); every thread keeps a
-// sliding window of 8 consecutive z in registers and receives one tap per step by broadcast.
-__global__ void __launch_bounds__(FIR_THREADS) k_wild_fir(const double *__restrict__ innov, long long innov_stride, uint2 key,
+// raw[i][j] = sum_k taps[k] * z[i][j + k],  k = 0 .. K-1, K = 2b + 1  (valid-mode correlation; the taps are symmetric, so
+// this is the reference's fftconvolve(..., mode="valid")).  One CTA per (tile of FIR_T outputs, sample); the z span of
+// the tile is staged in shared memory (generated in place when no innovations are supplied).  The Bartlett taps are a
+// triangle, taps[k] = h * (b + 1 - |k - b|), so consecutive outputs differ by h * (R_j - L_j) with the two box sums
+//   L_j = z[j] + .. + z[j+b],   R_j = z[j+b+1] + .. + z[j+2b+1]:
+// every thread forms its first output (and L, R) directly -- K fused multiply-adds -- and slides the next 15, which
+// keeps the rounding of a slide chain at 15 steps (~1e-15) instead of the row length.
+__global__ void __launch_bounds__(FIR_THREADS, 2) k_wild_fir(const double *__restrict__ innov, long long innov_stride, uint2 key,
                                                           unsigned draw, long long n, int K, const double *__restrict__ taps,
-                                                          double *__restrict__ raw, double2 *__restrict__ partial, int tiles)
+                                                          double h, double *__restrict__ raw, double2 *__restrict__ partial,
+                                                          int tiles)
 {
     extern __shared__ double s_fir[];
-    double *s_x = s_fir;                                   // padpos(FIR_T + K - 1 + 8)
+    double *s_x = s_fir;                                   // padpos(FIR_T + K + 8)
     double *s_t = s_fir + padpos(FIR_T + K + 8) + 8;       // K taps
     __shared__ double2 s_red[FIR_THREADS / 32];
     const int tid = threadIdx.x;
@@ -85,50 +90,42 @@ __global__ void __launch_bounds__(FIR_THREADS) k_wild_fir(const double *__restri
     const long long j0 = (long long)blockIdx.x * FIR_T;
     const int cnt = (int)min((long long)FIR_T, n - j0);
     const int span = cnt + K - 1;
+    const int staged = FIR_T + K + 1;                      // the last slide reads z[FIR_T - 2 + K + 1]
     for (int k = tid; k < K; k += FIR_THREADS) s_t[k] = taps[k];
     if (innov) {
         const double *src = innov + row * innov_stride + j0;
-        for (int e = tid; e < FIR_T + K + 7; e += FIR_THREADS) s_x[padpos(e)] = (e < span) ? src[e] : 0.0;
+        for (int e = tid; e < staged; e += FIR_THREADS) s_x[padpos(e)] = (e < span) ? src[e] : 0.0;
     } else {
         // j0 is even: pair p of this tile is global pair j0/2 + p, identical whichever tile generates it
-        const int pairs = (FIR_T + K + 7 + 1) / 2;
-        for (int p = tid; p < pairs; p += FIR_THREADS) {
+        for (int p = tid; 2 * p < staged; p += FIR_THREADS) {
             const int e = 2 * p;
             double2 z = make_double2(0.0, 0.0);
             if (e < span) z = normal_pair((unsigned long long)(j0 / 2 + p), (unsigned)row, draw, key);
             s_x[padpos(e)] = z.x;
-            if (e + 1 < FIR_T + K + 7) s_x[padpos(e + 1)] = (e + 1 < span) ? z.y : 0.0;
+            if (e + 1 < staged) s_x[padpos(e + 1)] = (e + 1 < span) ? z.y : 0.0;
         }
     }
     __syncthreads();
-    double acc[FIR_ITEMS], xs[FIR_ITEMS];
-    const int base = tid * FIR_ITEMS;
+    const int base = tid * FIR_ITEMS, b = (K - 1) / 2;
+    double w = 0.0, L = 0.0, R = 0.0;
+    for (int k = 0; k <= b; ++k) { const double z = s_x[padpos(base + k)]; w = fma(s_t[k], z, w); L += z; }
+    for (int k = b + 1; k < K; ++k) { const double z = s_x[padpos(base + k)]; w = fma(s_t[k], z, w); R += z; }
+    R += s_x[padpos(base + K)];
+    double out[FIR_ITEMS];
+    out[0] = w;
 #pragma unroll
-    for (int r = 0; r < FIR_ITEMS; ++r) { acc[r] = 0.0; xs[r] = s_x[padpos(base + r)]; }
-    int k = 0;
-    for (; k + FIR_ITEMS <= K; k += FIR_ITEMS) {
-#pragma unroll
-        for (int u = 0; u < FIR_ITEMS; ++u) {
-            const double c = s_t[k + u];
-#pragma unroll
-            for (int r = 0; r < FIR_ITEMS; ++r) acc[r] = fma(c, xs[(r + u) % FIR_ITEMS], acc[r]);
-            xs[u] = s_x[padpos(base + FIR_ITEMS + k + u)];           // slot u now holds z[base + 8 + k + u]
-        }
-    }
-    for (; k < K; ++k) {                                             // tail: plain shifts
-        const double c = s_t[k];
-#pragma unroll
-        for (int r = 0; r < FIR_ITEMS; ++r) acc[r] = fma(c, xs[r], acc[r]);
-#pragma unroll
-        for (int r = 0; r + 1 < FIR_ITEMS; ++r) xs[r] = xs[r + 1];
-        xs[FIR_ITEMS - 1] = s_x[padpos(base + FIR_ITEMS + k)];
+    for (int r = 1; r < FIR_ITEMS; ++r) {
+        w = fma(h, R - L, w);
+        out[r] = w;
+        const double zj = s_x[padpos(base + r - 1)], zm = s_x[padpos(base + r + b)], ze = s_x[padpos(base + r + K)];
+        L += zm - zj;
+        R += ze - zm;
     }
     __syncthreads();
     double s1 = 0.0, s2 = 0.0;
 #pragma unroll
     for (int r = 0; r < FIR_ITEMS; ++r) {
-        const bool live = base + r < cnt;
-        const double v = live ? acc[r] : 0.0;
+        const double v = (base + r < cnt) ? out[r] : 0.0;
         s_x[padpos(base + r)] = v;
         s1 += v; s2 = fma(v, v, s2);
     }
@@ -137,9 +134,9 @@ __global__ void __launch_bounds__(FIR_THREADS) k_wild_fir(const double *__restri
     if ((tid & 31) == 0) s_red[tid >> 5] = make_double2(s1, s2);
     __syncthreads();
     if (tid == 0) {
-        double a = 0.0, b = 0.0;
-        for (int w = 0; w < FIR_THREADS / 32; ++w) { a += s_red[w].x; b += s_red[w].y; }
-        partial[row * tiles + blockIdx.x] = make_double2(a, b);
+        double a = 0.0, c = 0.0;
+        for (int q = 0; q < FIR_THREADS / 32; ++q) { a += s_red[q].x; c += s_red[q].y; }
+        partial[row * tiles + blockIdx.x] = make_double2(a, c);
     }
     double *dst = raw + row * n + j0;
     for (int e = tid; e < cnt; e += FIR_THREADS) dst[e] = s_x[padpos(e)];
@@ -354,7 +351,7 @@ static int track_sums(const double *d_s, long long n, double c, double soft, dou
     return 0;
 }
 
-static void bartlett_taps(int b, std::vector<double> &taps)
+static double bartlett_taps(int b, std::vector<double> &taps)          // returns the slope h: taps[k] = h (b + 1 - |k - b|)
 {
     // inference.py:533-541, same operation order as NumPy: maximum(1 - |k| / (b + 1), 0) / sqrt(sum of squares)
     taps.resize((size_t)(2 * b + 1));
@@ -363,6 +360,7 @@ static void bartlett_taps(int b, std::vector<double> &taps)
     for (size_t i = 0; i < taps.size(); ++i) sq[i] = taps[i] * taps[i];
     const double nrm = std::sqrt(numpy_sum_f64(sq.data(), sq.size()));
     for (double &t : taps) t /= nrm;
+    return 1.0 / ((double)(b + 1) * nrm);
 }
 
 int resolve_bandwidth(long long n, int hint)
@@ -388,7 +386,7 @@ struct Welford {
 };
 
 // one multiplier field applied to the template:  d_out = template x W   (inference.py:656-662)
-static int wild_multiply(Arena &ar, const double *d_template, long long m, long long n, int bandwidth, const double *d_taps,
+static int wild_multiply(Arena &ar, const double *d_template, long long m, long long n, int bandwidth, const double *d_taps, double h,
                          unsigned long long seed, unsigned draw, const double *d_innov, double *d_out, int *d_bad, cudaStream_t st)
 {
     if (n == 1) {                                         // weights are exactly one (inference.py:556-557)
@@ -412,7 +410,7 @@ static int wild_multiply(Arena &ar, const double *d_template, long long m, long 
     const uint2 key = make_uint2((unsigned)seed, (unsigned)(seed >> 32));
     {
         RB_PROF("k_wild_fir", st, (double)m * n * 8.0);
-        k_wild_fir<<<dim3((unsigned)tiles, (unsigned)m), FIR_THREADS, smem, st>>>(d_innov, n + K - 1, key, draw, n, K, d_taps, d_out,
+        k_wild_fir<<<dim3((unsigned)tiles, (unsigned)m), FIR_THREADS, smem, st>>>(d_innov, n + K - 1, key, draw, n, K, d_taps, h, d_out,
                                                                                   d_part, tiles);
         RB_LAUNCH_CHECK();
     }
@@ -506,7 +504,7 @@ static int budget_core(const double *d_centered, long long m, long long n, const
     RB_TRY(ar.alloc(&d_bad, 1));
     RB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
     std::vector<double> taps;
-    bartlett_taps(bandwidth, taps);
+    const double tap_step = bartlett_taps(bandwidth, taps);
     RB_TRY(ar.alloc(&d_taps, taps.size()));
     RB_CUDA(cudaMemcpyAsync(d_taps, taps.data(), sizeof(double) * taps.size(), cudaMemcpyHostToDevice, st));
 
@@ -555,7 +553,7 @@ static int budget_core(const double *d_centered, long long m, long long n, const
     const size_t innov_per_draw = (size_t)m * (size_t)(n + 2 * bandwidth);
     for (int d = 0; d < draws; ++d) {
         const double *innov = P.d_innovations ? P.d_innovations + (size_t)d * innov_per_draw : nullptr;
-        RB_TRY(wild_multiply(ar, d_tmpl, m, n, bandwidth, d_taps, P.random_seed, (unsigned)d, innov, d_boot, d_bad, st));
+        RB_TRY(wild_multiply(ar, d_tmpl, m, n, bandwidth, d_taps, tap_step, P.random_seed, (unsigned)d, innov, d_boot, d_bad, st));
         rocco_b200_score_outputs sd{};
         sd.scores = d_ref;                                        // the reference field is no longer needed: reuse its buffer
         RB_TRY(score::centered_wls(d_boot, m, n, P.score, &sd, st));
@@ -647,14 +645,14 @@ RB_API int rocco_b200_wild_multiply_dev(const double *d_template, size_t m, size
     cudaStream_t st = (cudaStream_t)cuda_stream;
     Arena ar(st);
     std::vector<double> taps;
-    budget::bartlett_taps(bandwidth, taps);
+    const double tap_step = budget::bartlett_taps(bandwidth, taps);
     double *d_taps = nullptr;
     int *d_bad = nullptr;
     RB_TRY(ar.alloc(&d_taps, taps.size()));
     RB_TRY(ar.alloc(&d_bad, 1));
     RB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
     RB_CUDA(cudaMemcpyAsync(d_taps, taps.data(), sizeof(double) * taps.size(), cudaMemcpyHostToDevice, st));
-    RB_TRY(budget::wild_multiply(ar, d_template, (long long)m, (long long)n, bandwidth, d_taps, random_seed, draw_index,
+    RB_TRY(budget::wild_multiply(ar, d_template, (long long)m, (long long)n, bandwidth, d_taps, tap_step, random_seed, draw_index,
                                  d_innovations, d_out, d_bad, st));
     int bad = 0;
     RB_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -29,9 +29,12 @@
 namespace rb {
 namespace score {
 
-constexpr int NBX = 16384;              // |signal| buckets: bits >> 42 (exponent + 10 mantissa bits), 2^-8 .. 2^8
-constexpr int XSHIFT = 42;
-constexpr unsigned XB0 = (unsigned)(0x3F70000000000000ULL >> XSHIFT);   // bucket index of 2^-8
+constexpr int NBX = 16384;              // |signal| buckets, order preserving: 64 per octave on [2^-24, 2^-8) (1024 buckets),
+constexpr int XSHIFT = 42;              // 1024 per octave on [2^-8, 2^7) (15360 buckets); outside: first / last bucket
+constexpr int XSHIFT_LO = 46;
+constexpr unsigned XB0 = (unsigned)(0x3F70000000000000ULL >> XSHIFT);      // bits of 2^-8  >> 42
+constexpr unsigned XB0_LO = (unsigned)(0x3E70000000000000ULL >> XSHIFT_LO);   // bits of 2^-24 >> 46
+constexpr int NBX_LO = 1024;
 constexpr int NBY = 1024;               // variance buckets: bits >> 46 (exponent + 6 mantissa bits): 64 per octave,
 constexpr int YSHIFT = 46;              // 16 octaves centred on the row's sampled median variance
 constexpr int YSAMPLE = 2048;
@@ -43,11 +46,15 @@ constexpr int CHUNK = 131072;           // elements streamed per CTA
 constexpr int ST_THREADS = 512;
 int trend_fused_max_window() { return 1025; }
 
+// The fine region carries the bulk of a row; the coarse one exists for rows with much mass near zero (a bootstrap
+// draw  residual x multiplier  has a log-divergent density at 0), whose lowest equal-count bins end far below 2^-8.
 __device__ __forceinline__ int xbucket(double x)
 {
-    const unsigned u = (unsigned)((unsigned long long)__double_as_longlong(x) >> XSHIFT);
-    const int b = (int)u - (int)XB0;
-    return b < 0 ? 0 : (b >= NBX ? NBX - 1 : b);
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(x);
+    const int b = (int)(unsigned)(bits >> XSHIFT) - (int)XB0;
+    if (b >= 0) return min(NBX_LO + b, NBX - 1);
+    const int t = (int)(unsigned)(bits >> XSHIFT_LO) - (int)XB0_LO;
+    return max(t, 0);
 }
 __device__ __forceinline__ int ybucket(double y, int yb0)
 {

@@ -375,3 +375,44 @@ def score_loci_wls_sample_sharded(d_matrix_local, m_total: int, params=None, gro
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(acc, group=group)
     return score_finalize_device(acc, m_total, params, details=details)
+
+
+# ------------------------------------------------------------------ budget null on device tensors
+def budget_null_device(d_centered, d_observed_scores=None, params=None, dependence_lag_hint=None, num_null_draws=25,
+                       random_seed=0, min_null_draws=None, stability_abs_tol=5.0e-3, stability_rel_tol=5.0e-2):
+    """``estimate_budget_nonnull_fraction_from_wild_bootstrap_null`` (inference.py:988-1148) on CUDA tensors: the centred
+    matrix [samples, bins] (float64, as ``score_loci_wls_device(..., details=True)`` returns it) and optionally the observed
+    scores stay on the device; returns ``(nonnull_fraction, details)`` with the reference's keys plus the positive-score
+    median/count that ``rocco._resolve_chrom_gamma`` needs."""
+    from .inference import _budget_details, _hint
+    torch = _torch()
+    lib = _lib.load()
+    if d_centered.dim() != 2 or not d_centered.is_cuda or not d_centered.is_contiguous() or d_centered.dtype != torch.float64:
+        raise ValueError("`d_centered` must be a contiguous two-dimensional float64 CUDA tensor")
+    m, n = d_centered.shape
+    if m == 0 or n == 0:
+        raise ValueError("`centered_matrix` must contain at least one locus")
+    if d_observed_scores is not None and (d_observed_scores.numel() != n or d_observed_scores.dtype != torch.float64
+                                          or not d_observed_scores.is_cuda or not d_observed_scores.is_contiguous()):
+        raise ValueError("`observed_scores` must have the same number of loci as `centered_matrix`")
+    prm = _lib.BudgetParams()
+    lib.rocco_b200_default_budget_params(ctypes.byref(prm))
+    if params is not None:
+        prm.score = params
+    prm.dependence_lag_hint = _hint(dependence_lag_hint)
+    prm.num_null_draws = int(max(1, num_null_draws))
+    prm.min_null_draws = 0 if min_null_draws is None else int(max(1, min_null_draws))
+    prm.stability_abs_tol = float(stability_abs_tol)
+    prm.stability_rel_tol = float(stability_rel_tol)
+    prm.random_seed = int(random_seed) & 0xFFFFFFFFFFFFFFFF
+    res = _lib.BudgetResult()
+    dev = d_centered.device
+    with torch.cuda.device(dev):
+        st = lib.rocco_b200_budget_nonnull_fraction_dev(
+            ctypes.c_void_p(d_centered.data_ptr()), m, n,
+            None if d_observed_scores is None else ctypes.c_void_p(d_observed_scores.data_ptr()),
+            ctypes.byref(prm), ctypes.byref(res), ctypes.c_void_p(_stream_ptr(dev)))
+    if st == _lib.ST_NONFINITE:
+        raise ValueError("Budget initialization produced non-finite values")
+    _lib.check(st, "budget null")
+    return float(res.nonnull_fraction), _budget_details(res)
