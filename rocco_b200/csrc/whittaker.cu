@@ -178,24 +178,32 @@ static void build_log2_tables()
     g_log2_ready = true;
 }
 
+// polynomial coefficients live in the constant bank: a DFMA reads them as an operand, whereas 64-bit immediates cost two
+// uniform moves each per use
+__constant__ double c_log2poly[7] = {
+    0.20609929155656704,      //  1/(7 ln2)
+    -0.24044917348266152,     // -1/(6 ln2)
+    0.28853900817779268,      //  1/(5 ln2)
+    -0.36067376022224085,     // -1/(4 ln2)
+    0.48089834696298783,      //  1/(3 ln2)
+    -0.72134752044448170,     // -1/(2 ln2)
+    1.4426950408889634,       //  1/ln2
+};
+
 __device__ __forceinline__ double fast_log2_ge1(double v, const double *s_inv, const double *s_tab)
 {
     const long long bits = __double_as_longlong(v);
     const long long mant = bits & 0x000FFFFFFFFFFFFFLL;
     const int e = (int)(bits >> 52) - 1023;
-    if (mant == 0) return (double)e;                                 // exact powers of two (zero counts -> 0.0)
     const int i = (int)(mant >> 45);
     const double m = __longlong_as_double(mant | 0x3FF0000000000000LL);
     const double r = __fma_rn(m, s_inv[i], -1.0);
     // log2(1+r) = r/ln2 * (1 - r/2 + r^2/3 - ...)
-    double p = 0.20609929155656704;                                  //  1/(7 ln2)
-    p = __fma_rn(p, r, -0.24044917348266152);                        // -1/(6 ln2)
-    p = __fma_rn(p, r, 0.28853900817779268);                         //  1/(5 ln2)
-    p = __fma_rn(p, r, -0.36067376022224085);                        // -1/(4 ln2)
-    p = __fma_rn(p, r, 0.48089834696298783);                         //  1/(3 ln2)
-    p = __fma_rn(p, r, -0.72134752044448170);                        // -1/(2 ln2)
-    p = __fma_rn(p, r, 1.4426950408889634);                          //  1/ln2
-    return (double)e + __fma_rn(p, r, s_tab[i]);
+    double p = c_log2poly[0];
+#pragma unroll
+    for (int k = 1; k < 7; ++k) p = __fma_rn(p, r, c_log2poly[k]);
+    const double res = (double)e + __fma_rn(p, r, s_tab[i]);
+    return mant == 0 ? (double)e : res;                              // exact powers of two (zero counts -> 0.0), branch-free
 }
 
 // ------------------------------------------------------------------ device side
@@ -361,34 +369,42 @@ __global__ void __launch_bounds__(WT_THREADS, 1) k_whittaker(WhitParams P)
     double *outp = P.out + rbase;
     const double pil = (P.log_transform && P.pilot) ? P.pilot[row] : 0.0;
     const bool par0 = ((r0 & 1) == 0);
+    // STEADY: the region is always complete (rlen == WT_REGION) and all twelve loads of a thread are issued before
+    // any arithmetic; every bin is stored once, into the array of its own parity -- the other array's slot would hold the
+    // masked zero, which the forward sweeps below supply as a literal instead of loading it.
+    constexpr int LD = STEADY ? WT_ITEMS : 4;
 #pragma unroll 1
-    for (int e0 = tid; e0 < WT_REGION; e0 += 4 * WT_THREADS) {
-        double raw[4];
+    for (int e0 = tid; e0 < WT_REGION; e0 += LD * WT_THREADS) {
+        double raw[LD];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < LD; ++u) {
             const int e = e0 + u * WT_THREADS;
-            raw[u] = (e < rlen) ? (P.in_f32 ? (double)xf[e] : xd[e]) : 0.0;
+            raw[u] = (STEADY || e < rlen) ? (P.in_f32 ? (double)xf[e] : xd[e]) : 0.0;
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < LD; ++u) {
             const int e = e0 + u * WT_THREADS;
-            if (e >= WT_REGION) break;
+            if (!STEADY && e >= WT_REGION) break;
             double y = 0.0;
-            if (e < rlen) {
+            if (STEADY || e < rlen) {
                 y = raw[u];
-                if (P.log_transform) {
-                    // inference.py:45-46 rejects non-finite input (fmax would swallow NaN / -inf)
-                    y = isfinite(y) ? fast_log2_ge1(fmax(y, 0.0) + 1.0, s_log, s_log + 128) - pil : NAN;
-                }
-                bad |= !isfinite(y);
+                // inference.py:45-46 rejects non-finite input (fmax would swallow NaN / -inf); a finite input gives a
+                // finite y, so one test serves both the input check and the result check
+                const bool fin = isfinite(y);
+                if (P.log_transform) y = fin ? fast_log2_ge1(fmax(y, 0.0) + 1.0, s_log, s_log + 128) - pil : NAN;
+                bad |= !fin;
                 // park y of the tile's own bins in the output buffer: the epilogue needs it again and a second
                 // log2 per bin costs more issue slots than an L2 round trip
                 if (keep_y && e >= o_lo && e < o_hi) outp[e] = y;
             }
             const int a = e + e / WT_ITEMS;
             const bool even = (((e & 1) == 0) == par0);
-            s_f0[a] = even ? y : 0.0;
-            s_f1[a] = even ? 0.0 : y;
+            if (STEADY) {
+                if (even) s_f0[a] = y; else s_f1[a] = y;
+            } else {
+                s_f0[a] = even ? y : 0.0;
+                s_f1[a] = even ? 0.0 : y;
+            }
         }
     }
     if (bad) *P.bad = 1;
@@ -431,8 +447,9 @@ __global__ void __launch_bounds__(WT_THREADS, 1) k_whittaker(WhitParams P)
                         ha[p][2] = ha[p][0]; ha[p][3] = ha[p][1]; ha[p][0] = n0; ha[p][1] = n1;
                     }
                 }
-                const double na = fma(-l2a, a2, fma(-l1a, a1, f0[j]));
-                const double nb = fma(-l2b, b2, fma(-l1b, b1, f1[j]));
+                const double ra = (STEADY && (j & 1)) ? 0.0 : f0[j], rb_ = (STEADY && !(j & 1)) ? 0.0 : f1[j];
+                const double na = fma(-l2a, a2, fma(-l1a, a1, ra));
+                const double nb = fma(-l2b, b2, fma(-l1b, b1, rb_));
                 a2 = a1; a1 = na; b2 = b1; b1 = nb;
             }
         }
@@ -476,8 +493,9 @@ __global__ void __launch_bounds__(WT_THREADS, 1) k_whittaker(WhitParams P)
                     l1b = i >= 1 ? coef(P, 1, 1, i - 1) : 0.0; l2b = i >= 2 ? coef(P, 1, 2, i - 2) : 0.0;
                     da = coef(P, 0, 0, i); db = coef(P, 1, 0, i);
                 }
-                const double na = fma(-l2a, a2, fma(-l1a, a1, f0[j]));
-                const double nb = fma(-l2b, b2, fma(-l1b, b1, f1[j]));
+                const double ra = (STEADY && (j & 1)) ? 0.0 : f0[j], rb_ = (STEADY && !(j & 1)) ? 0.0 : f1[j];
+                const double na = fma(-l2a, a2, fma(-l1a, a1, ra));
+                const double nb = fma(-l2b, b2, fma(-l1b, b1, rb_));
                 a2 = a1; a1 = na; b2 = b1; b1 = nb;
                 f0[j] = na * da; f1[j] = nb * db;
             }
@@ -553,16 +571,17 @@ __global__ void __launch_bounds__(WT_THREADS, 1) k_whittaker(WhitParams P)
 
     // ---- write the tile (coalesced); y comes back from where the staging loop parked it (an L2 hit)
     int bad2 = 0;
+    constexpr int LDE = STEADY ? 5 : 4;                       // steady tiles: 9728 own bins = 9.5 per thread -> two rounds of five
 #pragma unroll 1
-    for (int e0 = o_lo + tid; e0 < o_hi; e0 += 4 * WT_THREADS) {
-        double yv[4];
+    for (int e0 = o_lo + tid; e0 < o_hi; e0 += LDE * WT_THREADS) {
+        double yv[LDE];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < LDE; ++u) {
             const int e = e0 + u * WT_THREADS;
             yv[u] = (!P.write_baseline && e < o_hi) ? __ldcg(outp + e) : 0.0;
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < LDE; ++u) {
             const int e = e0 + u * WT_THREADS;
             if (e >= o_hi) break;
             const double b = s_f0[e + e / WT_ITEMS];
