@@ -308,7 +308,7 @@ def main():
         def e2e_step():
             # the reference solves chromosomes in a pool of <= 4 workers (rocco.py:1146-1184); two host threads here let
             # the host->device copy of one chromosome overlap the kernels / BED writing of the other (ctypes drops the GIL)
-            jobs = list(zip(my_names, my_bins, host, budgets, gammas))
+            jobs = sorted(zip(my_names, my_bins, host, budgets, gammas), key=lambda j: -j[1])   # longest first: short tail
             with ThreadPoolExecutor(max_workers=args.e2e_threads) as pool:
                 files = list(pool.map(one_chrom, jobs))
             if files:

@@ -163,6 +163,9 @@ int rocco_b200_write_bed3(const char *path, const char *const *names, int n_name
  * reference-faithful line reader); *saw_extra_columns = 1 when any row had more than three fields. */
 long long rocco_b200_combine_bed3(const char *const *paths, int n_paths, const char *out_path, int name_features,
                                   int *saw_extra_columns);
+/* Upload `bytes` from PINNED host memory with a kernel that reads it over PCIe (no DMA command): small uploads are then
+ * not queued behind the bulk count-matrix copies other host threads have submitted.  Stream-ordered, asynchronous. */
+int rocco_b200_pull_pinned(void *d_dst, const void *h_pinned, size_t bytes, void *cuda_stream);
 int rocco_b200_uniform_step_i64(const long long *values, size_t n);   /* 1 iff all consecutive differences are equal */
 double rocco_b200_numpy_sum_f64(const double *values, size_t n);
 double rocco_b200_numpy_sum_const_f64(double value, size_t n);

@@ -229,11 +229,17 @@ extern "C" __attribute__((visibility("default"))) long long rocco_mask_to_interv
 {
     if (!mask || n == 0) return ST_INVALID;
     RB_TRY(ensure_device());
-    HostScope lease;
+    HostScope lease(true);
     cudaStream_t st = lease.stream();
     Arena ar(st);
     uint8_t *d_m = nullptr;
     RB_TRY(ar.alloc(&d_m, n));
-    RB_CUDA(cudaMemcpyAsync(d_m, mask, n, cudaMemcpyHostToDevice, st));
+    const void *src = mask;
+    if (void *stage = lease.staging(n)) {
+        memcpy(stage, mask, n);
+        RB_TRY(pull_from_pinned(d_m, stage, n, st));
+    } else {
+        RB_CUDA(cudaMemcpyAsync(d_m, src, n, cudaMemcpyHostToDevice, st));
+    }
     return rocco_b200_mask_to_intervals_dev(d_m, n, first_start, step, min_length_bp, starts_out, ends_out, capacity, st);
 }

@@ -1094,7 +1094,7 @@ static int host_chain(const double *scores, const double *costs, size_t n, int m
     if (!scores || !mask_out || n == 0) return ST_INVALID;
     if (n > 1 && !costs) return ST_INVALID;
     RB_TRY(ensure_device());
-    HostScope lease;
+    HostScope lease(true);
     cudaStream_t st = lease.stream();
     Arena ar(st);
     double *d_s = nullptr, *d_c = nullptr;
@@ -1102,11 +1102,19 @@ static int host_chain(const double *scores, const double *costs, size_t n, int m
     RB_TRY(ar.alloc(&d_s, n));
     RB_TRY(ar.alloc(&d_c, n));
     RB_TRY(ar.alloc(&d_m, n));
-    RB_CUDA(cudaMemcpyAsync(d_s, scores, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    double *stage = static_cast<double *>(lease.staging(2 * n * sizeof(double)));
+    const double *src_s = scores, *src_c = costs;
+    if (stage) {
+        memcpy(stage, scores, n * sizeof(double)); src_s = stage;
+        if (n > 1) { memcpy(stage + n, costs, (n - 1) * sizeof(double)); src_c = stage + n; }
+    }
+    if (stage) RB_TRY(pull_from_pinned(d_s, src_s, n * sizeof(double), st));
+    else RB_CUDA(cudaMemcpyAsync(d_s, src_s, n * sizeof(double), cudaMemcpyHostToDevice, st));
     RB_CUDA(cudaMemsetAsync(d_c, 0, n * sizeof(double), st));
     double csum = 0.0;
     if (n > 1) {
-        RB_CUDA(cudaMemcpyAsync(d_c, costs, (n - 1) * sizeof(double), cudaMemcpyHostToDevice, st));
+        if (stage) RB_TRY(pull_from_pinned(d_c, src_c, (n - 1) * sizeof(double), st));
+        else RB_CUDA(cudaMemcpyAsync(d_c, src_c, (n - 1) * sizeof(double), cudaMemcpyHostToDevice, st));
         for (size_t i = 0; i + 1 < n; ++i)
             if (!(costs[i] >= 0.0)) return ST_INVALID;      // negative / NaN switch costs are outside the clamp-map form
         csum = numpy_sum_f64(costs, n - 1);                  // dp.py:110-111 uses numpy.sum; its rounding defines the bracket

@@ -119,18 +119,26 @@ int ensure_device();     // returns 0 or ST_CUDA when no usable device
 cudaStream_t host_stream();
 // RAII lease of a (non-blocking stream, private memory pool) pair for one host-pointer call.  Pairs are recycled
 // through a global free list, so the number that exist equals the highest concurrency seen, whatever the threads do.
+// `urgent` leases carry the device's highest stream priority: the short launch chains of a solve or a mask->runs pass
+// then get SM slots ahead of the bulk scoring kernels another host thread has in flight, instead of queueing behind them.
 class HostScope {
   public:
-    HostScope();
+    explicit HostScope(bool urgent = false, size_t scratch_hint = 0);
     ~HostScope();
     HostScope(const HostScope &) = delete;
     HostScope &operator=(const HostScope &) = delete;
     cudaStream_t stream() const { return st_; }
+    // Pinned bounce buffer owned by the lease (grown on demand, kept for the next holder); nullptr when pinning fails.
+    // A pageable upload is split by the driver into many small DMA commands, each of which waits its turn behind the
+    // bulk copies other host threads have queued; one pinned transfer waits once.
+    void *staging(size_t bytes);
   private:
     int slot_;
     cudaStream_t st_;
 };
 int sm_count();
+// Kernel-driven upload from pinned (device-mapped) host memory; see runtime.cu.
+int pull_from_pinned(void *d_dst, const void *h_pinned, size_t bytes, cudaStream_t st);
 
 // ---------------------------------------------------------------- device helpers
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }

@@ -49,19 +49,34 @@ int ensure_device()
     return 0;
 }
 
-struct HostCtx { int dev; cudaStream_t st; cudaMemPool_t pool; bool busy; };
+struct HostCtx { int dev; cudaStream_t st; cudaMemPool_t pool; bool busy; int urgent; void *stage; size_t stage_bytes; };
 static std::mutex g_ctx_mu;
 static std::vector<HostCtx> g_ctx;
 
-HostScope::HostScope() : slot_(-1), st_(nullptr)
+HostScope::HostScope(bool urgent, size_t scratch_hint) : slot_(-1), st_(nullptr)
 {
     int dev = 0;
     cudaGetDevice(&dev);
     std::lock_guard<std::mutex> lk(g_ctx_mu);
-    for (size_t k = 0; k < g_ctx.size(); ++k)
-        if (!g_ctx[k].busy && g_ctx[k].dev == dev) { g_ctx[k].busy = true; slot_ = (int)k; st_ = g_ctx[k].st; return; }
-    HostCtx c{dev, nullptr, nullptr, true};
-    if (cudaStreamCreateWithFlags(&c.st, cudaStreamNonBlocking) != cudaSuccess) { (void)cudaGetLastError(); return; }
+    // Best fit on the pools' reserved sizes: growing a pool means creating and mapping physical memory (~50 ms per GB,
+    // under driver-wide locks that stall every other host thread), so a call takes the free lease whose pool already
+    // holds at least `scratch_hint` bytes and is the smallest such, else the largest one.
+    int best = -1;
+    unsigned long long best_res = 0;
+    for (size_t k = 0; k < g_ctx.size(); ++k) {
+        if (g_ctx[k].busy || g_ctx[k].dev != dev || g_ctx[k].urgent != (int)urgent) continue;
+        unsigned long long res = 0;
+        if (g_ctx[k].pool && cudaMemPoolGetAttribute(g_ctx[k].pool, cudaMemPoolAttrReservedMemCurrent, &res) != cudaSuccess) {
+            (void)cudaGetLastError(); res = 0;
+        }
+        const bool fits = res >= scratch_hint, best_fits = best >= 0 && best_res >= scratch_hint;
+        if (best < 0 || (fits && (!best_fits || res < best_res)) || (!fits && !best_fits && res > best_res)) { best = (int)k; best_res = res; }
+    }
+    if (best >= 0) { g_ctx[best].busy = true; slot_ = best; st_ = g_ctx[best].st; return; }
+    HostCtx c{dev, nullptr, nullptr, true, (int)urgent, nullptr, 0};
+    int least = 0, greatest = 0;
+    if (urgent && cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) { (void)cudaGetLastError(); greatest = 0; }
+    if (cudaStreamCreateWithPriority(&c.st, cudaStreamNonBlocking, urgent ? greatest : 0) != cudaSuccess) { (void)cudaGetLastError(); return; }
     cudaMemPoolProps props{};
     props.allocType = cudaMemAllocationTypePinned;
     props.handleTypes = cudaMemHandleTypeNone;
@@ -74,6 +89,25 @@ HostScope::HostScope() : slot_(-1), st_(nullptr)
     g_ctx.push_back(c);
     slot_ = (int)g_ctx.size() - 1;
     st_ = c.st;
+}
+
+void *HostScope::staging(size_t bytes)
+{
+    if (slot_ < 0) return nullptr;
+    void *cur = nullptr;
+    size_t have = 0;
+    { std::lock_guard<std::mutex> lk(g_ctx_mu); cur = g_ctx[slot_].stage; have = g_ctx[slot_].stage_bytes; }
+    if (have >= bytes) return cur;
+    if (cur) cudaFreeHost(cur);
+    void *p = nullptr;
+    // generous and sticky: (re)allocating pinned memory synchronises the device and stalls every other host thread, so a
+    // lease's buffer is sized once for the largest mask a genome produces (64 MB) and only ever grows past that
+    const size_t want = std::max<size_t>(bytes + bytes / 4, (size_t)64 << 20);
+    if (cudaMallocHost(&p, want) != cudaSuccess) { (void)cudaGetLastError(); p = nullptr; }
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    g_ctx[slot_].stage = p;
+    g_ctx[slot_].stage_bytes = p ? want : 0;
+    return p;
 }
 
 HostScope::~HostScope()
@@ -102,7 +136,7 @@ cudaMemPool_t pool_for_stream(cudaStream_t s)
     for (const HostCtx &c : g_user_ctx)
         if (c.st == s && c.dev == dev) return c.pool;
     if (g_user_ctx.size() >= 16) return nullptr;
-    HostCtx c{dev, s, nullptr, true};
+    HostCtx c{dev, s, nullptr, true, 0, nullptr, 0};
     cudaMemPoolProps props{};
     props.allocType = cudaMemAllocationTypePinned;
     props.handleTypes = cudaMemHandleTypeNone;
@@ -114,6 +148,33 @@ cudaMemPool_t pool_for_stream(cudaStream_t s)
     } else { (void)cudaGetLastError(); c.pool = nullptr; }
     g_user_ctx.push_back(c);
     return c.pool;
+}
+
+// Upload from PINNED host memory by a kernel that reads it over PCIe (zero-copy) instead of a DMA command.  The copy
+// engine serves H2D commands in submission order across all streams, so a 40 MB score vector submitted while other host
+// threads have gigabytes of count matrices queued would wait for that whole backlog; SM loads do not queue behind it.
+__global__ void __launch_bounds__(256) k_pull(uint4 *__restrict__ dst, const uint4 *__restrict__ src, size_t n16,
+                                              unsigned char *dst_tail, const unsigned char *src_tail, int tail)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+    if (blockIdx.x == 0 && (int)threadIdx.x < tail) dst_tail[threadIdx.x] = src_tail[threadIdx.x];
+}
+
+int pull_from_pinned(void *d_dst, const void *h_pinned, size_t bytes, cudaStream_t st)
+{
+    if (bytes == 0) return 0;
+    if ((reinterpret_cast<uintptr_t>(d_dst) | reinterpret_cast<uintptr_t>(h_pinned)) & 15) {
+        RB_CUDA(cudaMemcpyAsync(d_dst, h_pinned, bytes, cudaMemcpyHostToDevice, st));
+        return 0;
+    }
+    const size_t n16 = bytes / 16;
+    const int tail = (int)(bytes - n16 * 16);
+    const unsigned grid = (unsigned)std::min<size_t>((n16 + 255) / 256 + 1, (size_t)sm_count() * 8);
+    k_pull<<<grid, 256, 0, st>>>(static_cast<uint4 *>(d_dst), static_cast<const uint4 *>(h_pinned), n16,
+                                 static_cast<unsigned char *>(d_dst) + n16 * 16,
+                                 static_cast<const unsigned char *>(h_pinned) + n16 * 16, tail);
+    RB_LAUNCH_CHECK();
+    return 0;
 }
 
 int sm_count()
@@ -446,6 +507,11 @@ RB_API long long rocco_b200_combine_bed3(const char *const *paths, int n_paths, 
     }
     fclose(fo);
     return (long long)recs.size();
+}
+
+RB_API int rocco_b200_pull_pinned(void *d_dst, const void *h_pinned, size_t bytes, void *cuda_stream)
+{
+    return rb::pull_from_pinned(d_dst, h_pinned, bytes, (cudaStream_t)cuda_stream);
 }
 
 RB_API double rocco_b200_numpy_sum_f64(const double *a, size_t n) { return rb::numpy_sum_f64(a, n); }

@@ -5,6 +5,8 @@
 //   394-608  monotone variance-vs-|signal| trend -> exact order statistics per sample row, PAVA on <= 32 knots
 //   744-947  posterior precision + combine       -> k_combine   (fused column reduction over the sample axis)
 // and the Python driver inference.py:302-379.
+#include <mutex>
+
 #include "common.cuh"
 #include "score.cuh"
 #include "trend.cuh"
@@ -559,6 +561,10 @@ static int score_loci_core(const void *d_matrix_in, const void *h_matrix, int dt
         RB_TRY(ar.alloc(&d_x, (size_t)m * n * esz));
         d_matrix = d_x;
         cudaStream_t cs = copy_stream();
+        // one call's row groups go into the shared copy stream back to back: concurrent callers then finish one after
+        // the other at full PCIe rate (and start their next chromosome staggered) instead of all at once at 1/T of it
+        static std::mutex copy_mu;
+        std::lock_guard<std::mutex> copy_lock(copy_mu);
         cudaEvent_t ready;
         RB_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
         RB_CUDA(cudaEventRecord(ready, st));                       // the stream-ordered allocation is valid from here on
@@ -729,7 +735,8 @@ static int score_loci_host(const void *matrix, int dtype, size_t m, size_t n, co
 {
     if (!matrix || !out || m == 0 || n == 0) return ST_INVALID;
     RB_TRY(ensure_device());
-    HostScope lease;
+    // scratch of one call: input copy, centred matrix, variance track (m x n each) + ~1.5 GB of select / per-bin buffers
+    HostScope lease(false, m * n * ((dtype ? sizeof(float) : sizeof(double)) + 16) + ((size_t)3 << 29));
     cudaStream_t st = lease.stream();
     Arena ar(st);
     rocco_b200_score_outputs dev = *out;

@@ -9,6 +9,7 @@ PyTorch is used for device memory and streams only.
 from __future__ import annotations
 
 import ctypes
+import threading
 from typing import Optional, Sequence
 
 import numpy as np
@@ -120,13 +121,106 @@ def solve_packed(d_scores, offsets, lengths, budgets, gammas, selection_penaltie
 def solve_chromosomes(scores_list, budgets, gammas, selection_penalties=None, max_iter: int = 60,
                       levels_per_round: int = 0):
     """solve_chrom_exact for a list of chromosomes in one batched launch set; NumPy masks returned."""
-    d_scores, offsets, lengths = pack_scores(scores_list)
-    d_masks, res = solve_packed(d_scores, offsets, lengths, budgets, gammas, selection_penalties,
-                                max_iter=max_iter, levels_per_round=levels_per_round)
-    h_masks = d_masks.cpu().numpy()
+    torch = _torch()
+    if any(isinstance(s, torch.Tensor) and s.is_cuda for s in scores_list):
+        d_scores, offsets, lengths = pack_scores(scores_list)
+        d_masks, res = solve_packed(d_scores, offsets, lengths, budgets, gammas, selection_penalties,
+                                    max_iter=max_iter, levels_per_round=levels_per_round)
+        h_masks = d_masks.cpu().numpy()
+    else:
+        # Host inputs: run on this thread's own high-priority stream with pinned staging.  The solve is a chain of short
+        # launches; on the shared default stream (or at normal priority) it queues behind whatever bulk scoring kernels
+        # and 256 MB copies other host threads have in flight, and a pageable upload is cut into many small DMA commands
+        # each of which waits for one of those copies.
+        _lib.require_device()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        arrays = []
+        for s in scores_list:
+            a = np.ascontiguousarray(s, dtype=np.float64)
+            if a.ndim != 1:
+                raise ValueError("`scores` must be a one-dimensional array")
+            arrays.append(a)
+        lengths = [int(a.shape[0]) for a in arrays]
+        offsets, total = layout_offsets(lengths)
+        with _StageLease(total * 9) as stage, _UrgentStream(dev) as stream:
+            h_scores = stage[: total * 8].view(torch.float64)
+            h_scores.zero_()
+            for a, off, n in zip(arrays, offsets, lengths):
+                h_scores[off:off + n].copy_(torch.from_numpy(a))
+            with torch.cuda.stream(stream):
+                d_scores = torch.empty(total, dtype=torch.float64, device=dev)
+                # kernel-driven upload: a DMA command would wait for every bulk copy already queued (see runtime.cu)
+                _lib.check(_lib.load().rocco_b200_pull_pinned(ctypes.c_void_p(d_scores.data_ptr()), ctypes.c_void_p(h_scores.data_ptr()),
+                                                              total * 8, ctypes.c_void_p(stream.cuda_stream)), "upload")
+                d_masks, res = solve_packed(d_scores, offsets, lengths, budgets, gammas, selection_penalties,
+                                            max_iter=max_iter, levels_per_round=levels_per_round)
+                h_m = stage[total * 8: total * 9]
+                h_m.copy_(d_masks, non_blocking=True)
+                stream.synchronize()
+            h_masks = h_m.numpy().copy()
     for r, off, n in zip(res, offsets, lengths):
         r["solution"] = h_masks[off:off + n].copy()
     return res
+
+
+_URGENT: dict = {}
+
+
+class _UrgentStream:
+    """Borrow a highest-priority stream of `dev` from a process-wide free list (returned on exit).  The set of streams
+    stays as small as the peak number of concurrent host threads, so torch's per-stream caching allocator reaches a steady
+    state instead of seeing a fresh stream -- and a fresh cudaMalloc -- for every short-lived worker thread."""
+
+    def __init__(self, dev):
+        self.key = (dev.type, dev.index)
+        self.dev = dev
+        self.stream = None
+
+    def __enter__(self):
+        torch = _torch()
+        with _STAGES_LOCK:
+            free = _URGENT.setdefault(self.key, [])
+            self.stream = free.pop() if free else None
+        if self.stream is None:
+            self.stream = torch.cuda.Stream(device=self.dev, priority=-1)
+        return self.stream
+
+    def __exit__(self, *exc):
+        with _STAGES_LOCK:
+            _URGENT[self.key].append(self.stream)
+        self.stream = None
+        return False
+
+
+_STAGES: list = []
+_STAGES_LOCK = threading.Lock()
+
+
+class _StageLease:
+    """A pinned staging buffer (uint8) borrowed from a process-wide free list and returned on exit.  Buffers are sized in
+    64 MB steps and never freed: allocating or freeing pinned memory synchronises the device, which would stall the bulk
+    copies and kernels of every other host thread."""
+
+    def __init__(self, nbytes: int):
+        self.nbytes = int(nbytes)
+        self.buf = None
+
+    def __enter__(self):
+        torch = _torch()
+        with _STAGES_LOCK:
+            fit = [k for k, b in enumerate(_STAGES) if b.numel() >= self.nbytes]
+            if fit:
+                self.buf = _STAGES.pop(min(fit, key=lambda k: _STAGES[k].numel()))
+        if self.buf is None:
+            step = 64 << 20
+            self.buf = torch.empty(((self.nbytes + step - 1) // step) * step or step, dtype=torch.uint8, pin_memory=True)
+        return self.buf
+
+    def __exit__(self, *exc):
+        with _STAGES_LOCK:
+            _STAGES.append(self.buf)
+        self.buf = None
+        return False
 
 
 def masks_to_runs(d_masks, offsets, lengths):
