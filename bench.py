@@ -47,7 +47,7 @@ def parse_args():
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"], help="dtype of the resident count matrices")
     ap.add_argument("--e2e-steps", type=int, default=-1, help="-1: min(steps, 2); 0 disables the e2e leg")
     ap.add_argument("--score-streams", type=int, default=1, help="host threads / CUDA streams scoring chromosomes concurrently")
-    ap.add_argument("--e2e-threads", type=int, default=3, help="host threads driving chromosomes through the public API")
+    ap.add_argument("--e2e-threads", type=int, default=4, help="host threads driving chromosomes through the public API")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-bins", type=int, default=250_000)
     ap.add_argument("--levels", type=int, default=0, help="bisection levels per launch (0 = library default)")
@@ -306,8 +306,9 @@ def main():
             return rocco_b200.chrom_solution_to_bed(c, np.arange(0, args.step_bp * n, args.step_bp), sol, ID="bench")
 
         def e2e_step():
-            # the reference solves chromosomes in a pool of <= 4 workers (rocco.py:1146-1184); two host threads here let
-            # the host->device copy of one chromosome overlap the kernels / BED writing of the other (ctypes drops the GIL)
+            # the reference solves chromosomes in a pool of <= 4 workers (rocco.py:1146-1184); the host threads here keep
+            # the PCIe link busy: one chromosome's upload overlaps the kernels / solve / BED writing of the others (ctypes
+            # drops the GIL)
             jobs = sorted(zip(my_names, my_bins, host, budgets, gammas), key=lambda j: -j[1])   # longest first: short tail
             with ThreadPoolExecutor(max_workers=args.e2e_threads) as pool:
                 files = list(pool.map(one_chrom, jobs))

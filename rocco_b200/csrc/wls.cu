@@ -527,10 +527,16 @@ int centered_wls(const double *d_centered, long long m, long long n, const rocco
 static cudaStream_t copy_stream()
 {
     static cudaStream_t cs[32] = {nullptr};
+    static std::mutex mu;                      // first use races between host threads otherwise (a half-created handle is visible)
     int dev = 0;
     cudaGetDevice(&dev);
     dev &= 31;
-    if (!cs[dev]) cudaStreamCreateWithFlags(&cs[dev], cudaStreamNonBlocking);
+    std::lock_guard<std::mutex> lk(mu);
+    if (!cs[dev]) {
+        cudaStream_t s = nullptr;
+        if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) { (void)cudaGetLastError(); s = nullptr; }
+        cs[dev] = s;
+    }
     return cs[dev];
 }
 
