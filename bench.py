@@ -168,7 +168,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------- our arm
@@ -183,8 +183,26 @@ def cpu_baseline_single_core(args):
                       f"(budget {budget}, gamma {gamma}) + BED records, {dt:.1f} s on one core"}
 
 
+_RESULT_FD = None
+
+
+def emit(line: dict) -> None:
+    """The one JSON line goes to the process's ORIGINAL stdout; see main() for why fd 1 is redirected meanwhile."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    global _RESULT_FD
     args = parse_args()
+    # Libraries print to stdout behind Python's back (NCCL's "NCCL version ..." banner at communicator creation): keep a
+    # private handle on the real stdout for the JSON line and point fd 1 at stderr for everything else.
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
         return
@@ -310,7 +328,7 @@ def main():
             # the PCIe link busy: one chromosome's upload overlaps the kernels / solve / BED writing of the others (ctypes
             # drops the GIL)
             jobs = sorted(zip(my_names, my_bins, host, budgets, gammas), key=lambda j: -j[1])   # longest first: short tail
-            with ThreadPoolExecutor(max_workers=args.e2e_threads) as pool:
+            with ThreadPoolExecutor(max_workers=args.e2e_threads, initializer=torch.cuda.set_device, initargs=(local_rank,)) as pool:   # the CUDA current device is per host thread
                 files = list(pool.map(one_chrom, jobs))
             if files:
                 rocco_b200.combine_chrom_results(files, f"combined_r{rank}.bed")
@@ -381,7 +399,7 @@ def main():
                        "trend_fallback_reason_counts": list(reasons)[:5], "collective": "one NCCL all-reduce of [selected, bins] per step"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(lt.item()), "roofline": roof, "cpu_baseline": cpu,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
