@@ -72,15 +72,18 @@ class ClockSampler:
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
-        self.gpu = gpu_index
+    def __init__(self, gpu_indices):
+        self.gpus = ",".join(str(g) for g in gpu_indices)
         self.proc = None
-        self.lines: list[str] = []
+        self.lines: list[tuple[float, str]] = []
+        self.window = None
 
     def start(self):
+        # ONE nvidia-smi for all GPUs of the job, started before the warm-up steps: its start-up (NVML initialisation takes
+        # driver-wide locks for ~100 ms) must not fall into the timed region, least of all once per rank
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                ["nvidia-smi", "-i", self.gpus, f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -89,7 +92,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def mark(self, t0: float, t1: float):
+        """host-clock window of the timed region: only samples that arrived inside it are reported"""
+        self.window = (t0, t1)
 
     def stop(self):
         if self.proc is None:
@@ -99,9 +106,13 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except subprocess.TimeoutExpired:
             self.proc.kill()
+        lines = [ln for t, ln in self.lines if self.window is None or self.window[0] <= t <= self.window[1] + 0.1]
+        scope = "timed region"
+        if not lines:
+            lines, scope = [ln for _, ln in self.lines], "warm-up + timed region (timed region shorter than the sampling period)"
         sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -113,7 +124,8 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons),
+                "gpus": self.gpus, "sampled_over": scope}
 
 
 # ---------------------------------------------------------------------------------------------- reference arm
@@ -256,11 +268,12 @@ def main():
         if world > 1:
             dist.barrier()
 
+    sampler = ClockSampler(range(world)) if rank == 0 else None
+    if sampler:
+        sampler.start()
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     _lib.profile_enable(True)
     step()                                  # one profiled step outside the timed region fills the event pool
     _lib.profile_report()
@@ -268,12 +281,14 @@ def main():
     fb_rows0 = int(_lib.load().rocco_b200_trend_fallback_rows())
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_host0 = time.perf_counter()
     ev0.record()
     last = None
     for _ in range(args.steps):
         last = step()
     ev1.record()
     barrier()
+    t_host1 = time.perf_counter()
     ms = ev0.elapsed_time(ev1)
     launches = _lib.kernel_launches() - launches0
     fb_rows = int(_lib.load().rocco_b200_trend_fallback_rows()) - fb_rows0
@@ -281,7 +296,10 @@ def main():
     _lib.load().rocco_b200_trend_fallback_reasons(reasons)
     prof = _lib.profile_report()
     _lib.profile_enable(False)
-    clocks = sampler.stop()
+    clocks = None
+    if sampler:
+        sampler.mark(t_host0, t_host1)
+        clocks = sampler.stop()
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     lt = torch.tensor([launches], dtype=torch.int64, device=dev)
     if world > 1:
