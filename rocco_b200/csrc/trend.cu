@@ -29,36 +29,42 @@
 namespace rb {
 namespace score {
 
-constexpr int NBX = 16384;              // |signal| buckets, order preserving: 64 per octave on [2^-24, 2^-8) (1024 buckets),
-constexpr int XSHIFT = 42;              // 1024 per octave on [2^-8, 2^7) (15360 buckets); outside: first / last bucket
-constexpr int XSHIFT_LO = 46;
-constexpr unsigned XB0 = (unsigned)(0x3F70000000000000ULL >> XSHIFT);      // bits of 2^-8  >> 42
-constexpr unsigned XB0_LO = (unsigned)(0x3E70000000000000ULL >> XSHIFT_LO);   // bits of 2^-24 >> 46
-constexpr int NBX_LO = 1024;
-constexpr int NBY = 1024;               // variance buckets: bits >> 46 (exponent + 6 mantissa bits): 64 per octave,
-constexpr int YSHIFT = 46;              // 16 octaves centred on the row's sampled median variance
+constexpr int NBX = 16384;              // |signal| buckets, order preserving: a coarse region of 1024 buckets below a fine region
+constexpr int NBX_LO = 1024;            // of 15360 buckets; values outside both land in the first / last bucket
+constexpr int NBY = 1024;               // variance buckets centred on the row's sampled median variance
+// Bucket geometry, chosen from the row length so that the fullest bucket stays under the slot capacity:
+//   n <= 6 M bins : fine region 1024 per octave on [2^-8, 2^7),  coarse on [2^-24, 2^-8);  variances 64 per octave (16 octaves)
+//   n  > 6 M bins : fine region 2048 per octave on [2^-6, 2^1.5), coarse 128 per octave on [2^-14, 2^-6); variances 128 per
+//                   octave (8 octaves)
+struct BucketGeom { int xshift; unsigned xb0; int xshift_lo; unsigned xb0_lo; int yshift; };
+static BucketGeom bucket_geometry(long long n)
+{
+    if (n <= 6000000LL) return BucketGeom{42, (unsigned)(0x3F70000000000000ULL >> 42), 46, (unsigned)(0x3E70000000000000ULL >> 46), 46};
+    return BucketGeom{41, (unsigned)(0x3F90000000000000ULL >> 41), 45, (unsigned)(0x3F10000000000000ULL >> 45), 45};
+}
 constexpr int YSAMPLE = 2048;
 constexpr int MAXB = 32;                // bins per row (n < 2^31)
 constexpr int MAXSLOT = 3 * MAXB;
 constexpr int CAPX = 8192;              // pairs per x slot
-constexpr int CAPY = 8192;              // variances per (bin, k) slot
+constexpr int CAPY = 8192;              // variances per (bin, k) slot (rows > 6 M bins: 2x, see TrendBuffers::capy)
+constexpr int CAPY_MAX = 16384;
 constexpr int CHUNK = 131072;           // elements streamed per CTA
 constexpr int ST_THREADS = 512;
 int trend_fused_max_window() { return 1025; }
 
 // The fine region carries the bulk of a row; the coarse one exists for rows with much mass near zero (a bootstrap
-// draw  residual x multiplier  has a log-divergent density at 0), whose lowest equal-count bins end far below 2^-8.
-__device__ __forceinline__ int xbucket(double x)
+// draw  residual x multiplier  has a log-divergent density at 0), whose lowest equal-count bins end far below it.
+__device__ __forceinline__ int xbucket(double x, const BucketGeom &G)
 {
     const unsigned long long bits = (unsigned long long)__double_as_longlong(x);
-    const int b = (int)(unsigned)(bits >> XSHIFT) - (int)XB0;
+    const int b = (int)(unsigned)(bits >> G.xshift) - (int)G.xb0;
     if (b >= 0) return min(NBX_LO + b, NBX - 1);
-    const int t = (int)(unsigned)(bits >> XSHIFT_LO) - (int)XB0_LO;
-    return max(t, 0);
+    const int t = (int)(unsigned)(bits >> G.xshift_lo) - (int)G.xb0_lo;
+    return min(max(t, 0), NBX_LO - 1);
 }
-__device__ __forceinline__ int ybucket(double y, int yb0)
+__device__ __forceinline__ int ybucket(double y, int yb0, const BucketGeom &G)
 {
-    const int u = (int)((unsigned long long)__double_as_longlong(y) >> YSHIFT);
+    const int u = (int)((unsigned long long)__double_as_longlong(y) >> G.yshift);
     const int b = u - yb0;
     return b < 0 ? 0 : (b >= NBY ? NBY - 1 : b);
 }
@@ -103,10 +109,12 @@ struct TrendBuffers {
     double *ycand;         // [m][MAXB][2][CAPY]
     int *ycand_cnt;        // [m][MAXB][2]
     long long rows;
+    BucketGeom geom;
+    int capy;              // capacity of a ycand slot
 };
 
 // ------------------------------------------------------------------ T1
-__global__ void __launch_bounds__(ST_THREADS) k_xhist(const double *__restrict__ C, long long n, long long row_stride, int *xhist)
+__global__ void __launch_bounds__(ST_THREADS) k_xhist(const double *__restrict__ C, long long n, long long row_stride, int *xhist, BucketGeom G)
 {
     extern __shared__ int s_h[];
     const long long row = blockIdx.y;
@@ -114,7 +122,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_xhist(const double *__restrict__
     for (int k = threadIdx.x; k < NBX; k += ST_THREADS) s_h[k] = 0;
     __syncthreads();
     const double *c = C + row * row_stride;
-    for (long long j = c0 + threadIdx.x; j < c1; j += ST_THREADS) atomicAdd(&s_h[xbucket(fabs(c[j]))], 1);
+    for (long long j = c0 + threadIdx.x; j < c1; j += ST_THREADS) atomicAdd(&s_h[xbucket(fabs(c[j]), G)], 1);
     __syncthreads();
     int *g = xhist + row * NBX;
     for (int k = threadIdx.x; k < NBX; k += ST_THREADS) {
@@ -139,7 +147,7 @@ __host__ __device__ __forceinline__ int padpos(int i) { return i + (i >> 3); }
 // W > 0: compile-time window (31 = the reference default): interior tiles run fully unrolled from registers.
 template <int W>
 __global__ void __launch_bounds__(RV_THREADS) k_rollvar_xhist(const double *__restrict__ C, long long n, long long row_stride, int w_rt,
-                                                               double *__restrict__ V, int *xhist)
+                                                               double *__restrict__ V, int *xhist, BucketGeom G)
 {
     extern __shared__ int s_dyn[];
     const int w = W > 0 ? W : w_rt;
@@ -172,7 +180,7 @@ __global__ void __launch_bounds__(RV_THREADS) k_rollvar_xhist(const double *__re
                 const int e = e0 + u * RV_THREADS;
                 if (e >= span) break;
                 s_in[padpos(e)] = val[u];
-                if (e >= own0 && e < own1) atomicAdd(&s_h[xbucket(fabs(val[u]))], 1);
+                if (e >= own0 && e < own1) atomicAdd(&s_h[xbucket(fabs(val[u]), G)], 1);
             }
         }
         __syncthreads();
@@ -309,7 +317,7 @@ __global__ void __launch_bounds__(256) k_xplan(TrendBuffers T, const double *__r
             }
         if (threadIdx.x == 0) {
             const double med = s_smp[take / 2];
-            T.plan[row].yb0 = (int)((unsigned long long)__double_as_longlong(med) >> YSHIFT) - NBY / 2;
+            T.plan[row].yb0 = (int)((unsigned long long)__double_as_longlong(med) >> T.geom.yshift) - NBY / 2;
         }
     }
     if (threadIdx.x != 0) return;
@@ -385,7 +393,7 @@ __global__ void __launch_bounds__(XC_THREADS) k_xcollect(const double *__restric
         for (int u = 0; u < 4; ++u) {
             if (xs[u] < 0.0) continue;
             const double x = xs[u], y = ys[u];
-            const int b = xbucket(x);
+            const int b = xbucket(x, T.geom);
             const int s = s_lut[b];
             bool boundary = false;
             if (s != 0xFF) {
@@ -393,7 +401,7 @@ __global__ void __launch_bounds__(XC_THREADS) k_xcollect(const double *__restric
                 if (pos < CAPX) cand[(size_t)s * CAPX + pos] = make_double2(x, y);
                 boundary = P.slot_boundary[s] != 0;
             }
-            if (!boundary) atomicAdd(&s_yh[(int)s_bin[b] * NBY + ybucket(y, yb0)], 1);
+            if (!boundary) atomicAdd(&s_yh[(int)s_bin[b] * NBY + ybucket(y, yb0, T.geom)], 1);
         }
     }
     __syncthreads();
@@ -451,7 +459,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 256) ? 4 : (CAP_HI <= 409
         for (int k = threadIdx.x; k < cnt; k += ST_THREADS) {
             const double2 pr = s_p[k];
             cand[k] = pr;
-            atomicAdd(&g[bin_of_rank(pre + k, n, B) * NBY + ybucket(pr.y, P.yb0)], 1);
+            atomicAdd(&g[bin_of_rank(pre + k, n, B) * NBY + ybucket(pr.y, P.yb0, T.geom)], 1);
         }
     }
 }
@@ -488,7 +496,7 @@ __global__ void __launch_bounds__(256) k_yplan(TrendBuffers T, long long n, int 
                 const int b0 = bucket_of(r0);
                 P.ym_bucket[b][0] = b0; P.ym_rank[b][0] = (int)(r0 - s_pre[b0]); P.ym_count[b][0] = s_pre[b0 + 1] - s_pre[b0];
             }
-            if (P.ym_count[b][1] > CAPY || P.ym_count[b][0] > CAPY) atomicOr(&P.fallback, FB_YSLOT);
+            if (P.ym_count[b][1] > T.capy || P.ym_count[b][0] > T.capy) atomicOr(&P.fallback, FB_YSLOT);
         }
     }
 }
@@ -496,12 +504,12 @@ __global__ void __launch_bounds__(256) k_yplan(TrendBuffers T, long long n, int 
 // ------------------------------------------------------------------ T6
 __device__ __forceinline__ void ycollect_one(TrendBuffers &T, long long row, const int (*s_yb)[2], int bin, double y, int yb0)
 {
-    const int yb = ybucket(y, yb0);
+    const int yb = ybucket(y, yb0, T.geom);
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         if (s_yb[bin][k] == yb && (k == 1 || s_yb[bin][1] != yb)) {
             const int pos = atomicAdd(&T.ycand_cnt[(row * MAXB + bin) * 2 + k], 1);
-            if (pos < CAPY) T.ycand[(((size_t)row * MAXB + bin) * 2 + k) * CAPY + pos] = y;
+            if (pos < T.capy) T.ycand[(((size_t)row * MAXB + bin) * 2 + k) * T.capy + pos] = y;
         }
     }
 }
@@ -537,7 +545,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_ycollect(const double *__restric
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             if (xs[u] < 0.0) continue;
-            const int b = xbucket(xs[u]);
+            const int b = xbucket(xs[u], T.geom);
             const int s = s_lut[b];
             if (s != 0xFF && s_bnd[s]) continue;                    // boundary buckets: handled from the sorted slot below
             ycollect_one(T, row, s_yb, (int)s_bin[b], ys[u], yb0);
@@ -579,7 +587,7 @@ __global__ void __launch_bounds__(256) k_yresolve(TrendBuffers T, long long n, i
         if (s_fail) break;
         int len = 1;
         while (len < cnt) len <<= 1;
-        const double *src = T.ycand + (((size_t)row * MAXB + b) * 2 + k) * CAPY;
+        const double *src = T.ycand + (((size_t)row * MAXB + b) * 2 + k) * T.capy;
         for (int q = threadIdx.x; q < len; q += 256) s_v[q] = q < cnt ? src[q] : INFINITY;
         __syncthreads();
         for (int kk = 2; kk <= len; kk <<= 1)
@@ -672,6 +680,8 @@ int trend_knots_select(const double *d_C, double *d_V, long long m, long long n,
     Arena ar(st);
     TrendBuffers T{};
     T.rows = m;
+    T.geom = bucket_geometry(n);
+    T.capy = n <= 6000000LL ? CAPY : CAPY_MAX;
     RB_TRY(ar.alloc(&T.xhist, (size_t)m * NBX));
     RB_TRY(ar.alloc(&T.lut, (size_t)m * NBX));
     RB_TRY(ar.alloc(&T.binlo, (size_t)m * NBX));
@@ -679,7 +689,7 @@ int trend_knots_select(const double *d_C, double *d_V, long long m, long long n,
     RB_TRY(ar.alloc(&T.cand, (size_t)m * MAXSLOT * CAPX));
     RB_TRY(ar.alloc(&T.cand_cnt, (size_t)m * MAXSLOT));
     RB_TRY(ar.alloc(&T.yhist, (size_t)m * MAXB * NBY));
-    RB_TRY(ar.alloc(&T.ycand, (size_t)m * MAXB * 2 * CAPY));
+    RB_TRY(ar.alloc(&T.ycand, (size_t)m * MAXB * 2 * T.capy));
     RB_TRY(ar.alloc(&T.ycand_cnt, (size_t)m * MAXB * 2));
     RB_CUDA(cudaMemsetAsync(T.xhist, 0, sizeof(int) * (size_t)m * NBX, st));
     RB_CUDA(cudaMemsetAsync(T.cand_cnt, 0, sizeof(int) * (size_t)m * MAXSLOT, st));
@@ -700,7 +710,7 @@ int trend_knots_select(const double *d_C, double *d_V, long long m, long long n,
         RB_CUDA(cudaFuncSetAttribute(k_xresolve<512, 4096, CAPX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_resolve));
         RB_CUDA(cudaFuncSetAttribute(k_xresolve<512, 2048, 4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double2) * 4096)));
         RB_CUDA(cudaFuncSetAttribute(k_xplan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_plan));
-        RB_CUDA(cudaFuncSetAttribute(k_yresolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * CAPY)));
+        RB_CUDA(cudaFuncSetAttribute(k_yresolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * CAPY_MAX)));
         attr = true;
     }
     const unsigned chunks = (unsigned)((n + CHUNK - 1) / CHUNK);
@@ -718,12 +728,12 @@ int trend_knots_select(const double *d_C, double *d_V, long long m, long long n,
             attr2 = true;
         }
         RB_PROF("k_rollvar_xhist", st, (double)m * n * 16.0);
-        if (fused_window == 31) k_rollvar_xhist<31><<<gstream, RV_THREADS, sm_fused, st>>>(d_C, n, row_stride, fused_window, d_V, T.xhist);
-        else k_rollvar_xhist<0><<<gstream, RV_THREADS, sm_fused, st>>>(d_C, n, row_stride, fused_window, d_V, T.xhist);
+        if (fused_window == 31) k_rollvar_xhist<31><<<gstream, RV_THREADS, sm_fused, st>>>(d_C, n, row_stride, fused_window, d_V, T.xhist, T.geom);
+        else k_rollvar_xhist<0><<<gstream, RV_THREADS, sm_fused, st>>>(d_C, n, row_stride, fused_window, d_V, T.xhist, T.geom);
         RB_LAUNCH_CHECK();
     } else {
         RB_PROF("trend_xhist", st, (double)m * n * 8.0);
-        k_xhist<<<gstream, ST_THREADS, sm_xhist, st>>>(d_C, n, row_stride, T.xhist);
+        k_xhist<<<gstream, ST_THREADS, sm_xhist, st>>>(d_C, n, row_stride, T.xhist, T.geom);
         RB_LAUNCH_CHECK();
     }
     {
@@ -755,7 +765,7 @@ int trend_knots_select(const double *d_C, double *d_V, long long m, long long n,
     }
     {
         RB_PROF("trend_plan_resolve", st, 0.0);
-        k_yresolve<<<dim3((unsigned)B, (unsigned)m), 256, sizeof(double) * CAPY, st>>>(T, n, B);
+        k_yresolve<<<dim3((unsigned)B, (unsigned)m), 256, sizeof(double) * T.capy, st>>>(T, n, B);
         RB_LAUNCH_CHECK();
         k_row_knots<<<(unsigned)((m + 63) / 64), 64, 0, st>>>(T, n, B, d_knots, d_row_fallback);
         RB_LAUNCH_CHECK();

@@ -55,8 +55,11 @@ def chrom_matrix_numpy(n_samples: int, n_bins: int, seed: int = 0, dtype=np.floa
     return np.ascontiguousarray(np.round(counts * norm, 5), dtype=dtype)
 
 
-def chrom_matrix_torch(n_samples: int, n_bins: int, seed: int, device, dtype=None):
-    """Same distribution drawn with torch's device RNG (not bit-identical to the NumPy generator)."""
+def chrom_matrix_torch(n_samples: int, n_bins: int, seed: int, device, dtype=None, sample_stream: int = 0):
+    """Same distribution drawn with torch's device RNG (not bit-identical to the NumPy generator).
+
+    ``sample_stream`` != 0 keeps the chromosome's background rate and peaks (functions of ``seed``) but draws the samples
+    from another stream: ranks that shard the SAMPLES of one chromosome pass their rank + 1."""
     import torch
 
     dtype = dtype or torch.float64
@@ -76,6 +79,8 @@ def chrom_matrix_torch(n_samples: int, n_bins: int, seed: int, device, dtype=Non
     np.add.at(delta_h, starts + widths, -heights)
     peaks = np.clip(np.cumsum(delta_h)[:n_bins], 0.0, None).astype(np.float32)
     rate = rate + torch.from_numpy(peaks).to(device)
+    if sample_stream:
+        g.manual_seed(int(seed) * 1000003 + int(sample_stream))
     depth = torch.empty((n_samples, 1), device=device).uniform_(0.5, 1.5, generator=g)
     norm = torch.empty((n_samples, 1), device=device).uniform_(0.2, 0.5, generator=g)
     out = torch.empty((n_samples, n_bins), device=device, dtype=dtype)

@@ -226,6 +226,29 @@ def test_trend_multiselect_equals_sort_path_bitwise(rb, m, n, seed, ties):
         assert lib.rocco_b200_trend_fallback_rows() == fb0       # the fast path really ran
 
 
+def test_trend_large_rows_take_the_fine_bucket_geometry_and_stay_exact(rb):
+    """Rows longer than 6 M bins (hg38 @ 20 bp: chr1 has 12.4 M) switch to 2048 |signal| buckets / 128 variance buckets per
+    octave so that no bucket outgrows its slot; the result must still equal the sort path bit for bit, without fallback."""
+    from rocco_b200 import _lib, inference
+    lib = _lib.load()
+    rng = np.random.default_rng(11)
+    m, n = 2, 12_500_000
+    c = rng.normal(size=(m, n)) * (0.25 + 0.1 * np.abs(np.sin(np.arange(n) / 5000.0)))
+    c[1] *= rng.standard_normal(n)                     # a bootstrap-like row: much mass near zero
+    prev = lib.rocco_b200_trend_set_mode(1)
+    try:
+        want_s, want = inference._score_centered_wls_matrix(c, prior_df=6.0)
+    finally:
+        lib.rocco_b200_trend_set_mode(0)
+    fb0 = lib.rocco_b200_trend_fallback_rows()
+    got_s, got = inference._score_centered_wls_matrix(c, prior_df=6.0)
+    lib.rocco_b200_trend_set_mode(prev)
+    assert lib.rocco_b200_trend_fallback_rows() == fb0
+    assert np.array_equal(got_s, want_s)
+    for k in DETAIL_KEYS:
+        assert np.array_equal(got[k], want[k]), k
+
+
 def test_trend_fallback_on_massive_ties(rb):
     from rocco_b200 import _lib, inference
     lib = _lib.load()
