@@ -151,6 +151,17 @@ long long rocco_b200_mask_to_runs_batch_dev(
     long long *start_bin_out, long long *end_bin_out, int *chrom_index_out, size_t capacity,
     void *cuda_stream);
 
+/* narrowPeak summit offsets (rocco.py:840-872): for peak p = [peak_starts[p], peak_ends[p]) the bins
+ * whose start lies inside it are searched for the largest mean (float32 track as the reference stores it; NaN ignored,
+ * first occurrence wins, at least one finite value required); offsets_out[p] = clip(centre of that bin - start, 0, len-1),
+ * or -1 when the peak is empty, has non-positive length or no finite mean.  track_starts must be ascending. */
+int rocco_narrowpeak_summit_offsets_f32(const long long *track_starts, const long long *track_centers, const float *track_mean,
+                                        size_t n_track, const long long *peak_starts, const long long *peak_ends,
+                                        size_t n_peaks, long long *offsets_out);
+int rocco_b200_summit_offsets_dev(const long long *d_track_starts, const long long *d_track_centers, const float *d_track_mean,
+                                  size_t n_track, const long long *d_peak_starts, const long long *d_peak_ends,
+                                  size_t n_peaks, long long *d_offsets_out, void *cuda_stream);
+
 /* numpy.sum of a float64 vector / of n copies of one value, restated bit-exactly (host helpers:
  * dp.py:110-111 builds the search bracket from numpy.sum(switch_costs)). */
 /* Host helper: write n BED3 records (BED4 with chrom_start_end names when name_features != 0) to `path`

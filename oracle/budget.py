@@ -288,3 +288,22 @@ def resolve_chrom_gamma(chrom_scores, autocorrelation_time: float = 1.0, gamma=N
     return g, {"method": "auto_score_autocorr", "autocorrelation_time": tau, "characteristic_run_length": run,
                "positive_score_median": scale, "positive_score_count": count, "gamma_raw": float(raw),
                "gamma_clipped": g, "gamma_clip_min": 0.5, "gamma_clip_max": 10.0}
+
+
+# ------------------------------------------------------------------ narrowPeak summit offsets (rocco.py:840-872)
+def narrowpeak_summit_offsets(track_starts, track_centers, track_mean, peak_starts, peak_ends) -> np.ndarray:
+    """Per peak: arg-max of the (float32 -> float64) mean over the bins whose start lies in [start, end), NaN ignored,
+    at least one finite value required; offset of that bin's centre clipped to the peak; else -1."""
+    starts = np.asarray(track_starts, dtype=np.int64)
+    centers = np.asarray(track_centers, dtype=np.int64)
+    mean = np.asarray(np.asarray(track_mean, dtype=np.float32), dtype=np.float64)
+    out = []
+    for s, e in zip(peak_starts, peak_ends):
+        off, length = -1, int(e) - int(s)
+        if length > 0 and starts.size:
+            lo, hi = int(np.searchsorted(starts, int(s), side="left")), int(np.searchsorted(starts, int(e), side="left"))
+            if hi > lo and np.any(np.isfinite(mean[lo:hi])):
+                k = int(np.nanargmax(mean[lo:hi]))
+                off = int(np.clip(int(centers[lo + k]) - int(s), 0, max(length - 1, 0)))
+        out.append(off)
+    return np.array(out, dtype=np.int64)

@@ -103,6 +103,8 @@ def _declare(lib):
         "rocco_effective_sample_size_f64": (c_int, [c_void_p, c_size_t, c_int, dp, dp, ip]),
         "rocco_positive_score_median_f64": (c_int, [c_void_p, c_size_t, dp, llp]),
         "rocco_b200_pull_pinned": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+        "rocco_narrowpeak_summit_offsets_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, c_void_p]),
+        "rocco_b200_summit_offsets_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
         "rocco_b200_numpy_sum_f64": (c_double, [c_void_p, c_size_t]),
         "rocco_b200_numpy_sum_const_f64": (c_double, [c_double, c_size_t]),
         "rocco_solve_penalized_chain_f64": (c_int, [c_void_p, c_void_p, c_size_t, c_double, c_void_p, dp, llp]),

@@ -243,3 +243,97 @@ extern "C" __attribute__((visibility("default"))) long long rocco_mask_to_interv
     }
     return rocco_b200_mask_to_intervals_dev(d_m, n, first_start, step, min_length_bp, starts_out, ends_out, capacity, st);
 }
+
+// ------------------------------------------------------------------ narrowPeak summit offsets
+// rocco.py:840-872: for every peak [start, end) the bins whose start lies inside it are searched for the largest WLS mean
+// (NaN ignored, first occurrence wins, at least one finite value required); the summit is that bin's centre, reported as
+// an offset clipped to the peak.  One warp per peak.
+namespace rb {
+namespace bed {
+
+__device__ __forceinline__ long long lower_bound_ll(const long long *a, long long n, long long key)
+{
+    long long lo = 0, hi = n;
+    while (lo < hi) { const long long mid = (lo + hi) >> 1; if (a[mid] < key) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256) k_summit_offsets(const long long *__restrict__ starts, const long long *__restrict__ centers,
+                                                        const float *__restrict__ mean, long long n_track,
+                                                        const long long *__restrict__ pstart, const long long *__restrict__ pend,
+                                                        long long n_peaks, long long *__restrict__ out)
+{
+    const long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (p >= n_peaks) return;
+    const long long s = pstart[p], e = pend[p], len = e - s;
+    long long result = -1;
+    if (len > 0 && n_track > 0) {
+        const long long left = lower_bound_ll(starts, n_track, s), right = lower_bound_ll(starts, n_track, e);
+        double best = -INFINITY;
+        long long best_i = -1;
+        bool finite = false;
+        for (long long i = left + lane; i < right; i += 32) {
+            const double v = (double)mean[i];
+            if (isfinite(v)) finite = true;
+            if (!isnan(v) && (best_i < 0 || v > best)) { best = v; best_i = i; }       // ascending i: first occurrence kept
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const double ob = __shfl_down_sync(0xffffffffu, best, d);
+            const long long oi = __shfl_down_sync(0xffffffffu, best_i, d);
+            if (oi >= 0 && (best_i < 0 || ob > best || (ob == best && oi < best_i))) { best = ob; best_i = oi; }
+        }
+        const unsigned any = __ballot_sync(0xffffffffu, finite);
+        if (lane == 0 && any && best_i >= 0) {
+            const long long off = centers[best_i] - s, cap = len - 1 > 0 ? len - 1 : 0;
+            result = off < 0 ? 0 : (off > cap ? cap : off);
+        }
+    }
+    if (lane == 0) out[p] = result;
+}
+
+}  // namespace bed
+}  // namespace rb
+
+extern "C" __attribute__((visibility("default"))) int rocco_b200_summit_offsets_dev(
+    const long long *d_track_starts, const long long *d_track_centers, const float *d_track_mean, size_t n_track,
+    const long long *d_peak_starts, const long long *d_peak_ends, size_t n_peaks, long long *d_offsets_out, void *cuda_stream)
+{
+    if (n_peaks == 0) return 0;
+    if (!d_peak_starts || !d_peak_ends || !d_offsets_out || (n_track && (!d_track_starts || !d_track_centers || !d_track_mean)))
+        return ST_INVALID;
+    const unsigned grid = (unsigned)((n_peaks * 32 + 255) / 256);
+    rb::bed::k_summit_offsets<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(d_track_starts, d_track_centers, d_track_mean,
+                                                                          (long long)n_track, d_peak_starts, d_peak_ends,
+                                                                          (long long)n_peaks, d_offsets_out);
+    RB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int rocco_narrowpeak_summit_offsets_f32(
+    const long long *track_starts, const long long *track_centers, const float *track_mean, size_t n_track,
+    const long long *peak_starts, const long long *peak_ends, size_t n_peaks, long long *offsets_out)
+{
+    if (n_peaks == 0) return 0;
+    if (!peak_starts || !peak_ends || !offsets_out) return ST_INVALID;
+    RB_TRY(ensure_device());
+    HostScope lease(true);
+    cudaStream_t st = lease.stream();
+    Arena ar(st);
+    long long *d_s = nullptr, *d_c = nullptr, *d_ps = nullptr, *d_pe = nullptr, *d_o = nullptr;
+    float *d_m = nullptr;
+    RB_TRY(ar.alloc(&d_s, n_track)); RB_TRY(ar.alloc(&d_c, n_track)); RB_TRY(ar.alloc(&d_m, n_track));
+    RB_TRY(ar.alloc(&d_ps, n_peaks)); RB_TRY(ar.alloc(&d_pe, n_peaks)); RB_TRY(ar.alloc(&d_o, n_peaks));
+    if (n_track) {
+        RB_CUDA(cudaMemcpyAsync(d_s, track_starts, n_track * sizeof(long long), cudaMemcpyHostToDevice, st));
+        RB_CUDA(cudaMemcpyAsync(d_c, track_centers, n_track * sizeof(long long), cudaMemcpyHostToDevice, st));
+        RB_CUDA(cudaMemcpyAsync(d_m, track_mean, n_track * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
+    RB_CUDA(cudaMemcpyAsync(d_ps, peak_starts, n_peaks * sizeof(long long), cudaMemcpyHostToDevice, st));
+    RB_CUDA(cudaMemcpyAsync(d_pe, peak_ends, n_peaks * sizeof(long long), cudaMemcpyHostToDevice, st));
+    RB_TRY(rocco_b200_summit_offsets_dev(d_s, d_c, d_m, n_track, d_ps, d_pe, n_peaks, d_o, st));
+    RB_CUDA(cudaMemcpyAsync(offsets_out, d_o, n_peaks * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    RB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}

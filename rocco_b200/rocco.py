@@ -305,3 +305,63 @@ def _resolve_chrom_gamma(chrom: str, args: dict, chrom_scores: np.ndarray, budge
     }
     logger.info("%s auto gamma estimate: %s", chrom, gamma_meta)
     return float(chrom_gamma), gamma_meta
+
+
+# ------------------------------------------------------------------------------------------------
+# narrowPeak summit offsets (rocco.py:809-872) -- SURVEY.md 8(f) rank 4
+# ------------------------------------------------------------------------------------------------
+def _cpy_narrowpeak_summit_track(chrom: str, intervals: np.ndarray, effect_mean: np.ndarray) -> str | None:
+    r"""Park (bin starts, bin centres, float32 WLS mean) of one chromosome in a temporary ``.npz`` (rocco.py:809-837);
+    host-side I/O only."""
+    import tempfile
+    intervals_ = np.asarray(intervals, dtype=np.int64)
+    effect_mean_ = np.asarray(effect_mean, dtype=np.float32)
+    usable = int(min(max(intervals_.shape[0] - 1, 0), effect_mean_.shape[0]))
+    if usable <= 0:
+        return None
+    fd, summit_track_file = tempfile.mkstemp(prefix=f"rocco_summit_track_{chrom}_", suffix=".npz")
+    os.close(fd)
+    np.savez(summit_track_file, starts=intervals_[:usable], centers=(intervals_[:usable] + intervals_[1:usable + 1]) // 2,
+             mean=effect_mean_[:usable])
+    return summit_track_file
+
+
+def narrowpeak_summit_offsets(track_starts, track_centers, track_mean, peak_starts, peak_ends) -> np.ndarray:
+    """Summit offset of every peak of one chromosome (segmented arg-max of the mean on the GPU); -1 where the reference
+    writes -1."""
+    ps = np.ascontiguousarray(peak_starts, dtype=np.int64)
+    pe = np.ascontiguousarray(peak_ends, dtype=np.int64)
+    out = np.full(ps.shape[0], -1, dtype=np.int64)
+    if ps.shape[0] == 0:
+        return out
+    ts = np.ascontiguousarray(track_starts, dtype=np.int64)
+    tc = np.ascontiguousarray(track_centers, dtype=np.int64)
+    tm = np.ascontiguousarray(track_mean, dtype=np.float32)
+    _lib.require_device()
+    _lib.check(_lib.load().rocco_narrowpeak_summit_offsets_f32(_lib.np_ptr(ts), _lib.np_ptr(tc), _lib.np_ptr(tm), ts.shape[0],
+                                                               _lib.np_ptr(ps), _lib.np_ptr(pe), ps.shape[0], _lib.np_ptr(out)),
+               "narrowPeak summit offsets")
+    return out
+
+
+def _write_narrowpeak_summit_offsets(peak_file: str, chrom_cache: dict, output_file: str) -> str:
+    r"""``<chrom>_<start>_<end>\t<summit offset>`` for every record of ``peak_file`` (rocco.py:840-872); the arg-max over
+    each peak runs on the GPU, one launch per chromosome."""
+    records, _ = _read_bed_records(peak_file)
+    offsets = np.full(len(records), -1, dtype=np.int64)
+    by_chrom: dict[str, list[int]] = {}
+    for k, (chrom, _s, _e) in enumerate(records):
+        by_chrom.setdefault(chrom, []).append(k)
+    for chrom, idx in by_chrom.items():
+        summit_track_file = chrom_cache.get(chrom, {}).get("summit_track_file")
+        if summit_track_file is None:
+            continue
+        with np.load(summit_track_file) as summit_track:
+            starts = np.asarray(summit_track["starts"], dtype=np.int64)
+            centers = np.asarray(summit_track["centers"], dtype=np.int64)
+            mean_track = np.asarray(summit_track["mean"], dtype=np.float32)
+        offsets[idx] = narrowpeak_summit_offsets(starts, centers, mean_track, [records[k][1] for k in idx],
+                                                 [records[k][2] for k in idx])
+    with open(output_file, "w", encoding="utf-8") as handle:
+        handle.write("".join(f"{c}_{s}_{e}\t{int(o)}\n" for (c, s, e), o in zip(records, offsets)))
+    return output_file

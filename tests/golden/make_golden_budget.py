@@ -64,6 +64,32 @@ def main():
     g["bandwidth_rules"] = np.array([[n, -1 if h is None else h, inf._resolve_budget_bootstrap_bandwidth(n, h),
                                       inf._resolve_budget_ess_max_lag(n, h)]
                                      for n in (1, 2, 9, 512, 3000, 934200, 4980000) for h in (None, 16, 25, 101, 1000)], dtype=np.int64)
+    # narrowPeak summit offsets (rocco.py:809-872): awkward tracks (NaN / inf means, ties, peaks off the track, empty peaks)
+    import tempfile
+    rng = np.random.default_rng(9)
+    tmp = tempfile.mkdtemp(prefix="summit_")
+    chrom_cache, lines = {}, []
+    for chrom, nb in (("chrA", 4000), ("chrB", 777)):
+        intervals = np.arange(0, 50 * (nb + 1), 50, dtype=np.int64) + 1000
+        mean = rng.normal(size=nb + 1)
+        mean[rng.integers(0, nb, 60)] = np.nan
+        mean[rng.integers(0, nb, 10)] = np.inf
+        mean[rng.integers(0, nb, 10)] = -np.inf
+        mean[100:140] = 2.5                                   # a tie plateau: first occurrence must win
+        mean[300:320] = np.nan                                # a peak with no finite value
+        chrom_cache[chrom] = {"summit_track_file": rr._cpy_narrowpeak_summit_track(chrom, intervals, mean)}
+        g[f"summit_{chrom}_intervals"], g[f"summit_{chrom}_mean"] = intervals, mean
+        starts = np.sort(rng.integers(0, 50 * nb + 3000, 300))
+        for s_ in starts:
+            lines.append(f"{chrom}\t{int(s_)}\t{int(s_ + rng.integers(0, 900))}")
+        lines += [f"{chrom}\t{1000 + 50 * 100}\t{1000 + 50 * 140}", f"{chrom}\t{1000 + 50 * 300}\t{1000 + 50 * 320}",
+                  f"{chrom}\t{1000 + 50 * 100 + 7}\t{1000 + 50 * 100 + 8}"]
+    lines.append("chrNone\t10\t500")                          # chromosome without a track
+    peak_file = os.path.join(tmp, "peaks.bed")
+    open(peak_file, "w").write("\n".join(lines) + "\n")
+    out = rr._write_narrowpeak_summit_offsets(peak_file, chrom_cache, os.path.join(tmp, "offsets.tsv"))
+    g["summit_peaks_text"] = np.array(open(peak_file).read())
+    g["summit_offsets_text"] = np.array(open(out).read())
     np.savez_compressed(os.path.join(OUT, "reference_budget_v1_11_0.npz"), **g)
     print("wrote", len(g), "arrays")
 

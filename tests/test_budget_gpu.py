@@ -227,3 +227,20 @@ def test_budget_chr21_size_runs_and_is_sane(inf):
     assert 1.0 <= meta["autocorrelation_time"] < 100.0
     assert meta["positive_score_count"] == int(np.sum(scores > 0))
     assert meta["positive_score_median"] == float(np.median(scores[scores > 0]))
+
+
+def test_narrowpeak_summit_offsets_match_reference(budget_golden, tmp_path):
+    """rocco.py:809-872 through the CUDA path: the reference's own output file must be reproduced byte for byte
+    (NaN / +-inf means, tie plateaus, peaks off the track, zero-length peaks, a chromosome without a track)."""
+    from rocco_b200.rocco import _cpy_narrowpeak_summit_track, _write_narrowpeak_summit_offsets, narrowpeak_summit_offsets
+    g = budget_golden
+    cache = {c: {"summit_track_file": _cpy_narrowpeak_summit_track(c, g[f"summit_{c}_intervals"], g[f"summit_{c}_mean"])}
+             for c in ("chrA", "chrB")}
+    peak_file = tmp_path / "peaks.bed"
+    peak_file.write_text(str(g["summit_peaks_text"]))
+    out = _write_narrowpeak_summit_offsets(str(peak_file), cache, str(tmp_path / "offsets.tsv"))
+    assert open(out).read() == str(g["summit_offsets_text"])
+    assert _cpy_narrowpeak_summit_track("c", np.array([5]), np.array([1.0])) is None
+    assert narrowpeak_summit_offsets([], [], [], [1, 2], [5, 2]).tolist() == [-1, -1]
+    for f in cache.values():
+        os.remove(f["summit_track_file"])

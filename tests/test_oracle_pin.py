@@ -295,3 +295,26 @@ def test_budget_estimator_matches_reference(budget_golden, tag):
     assert _close(gam, float(g[f"{tag}_gamma"]), 1e-12)
     for k, v in wantg.items():
         assert (gmeta[k] == v) if isinstance(v, str) else _close(gmeta[k], v, 1e-10), k
+
+
+def _summit_case(g):
+    peaks = [ln.split("\t") for ln in str(g["summit_peaks_text"]).strip().split("\n")]
+    want = [ln.split("\t") for ln in str(g["summit_offsets_text"]).strip().split("\n")]
+    assert [f"{c}_{s}_{e}" for c, s, e in peaks] == [w[0] for w in want]
+    tracks = {}
+    for chrom in ("chrA", "chrB"):
+        iv, mean = g[f"summit_{chrom}_intervals"], g[f"summit_{chrom}_mean"]
+        usable = min(iv.shape[0] - 1, mean.shape[0])
+        tracks[chrom] = (iv[:usable], (iv[:usable] + iv[1:usable + 1]) // 2, mean[:usable].astype(np.float32))
+    return peaks, np.array([int(w[1]) for w in want]), tracks
+
+
+def test_narrowpeak_summit_offsets_match_reference(budget_golden):
+    from oracle import budget as ob
+    peaks, want, tracks = _summit_case(budget_golden)
+    got = np.full(len(peaks), -1, dtype=np.int64)
+    for chrom, (ts, tc, tm) in tracks.items():
+        idx = [k for k, p in enumerate(peaks) if p[0] == chrom]
+        got[idx] = ob.narrowpeak_summit_offsets(ts, tc, tm, [int(peaks[k][1]) for k in idx], [int(peaks[k][2]) for k in idx])
+    assert np.array_equal(got, want)
+    assert (want == -1).sum() > 3 and (want >= 0).sum() > 400
