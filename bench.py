@@ -200,6 +200,10 @@ _RESULT_FD = None
 
 def emit(line: dict) -> None:
     """The one JSON line goes to the process's ORIGINAL stdout; see main() for why fd 1 is redirected meanwhile."""
+    try:                                       # the literal metric string of BASELINE.json, next to this line's short name for it
+        line.setdefault("baseline_metric", json.load(open(os.path.join(REPO, "BASELINE.json")))["metric"])
+    except (OSError, KeyError, ValueError):
+        pass
     data = (json.dumps(line) + "\n").encode()
     if _RESULT_FD is None:
         sys.stdout.write(data.decode()); sys.stdout.flush()
