@@ -181,9 +181,23 @@ def check(status: int, what: str = "rocco_b200") -> None:
     raise RuntimeError(f"{what}: CUDA error: {last_error()}")
 
 
+_CUDA_PID = None
+
+
 def require_device() -> None:
+    """Every compute entry passes through here first.  The reference runs its native kernels from FORKED worker pools
+    (rocco.py:1176-1180, inference.py:871-893); a CUDA context does not survive a fork, and the driver's own message for that
+    is an opaque "initialization error", so the situation is named here instead."""
+    global _CUDA_PID
+    pid = os.getpid()
+    if _CUDA_PID is not None and _CUDA_PID != pid:
+        raise RuntimeError(
+            f"rocco_b200: the CUDA context was created in process {_CUDA_PID}; this forked child ({pid}) cannot use it. "
+            "Drive chromosomes from threads (each call leases its own stream), start workers with the 'spawn' method, or pass "
+            "all chromosomes to one call (rocco_b200.pipeline.solve_chromosomes / run_shard).")
     if load().rocco_b200_device_count() <= 0:
         raise RuntimeError("rocco_b200: no CUDA device visible and there is no CPU fallback")
+    _CUDA_PID = pid
 
 
 def np_ptr(a: np.ndarray) -> c_void_p:

@@ -121,3 +121,11 @@ def test_combine_native_and_fallback_paths_agree_with_oracle(oracle, tmp_path):
     b = oracle.combine_chrom_results([str(canon)], str(tmp_path / "b2.bed"), name_features=True)
     assert open(a).read() == open(b).read()
     assert open(combine_chrom_results([], str(tmp_path / "none.bed"))).read() == ""
+
+
+def test_forked_child_gets_a_named_error(monkeypatch):
+    """A CUDA context does not survive fork(); the reference's callers fork worker pools (rocco.py:1176-1180)."""
+    from rocco_b200 import _lib
+    monkeypatch.setattr(_lib, "_CUDA_PID", os.getpid() + 1)          # as if the context had been created by a parent
+    with pytest.raises(RuntimeError, match="forked child"):
+        _lib.require_device()
