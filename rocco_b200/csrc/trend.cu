@@ -432,6 +432,31 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 256) ? 4 : (CAP_HI <= 409
     int len = 1;
     while (len < cnt) len <<= 1;
     double2 *cand = T.cand + ((size_t)row * MAXSLOT + s) * CAPX;
+    if (!P.slot_boundary[s]) {
+        // median-only slot: only the |signal| value at one or two ranks is wanted, so the keys are sorted alone (half the
+        // shared-memory traffic of the pair sort, one compare instead of the lexicographic one)
+        double *s_x = reinterpret_cast<double *>(s_p);
+        for (int k = threadIdx.x; k < len; k += ST_THREADS) s_x[k] = (k < cnt) ? cand[k].x : INFINITY;
+        __syncthreads();
+        for (int k = 2; k <= len; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = threadIdx.x; i < len; i += ST_THREADS) {
+                    const int ixj = i ^ j;
+                    if (ixj > i) {
+                        const double a = s_x[i], b = s_x[ixj];
+                        const bool up = ((i & k) == 0);
+                        if ((a > b) == up) { s_x[i] = b; s_x[ixj] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        for (int q = threadIdx.x; q < 2 * B; q += ST_THREADS) {
+            const int b = q >> 1, k = q & 1;
+            if (P.xm_slot[b][k] == s) P.xm_val[b][k] = s_x[P.xm_rank[b][k]];
+        }
+        return;
+    }
     for (int k = threadIdx.x; k < len; k += ST_THREADS) s_p[k] = (k < cnt) ? cand[k] : make_double2(INFINITY, INFINITY);
     __syncthreads();
     for (int k = 2; k <= len; k <<= 1) {
