@@ -355,11 +355,14 @@ def main():
             if files:
                 rocco_b200.combine_chrom_results(files, f"combined_r{rank}.bed")
 
-        e2e_step()                                      # warm-up
+        for _ in range(2):                              # warm-up: the per-lease scratch pools reach their steady-state sizes
+            e2e_step()
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
+            t_step = time.perf_counter()
             e2e_step()
+            print(f"[bench] rank {rank} e2e step: {1e3 * (time.perf_counter() - t_step):.0f} ms", file=sys.stderr)
         barrier()
         dt = time.perf_counter() - t0
         os.chdir(cwd)
