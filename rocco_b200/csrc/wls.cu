@@ -562,7 +562,11 @@ static int score_loci_core(const void *d_matrix_in, const void *h_matrix, int dt
     long long group = std::max<long long>(1, std::min<long long>(m, (256LL << 20) / std::max<long long>(1, n * (long long)esz)));
     if (!h_matrix) group = m;
     const int ngroups = (int)((m + group - 1) / group);
-    std::vector<cudaEvent_t> ev;
+    struct EventList {                            // destroyed on every exit path, including the early error returns
+        std::vector<cudaEvent_t> v;
+        ~EventList() { for (cudaEvent_t e : v) if (e) cudaEventDestroy(e); }
+        cudaEvent_t &operator[](int i) { return v[(size_t)i]; }
+    } ev;
     if (h_matrix) {
         RB_TRY(ar.alloc(&d_x, (size_t)m * n * esz));
         d_matrix = d_x;
@@ -576,7 +580,7 @@ static int score_loci_core(const void *d_matrix_in, const void *h_matrix, int dt
         RB_CUDA(cudaEventRecord(ready, st));                       // the stream-ordered allocation is valid from here on
         RB_CUDA(cudaStreamWaitEvent(cs, ready, 0));
         cudaEventDestroy(ready);
-        ev.resize(ngroups);
+        ev.v.assign((size_t)ngroups, nullptr);
         for (int g = 0; g < ngroups; ++g) {
             const long long r0 = g * group, r1 = std::min(m, r0 + group);
             RB_CUDA(cudaMemcpyAsync(d_x + (size_t)r0 * n * esz, (const char *)h_matrix + (size_t)r0 * n * esz,
@@ -603,7 +607,6 @@ static int score_loci_core(const void *d_matrix_in, const void *h_matrix, int dt
         if (status == 0) status = whittaker_rows(xg, dtype, 1, d_pilot + r0, r1 - r0, n, n, lam, 0, d_cent + r0 * n, d_bad, st);
         if (status == 0) status = wls_rows(d_cent, R, r0, r1, st);
     }
-    for (cudaEvent_t e : ev) cudaEventDestroy(e);
     if (status != 0) { cudaStreamSynchronize(st); return status; }
     int bad = 0;
     RB_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
