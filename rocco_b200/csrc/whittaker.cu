@@ -21,10 +21,12 @@
 #include "common.cuh"
 #include "score.cuh"
 
+#include <cooperative_groups.h>
 #include <math.h>
 
 #include <algorithm>
 #include <map>
+#include <memory>
 #include <mutex>
 
 namespace rb {
@@ -71,8 +73,28 @@ static void host_factor(long long n_true, long long len, int parity, double lam,
     }
 }
 
+// Tables of the cluster-pair kernel for one alignment shift parity `ap` (region position 0 has index parity ap):
+// chain A carries the rhs of the even region positions (parity p = ap), chain B the odd ones (p = 1 - ap).
+constexpr int WP_HALF = 6144;                      // bins per CTA, two CTAs per region
+constexpr int WP_MAXWARPS = 16;
+constexpr int WP_LEVELS = 9;                       // 5 in-warp levels + 4 across the warps of a CTA
+// thread geometries of the pair kernel (threads x bins per thread = WP_HALF): 0 = 512 x 12, 1 = 384 x 16
+constexpr int WP_NGEOM = 2;
+constexpr int WP_GEOM_THREADS[WP_NGEOM] = {512, 384};
+constexpr int WP_GEOM_ITEMS[WP_NGEOM] = {12, 16};
+struct PairTab {
+    double cf[2][3][2];                            // [chain][dinv, l1, l2][position parity]
+    double trans[2][2][WP_LEVELS][4];              // [chain][fwd/bwd][level]: transition over ITEMS * 2^level bins
+};
+struct PairPow {
+    double lane[2][2][32][4];                      // [chain][dir][k]: T^k chunks (k = 0: identity)
+    double warp[2][2][WP_MAXWARPS][4];             // [chain][dir][w]: T^(32 w) chunks (w = 0: identity)
+};
+
 struct FactorHost {
     int head_len = 0;
+    PairTab pair_tab[WP_NGEOM][2];                 // [geometry][alignment shift parity]
+    PairPow pair_pow[WP_NGEOM][2];
     std::vector<double> head[2][3];      // [parity][dinv,l1,l2][head_len]
     double steady[2][3][2];              // [parity][coef][index parity]
     double tail[2][3][4];                // rows n-4 .. n-1
@@ -155,6 +177,41 @@ static void build_factor(long long n, double lam, FactorHost &F)
             }
         }
     }
+    // cluster-pair kernel: chains by region-position parity, for both alignment shift parities
+    for (int gm = 0; gm < WP_NGEOM; ++gm)
+    for (int ap = 0; ap < 2; ++ap) {
+        const int WP_ITEMS = WP_GEOM_ITEMS[gm], WP_WARPS = WP_GEOM_THREADS[gm] / 32;
+        PairTab &T = F.pair_tab[gm][ap];
+        PairPow &W = F.pair_pow[gm][ap];
+        for (int ch = 0; ch < 2; ++ch) {
+            const int p = ch ^ ap;                                  // parity mask served by this chain
+            for (int k = 0; k < 3; ++k)
+                for (int q = 0; q < 2; ++q) T.cf[ch][k][q] = F.steady[p][k][q ^ ap];
+            double Tf[4] = {1, 0, 0, 1}, Tb[4] = {1, 0, 0, 1};
+            for (int j = 0; j < WP_ITEMS; ++j) {                    // position j of a chunk (chunks start on even positions)
+                const double S[4] = {-T.cf[ch][1][(j + 1) & 1], -T.cf[ch][2][j & 1], 1.0, 0.0};
+                mat2_mul(S, Tf, Tf);
+            }
+            for (int j = WP_ITEMS - 1; j >= 0; --j) {
+                const double S[4] = {-T.cf[ch][1][j & 1], -T.cf[ch][2][j & 1], 1.0, 0.0};
+                mat2_mul(S, Tb, Tb);
+            }
+            for (int k = 0; k < 4; ++k) { T.trans[ch][0][0][k] = Tf[k]; T.trans[ch][1][0][k] = Tb[k]; }
+            for (int dct = 0; dct < 2; ++dct) {
+                for (int l = 1; l < WP_LEVELS; ++l) mat2_mul(T.trans[ch][dct][l - 1], T.trans[ch][dct][l - 1], T.trans[ch][dct][l]);
+                double acc[4] = {1, 0, 0, 1};
+                for (int k = 0; k < 32; ++k) {
+                    for (int q = 0; q < 4; ++q) W.lane[ch][dct][k][q] = acc[q];
+                    mat2_mul(T.trans[ch][dct][0], acc, acc);
+                }
+                double wacc[4] = {1, 0, 0, 1};
+                for (int w = 0; w < WP_WARPS; ++w) {
+                    for (int q = 0; q < 4; ++q) W.warp[ch][dct][w][q] = wacc[q];
+                    mat2_mul(T.trans[ch][dct][5], wacc, wacc);
+                }
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------ fast log2 for arguments >= 1
@@ -204,6 +261,33 @@ __device__ __forceinline__ double fast_log2_ge1(double v, const double *s_inv, c
     for (int k = 1; k < 7; ++k) p = __fma_rn(p, r, c_log2poly[k]);
     const double res = (double)e + __fma_rn(p, r, s_tab[i]);
     return mant == 0 ? (double)e : res;                              // exact powers of two (zero counts -> 0.0), branch-free
+}
+
+
+// Leaner variant for the pair kernel: interleaved table {inv[i], tab[i]} (one 128-bit shared load), degree-5 polynomial
+// (|r| <= 2^-8: truncation r^6 / (6 ln 2) < 1e-15 absolute, five orders below the solver's noise floor), exponent converted
+// with the 2^52 trick instead of I2F.  Exact for powers of two (zero counts give 0.0) like the function above.
+__constant__ double c_log2poly5[5] = {
+    0.28853900817779268,      //  1/(5 ln2)
+    -0.36067376022224085,     // -1/(4 ln2)
+    0.48089834696298783,      //  1/(3 ln2)
+    -0.72134752044448170,     // -1/(2 ln2)
+    1.4426950408889634,       //  1/ln2
+};
+__device__ __forceinline__ double fast_log2_ge1_v2(double v, const double2 *s_it)
+{
+    const int hi = __double2hiint(v), lo = __double2loint(v);
+    const int mhi = hi & 0x000FFFFF;
+    const double2 it = s_it[mhi >> 13];
+    const double m = __hiloint2double(mhi | 0x3FF00000, lo);
+    const double r = __fma_rn(m, it.x, -1.0);
+    double p = c_log2poly5[0];
+#pragma unroll
+    for (int k = 1; k < 5; ++k) p = __fma_rn(p, r, c_log2poly5[k]);
+    // exponent as a double: 2^52 + (biased exponent) - (2^52 + 1023)
+    const double e = __hiloint2double(0x43300000, hi >> 20) - 4503599627371519.0;
+    const double res = e + __fma_rn(p, r, it.y);
+    return ((mhi | lo) == 0) ? e : res;
 }
 
 // ------------------------------------------------------------------ device side
@@ -593,6 +677,274 @@ __global__ void __launch_bounds__(WT_THREADS, 1) k_whittaker(WhitParams P)
     if (bad2) *P.bad = 1;
 }
 
+
+// ------------------------------------------------------------------ steady tiles, cluster-pair form
+// The same 12288-bin region (9728 own bins + two 1280-bin halos) is solved by a CLUSTER of two CTAs of 512 threads, each
+// holding one half (6144 bins, 106 KB of shared memory), so that two CTAs of different tiles are resident per SM and
+// the barrier-separated phases of one overlap the sweeps of the other:
+//   * the half's raw input arrives by ONE bulk async copy (cp.async.bulk, completion on an mbarrier) into the shared
+//     memory that later holds the second chain's forward solution; every thread then reads its own 12 consecutive
+//     bins with 128-bit shared loads and keeps y = log2(max(x,0)+1) - pilot in registers until the epilogue;
+//   * the carry scan runs inside the warp (shuffles), across the 16 warps (warp 0), and across the two CTAs: the
+//     left CTA hands its total to the right one for the forward substitution, the right CTA to the left one for the
+//     backward substitution, by a store into the peer's shared memory (DSMEM) followed by a cluster barrier;
+//   * centered = y - baseline goes from registers straight to global memory as 128-bit stores (96 contiguous bytes
+//     per thread: whole 32-byte sectors).
+// A bulk copy needs a 16-byte aligned source: the region starts `shift` bins left of the tile's nominal (even) start.
+// An odd shift swaps which parity mask sits on the even region positions, hence the per-launch chain tables.
+struct PairParams {
+    const void *x; const double *pilot; double *out; int *bad;
+    const double *lanepow;      // PairPow::lane of this shift parity (device)
+    const double *warppow;      // PairPow::warp
+    const double *log2tab;
+    PairTab tab;
+    long long n, row_stride;
+    int row0, row_step;         // rows handled by this launch: row0 + k * row_step
+    int tile_offset, span_tiles;
+    int shift;
+    int log_transform, write_baseline;
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// Carry scan of both chains at once.  v[0..1]: chain A zero-state end vector of this thread's chunk, v[2..3]: chain B.
+// On exit `in` holds the true state entering the chunk.  REV: scan runs right to left (backward substitution).
+template <bool REV, int WP_WARPS>
+__device__ __forceinline__ void pair_scan(double (&v)[4], double (&in)[4], const PairParams &P, double (*s_wtot)[4],
+                                          double (*s_excl)[4], double (*s_nbr)[4], int rank)
+{
+    namespace cg = cooperative_groups;
+    constexpr int D = REV ? 1 : 0;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int lpos = REV ? 31 - lane : lane;
+    const int wpos = REV ? WP_WARPS - 1 - wid : wid;
+#pragma unroll
+    for (int l = 0; l < 5; ++l) {
+        const int dlt = 1 << l;
+        double o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] = REV ? __shfl_down_sync(0xffffffffu, v[k], dlt) : __shfl_up_sync(0xffffffffu, v[k], dlt);
+        if (lpos >= dlt) {
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                const double *T = P.tab.trans[ch][D][l];
+                v[2 * ch + 0] += T[0] * o[2 * ch] + T[1] * o[2 * ch + 1];
+                v[2 * ch + 1] += T[2] * o[2 * ch] + T[3] * o[2 * ch + 1];
+            }
+        }
+    }
+    double e[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        e[k] = REV ? __shfl_down_sync(0xffffffffu, v[k], 1) : __shfl_up_sync(0xffffffffu, v[k], 1);
+        if (lpos == 0) e[k] = 0.0;
+    }
+    if (lpos == 31) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s_wtot[wpos][k] = v[k];
+    }
+    __syncthreads();
+    if (wid == 0) {
+        double a[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a[k] = (lane < WP_WARPS) ? s_wtot[lane][k] : 0.0;
+#pragma unroll
+        for (int l = 0; (1 << l) < WP_WARPS; ++l) {
+            const int dlt = 1 << l;
+            double o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] = __shfl_up_sync(0xffffffffu, a[k], dlt);
+            if (lane >= dlt) {
+#pragma unroll
+                for (int ch = 0; ch < 2; ++ch) {
+                    const double *T = P.tab.trans[ch][D][5 + l];
+                    a[2 * ch + 0] += T[0] * o[2 * ch] + T[1] * o[2 * ch + 1];
+                    a[2 * ch + 1] += T[2] * o[2 * ch] + T[3] * o[2 * ch + 1];
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double ex = __shfl_up_sync(0xffffffffu, a[k], 1);
+            if (lane < WP_WARPS) s_excl[lane][k] = (lane == 0) ? 0.0 : ex;
+        }
+        // the CTA that comes first in scan order hands its total to its peer
+        const bool sender = REV ? (rank == 1) : (rank == 0);
+        if (sender && lane == WP_WARPS - 1) {
+            double *dst = cg::this_cluster().map_shared_rank(&s_nbr[D][0], rank ^ 1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) dst[k] = a[k];
+        }
+    }
+    cg::this_cluster().sync();                          // also a CTA barrier: s_excl and the peer's total are visible
+    double E[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) E[k] = s_excl[wpos][k];
+    const bool receiver = REV ? (rank == 0) : (rank == 1);
+    if (receiver) {
+        const double n0 = s_nbr[D][0], n1 = s_nbr[D][1], n2 = s_nbr[D][2], n3 = s_nbr[D][3];
+        const double *wa = P.warppow + ((0 * 2 + D) * WP_MAXWARPS + wpos) * 4;
+        const double *wb = P.warppow + ((1 * 2 + D) * WP_MAXWARPS + wpos) * 4;
+        E[0] += __ldg(wa + 0) * n0 + __ldg(wa + 1) * n1;
+        E[1] += __ldg(wa + 2) * n0 + __ldg(wa + 3) * n1;
+        E[2] += __ldg(wb + 0) * n2 + __ldg(wb + 1) * n3;
+        E[3] += __ldg(wb + 2) * n2 + __ldg(wb + 3) * n3;
+    }
+    {
+        const double *la = P.lanepow + ((0 * 2 + D) * 32 + lpos) * 4;
+        const double *lb = P.lanepow + ((1 * 2 + D) * 32 + lpos) * 4;
+        in[0] = e[0] + __ldg(la + 0) * E[0] + __ldg(la + 1) * E[1];
+        in[1] = e[1] + __ldg(la + 2) * E[0] + __ldg(la + 3) * E[1];
+        in[2] = e[2] + __ldg(lb + 0) * E[2] + __ldg(lb + 1) * E[3];
+        in[3] = e[3] + __ldg(lb + 2) * E[2] + __ldg(lb + 3) * E[3];
+    }
+}
+
+template <bool F32, int WP_THREADS, int WP_ITEMS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WP_THREADS, 2) k_whittaker_pair(const __grid_constant__ PairParams P)
+{
+    namespace cg = cooperative_groups;
+    static_assert(WP_THREADS * WP_ITEMS == WP_HALF && WP_ITEMS % 4 == 0, "pair geometry");
+    constexpr int WP_WARPS = WP_THREADS / 32;
+    constexpr int PAD = WP_ITEMS + 1;
+    extern __shared__ __align__(128) double smem_pair[];
+    double *s_f0 = smem_pair;                             // chain A forward solution, thread-blocked with one pad word
+    double *s_f1 = smem_pair + WP_THREADS * PAD;          // chain B; before that: landing zone of the bulk copy
+    __shared__ __align__(8) unsigned long long s_mbar;
+    __shared__ double2 s_log[128];                        // {inv[i], tab[i]}
+    __shared__ double s_wtot[WP_MAXWARPS][4], s_excl[WP_MAXWARPS][4];
+    __shared__ double s_nbr[2][4];
+
+    const int rank = (int)cg::this_cluster().block_rank();
+    const int tid = threadIdx.x;
+    const int pair_idx = blockIdx.x >> 1;
+    const long long row = P.row0 + (long long)(pair_idx / P.span_tiles) * P.row_step;
+    const int tile = P.tile_offset + pair_idx % P.span_tiles;
+    const long long r0 = (long long)tile * WT_OUT - WT_HALO - P.shift;               // region start (inside the row: steady tiles only)
+    const long long hbase = row * P.row_stride + r0 + (long long)rank * WP_HALF;     // first element of this CTA's half
+    constexpr unsigned BYTES = WP_HALF * (F32 ? 4u : 8u);
+
+    const unsigned mbar = smem_u32(&s_mbar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const char *src = reinterpret_cast<const char *>(P.x) + hbase * (F32 ? 4 : 8);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(BYTES) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(s_f1)), "l"(src), "r"(BYTES), "r"(mbar) : "memory");
+    }
+    if (tid < 128) s_log[tid] = make_double2(P.log2tab[tid], P.log2tab[128 + tid]);
+    const double pil = (P.log_transform && P.pilot) ? P.pilot[row] : 0.0;
+    __syncthreads();
+    {
+        unsigned done = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(mbar) : "memory");
+        }
+    }
+
+    // ---- this thread's 12 bins: raw -> y (registers)
+    double y[WP_ITEMS];
+    if (F32) {
+        const float4 *rp = reinterpret_cast<const float4 *>(s_f1) + tid * (WP_ITEMS / 4);
+#pragma unroll
+        for (int u = 0; u < WP_ITEMS / 4; ++u) {
+            const float4 q = rp[u];
+            y[4 * u + 0] = (double)q.x; y[4 * u + 1] = (double)q.y; y[4 * u + 2] = (double)q.z; y[4 * u + 3] = (double)q.w;
+        }
+    } else {
+        const double2 *rp = reinterpret_cast<const double2 *>(s_f1) + tid * (WP_ITEMS / 2);
+#pragma unroll
+        for (int u = 0; u < WP_ITEMS / 2; ++u) { const double2 q = rp[u]; y[2 * u] = q.x; y[2 * u + 1] = q.y; }
+    }
+    // inference.py:45-46 rejects non-finite input: the largest exponent field seen decides at the end (a flagged call
+    // returns ST_NONFINITE and its output is discarded, so the transform need not special-case those bins)
+    int expmax = 0;
+#pragma unroll
+    for (int j = 0; j < WP_ITEMS; ++j) expmax = max(expmax, __double2hiint(y[j]) & 0x7FF00000);
+    int bad = (expmax == 0x7FF00000);
+    if (P.log_transform) {
+#pragma unroll
+        for (int j = 0; j < WP_ITEMS; ++j) {
+            y[j] = fast_log2_ge1_v2(fmax(y[j], 0.0) + 1.0, s_log) - pil;
+            // four evaluations in flight at a time: interleaving all of them costs more in spills than it hides latency
+            if ((j & 3) == 3) asm volatile("" : "+d"(y[j]), "+d"(y[j - 1]), "+d"(y[j - 2]), "+d"(y[j - 3]));
+        }
+    }
+
+    const double (*cfA)[2] = P.tab.cf[0];                 // [dinv, l1, l2][position parity]
+    const double (*cfB)[2] = P.tab.cf[1];
+    double *f0 = s_f0 + tid * PAD, *f1 = s_f1 + tid * PAD;
+    double v[4], in[4];
+
+    // ================= forward substitution: zero-state sweep, carry scan, true sweep (scaled by 1/d on the way out)
+    {
+        double a1 = 0.0, a2 = 0.0, b1 = 0.0, b2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < WP_ITEMS; ++j) {
+            const double ra = (j & 1) ? 0.0 : y[j], rb_ = (j & 1) ? y[j] : 0.0;
+            const double na = fma(-cfA[2][j & 1], a2, fma(-cfA[1][(j + 1) & 1], a1, ra));
+            const double nb = fma(-cfB[2][j & 1], b2, fma(-cfB[1][(j + 1) & 1], b1, rb_));
+            a2 = a1; a1 = na; b2 = b1; b1 = nb;
+        }
+        v[0] = a1; v[1] = a2; v[2] = b1; v[3] = b2;
+    }
+    pair_scan<false, WP_WARPS>(v, in, P, s_wtot, s_excl, s_nbr, rank);      // (its barriers also order the raw reads before the writes below)
+    {
+        double a1 = in[0], a2 = in[1], b1 = in[2], b2 = in[3];
+#pragma unroll
+        for (int j = 0; j < WP_ITEMS; ++j) {
+            const double ra = (j & 1) ? 0.0 : y[j], rb_ = (j & 1) ? y[j] : 0.0;
+            const double na = fma(-cfA[2][j & 1], a2, fma(-cfA[1][(j + 1) & 1], a1, ra));
+            const double nb = fma(-cfB[2][j & 1], b2, fma(-cfB[1][(j + 1) & 1], b1, rb_));
+            a2 = a1; a1 = na; b2 = b1; b1 = nb;
+            f0[j] = na * cfA[0][j & 1]; f1[j] = nb * cfB[0][j & 1];
+        }
+    }
+    // ================= backward substitution (right to left)
+    {
+        double a1 = 0.0, a2 = 0.0, b1 = 0.0, b2 = 0.0;
+#pragma unroll
+        for (int j = WP_ITEMS - 1; j >= 0; --j) {
+            const double na = fma(-cfA[2][j & 1], a2, fma(-cfA[1][j & 1], a1, f0[j]));
+            const double nb = fma(-cfB[2][j & 1], b2, fma(-cfB[1][j & 1], b1, f1[j]));
+            a2 = a1; a1 = na; b2 = b1; b1 = nb;
+        }
+        v[0] = a1; v[1] = a2; v[2] = b1; v[3] = b2;
+    }
+    pair_scan<true, WP_WARPS>(v, in, P, s_wtot, s_excl, s_nbr, rank);
+
+    // ---- true backward sweep + epilogue: own bins only, straight from registers
+    const int p0 = rank * WP_HALF + tid * WP_ITEMS;                   // region position of this thread's first bin
+    const int o_lo = WT_HALO + P.shift, o_hi = o_lo + WT_OUT;
+    double *outp = P.out + hbase + tid * WP_ITEMS;
+    const bool full = (p0 >= o_lo) && (p0 + WP_ITEMS <= o_hi) && ((reinterpret_cast<uintptr_t>(outp) & 15) == 0);
+    {
+        double a1 = in[0], a2 = in[1], b1 = in[2], b2 = in[3];
+        double hold = 0.0;
+#pragma unroll
+        for (int j = WP_ITEMS - 1; j >= 0; --j) {
+            const double na = fma(-cfA[2][j & 1], a2, fma(-cfA[1][j & 1], a1, f0[j]));
+            const double nb = fma(-cfB[2][j & 1], b2, fma(-cfB[1][j & 1], b1, f1[j]));
+            a2 = a1; a1 = na; b2 = b1; b1 = nb;
+            const double bsl = 0.5 * (na + nb);                       // cross-fit average (baseline_backend.c:296-299)
+            const double c = P.write_baseline ? bsl : y[j] - bsl;
+            bad |= !isfinite(c);
+            if (full) {
+                if (j & 1) hold = c;
+                else *reinterpret_cast<double2 *>(outp + j) = make_double2(c, hold);
+            } else if (p0 + j >= o_lo && p0 + j < o_hi) {
+                outp[j] = c;
+            }
+        }
+    }
+    if (bad) *P.bad = 1;
+}
+
 // n < 25: the reference returns a zero baseline (baseline_backend.c:266-273) -> centered = y
 __global__ void k_small_rows(WhitParams P)
 {
@@ -608,45 +960,114 @@ __global__ void k_small_rows(WhitParams P)
 }
 
 // ------------------------------------------------------------------ factor cache (device tables per (n, lambda))
+// Entries are handed out as shared_ptr: a caller keeps its tables alive across its launches whatever the cache does
+// meanwhile (eviction only drops the cache's own reference), and the device buffers are released by the destructor on
+// every path, including a failed construction.
 struct FactorDev {
     FactorHost host;
     double *d_head[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     double *d_lanepow = nullptr;
     double *d_log2 = nullptr;
+    double *d_pairpow[WP_NGEOM][2] = {{nullptr, nullptr}, {nullptr, nullptr}};       // PairPow per geometry and shift parity
+    int device = 0;
+    unsigned long long last_use = 0;
+    FactorDev() = default;
+    FactorDev(const FactorDev &) = delete;
+    FactorDev &operator=(const FactorDev &) = delete;
+    ~FactorDev()
+    {
+        for (int p = 0; p < 2; ++p) {
+            for (int k = 0; k < 3; ++k) if (d_head[p][k]) cudaFree(d_head[p][k]);
+            for (int gm = 0; gm < WP_NGEOM; ++gm) if (d_pairpow[gm][p]) cudaFree(d_pairpow[gm][p]);
+        }
+        if (d_lanepow) cudaFree(d_lanepow);
+        if (d_log2) cudaFree(d_log2);
+    }
 };
+using FactorRef = std::shared_ptr<FactorDev>;
 static std::mutex g_fmutex;
-static std::map<std::pair<long long, double>, FactorDev *> g_fcache[16];
+static std::map<std::pair<long long, double>, FactorRef> g_fcache[16];
+static unsigned long long g_fclock = 0;
+constexpr size_t FACTOR_CACHE_MAX = 256;
 
-static int get_factor(long long n, double lam, FactorDev **out)
+static int upload_factor(FactorDev &F)
+{
+    for (int p = 0; p < 2; ++p)
+        for (int k = 0; k < 3; ++k) {
+            RB_CUDA(cudaMalloc(&F.d_head[p][k], sizeof(double) * std::max(1, F.host.head_len)));
+            RB_CUDA(cudaMemcpy(F.d_head[p][k], F.host.head[p][k].data(), sizeof(double) * F.host.head_len, cudaMemcpyHostToDevice));
+        }
+    build_log2_tables();
+    RB_CUDA(cudaMalloc(&F.d_log2, sizeof(Log2Tables)));
+    RB_CUDA(cudaMemcpy(F.d_log2, &g_log2_host, sizeof(Log2Tables), cudaMemcpyHostToDevice));
+    RB_CUDA(cudaMalloc(&F.d_lanepow, sizeof(F.host.lanepow)));
+    RB_CUDA(cudaMemcpy(F.d_lanepow, F.host.lanepow, sizeof(F.host.lanepow), cudaMemcpyHostToDevice));
+    for (int gm = 0; gm < WP_NGEOM; ++gm)
+        for (int ap = 0; ap < 2; ++ap) {
+            RB_CUDA(cudaMalloc(&F.d_pairpow[gm][ap], sizeof(PairPow)));
+            RB_CUDA(cudaMemcpy(F.d_pairpow[gm][ap], &F.host.pair_pow[gm][ap], sizeof(PairPow), cudaMemcpyHostToDevice));
+        }
+    return 0;
+}
+
+static int get_factor(long long n, double lam, FactorRef *out)
 {
     int dev = 0;
     RB_CUDA(cudaGetDevice(&dev));
+    const auto key = std::make_pair(n, lam);
+    {
+        std::lock_guard<std::mutex> lock(g_fmutex);
+        auto &cache = g_fcache[dev & 15];
+        auto it = cache.find(key);
+        if (it != cache.end()) { it->second->last_use = ++g_fclock; *out = it->second; return 0; }
+    }
+    // build and upload outside the lock (first use costs a few synchronous copies); a racing thread may build the same
+    // key, in which case the first one to publish wins and the other copy dies with its last reference
+    FactorRef F = std::make_shared<FactorDev>();
+    F->device = dev;
+    build_factor(n, lam, F->host);
+    RB_TRY(upload_factor(*F));
     std::lock_guard<std::mutex> lock(g_fmutex);
-    // only the head table and the tail depend on n; key small inputs by n, large ones by (n mod 2-insensitive) n as well
-    auto key = std::make_pair(n, lam);
     auto &cache = g_fcache[dev & 15];
     auto it = cache.find(key);
-    if (it != cache.end()) { *out = it->second; return 0; }
-    FactorDev *F = new FactorDev();
-    build_factor(n, lam, F->host);
-    for (int p = 0; p < 2; ++p)
-        for (int k = 0; k < 3; ++k) {
-            RB_CUDA(cudaMalloc(&F->d_head[p][k], sizeof(double) * std::max(1, F->host.head_len)));
-            RB_CUDA(cudaMemcpy(F->d_head[p][k], F->host.head[p][k].data(), sizeof(double) * F->host.head_len, cudaMemcpyHostToDevice));
-        }
-    build_log2_tables();
-    RB_CUDA(cudaMalloc(&F->d_log2, sizeof(Log2Tables)));
-    RB_CUDA(cudaMemcpy(F->d_log2, &g_log2_host, sizeof(Log2Tables), cudaMemcpyHostToDevice));
-    RB_CUDA(cudaMalloc(&F->d_lanepow, sizeof(F->host.lanepow)));
-    RB_CUDA(cudaMemcpy(F->d_lanepow, F->host.lanepow, sizeof(F->host.lanepow), cudaMemcpyHostToDevice));
-    if (cache.size() > 256) {                        // bounded: drop everything (tables are tiny)
-        for (auto &kv : cache) { for (int p = 0; p < 2; ++p) for (int k = 0; k < 3; ++k) cudaFree(kv.second->d_head[p][k]); cudaFree(kv.second->d_lanepow); cudaFree(kv.second->d_log2); delete kv.second; }
-        cache.clear();
+    if (it != cache.end()) { it->second->last_use = ++g_fclock; *out = it->second; return 0; }
+    while (cache.size() >= FACTOR_CACHE_MAX) {              // evict the least recently used entry nobody else holds
+        auto victim = cache.end();
+        for (auto e = cache.begin(); e != cache.end(); ++e)
+            if (e->second.use_count() == 1 && (victim == cache.end() || e->second->last_use < victim->second->last_use)) victim = e;
+        if (victim == cache.end()) break;                    // everything is in use: let the cache grow
+        cache.erase(victim);
     }
+    F->last_use = ++g_fclock;
     cache[key] = F;
     *out = F;
     return 0;
 }
+
+// steady tiles: 0 = cluster-pair kernel 512 x 12 (default), 2 = cluster-pair kernel 384 x 16, 1 = the single-CTA kernel
+// (kept for A/B checks)
+static std::atomic<int> g_whit_mode{0};
+int whittaker_set_mode(int mode) { return g_whit_mode.exchange((mode >= 0 && mode <= 2) ? mode : 0); }
+
+template <bool F32, int THREADS, int ITEMS>
+static int launch_pair(const PairParams &R, unsigned grid, cudaStream_t st)
+{
+    constexpr size_t sm = sizeof(double) * 2 * THREADS * (ITEMS + 1);
+    static bool attr_dev[64] = {false};
+    int d = 0;
+    cudaGetDevice(&d);
+    bool &attr = attr_dev[d & 63];
+    if (!attr) {
+        RB_CUDA(cudaFuncSetAttribute(k_whittaker_pair<F32, THREADS, ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        RB_CUDA(cudaFuncSetAttribute(k_whittaker_pair<F32, THREADS, ITEMS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        attr = true;
+    }
+    k_whittaker_pair<F32, THREADS, ITEMS><<<grid, THREADS, sm, st>>>(R);
+    RB_LAUNCH_CHECK();
+    return 0;
+}
+
+static long long gcd_ll(long long a, long long b) { while (b) { const long long t = a % b; a = b; b = t; } return a < 0 ? -a : a; }
 
 int whittaker_rows(const void *d_x, int in_f32, int log_transform, const double *d_pilot, long long rows, long long n,
                    long long row_stride, double lam, int write_baseline, double *d_out, int *d_bad, cudaStream_t st)
@@ -662,7 +1083,7 @@ int whittaker_rows(const void *d_x, int in_f32, int log_transform, const double 
         RB_LAUNCH_CHECK();
         return 0;
     }
-    FactorDev *F = nullptr;
+    FactorRef F;                                       // keeps the host tables alive while this call reads them
     RB_TRY(get_factor(n, lam, &F));
     P.head_len = F->host.head_len;
     for (int p = 0; p < 2; ++p)
@@ -691,7 +1112,7 @@ int whittaker_rows(const void *d_x, int in_f32, int log_transform, const double 
     for (int t = 0; t < P.tiles_per_row; ++t) {
         const long long o0 = (long long)t * WT_OUT, o1 = std::min(n, o0 + WT_OUT);
         const long long r0 = std::max<long long>(0, o0 - WT_HALO), r1 = std::min(n, o1 + WT_HALO);
-        const bool steady = (r0 >= P.head_len + 2) && (r1 <= n - 6) && (r1 - r0 == WT_REGION);
+        const bool steady = (r0 >= P.head_len + 8) && (r1 <= n - 6) && (r1 - r0 == WT_REGION);      // (+8: room for the pair kernel's alignment shift)
         if (steady) { first_steady = std::min(first_steady, t); last_steady = std::max(last_steady, t); }
     }
     // general tiles: [0, first_steady) and (last_steady, tiles); steady tiles are contiguous in between
@@ -704,19 +1125,48 @@ int whittaker_rows(const void *d_x, int in_f32, int log_transform, const double 
     } else {
         spans.push_back({0, P.tiles_per_row, false});
     }
+    const size_t esz = in_f32 ? 4 : 8;
+    const int mode = g_whit_mode.load();
+    const int gm = mode == 2 ? 1 : 0;
+    const bool pair_ok = mode != 1 && (reinterpret_cast<uintptr_t>(d_x) % esz) == 0;
     for (const Span &sp : spans) {
         WhitParams Q = P;
         Q.tile_offset = sp.t0;
         Q.span_tiles = sp.t1 - sp.t0;
         const long long blocks = rows * (long long)Q.span_tiles;
-        if (blocks > 0x7fffffffLL) return ST_INVALID;
+        if (blocks > 0x3fffffffLL) return ST_INVALID;
         // algorithmic bytes of this launch: read the input once, write the centered matrix once
         const double span_bins = (double)std::min<long long>(n, (long long)sp.t1 * WT_OUT) - (double)sp.t0 * WT_OUT;
         RB_PROF(sp.steady ? "k_whittaker_steady" : "k_whittaker_edge", st, (double)rows * span_bins * ((in_f32 ? 4.0 : 8.0) + 8.0));
-        if (sp.steady) k_whittaker<true, WT_THREADS_S, WT_ITEMS_S><<<(unsigned)blocks, WT_THREADS_S, sm_steady, st>>>(Q);
-        else k_whittaker<false, WT_THREADS_G, WT_ITEMS_G><<<(unsigned)blocks, WT_THREADS_G, sm_general, st>>>(Q);
-        RB_LAUNCH_CHECK();
+        if (sp.steady && pair_ok) {
+            // rows whose start has the same offset inside a 16-byte unit share a launch (the bulk copy needs an aligned source)
+            const long long M = 16 / (long long)esz;
+            const long long base_off = (long long)((reinterpret_cast<uintptr_t>(d_x) / esz) % (uintptr_t)M);
+            const long long period = M / gcd_ll(row_stride % M, M);
+            for (long long p = 0; p < period && p < rows; ++p) {
+                PairParams R{};
+                R.x = d_x; R.pilot = d_pilot; R.out = d_out; R.bad = d_bad; R.n = n; R.row_stride = row_stride;
+                R.row0 = (int)p; R.row_step = (int)period; R.tile_offset = sp.t0; R.span_tiles = Q.span_tiles;
+                R.shift = (int)((base_off + p * (row_stride % M)) % M);
+                R.log_transform = log_transform; R.write_baseline = write_baseline;
+                R.tab = F->host.pair_tab[gm][R.shift & 1];
+                const double *pw = F->d_pairpow[gm][R.shift & 1];
+                R.lanepow = pw; R.warppow = pw + sizeof(PairPow::lane) / sizeof(double);
+                R.log2tab = F->d_log2;
+                const long long nrows = (rows - p + period - 1) / period;
+                const unsigned grid = (unsigned)(nrows * Q.span_tiles * 2);
+                if (gm == 0) RB_TRY(in_f32 ? (launch_pair<true, 512, 12>(R, grid, st)) : (launch_pair<false, 512, 12>(R, grid, st)));
+                else RB_TRY(in_f32 ? (launch_pair<true, 384, 16>(R, grid, st)) : (launch_pair<false, 384, 16>(R, grid, st)));
+            }
+        } else if (sp.steady) {
+            k_whittaker<true, WT_THREADS_S, WT_ITEMS_S><<<(unsigned)blocks, WT_THREADS_S, sm_steady, st>>>(Q);
+            RB_LAUNCH_CHECK();
+        } else {
+            k_whittaker<false, WT_THREADS_G, WT_ITEMS_G><<<(unsigned)blocks, WT_THREADS_G, sm_general, st>>>(Q);
+            RB_LAUNCH_CHECK();
+        }
     }
+    // (kernels still in flight when an evicted entry dies are safe: cudaFree synchronises with the device first)
     return 0;
 }
 
