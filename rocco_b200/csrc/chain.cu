@@ -485,6 +485,35 @@ __global__ void __launch_bounds__(256) k_chain_seq(Params P)
 
 // ------------------------------------------------------------------ per-chromosome finish + search controller
 // One block per chromosome, one warp per multiplier slot (looping when there are more slots than warps).
+// Multipliers whose count needs no DP pass (costs are >= 0):
+//   lambda > max(s): every s_i - lambda < 0, so d_i <= 0 throughout and nothing is selected (count = 0);
+//   min(s) - lambda > 2 c_max + 1/2: d_0 > c and d_i >= -c + (s_i - lambda) > c, every bin is decided "selected" (count = n).
+// The reference's bracket (dp.py:110-111) is min(s) - sum(c) - 1 .. max(s) + sum(c) + 1, about 2 sum(c) wide, while
+// counts only vary on [min(s) - 2c, max(s)]: the first ~log2(sum(c) / range(s)) bisection levels land in these two
+// regions and are resolved here, with the margins (1/2, strict) far above any rounding of either implementation.
+// +1: count = n, -1: count = 0, 0: evaluate.
+__device__ __forceinline__ int known_side(const ChromDev &cd, double smin, double smax, double lam, int vec)
+{
+    if (!(smin == smin)) return 0;
+    if (lam > smax) return -1;
+    const double cb = cd.n >= 2 ? (vec ? cd.cost_sum : cd.gamma) : 0.0;
+    if (smin - lam > 2.0 * cb + 0.5) return +1;
+    return 0;
+}
+
+// Walk the bisection (dp.py:141-162) through every level whose midpoint has a known count.
+__device__ void skip_known_levels(const ChromDev &cd, SearchDev &sd, int vec)
+{
+    while (sd.iters_left > 0) {
+        const double mid = (sd.lower + sd.upper) / 2.0;
+        const int k = known_side(cd, sd.smin, sd.smax, mid, vec);
+        if (k == 0) break;
+        if (k > 0) sd.lower = mid; else sd.upper = mid;           // count = n > target / count = 0 <= target
+        sd.iters_left -= 1;
+        sd.passes += 1;
+    }
+}
+
 __device__ void gen_tree(const SearchDev &sd, double *lam, int levels)
 {
     // heap-ordered complete tree of the next `levels` bisection midpoints; every midpoint is formed
@@ -598,6 +627,7 @@ __global__ void __launch_bounds__(256) k_chain_finish(Params P, int emit)
         sd.iters_left -= sd.levels;
     }
     if (sd.phase == PH_BISECT) {
+        skip_known_levels(cd, sd, P.costs != nullptr);
         if (sd.iters_left <= 0) {
             sd.phase = PH_DONE;
             sd.nslots = 1;
@@ -647,7 +677,7 @@ __global__ void __launch_bounds__(256) k_chain_minmax(const double *scores, cons
 }
 
 __global__ void k_chain_init(const ChromDev *chroms, SearchDev *search, double *lam, const double *partial,
-                             int nparts, int levels, int nchrom)
+                             int nparts, int levels, int nchrom, int vec)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nchrom) return;
@@ -671,7 +701,20 @@ __global__ void k_chain_init(const ChromDev *chroms, SearchDev *search, double *
         sd.upper = hi + cd.cost_sum + 1.0;
         sd.phase = PH_BRACKET; sd.iters_left = cd.max_iter; sd.levels = levels; sd.nslots = 2;
         l[0] = sd.lower; l[1] = sd.upper;
-        if (cd.max_iter <= 0) { /* bracket only */ }
+        // both bracket ends have known counts (n > target and 0 <= target): the two bracket solves of dp.py:113-138 and
+        // the leading bisection levels need no DP pass
+        if (known_side(cd, sd.smin, sd.smax, sd.lower, vec) > 0 && known_side(cd, sd.smin, sd.smax, sd.upper, vec) < 0) {
+            sd.phase = PH_BISECT;
+            sd.passes = 2;
+            skip_known_levels(cd, sd, vec);
+            if (sd.iters_left <= 0) {
+                sd.phase = PH_DONE; sd.nslots = 1; l[0] = sd.upper;
+            } else {
+                const int lv = min(levels, sd.iters_left);
+                sd.levels = lv; sd.nslots = (1 << lv) - 1;
+                gen_tree(sd, l, lv);
+            }
+        }
     }
     search[c] = sd;
 }
@@ -917,7 +960,7 @@ static int solve_batch(const double *d_scores, const double *d_costs, const rocc
 
     k_chain_minmax<<<dim3(ntask, nparts), 256, 0, st>>>(d_scores, w.d_chroms, w.d_search, w.d_partial);
     RB_LAUNCH_CHECK();
-    k_chain_init<<<(ntask + 63) / 64, 64, 0, st>>>(w.d_chroms, w.d_search, w.d_lam, w.d_partial, nparts, levels, ntask);
+    k_chain_init<<<(ntask + 63) / 64, 64, 0, st>>>(w.d_chroms, w.d_search, w.d_lam, w.d_partial, nparts, levels, ntask, vec ? 1 : 0);
     RB_LAUNCH_CHECK();
 
     Params P{};
@@ -931,9 +974,19 @@ static int solve_batch(const double *d_scores, const double *d_costs, const rocc
 
     std::vector<SearchDev> hsearch(ntask);
     if (any_search) {
-        RB_TRY((launch_round<false>(P, vec, 2, epoch, any_seq, st)));                 // bracket ends
+        // the controller has already walked through the levels that need no DP pass: fetch its state (a few hundred
+        // bytes, behind two tiny kernels) so that only the rounds that still have work are launched
+        RB_CUDA(cudaMemcpyAsync(hsearch.data(), w.d_search, sizeof(SearchDev) * ntask, cudaMemcpyDeviceToHost, st));
+        RB_CUDA(cudaStreamSynchronize(st));
+        bool need_bracket = false;
+        int rounds = 0;
+        for (int c = 0; c < ntask; ++c) {
+            if (chroms[c].mode != 1) continue;
+            if (hsearch[c].phase == PH_BRACKET) { need_bracket = true; rounds = std::max(rounds, (chroms[c].max_iter + levels - 1) / levels); }
+            else if (hsearch[c].phase == PH_BISECT) rounds = std::max(rounds, (hsearch[c].iters_left + levels - 1) / levels);
+        }
+        if (need_bracket) RB_TRY((launch_round<false>(P, vec, 2, epoch, any_seq, st)));     // bracket ends
         // PH_BRACKET -> PH_BISECT generates the first tree in the same finish kernel
-        const int rounds = (max_iter + levels - 1) / levels;
         for (int r = 0; r < rounds; ++r) RB_TRY((launch_round<false>(P, vec, max_slots, epoch, any_seq, st)));
         // rare: bracket expansion (dp.py:119-125, 132-138) is driven from the host with single solves
         RB_CUDA(cudaMemcpyAsync(hsearch.data(), w.d_search, sizeof(SearchDev) * ntask, cudaMemcpyDeviceToHost, st));

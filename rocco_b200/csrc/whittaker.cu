@@ -85,9 +85,10 @@ constexpr int WP_GEOM_ITEMS[WP_NGEOM] = {12, 16};
 struct PairTab {
     double cf[2][3][2];                            // [chain][dinv, l1, l2][position parity]
     double trans[2][2][WP_LEVELS][4];              // [chain][fwd/bwd][level]: transition over ITEMS * 2^level bins
+    double g[2][16][2];                            // [chain][j]: response of the zero-state backward sweep of a chunk to z_j = 1: (x_0, x_1)
 };
 struct PairPow {
-    double lane[2][2][32][4];                      // [chain][dir][k]: T^k chunks (k = 0: identity)
+    double lane[2][2][2][32][2];                   // [chain][dir][matrix row][k]: row of T^k chunks (k = 0: identity); 16-byte lane stride
     double warp[2][2][WP_MAXWARPS][4];             // [chain][dir][w]: T^(32 w) chunks (w = 0: identity)
 };
 
@@ -197,11 +198,19 @@ static void build_factor(long long n, double lam, FactorHost &F)
                 mat2_mul(S, Tb, Tb);
             }
             for (int k = 0; k < 4; ++k) { T.trans[ch][0][0][k] = Tf[k]; T.trans[ch][1][0][k] = Tb[k]; }
+            for (int j0 = 0; j0 < 16; ++j0) {
+                double a1 = 0.0, a2 = 0.0;
+                for (int j = WP_ITEMS - 1; j >= 0 && j0 < WP_ITEMS; --j) {
+                    const double na = (j == j0 ? 1.0 : 0.0) - T.cf[ch][2][j & 1] * a2 - T.cf[ch][1][j & 1] * a1;
+                    a2 = a1; a1 = na;
+                }
+                T.g[ch][j0][0] = a1; T.g[ch][j0][1] = a2;
+            }
             for (int dct = 0; dct < 2; ++dct) {
                 for (int l = 1; l < WP_LEVELS; ++l) mat2_mul(T.trans[ch][dct][l - 1], T.trans[ch][dct][l - 1], T.trans[ch][dct][l]);
                 double acc[4] = {1, 0, 0, 1};
                 for (int k = 0; k < 32; ++k) {
-                    for (int q = 0; q < 4; ++q) W.lane[ch][dct][k][q] = acc[q];
+                    for (int q = 0; q < 4; ++q) W.lane[ch][dct][q >> 1][k][q & 1] = acc[q];
                     mat2_mul(T.trans[ch][dct][0], acc, acc);
                 }
                 double wacc[4] = {1, 0, 0, 1};
@@ -264,30 +273,24 @@ __device__ __forceinline__ double fast_log2_ge1(double v, const double *s_inv, c
 }
 
 
-// Leaner variant for the pair kernel: interleaved table {inv[i], tab[i]} (one 128-bit shared load), degree-5 polynomial
-// (|r| <= 2^-8: truncation r^6 / (6 ln 2) < 1e-15 absolute, five orders below the solver's noise floor), exponent converted
-// with the 2^52 trick instead of I2F.  Exact for powers of two (zero counts give 0.0) like the function above.
-__constant__ double c_log2poly5[5] = {
-    0.28853900817779268,      //  1/(5 ln2)
-    -0.36067376022224085,     // -1/(4 ln2)
-    0.48089834696298783,      //  1/(3 ln2)
-    -0.72134752044448170,     // -1/(2 ln2)
-    1.4426950408889634,       //  1/ln2
-};
+// Leaner variant for the pair kernel: a 32-entry interleaved table {inv[i], tab[i]} (one 128-bit shared load; 512 bytes, so
+// that the 32 lanes' lookups rarely collide on a bank), |r| <= 2^-6 and the degree-7 polynomial above (truncation
+// r^8 / (8 ln 2) < 1e-15 absolute, five orders below the solver's noise floor), exponent converted with the 2^52 trick
+// instead of I2F.  Exact for powers of two (zero counts give 0.0) like the function above.
+constexpr int LOG2_V2_ENTRIES = 34;               // centres 1 + i/32, i = 0..32 (+1 pad: the bulk copy moves multiples of 16 bytes anyway)
 __device__ __forceinline__ double fast_log2_ge1_v2(double v, const double2 *s_it)
 {
     const int hi = __double2hiint(v), lo = __double2loint(v);
     const int mhi = hi & 0x000FFFFF;
-    const double2 it = s_it[mhi >> 13];
+    const double2 it = s_it[(mhi + 0x4000) >> 15];           // nearest centre; entry 0 is {1, 0}: m = 1 gives r = 0 and log2 = e exactly
     const double m = __hiloint2double(mhi | 0x3FF00000, lo);
     const double r = __fma_rn(m, it.x, -1.0);
-    double p = c_log2poly5[0];
+    double p = c_log2poly[0];
 #pragma unroll
-    for (int k = 1; k < 5; ++k) p = __fma_rn(p, r, c_log2poly5[k]);
+    for (int k = 1; k < 7; ++k) p = __fma_rn(p, r, c_log2poly[k]);
     // exponent as a double: 2^52 + (biased exponent) - (2^52 + 1023)
     const double e = __hiloint2double(0x43300000, hi >> 20) - 4503599627371519.0;
-    const double res = e + __fma_rn(p, r, it.y);
-    return ((mhi | lo) == 0) ? e : res;
+    return e + __fma_rn(p, r, it.y);
 }
 
 // ------------------------------------------------------------------ device side
@@ -679,24 +682,24 @@ __global__ void __launch_bounds__(WT_THREADS, 1) k_whittaker(WhitParams P)
 
 
 // ------------------------------------------------------------------ steady tiles, cluster-pair form
-// The same 12288-bin region (9728 own bins + two 1280-bin halos) is solved by a CLUSTER of two CTAs of 512 threads, each
-// holding one half (6144 bins, 106 KB of shared memory), so that two CTAs of different tiles are resident per SM and
-// the barrier-separated phases of one overlap the sweeps of the other:
-//   * the half's raw input arrives by ONE bulk async copy (cp.async.bulk, completion on an mbarrier) into the shared
-//     memory that later holds the second chain's forward solution; every thread then reads its own 12 consecutive
-//     bins with 128-bit shared loads and keeps y = log2(max(x,0)+1) - pilot in registers until the epilogue;
-//   * the carry scan runs inside the warp (shuffles), across the 16 warps (warp 0), and across the two CTAs: the
-//     left CTA hands its total to the right one for the forward substitution, the right CTA to the left one for the
-//     backward substitution, by a store into the peer's shared memory (DSMEM) followed by a cluster barrier;
-//   * centered = y - baseline goes from registers straight to global memory as 128-bit stores (96 contiguous bytes
-//     per thread: whole 32-byte sectors).
+// The same 12288-bin region (9728 own bins + two 1280-bin halos) is solved by a CLUSTER of two CTAs, each holding one
+// half (6144 bins, ~113 KB of shared memory), so that two CTAs of different tiles are resident per SM and the
+// barrier-separated phases of one overlap the sweeps of the other:
+//   * the half's raw input and the scan tables arrive by bulk async copies (cp.async.bulk, completion on an mbarrier);
+//     the raw bins land in the shared memory that later holds the second chain's forward solution.  Every thread reads
+//     its own consecutive bins with 128-bit shared loads and keeps y = log2(max(x,0)+1) - pilot in registers;
+//   * the carry scan runs inside the warp (shuffles), across the warps (warp 0), and across the two CTAs: the left CTA
+//     hands its total to the right one for the forward substitution, the right CTA to the left one for the backward
+//     substitution, with st.async into the peer's shared memory (DSMEM) completing on the peer's mbarrier -- only the
+//     receiver waits, and there is no cluster-scope fence after start-up (which would also invalidate L1);
+//   * centered = y - baseline is laid out contiguously in shared memory and leaves as ONE bulk store per CTA
+//     (whole lines; a scalar head/tail element where the row start is only 8-byte aligned).
 // A bulk copy needs a 16-byte aligned source: the region starts `shift` bins left of the tile's nominal (even) start.
 // An odd shift swaps which parity mask sits on the even region positions, hence the per-launch chain tables.
 struct PairParams {
     const void *x; const double *pilot; double *out; int *bad;
-    const double *lanepow;      // PairPow::lane of this shift parity (device)
-    const double *warppow;      // PairPow::warp
-    const double *log2tab;
+    const double *pow_tab;      // PairPow of this geometry and shift parity (device)
+    const double *log2tab;      // LOG2_V2_ENTRIES x {inv, tab} interleaved (device)
     PairTab tab;
     long long n, row_stride;
     int row0, row_step;         // rows handled by this launch: row0 + k * row_step
@@ -706,14 +709,65 @@ struct PairParams {
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity)
+{
+    unsigned done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void bulk_load(unsigned dst, const void *src, unsigned bytes, unsigned mbar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+
+constexpr int WP_POW_LANE = 2 * 2 * 32 * 4;               // doubles in PairPow::lane
 
 // Carry scan of both chains at once.  v[0..1]: chain A zero-state end vector of this thread's chunk, v[2..3]: chain B.
 // On exit `in` holds the true state entering the chunk.  REV: scan runs right to left (backward substitution).
-template <bool REV, int WP_WARPS>
-__device__ __forceinline__ void pair_scan(double (&v)[4], double (&in)[4], const PairParams &P, double (*s_wtot)[4],
-                                          double (*s_excl)[4], double (*s_nbr)[4], int rank)
+//   1. Kogge-Stone inside the warp (shuffles, T^(2^l chunks));
+//   2. every warp publishes its total; the state entering a warp is the sum over the FOUR warps before it in scan order of
+//      T^(32 j chunks) x total -- a transition over 128 chunks (1536 bins) is below 1e-15, so older warps do not matter --
+//      formed by four lanes in parallel and summed with two butterfly shuffles (no serial section, one CTA barrier);
+//   3. the warps next to the CTA boundary add the peer CTA's total, which arrives by st.async on this CTA's mbarrier.
+template <int WP_WARPS>
+__device__ __forceinline__ void warp_entry_state(double (&E)[4], int target, int D, bool use_peer, const double (*s_wex)[4],
+                                                 const double *s_pow, const double (*s_nbr)[4])
 {
-    namespace cg = cooperative_groups;
+    // state entering scan-order warp `target`: lane group member k-1 handles the warp k places earlier
+    const int k = (threadIdx.x & 3) + 1;
+    const int ws = target - k;
+    double2 t0 = make_double2(0.0, 0.0), t1 = make_double2(0.0, 0.0);
+    int wsel = k - 1;
+    bool have = false;
+    if (ws >= 0) {
+        t0 = *reinterpret_cast<const double2 *>(&s_wex[ws][0]); t1 = *reinterpret_cast<const double2 *>(&s_wex[ws][2]);
+        have = true;
+    } else if (ws == -1 && use_peer) {            // the peer's total is the state entering scan-order warp 0
+        t0 = *reinterpret_cast<const double2 *>(&s_nbr[D][0]); t1 = *reinterpret_cast<const double2 *>(&s_nbr[D][2]);
+        have = true;
+    }
+    E[0] = E[1] = E[2] = E[3] = 0.0;
+    if (have) {
+        const double2 *wa = reinterpret_cast<const double2 *>(s_pow + WP_POW_LANE + ((0 * 2 + D) * WP_MAXWARPS + wsel) * 4);
+        const double2 *wb = reinterpret_cast<const double2 *>(s_pow + WP_POW_LANE + ((1 * 2 + D) * WP_MAXWARPS + wsel) * 4);
+        const double2 a0 = wa[0], a1 = wa[1], b0 = wb[0], b1 = wb[1];
+        E[0] = fma(a0.x, t0.x, a0.y * t0.y); E[1] = fma(a1.x, t0.x, a1.y * t0.y);
+        E[2] = fma(b0.x, t1.x, b0.y * t1.y); E[3] = fma(b1.x, t1.x, b1.y * t1.y);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        E[q] += __shfl_xor_sync(0xffffffffu, E[q], 1);
+        E[q] += __shfl_xor_sync(0xffffffffu, E[q], 2);
+    }
+}
+
+template <bool REV, int WP_WARPS>
+__device__ __forceinline__ void pair_scan(double (&v)[4], double (&in)[4], const PairParams &P, double (*s_wex)[4],
+                                          const double *s_pow, double (*s_nbr)[4], unsigned long long *s_cbar, int rank)
+{
     constexpr int D = REV ? 1 : 0;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int lpos = REV ? 31 - lane : lane;
@@ -728,8 +782,8 @@ __device__ __forceinline__ void pair_scan(double (&v)[4], double (&in)[4], const
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
                 const double *T = P.tab.trans[ch][D][l];
-                v[2 * ch + 0] += T[0] * o[2 * ch] + T[1] * o[2 * ch + 1];
-                v[2 * ch + 1] += T[2] * o[2 * ch] + T[3] * o[2 * ch + 1];
+                v[2 * ch + 0] = fma(T[0], o[2 * ch], fma(T[1], o[2 * ch + 1], v[2 * ch + 0]));
+                v[2 * ch + 1] = fma(T[2], o[2 * ch], fma(T[3], o[2 * ch + 1], v[2 * ch + 1]));
             }
         }
     }
@@ -740,63 +794,39 @@ __device__ __forceinline__ void pair_scan(double (&v)[4], double (&in)[4], const
         if (lpos == 0) e[k] = 0.0;
     }
     if (lpos == 31) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) s_wtot[wpos][k] = v[k];
+        *reinterpret_cast<double2 *>(&s_wex[wpos][0]) = make_double2(v[0], v[1]);
+        *reinterpret_cast<double2 *>(&s_wex[wpos][2]) = make_double2(v[2], v[3]);
     }
     __syncthreads();
-    if (wid == 0) {
-        double a[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) a[k] = (lane < WP_WARPS) ? s_wtot[lane][k] : 0.0;
-#pragma unroll
-        for (int l = 0; (1 << l) < WP_WARPS; ++l) {
-            const int dlt = 1 << l;
-            double o[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) o[k] = __shfl_up_sync(0xffffffffu, a[k], dlt);
-            if (lane >= dlt) {
-#pragma unroll
-                for (int ch = 0; ch < 2; ++ch) {
-                    const double *T = P.tab.trans[ch][D][5 + l];
-                    a[2 * ch + 0] += T[0] * o[2 * ch] + T[1] * o[2 * ch + 1];
-                    a[2 * ch + 1] += T[2] * o[2 * ch] + T[3] * o[2 * ch + 1];
-                }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const double ex = __shfl_up_sync(0xffffffffu, a[k], 1);
-            if (lane < WP_WARPS) s_excl[lane][k] = (lane == 0) ? 0.0 : ex;
-        }
-        // the CTA that comes first in scan order hands its total to its peer
-        const bool sender = REV ? (rank == 1) : (rank == 0);
-        if (sender && lane == WP_WARPS - 1) {
-            double *dst = cg::this_cluster().map_shared_rank(&s_nbr[D][0], rank ^ 1);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) dst[k] = a[k];
+    const bool sender = REV ? (rank == 1) : (rank == 0);
+    const bool receiver = !sender;
+    if (sender && wpos == WP_WARPS - 1) {
+        // this CTA's total = the state that would enter a warp after the last one; 32 bytes into the peer's shared memory,
+        // completing on the peer's mbarrier
+        double N[4];
+        warp_entry_state<WP_WARPS>(N, WP_WARPS, D, false, s_wex, s_pow, s_nbr);
+        if (lane == 0) {
+            unsigned rdst, rbar;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rdst) : "r"(smem_u32(&s_nbr[D][0])), "r"(rank ^ 1));
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(smem_u32(&s_cbar[D])), "r"(rank ^ 1));
+            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];"
+                         ::"r"(rdst), "d"(N[0]), "d"(N[1]), "r"(rbar) : "memory");
+            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];"
+                         ::"r"(rdst + 16), "d"(N[2]), "d"(N[3]), "r"(rbar) : "memory");
         }
     }
-    cg::this_cluster().sync();                          // also a CTA barrier: s_excl and the peer's total are visible
+    const bool use_peer = receiver && wpos < 4;
+    if (use_peer) mbar_wait(smem_u32(&s_cbar[D]), 0);
     double E[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) E[k] = s_excl[wpos][k];
-    const bool receiver = REV ? (rank == 0) : (rank == 1);
-    if (receiver) {
-        const double n0 = s_nbr[D][0], n1 = s_nbr[D][1], n2 = s_nbr[D][2], n3 = s_nbr[D][3];
-        const double *wa = P.warppow + ((0 * 2 + D) * WP_MAXWARPS + wpos) * 4;
-        const double *wb = P.warppow + ((1 * 2 + D) * WP_MAXWARPS + wpos) * 4;
-        E[0] += __ldg(wa + 0) * n0 + __ldg(wa + 1) * n1;
-        E[1] += __ldg(wa + 2) * n0 + __ldg(wa + 3) * n1;
-        E[2] += __ldg(wb + 0) * n2 + __ldg(wb + 1) * n3;
-        E[3] += __ldg(wb + 2) * n2 + __ldg(wb + 3) * n3;
-    }
+    warp_entry_state<WP_WARPS>(E, wpos, D, use_peer, s_wex, s_pow, s_nbr);
     {
-        const double *la = P.lanepow + ((0 * 2 + D) * 32 + lpos) * 4;
-        const double *lb = P.lanepow + ((1 * 2 + D) * 32 + lpos) * 4;
-        in[0] = e[0] + __ldg(la + 0) * E[0] + __ldg(la + 1) * E[1];
-        in[1] = e[1] + __ldg(la + 2) * E[0] + __ldg(la + 3) * E[1];
-        in[2] = e[2] + __ldg(lb + 0) * E[2] + __ldg(lb + 1) * E[3];
-        in[3] = e[3] + __ldg(lb + 2) * E[2] + __ldg(lb + 3) * E[3];
+        const double2 *lp = reinterpret_cast<const double2 *>(s_pow);
+        const double2 a0 = lp[((0 * 2 + D) * 2 + 0) * 32 + lpos], a1 = lp[((0 * 2 + D) * 2 + 1) * 32 + lpos];
+        const double2 b0 = lp[((1 * 2 + D) * 2 + 0) * 32 + lpos], b1 = lp[((1 * 2 + D) * 2 + 1) * 32 + lpos];
+        in[0] = fma(a0.x, E[0], fma(a0.y, E[1], e[0]));
+        in[1] = fma(a1.x, E[0], fma(a1.y, E[1], e[1]));
+        in[2] = fma(b0.x, E[2], fma(b0.y, E[3], e[2]));
+        in[3] = fma(b1.x, E[2], fma(b1.y, E[3], e[3]));
     }
 }
 
@@ -804,16 +834,19 @@ template <bool F32, int WP_THREADS, int WP_ITEMS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WP_THREADS, 2) k_whittaker_pair(const __grid_constant__ PairParams P)
 {
     namespace cg = cooperative_groups;
-    static_assert(WP_THREADS * WP_ITEMS == WP_HALF && WP_ITEMS % 4 == 0, "pair geometry");
+    static_assert(WP_THREADS * WP_ITEMS == WP_HALF && WP_ITEMS % 4 == 0 && WP_ITEMS <= 16, "pair geometry");
     constexpr int WP_WARPS = WP_THREADS / 32;
-    constexpr int PAD = WP_ITEMS + 1;
+    constexpr int PAD = WP_ITEMS + 1;                     // thread stride in 16-byte units: odd, so 128-bit accesses are conflict-free
     extern __shared__ __align__(128) double smem_pair[];
-    double *s_f0 = smem_pair;                             // chain A forward solution, thread-blocked with one pad word
-    double *s_f1 = smem_pair + WP_THREADS * PAD;          // chain B; before that: landing zone of the bulk copy
-    __shared__ __align__(8) unsigned long long s_mbar;
-    __shared__ double2 s_log[128];                        // {inv[i], tab[i]}
-    __shared__ double s_wtot[WP_MAXWARPS][4], s_excl[WP_MAXWARPS][4];
-    __shared__ double s_nbr[2][4];
+    // forward solutions of both chains, interleaved {zA_j, zB_j}, thread-blocked with one pad unit; the same memory is
+    // first the landing zone of the raw input and last the contiguous output stage
+    double2 *s_z = reinterpret_cast<double2 *>(smem_pair);
+    double *s_pow = smem_pair + 2 * WP_THREADS * PAD;     // PairPow (lane + warp tables)
+    const double2 *s_log = reinterpret_cast<const double2 *>(s_pow + sizeof(PairPow) / sizeof(double));   // {inv[i], tab[i]}
+    __shared__ __align__(8) unsigned long long s_mbar;    // input + tables
+    __shared__ __align__(8) unsigned long long s_cbar[2]; // carry from the peer CTA: [forward, backward]
+    __shared__ __align__(16) double s_nbr[2][4];
+    __shared__ __align__(16) double s_wex[2][WP_MAXWARPS][4];   // warp totals, one array per scan direction (no reuse, no hazard)
 
     const int rank = (int)cg::this_cluster().block_rank();
     const int tid = threadIdx.x;
@@ -823,41 +856,41 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WP_THREADS, 2) k_whi
     const long long r0 = (long long)tile * WT_OUT - WT_HALO - P.shift;               // region start (inside the row: steady tiles only)
     const long long hbase = row * P.row_stride + r0 + (long long)rank * WP_HALF;     // first element of this CTA's half
     constexpr unsigned BYTES = WP_HALF * (F32 ? 4u : 8u);
+    constexpr unsigned LOG_BYTES = 16u * LOG2_V2_ENTRIES;
+    constexpr unsigned TAB_BYTES = (unsigned)sizeof(PairPow) + LOG_BYTES;
 
     const unsigned mbar = smem_u32(&s_mbar);
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_cbar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_cbar[1])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (tid == 0) {
         const char *src = reinterpret_cast<const char *>(P.x) + hbase * (F32 ? 4 : 8);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(BYTES) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_u32(s_f1)), "l"(src), "r"(BYTES), "r"(mbar) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(BYTES + TAB_BYTES) : "memory");
+        bulk_load(smem_u32(s_z), src, BYTES, mbar);
+        bulk_load(smem_u32(s_pow), P.pow_tab, (unsigned)sizeof(PairPow), mbar);
+        bulk_load(smem_u32(s_log), P.log2tab, LOG_BYTES, mbar);
+        // this CTA receives one 32-byte carry: the right half in the forward scan, the left half in the backward scan
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 32;" ::"r"(smem_u32(&s_cbar[rank == 1 ? 0 : 1])) : "memory");
     }
-    if (tid < 128) s_log[tid] = make_double2(P.log2tab[tid], P.log2tab[128 + tid]);
+    // both CTAs' barriers must exist before anything is sent to them: fence.mbarrier_init + a RELAXED cluster arrive (no
+    // memory fence: nothing else has to be published) and the matching wait, whose latency hides under the bulk copy
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
     const double pil = (P.log_transform && P.pilot) ? P.pilot[row] : 0.0;
-    __syncthreads();
-    {
-        unsigned done = 0;
-        while (!done) {
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                         : "=r"(done) : "r"(mbar) : "memory");
-        }
-    }
+    asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+    mbar_wait(mbar, 0);
 
-    // ---- this thread's 12 bins: raw -> y (registers)
+    // ---- this thread's bins: raw -> y (registers)
     double y[WP_ITEMS];
     if (F32) {
-        const float4 *rp = reinterpret_cast<const float4 *>(s_f1) + tid * (WP_ITEMS / 4);
+        const float4 *rp = reinterpret_cast<const float4 *>(smem_pair) + tid * (WP_ITEMS / 4);
 #pragma unroll
         for (int u = 0; u < WP_ITEMS / 4; ++u) {
             const float4 q = rp[u];
             y[4 * u + 0] = (double)q.x; y[4 * u + 1] = (double)q.y; y[4 * u + 2] = (double)q.z; y[4 * u + 3] = (double)q.w;
         }
     } else {
-        const double2 *rp = reinterpret_cast<const double2 *>(s_f1) + tid * (WP_ITEMS / 2);
+        const double2 *rp = reinterpret_cast<const double2 *>(smem_pair) + tid * (WP_ITEMS / 2);
 #pragma unroll
         for (int u = 0; u < WP_ITEMS / 2; ++u) { const double2 q = rp[u]; y[2 * u] = q.x; y[2 * u + 1] = q.y; }
     }
@@ -869,17 +902,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WP_THREADS, 2) k_whi
     int bad = (expmax == 0x7FF00000);
     if (P.log_transform) {
 #pragma unroll
-        for (int j = 0; j < WP_ITEMS; ++j) {
-            y[j] = fast_log2_ge1_v2(fmax(y[j], 0.0) + 1.0, s_log) - pil;
-            // four evaluations in flight at a time: interleaving all of them costs more in spills than it hides latency
-            if ((j & 3) == 3) asm volatile("" : "+d"(y[j]), "+d"(y[j - 1]), "+d"(y[j - 2]), "+d"(y[j - 3]));
-        }
+        for (int j = 0; j < WP_ITEMS; ++j) y[j] = fast_log2_ge1_v2(fmax(y[j], 0.0) + 1.0, s_log) - pil;
     }
 
     const double (*cfA)[2] = P.tab.cf[0];                 // [dinv, l1, l2][position parity]
     const double (*cfB)[2] = P.tab.cf[1];
-    double *f0 = s_f0 + tid * PAD, *f1 = s_f1 + tid * PAD;
+    double2 *fz = s_z + tid * PAD;
     double v[4], in[4];
+    // own bins in region positions; the left CTA's threads that lie entirely in the left halo only feed the forward
+    // scan: nothing downstream reads their forward solution, so they skip everything after it
+    const int p0 = rank * WP_HALF + tid * WP_ITEMS;
+    const int o_lo = WT_HALO + P.shift, o_hi = o_lo + WT_OUT;
+    const bool dead = (p0 + WP_ITEMS <= o_lo);
 
     // ================= forward substitution: zero-state sweep, carry scan, true sweep (scaled by 1/d on the way out)
     {
@@ -893,8 +927,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WP_THREADS, 2) k_whi
         }
         v[0] = a1; v[1] = a2; v[2] = b1; v[3] = b2;
     }
-    pair_scan<false, WP_WARPS>(v, in, P, s_wtot, s_excl, s_nbr, rank);      // (its barriers also order the raw reads before the writes below)
-    {
+    pair_scan<false, WP_WARPS>(v, in, P, s_wex[0], s_pow, s_nbr, s_cbar, rank);   // (its barriers also order the raw reads before the writes below)
+    // The true sweep also accumulates the zero-state END VECTOR of the chunk's backward sweep, which is linear in the z_j
+    // (table g): the backward substitution then needs one pass over shared memory instead of two.
+    v[0] = v[1] = v[2] = v[3] = 0.0;
+    if (!dead) {
         double a1 = in[0], a2 = in[1], b1 = in[2], b2 = in[3];
 #pragma unroll
         for (int j = 0; j < WP_ITEMS; ++j) {
@@ -902,47 +939,58 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WP_THREADS, 2) k_whi
             const double na = fma(-cfA[2][j & 1], a2, fma(-cfA[1][(j + 1) & 1], a1, ra));
             const double nb = fma(-cfB[2][j & 1], b2, fma(-cfB[1][(j + 1) & 1], b1, rb_));
             a2 = a1; a1 = na; b2 = b1; b1 = nb;
-            f0[j] = na * cfA[0][j & 1]; f1[j] = nb * cfB[0][j & 1];
+            const double za = na * cfA[0][j & 1], zb = nb * cfB[0][j & 1];
+            fz[j] = make_double2(za, zb);
+            v[0] = fma(P.tab.g[0][j][0], za, v[0]); v[1] = fma(P.tab.g[0][j][1], za, v[1]);
+            v[2] = fma(P.tab.g[1][j][0], zb, v[2]); v[3] = fma(P.tab.g[1][j][1], zb, v[3]);
         }
     }
     // ================= backward substitution (right to left)
-    {
-        double a1 = 0.0, a2 = 0.0, b1 = 0.0, b2 = 0.0;
-#pragma unroll
-        for (int j = WP_ITEMS - 1; j >= 0; --j) {
-            const double na = fma(-cfA[2][j & 1], a2, fma(-cfA[1][j & 1], a1, f0[j]));
-            const double nb = fma(-cfB[2][j & 1], b2, fma(-cfB[1][j & 1], b1, f1[j]));
-            a2 = a1; a1 = na; b2 = b1; b1 = nb;
-        }
-        v[0] = a1; v[1] = a2; v[2] = b1; v[3] = b2;
-    }
-    pair_scan<true, WP_WARPS>(v, in, P, s_wtot, s_excl, s_nbr, rank);
-
-    // ---- true backward sweep + epilogue: own bins only, straight from registers
-    const int p0 = rank * WP_HALF + tid * WP_ITEMS;                   // region position of this thread's first bin
-    const int o_lo = WT_HALO + P.shift, o_hi = o_lo + WT_OUT;
-    double *outp = P.out + hbase + tid * WP_ITEMS;
-    const bool full = (p0 >= o_lo) && (p0 + WP_ITEMS <= o_hi) && ((reinterpret_cast<uintptr_t>(outp) & 15) == 0);
-    {
+    pair_scan<true, WP_WARPS>(v, in, P, s_wex[1], s_pow, s_nbr, s_cbar, rank);
+    if (!dead) {
         double a1 = in[0], a2 = in[1], b1 = in[2], b2 = in[3];
-        double hold = 0.0;
 #pragma unroll
         for (int j = WP_ITEMS - 1; j >= 0; --j) {
-            const double na = fma(-cfA[2][j & 1], a2, fma(-cfA[1][j & 1], a1, f0[j]));
-            const double nb = fma(-cfB[2][j & 1], b2, fma(-cfB[1][j & 1], b1, f1[j]));
+            const double2 z = fz[j];
+            const double na = fma(-cfA[2][j & 1], a2, fma(-cfA[1][j & 1], a1, z.x));
+            const double nb = fma(-cfB[2][j & 1], b2, fma(-cfB[1][j & 1], b1, z.y));
             a2 = a1; a1 = na; b2 = b1; b1 = nb;
             const double bsl = 0.5 * (na + nb);                       // cross-fit average (baseline_backend.c:296-299)
-            const double c = P.write_baseline ? bsl : y[j] - bsl;
-            bad |= !isfinite(c);
-            if (full) {
-                if (j & 1) hold = c;
-                else *reinterpret_cast<double2 *>(outp + j) = make_double2(c, hold);
-            } else if (p0 + j >= o_lo && p0 + j < o_hi) {
-                outp[j] = c;
-            }
+            y[j] = P.write_baseline ? bsl : y[j] - bsl;
         }
     }
+    expmax = 0;
+#pragma unroll
+    for (int j = 0; j < WP_ITEMS; ++j) expmax = max(expmax, __double2hiint(y[j]) & 0x7FF00000);
+    bad |= (expmax == 0x7FF00000);
     if (bad) *P.bad = 1;
+
+    // ---- epilogue: the half's results contiguous in shared memory (the forward solutions are dead), own bins out in bulk
+    __syncthreads();                                                  // every thread is done reading its z slots
+    if (!dead) {
+        double2 *sp = reinterpret_cast<double2 *>(smem_pair) + tid * (WP_ITEMS / 2);
+#pragma unroll
+        for (int u = 0; u < WP_ITEMS / 2; ++u) sp[u] = make_double2(y[2 * u], y[2 * u + 1]);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the bulk (async proxy) read
+    __syncthreads();
+    const int q0 = max(o_lo, rank * WP_HALF) - rank * WP_HALF, q1 = min(o_hi, (rank + 1) * WP_HALF) - rank * WP_HALF;   // own bins in half positions
+    double *outp = P.out + hbase;
+    if ((reinterpret_cast<uintptr_t>(outp) & 15) == 0) {
+        if (tid == 0) {
+            const int b0 = (q0 + 1) & ~1, b1 = q1 & ~1;               // 16-byte aligned middle part
+            if (q0 < b0) outp[q0] = smem_pair[q0];
+            if (b1 < q1) outp[b1] = smem_pair[b1];
+            if (b1 > b0) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             ::"l"(outp + b0), "r"(smem_u32(smem_pair + b0)), "r"((unsigned)(b1 - b0) * 8u) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory must outlive the read
+            }
+        }
+    } else {
+        for (int q = q0 + tid; q < q1; q += WP_THREADS) outp[q] = smem_pair[q];       // coalesced fallback
+    }
 }
 
 // n < 25: the reference returns a zero baseline (baseline_backend.c:266-273) -> centered = y
@@ -968,6 +1016,7 @@ struct FactorDev {
     double *d_head[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     double *d_lanepow = nullptr;
     double *d_log2 = nullptr;
+    double *d_log2i = nullptr;                       // the same tables interleaved {inv[i], tab[i]} (pair kernel)
     double *d_pairpow[WP_NGEOM][2] = {{nullptr, nullptr}, {nullptr, nullptr}};       // PairPow per geometry and shift parity
     int device = 0;
     unsigned long long last_use = 0;
@@ -982,6 +1031,7 @@ struct FactorDev {
         }
         if (d_lanepow) cudaFree(d_lanepow);
         if (d_log2) cudaFree(d_log2);
+        if (d_log2i) cudaFree(d_log2i);
     }
 };
 using FactorRef = std::shared_ptr<FactorDev>;
@@ -1000,6 +1050,17 @@ static int upload_factor(FactorDev &F)
     build_log2_tables();
     RB_CUDA(cudaMalloc(&F.d_log2, sizeof(Log2Tables)));
     RB_CUDA(cudaMemcpy(F.d_log2, &g_log2_host, sizeof(Log2Tables), cudaMemcpyHostToDevice));
+    {
+        double il[2 * LOG2_V2_ENTRIES];
+        for (int i = 0; i < LOG2_V2_ENTRIES; ++i) {
+            const long double c = 1.0L + (long double)i / 32.0L;
+            const double inv = (double)(1.0L / c);
+            il[2 * i] = inv;
+            il[2 * i + 1] = (i == 0) ? 0.0 : (double)(-log2l((long double)inv));   // tab matches the ROUNDED inv
+        }
+        RB_CUDA(cudaMalloc(&F.d_log2i, sizeof(il)));
+        RB_CUDA(cudaMemcpy(F.d_log2i, il, sizeof(il), cudaMemcpyHostToDevice));
+    }
     RB_CUDA(cudaMalloc(&F.d_lanepow, sizeof(F.host.lanepow)));
     RB_CUDA(cudaMemcpy(F.d_lanepow, F.host.lanepow, sizeof(F.host.lanepow), cudaMemcpyHostToDevice));
     for (int gm = 0; gm < WP_NGEOM; ++gm)
@@ -1052,7 +1113,7 @@ int whittaker_set_mode(int mode) { return g_whit_mode.exchange((mode >= 0 && mod
 template <bool F32, int THREADS, int ITEMS>
 static int launch_pair(const PairParams &R, unsigned grid, cudaStream_t st)
 {
-    constexpr size_t sm = sizeof(double) * 2 * THREADS * (ITEMS + 1);
+    constexpr size_t sm = sizeof(double) * 2 * THREADS * (ITEMS + 1) + sizeof(PairPow) + 16 * LOG2_V2_ENTRIES;
     static bool attr_dev[64] = {false};
     int d = 0;
     cudaGetDevice(&d);
@@ -1150,9 +1211,8 @@ int whittaker_rows(const void *d_x, int in_f32, int log_transform, const double 
                 R.shift = (int)((base_off + p * (row_stride % M)) % M);
                 R.log_transform = log_transform; R.write_baseline = write_baseline;
                 R.tab = F->host.pair_tab[gm][R.shift & 1];
-                const double *pw = F->d_pairpow[gm][R.shift & 1];
-                R.lanepow = pw; R.warppow = pw + sizeof(PairPow::lane) / sizeof(double);
-                R.log2tab = F->d_log2;
+                R.pow_tab = F->d_pairpow[gm][R.shift & 1];
+                R.log2tab = F->d_log2i;
                 const long long nrows = (rows - p + period - 1) / period;
                 const unsigned grid = (unsigned)(nrows * Q.span_tiles * 2);
                 if (gm == 0) RB_TRY(in_f32 ? (launch_pair<true, 512, 12>(R, grid, st)) : (launch_pair<false, 512, 12>(R, grid, st)));
