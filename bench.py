@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--score-streams", type=int, default=1, help="host threads / CUDA streams scoring chromosomes concurrently")
     ap.add_argument("--e2e-threads", type=int, default=4, help="host threads driving chromosomes through the public API")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e-extra-legs", dest="e2e_extra_legs", action="store_false",
+                    help="skip the pinned-input and float32-input end-to-end legs (the pageable float64 leg is the headline)")
     ap.add_argument("--cpu-sample-bins", type=int, default=250_000)
     ap.add_argument("--levels", type=int, default=0, help="bisection levels per launch (0 = library default)")
     return ap.parse_args()
@@ -129,16 +131,19 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------- reference arm
-def _ref_worker(task):
+def _ref_worker(task, keep=False):
     """One worker = the reference's own kernels (oracle/_ref, else the oracle port) on one slice."""
     m, n, seed, budget, gamma, kind = task
     from oracle import oracle as orc
     x = chrom_matrix_numpy(m, n, seed=seed)
     t0 = time.perf_counter()
     scores = orc.score_loci_wls(x, prior_df=PRIOR_DF, kind=kind)
-    sol, obj = orc.solve_chrom_exact(scores, budget=budget, gamma=gamma, kind=kind)
+    sol, obj, det = orc.solve_chrom_exact(scores, budget=budget, gamma=gamma, kind=kind, return_details=True)
     recs = orc.solution_to_records("chr21", np.arange(0, 50 * n, 50), sol)
-    return n, time.perf_counter() - t0, len(recs)
+    dt = time.perf_counter() - t0
+    if keep:
+        return n, dt, len(recs), {"x": x, "scores": scores, "solution": sol, "objective": obj, "details": det, "records": recs}
+    return n, dt, len(recs)
 
 
 def run_reference(args):
@@ -148,6 +153,7 @@ def run_reference(args):
     from oracle import oracle as orc
     names, bins = workload(args)
     kind = "reference" if orc.reference_available() else "port"
+    orc.native(kind)             # mapped in THIS process (and inherited by the forked workers): the run's loaded-library record shows it
     cores = os.cpu_count() or 1
     import multiprocessing as mp
     # per-step sample: one slice per core, sized for ~4-6 s of single-core work each
@@ -189,10 +195,40 @@ def cpu_baseline_single_core(args):
     kind = "reference" if orc.reference_available() else "port"
     n = int(args.cpu_sample_bins * min(1.0, 100.0 / max(args.samples, 1)))
     budget, gamma = HG_PARAMS["chr21"]
-    n_done, dt, _ = _ref_worker((args.samples, n, chrom_seed("chr21"), budget, gamma, kind))
-    return {"value": n_done / dt, "unit": UNIT, "cores": 1, "kind": kind,
-            "sample": f"first {n} bins of synthetic chr21 x {args.samples} samples: score_loci_wls + solve_chrom_exact "
-                      f"(budget {budget}, gamma {gamma}) + BED records, {dt:.1f} s on one core"}
+    n_done, dt, _, ref = _ref_worker((args.samples, n, chrom_seed("chr21"), budget, gamma, kind), keep=True)
+    cpu = {"value": n_done / dt, "unit": UNIT, "cores": 1, "kind": kind,
+           "sample": f"first {n} bins of synthetic chr21 x {args.samples} samples: score_loci_wls + solve_chrom_exact "
+                     f"(budget {budget}, gamma {gamma}) + BED records, {dt:.1f} s on one core"}
+    return cpu, parity_against(ref, budget, gamma, kind)
+
+
+def parity_against(ref, budget, gamma, kind):
+    """The GPU path on the SAME bytes the CPU baseline just processed, compared output by output (SURVEY.md 8d gates)."""
+    import rocco_b200
+    from rocco_b200.rocco import solution_runs
+    x = ref["x"]
+    scores = rocco_b200.score_loci_wls(x, prior_df=PRIOR_DF)
+    sol, obj, det = rocco_b200.solve_chrom_exact(scores, budget=budget, gamma=gamma, return_details=True)
+    starts, ends = solution_runs(sol)
+    n = x.shape[1]
+    recs = [("chr21", int(50 * a), int(50 * b)) for a, b in zip(starts.tolist(), ends.tolist())]
+    want = ref["scores"]
+    rel = float(np.max(np.abs(scores - want) / np.maximum(np.abs(want), 1e-3)))
+    wdet = ref["details"]
+    # the multiplier search on identical scores: the searched double itself
+    sol2, obj2, det2 = rocco_b200.solve_chrom_exact(want, budget=budget, gamma=gamma, return_details=True)
+    return {
+        "against": f"oracle kind={kind}, same input bytes ({x.shape[0]} x {n})",
+        "scores_max_rel_err": rel, "scores_tolerance": 1e-5,
+        "mask_identical": bool(np.array_equal(sol, ref["solution"])), "mask_differing_bins": int(np.sum(sol != ref["solution"])),
+        "selected_count": [int(det["selected_count"]), int(wdet["selected_count"])],
+        "intervals_identical": [tuple(r) for r in recs] == [tuple(r) for r in ref["records"]],
+        "objective_rel_err": float(abs(obj - ref["objective"]) / max(abs(ref["objective"]), 1e-300)),
+        "lambda_abs_diff": float(abs(det["selection_penalty"] - wdet["selection_penalty"])),
+        "same_scores_search": {"mask_identical": bool(np.array_equal(sol2, ref["solution"])),
+                               "lambda_identical": bool(det2["selection_penalty"] == wdet["selection_penalty"]),
+                               "lambda_abs_diff": float(abs(det2["selection_penalty"] - wdet["selection_penalty"]))},
+    }
 
 
 _RESULT_FD = None
@@ -251,20 +287,33 @@ def main():
     d_mats = [chrom_matrix_torch(args.samples, n, chrom_seed(c), dev, tdtype) for c, n in zip(my_names, my_bins)]
     params = pipeline.score_params(prior_df=PRIOR_DF)
     genome_bins = int(sum(bins))
-    tmpdir = tempfile.mkdtemp(prefix=f"rocco_b200_bench_r{rank}_")
+    from rocco_b200 import distributed as rdist
+    tmp_holder = [tempfile.mkdtemp(prefix="rocco_b200_bench_") if rank == 0 else None]
+    if world > 1:
+        dist.broadcast_object_list(tmp_holder, src=0)          # one node: every rank sees rank 0's directory
+    tmpdir = tmp_holder[0]
     count_buf = torch.zeros(2, dtype=torch.int64, device=dev)
+    # record order of the reference's combined BED (rocco.py:74-95 sorts by the chromosome STRING: chr1 < chr10 < chr2)
+    lex_names = sorted(names)
+    lex_rank = np.array([lex_names.index(c) for c in my_names], dtype=np.int64)
 
     def step():
-        if not mine:
-            return None
         shard = pipeline.run_shard(d_mats, budgets, gammas, params=params, levels_per_round=args.levels,
-                                   score_streams=args.score_streams)
-        pipeline.runs_to_bed_file(os.path.join(tmpdir, "shard.bed"), my_names, shard["runs"], args.step_bp)
+                                   score_streams=args.score_streams) if mine else None
         # the one cross-GPU exchange of the path: genome-wide selected-bin count (reporting only)
-        count_buf[0] = sum(r["selected_count"] for r in shard["results"])
+        count_buf[0] = sum(r["selected_count"] for r in shard["results"]) if mine else 0
         count_buf[1] = sum(my_bins)
         if world > 1:
             dist.all_reduce(count_buf)
+        # ONE merged BED for the genome: every rank's runs go to rank 0 (a few hundred KB), which writes them in the
+        # reference's record order
+        if mine:
+            chrom, starts, ends = shard["runs"]
+            merged = rdist.gather_runs(lex_rank[chrom], starts, ends, device=dev)
+        else:
+            merged = rdist.gather_runs(np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.int64), device=dev)
+        if rank == 0:
+            pipeline.runs_to_bed_file(os.path.join(tmpdir, "genome.bed"), lex_names, (merged[0].astype(np.int32), merged[1], merged[2]), args.step_bp)
         return shard
 
     def barrier():
@@ -322,22 +371,9 @@ def main():
     e2e = None
     e2e_steps = min(args.steps, 2) if args.e2e_steps < 0 else args.e2e_steps
     if e2e_steps > 0:
-        host = []
-        pinned = True
-        for x in d_mats:
-            try:
-                h = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
-            except RuntimeError:
-                h = torch.empty(x.shape, dtype=x.dtype)
-                pinned = False
-            h.copy_(x)
-            host.append(h.numpy())
-        del d_mats
-        torch.cuda.empty_cache()
+        from concurrent.futures import ThreadPoolExecutor
         cwd = os.getcwd()
         os.chdir(tmpdir)
-
-        from concurrent.futures import ThreadPoolExecutor
 
         def one_chrom(job):
             c, n, x, b, g = job
@@ -345,40 +381,81 @@ def main():
             sol, obj = rocco_b200.solve_chrom_exact(scores, budget=b, gamma=g)
             return rocco_b200.chrom_solution_to_bed(c, np.arange(0, args.step_bp * n, args.step_bp), sol, ID="bench")
 
-        def e2e_step():
+        def e2e_step(host):
             # the reference solves chromosomes in a pool of <= 4 workers (rocco.py:1146-1184); the host threads here keep
             # the PCIe link busy: one chromosome's upload overlaps the kernels / solve / BED writing of the others (ctypes
             # drops the GIL)
             jobs = sorted(zip(my_names, my_bins, host, budgets, gammas), key=lambda j: -j[1])   # longest first: short tail
             with ThreadPoolExecutor(max_workers=args.e2e_threads, initializer=torch.cuda.set_device, initargs=(local_rank,)) as pool:   # the CUDA current device is per host thread
                 files = list(pool.map(one_chrom, jobs))
-            if files:
-                rocco_b200.combine_chrom_results(files, f"combined_r{rank}.bed")
+            # ONE combined BED for the genome, as the reference's parent process builds it from its workers' files
+            # (rocco.py:194-240): the ranks share the node's file system, rank 0 combines all 24 per-chromosome files
+            if world > 1:
+                dist.barrier()
+            if rank == 0:
+                allf = [os.path.join(tmpdir, f"rocco_bench_{c}.bed") for c in names]
+                rocco_b200.combine_chrom_results([f for f in allf if os.path.exists(f)], "combined.bed")
+            return files
 
-        for _ in range(2):                              # warm-up: the per-lease scratch pools reach their steady-state sizes
-            e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            t_step = time.perf_counter()
-            e2e_step()
-            print(f"[bench] rank {rank} e2e step: {1e3 * (time.perf_counter() - t_step):.0f} ms", file=sys.stderr)
-        barrier()
-        dt = time.perf_counter() - t0
+        def e2e_leg(host, warm, steps, label):
+            for _ in range(warm):                           # warm-up: the per-lease scratch pools reach their steady-state sizes
+                e2e_step(host)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                t_step = time.perf_counter()
+                e2e_step(host)
+                print(f"[bench] rank {rank} e2e ({label}) step: {1e3 * (time.perf_counter() - t_step):.0f} ms", file=sys.stderr)
+            barrier()
+            dt = time.perf_counter() - t0
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return genome_bins * steps / float(tt.item())
+
+        def host_bytes(esz_):
+            h2d = sum(args.samples * n * esz_ + n * 8 + n for n in my_bins)     # matrix + scores (solve) + mask (BED)
+            d2h = sum(n * 8 + n for n in my_bins)                               # scores + mask
+            bb = torch.tensor([h2d, d2h], dtype=torch.int64, device=dev)
+            if world > 1:
+                dist.all_reduce(bb)
+            return int(bb[0].item()), int(bb[1].item())
+
+        # leg 1 (headline): the caller's arrays are PAGEABLE NumPy memory, which is what score_loci_wls is handed in practice
+        host = []
+        for x in d_mats:
+            h = np.empty(tuple(x.shape), dtype=np.float64 if args.dtype == "f64" else np.float32)
+            torch.from_numpy(h).copy_(x)
+            host.append(h)
+        del d_mats
+        torch.cuda.empty_cache()
+        pageable = e2e_leg(host, 2, e2e_steps, "pageable")
+        h2d, d2h = host_bytes(esz)
+        e2e = {"value": pageable, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+               "pinned_host": False, "host_threads": args.e2e_threads,
+               "api": "score_loci_wls + solve_chrom_exact + chrom_solution_to_bed + combine_chrom_results (pageable NumPy in, ONE combined BED out)"}
+        if args.e2e_extra_legs:
+            # leg 2: the same arrays in pinned memory (the best the link can do; round 1's headline)
+            pinned_ok = True
+            for k in range(len(host)):
+                try:
+                    t = torch.empty(host[k].shape, dtype=torch.from_numpy(host[k]).dtype, pin_memory=True)
+                except RuntimeError:
+                    pinned_ok = False
+                    break
+                t.copy_(torch.from_numpy(host[k]))
+                host[k] = t.numpy()
+            if pinned_ok:
+                e2e["pinned_input"] = {"value": e2e_leg(host, 1, 1, "pinned"), "unit": UNIT, "steps": 1}
+                e2e["pageable_over_pinned"] = e2e["value"] / e2e["pinned_input"]["value"]
+            # leg 3: float32 counts, what the reference's --low_memory path hands over (readtracks.py:621)
+            if args.dtype == "f64":
+                for k in range(len(host)):
+                    host[k] = np.ascontiguousarray(host[k], dtype=np.float32)
+                h2d32, d2h32 = host_bytes(4)
+                e2e["float32_input"] = {"value": e2e_leg(host, 1, 1, "float32 pageable"), "unit": UNIT, "steps": 1,
+                                        "h2d_bytes_per_step": h2d32, "d2h_bytes_per_step": d2h32, "pinned_host": False}
         os.chdir(cwd)
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        h2d = sum(args.samples * n * esz + n * 8 + n for n in my_bins)       # matrix + scores (solve) + mask (BED)
-        d2h = sum(n * 8 + n for n in my_bins)                                # scores + mask
-        bb = torch.tensor([h2d, d2h], dtype=torch.int64, device=dev)
-        if world > 1:
-            dist.all_reduce(bb)
-        e2e = {"value": genome_bins * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(bb[0].item()),
-               "d2h_bytes_per_step": int(bb[1].item()), "steps": e2e_steps, "pinned_host": pinned,
-               "host_threads": args.e2e_threads,
-               "api": "score_loci_wls + solve_chrom_exact + chrom_solution_to_bed + combine_chrom_results (NumPy in, BED files out)"}
 
     if rank == 0:
         peaks_path = os.path.join(REPO, "MEASURED_PEAKS.json")
@@ -408,9 +485,9 @@ def main():
                     "all_scopes": {k: {"ms": round(v[0], 3), "launch_sets": v[1],
                                        "GBps_algorithmic": round((v[2] / 1e9) / (v[0] / 1e3), 1) if v[0] > 0 else 0.0}
                                    for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}}
-        cpu = None
+        cpu, parity = None, None
         if world == 1 and not args.no_cpu_baseline:
-            cpu = cpu_baseline_single_core(args)
+            cpu, parity = cpu_baseline_single_core(args)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -422,7 +499,7 @@ def main():
                        "selected_by_chrom": {c: by_chrom[c][0] for c in names if c in by_chrom},
                        "lambda_by_chrom": {c: by_chrom[c][1] for c in names if c in by_chrom}, "trend_sort_fallback_rows": fb_rows,
                        "trend_fallback_reason_counts": list(reasons)[:5], "collective": "one NCCL all-reduce of [selected, bins] per step"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(lt.item()), "roofline": roof, "cpu_baseline": cpu,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(lt.item()), "roofline": roof, "cpu_baseline": cpu, "parity": parity,
         }
         emit(line)
     if world > 1:

@@ -5,7 +5,10 @@
 //   394-608  monotone variance-vs-|signal| trend -> exact order statistics per sample row, PAVA on <= 32 knots
 //   744-947  posterior precision + combine       -> k_combine   (fused column reduction over the sample axis)
 // and the Python driver inference.py:302-379.
+#include <condition_variable>
+#include <deque>
 #include <mutex>
+#include <thread>
 
 #include "common.cuh"
 #include "score.cuh"
@@ -540,6 +543,126 @@ static cudaStream_t copy_stream()
     return cs[dev];
 }
 
+// Pageable caller memory (what a NumPy array is): a cudaMemcpyAsync from it is staged by the driver through its own
+// small pinned buffer by ONE thread at a fraction of the link rate, and blocks the caller meanwhile.  The matrix is
+// instead copied into a ring of pinned chunks by several host threads (the copy is memory-bandwidth bound: one core
+// moves ~10 GB/s, the link takes 55) and each chunk goes to the device as a true asynchronous DMA while the next one
+// is being filled.  (cudaHostRegister on the caller's buffer would avoid the extra pass but costs ~0.2 s per GB of
+// page pinning, more than the copy itself.)
+class StageCopier {
+  public:
+    static StageCopier &get() { static StageCopier *inst = new StageCopier(); return *inst; }     // never destroyed: worker threads outlive main
+    void copy(char *dst, const char *src, size_t bytes)
+    {
+        const size_t piece = std::max<size_t>((size_t)1 << 20, (bytes + nthreads_) / (nthreads_ + 1));
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            for (size_t off = 0; off < bytes; off += piece) { jobs_.push_back({dst + off, src + off, std::min(piece, bytes - off)}); ++pending_; }
+        }
+        cv_.notify_all();
+        for (;;) {                                    // the caller works too
+            Job j;
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (jobs_.empty()) break;
+                j = jobs_.front(); jobs_.pop_front();
+            }
+            memcpy(j.dst, j.src, j.n);
+            finish_one();
+        }
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [&] { return pending_ == 0; });
+    }
+
+  private:
+    struct Job { char *dst; const char *src; size_t n; };
+    StageCopier()
+    {
+        unsigned hw = std::thread::hardware_concurrency();
+        nthreads_ = (int)std::max(1u, std::min(7u, hw > 2 ? hw / 2 - 1 : 1u));
+        for (int t = 0; t < nthreads_; ++t) std::thread([this] { worker(); }).detach();
+    }
+    void finish_one()
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (--pending_ == 0) done_.notify_all();
+    }
+    void worker()
+    {
+        for (;;) {
+            Job j;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return !jobs_.empty(); });
+                j = jobs_.front(); jobs_.pop_front();
+            }
+            memcpy(j.dst, j.src, j.n);
+            finish_one();
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    std::deque<Job> jobs_;
+    int pending_ = 0;
+    int nthreads_ = 1;
+};
+
+constexpr int STAGE_SLOTS = 4;
+constexpr size_t STAGE_CHUNK = (size_t)32 << 20;
+struct StageRing {
+    char *buf[STAGE_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t done[STAGE_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+    bool used[STAGE_SLOTS] = {false, false, false, false};
+    int next = 0;
+    bool ok = false;
+};
+// one ring per device, created on first use; only touched under the copy mutex of score_loci_core
+static StageRing *stage_ring()
+{
+    static StageRing rings[32];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    StageRing &R = rings[dev & 31];
+    if (!R.ok) {
+        bool good = true;
+        for (int k = 0; k < STAGE_SLOTS && good; ++k) {
+            good = cudaMallocHost(reinterpret_cast<void **>(&R.buf[k]), STAGE_CHUNK) == cudaSuccess &&
+                   cudaEventCreateWithFlags(&R.done[k], cudaEventDisableTiming) == cudaSuccess;
+        }
+        if (!good) { (void)cudaGetLastError(); return nullptr; }
+        R.ok = true;
+    }
+    return &R;
+}
+
+static bool host_pointer_is_pinned(const void *p)
+{
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+
+// host -> device copy of `bytes` on stream cs: direct DMA for pinned memory, the staged ring otherwise
+static int upload_rows(char *d_dst, const char *h_src, size_t bytes, bool pinned, cudaStream_t cs)
+{
+    StageRing *R = pinned ? nullptr : stage_ring();
+    if (!R) {
+        RB_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, cs));
+        return 0;
+    }
+    for (size_t off = 0; off < bytes; off += STAGE_CHUNK) {
+        const size_t len = std::min(STAGE_CHUNK, bytes - off);
+        const int k = R->next;
+        R->next = (k + 1) % STAGE_SLOTS;
+        if (R->used[k]) RB_CUDA(cudaEventSynchronize(R->done[k]));          // the DMA that last read this slot has finished
+        StageCopier::get().copy(R->buf[k], h_src + off, len);
+        RB_CUDA(cudaMemcpyAsync(d_dst + off, R->buf[k], len, cudaMemcpyHostToDevice, cs));
+        RB_CUDA(cudaEventRecord(R->done[k], cs));
+        R->used[k] = true;
+    }
+    return 0;
+}
+
 static int score_loci_core(const void *d_matrix_in, const void *h_matrix, int dtype, long long m, long long n,
                            const rocco_b200_score_params *params, rocco_b200_score_outputs *out, cudaStream_t st,
                            double *d_acc = nullptr)
@@ -567,38 +690,52 @@ static int score_loci_core(const void *d_matrix_in, const void *h_matrix, int dt
         ~EventList() { for (cudaEvent_t e : v) if (e) cudaEventDestroy(e); }
         cudaEvent_t &operator[](int i) { return v[(size_t)i]; }
     } ev;
-    if (h_matrix) {
-        RB_TRY(ar.alloc(&d_x, (size_t)m * n * esz));
-        d_matrix = d_x;
-        cudaStream_t cs = copy_stream();
-        // one call's row groups go into the shared copy stream back to back: concurrent callers then finish one after
-        // the other at full PCIe rate (and start their next chromosome staggered) instead of all at once at 1/T of it
-        static std::mutex copy_mu;
-        std::lock_guard<std::mutex> copy_lock(copy_mu);
-        cudaEvent_t ready;
-        RB_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
-        RB_CUDA(cudaEventRecord(ready, st));                       // the stream-ordered allocation is valid from here on
-        RB_CUDA(cudaStreamWaitEvent(cs, ready, 0));
-        cudaEventDestroy(ready);
-        ev.v.assign((size_t)ngroups, nullptr);
-        for (int g = 0; g < ngroups; ++g) {
-            const long long r0 = g * group, r1 = std::min(m, r0 + group);
-            RB_CUDA(cudaMemcpyAsync(d_x + (size_t)r0 * n * esz, (const char *)h_matrix + (size_t)r0 * n * esz,
-                                    (size_t)(r1 - r0) * n * esz, cudaMemcpyHostToDevice, cs));
-            RB_CUDA(cudaEventCreateWithFlags(&ev[g], cudaEventDisableTiming));
-            RB_CUDA(cudaEventRecord(ev[g], cs));
-        }
-    }
+    bool copies_queued = false;
+    struct CopyDrain {                            // any exit after the uploads were queued waits for them before d_x is released
+        const bool &on; cudaStream_t cs;
+        ~CopyDrain() { if (on && cs) cudaStreamSynchronize(cs); }
+    };
+    cudaStream_t cs_drain = h_matrix ? copy_stream() : nullptr;
+    CopyDrain drain{copies_queued, cs_drain};     // declared after the arena: runs before the arena frees d_x
     const int bw = resolve_baseline_window(n, prm.baseline_window > 0 ? prm.baseline_window : 101);
     const double lam = bw > 0 ? whittaker_lambda(bw) : 0.0;
     out->baseline_window = bw;
     out->baseline_lambda = lam;
     WlsRun R;
     RB_TRY(wls_prepare(ar, m, n, prm, out, R, st));
+    // one call's row groups go into the shared copy stream back to back: concurrent callers then finish one after
+    // the other at full PCIe rate (and start their next chromosome staggered) instead of all at once at 1/T of it
+    static std::mutex copy_mu;
+    std::unique_lock<std::mutex> copy_lock(copy_mu, std::defer_lock);
+    bool pinned = true;
+    cudaStream_t cs = cs_drain;
+    if (h_matrix) {
+        RB_TRY(ar.alloc(&d_x, (size_t)m * n * esz));
+        d_matrix = d_x;
+        copy_lock.lock();
+        cudaEvent_t ready;
+        RB_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+        RB_CUDA(cudaEventRecord(ready, st));                       // the stream-ordered allocation is valid from here on
+        RB_CUDA(cudaStreamWaitEvent(cs, ready, 0));
+        cudaEventDestroy(ready);
+        ev.v.assign((size_t)ngroups, nullptr);
+        pinned = host_pointer_is_pinned(h_matrix);
+    }
     int status = 0;
     for (int g = 0; g < ngroups && status == 0; ++g) {
         const long long r0 = g * group, r1 = std::min(m, r0 + group);
-        if (h_matrix) { cudaStreamWaitEvent(st, ev[g], 0); }
+        if (h_matrix) {
+            // queue (pinned source) or stage-and-queue (pageable source) this group's rows, then launch its per-row stages
+            // behind the copy: the kernels of group g run while the host stages group g+1
+            copies_queued = true;
+            status = upload_rows(d_x + (size_t)r0 * n * esz, (const char *)h_matrix + (size_t)r0 * n * esz,
+                                 (size_t)(r1 - r0) * n * esz, pinned, cs);
+            if (status != 0) break;
+            RB_CUDA(cudaEventCreateWithFlags(&ev[g], cudaEventDisableTiming));
+            RB_CUDA(cudaEventRecord(ev[g], cs));
+            RB_CUDA(cudaStreamWaitEvent(st, ev[g], 0));
+            if (g == ngroups - 1) copy_lock.unlock();
+        }
         const char *xg = (const char *)d_matrix + (size_t)r0 * n * esz;
         {
             RB_PROF("k_pilot", st, 0.0);
@@ -607,10 +744,12 @@ static int score_loci_core(const void *d_matrix_in, const void *h_matrix, int dt
         if (status == 0) status = whittaker_rows(xg, dtype, 1, d_pilot + r0, r1 - r0, n, n, lam, 0, d_cent + r0 * n, d_bad, st);
         if (status == 0) status = wls_rows(d_cent, R, r0, r1, st);
     }
+    if (copy_lock.owns_lock()) copy_lock.unlock();
     if (status != 0) { cudaStreamSynchronize(st); return status; }
     int bad = 0;
     RB_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
     RB_CUDA(cudaStreamSynchronize(st));
+    copies_queued = false;                        // st waited on every group's copy: nothing of this call is left in the copy stream
     if (bad) return ST_NONFINITE;
     return wls_finish(d_cent, R, prm, out, st, d_acc);
 }

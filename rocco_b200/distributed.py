@@ -57,3 +57,31 @@ def gather_bed_records(records: list[tuple[str, int, int]]):
         return None
     flat = [r for part in gathered for r in part]
     return _merge_bed_records(flat)
+
+
+def gather_runs(chrom_index, starts, ends, device=None):
+    """All ranks' runs (global chromosome index, first bin, last bin + 1) on rank 0, as three int64 arrays ordered by
+    (chromosome index, start); other ranks get None.  Tensor collectives only (one all-gather of the counts, one of the
+    padded records), so it runs on NCCL with CUDA tensors and on gloo with CPU tensors alike."""
+    import numpy as np
+    import torch
+    dist = _dist()
+    rank, size = world()
+    rec = np.stack([np.asarray(chrom_index, dtype=np.int64), np.asarray(starts, dtype=np.int64),
+                    np.asarray(ends, dtype=np.int64)]) if len(starts) else np.zeros((3, 0), dtype=np.int64)
+    if size > 1:
+        dev = device or "cpu"
+        cnt = torch.tensor([rec.shape[1]], dtype=torch.int64, device=dev)
+        counts = [torch.zeros_like(cnt) for _ in range(size)]
+        dist.all_gather(counts, cnt)
+        counts = [int(c.item()) for c in counts]
+        kmax = max(max(counts), 1)
+        pad = torch.zeros((3, kmax), dtype=torch.int64, device=dev)
+        pad[:, :rec.shape[1]] = torch.from_numpy(rec).to(dev)
+        parts = [torch.zeros_like(pad) for _ in range(size)]
+        dist.all_gather(parts, pad)
+        if rank != 0:
+            return None
+        rec = np.concatenate([p[:, :k].cpu().numpy() for p, k in zip(parts, counts)], axis=1)
+    order = np.lexsort((rec[1], rec[0]))
+    return rec[0][order], rec[1][order], rec[2][order]
