@@ -32,29 +32,34 @@ __device__ __forceinline__ double div_rcp(double a, double b, double rb)
     return __fma_rn(r, rb, q);
 }
 
-// AR(1) innovation variance of one window from its three sums (wls_backend.c:665-712), same association order;
-// intrinsics keep nvcc from contracting the products into FMAs.  rwd = RN(1/wd), shrink = 1/(wd+1).
-__device__ __forceinline__ double ar1_window_variance(double s1, double s2, double sl, double first, double last, double wd,
-                                                      double rwd, double pairs, double shrink)
+// 1 / d for d in the normal range: hardware seed (MUFU.RCP64H, ~20 bits) and two Newton steps (~1 ulp), without the
+// generic division's special-case slow path.
+__device__ __forceinline__ double rcp_nr(double d)
 {
-    const double sum_head = __dsub_rn(s1, last);
-    const double sum_tail = __dsub_rn(s1, first);
-    const double mu = div_rcp(s1, wd, rwd);
-    double g0 = __dsub_rn(s2, __dmul_rn(__dmul_rn(wd, mu), mu));
-    if (g0 < 0.0) g0 = 0.0;
-    double g1 = __dsub_rn(sl, __dmul_rn(mu, sum_head));
-    g1 = __dsub_rn(g1, __dmul_rn(mu, sum_tail));
-    g1 = __dadd_rn(g1, __dmul_rn(__dmul_rn(pairs, mu), mu));
-    const double flo = __dmul_rn(1.0e-4, __dadd_rn(g0, 1.0));
-    const double den = __dadd_rn(__dmul_rn(g0, __dadd_rn(1.0, shrink)), flo);
-    const double eps = __dmul_rn(1.0e-12, __dadd_rn(g0, 1.0));
-    double beta = 0.0;
-    if (den > eps) beta = div_rcp(g1, den, __drcp_rn(den));
-    if (beta > 0.99) beta = 0.99; else if (beta < 0.0) beta = 0.0;
-    const double gam0 = div_rcp(g0, wd, rwd);
-    double omb = __dsub_rn(1.0, __dmul_rn(beta, beta));
-    if (omb < 0.0) omb = 0.0;
-    return fmax(__dmul_rn(gam0, omb), 0.0);
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = __fma_rn(-d, r, 1.0);
+    r = __fma_rn(r, e, r);
+    e = __fma_rn(-d, r, 1.0);
+    return __fma_rn(r, e, r);
+}
+
+// AR(1) innovation variance of one window from its three sums (wls_backend.c:665-712).  The algebra is the reference's;
+// the operations are fused (FMA) and regrouped:  g1 = sl - mu (sum_head + sum_tail) + pairs mu^2,
+// denom = g0 (1 + lambda_eff) + 1e-4 (g0 + 1) = g0 c1 + 1e-4 with c1 = 1 + lambda_eff + 1e-4 (always > eps = 1e-12 (g0 + 1), so
+// the reference's guard never fires), beta = g1 / denom by reciprocal.  Differences from the reference's own rounding
+// are ~1e-16 relative per operation, far below the ~1e-12 drift of its whole-row sliding sums.
+// rwd = 1/wd, c1 as above.
+__device__ __forceinline__ double ar1_window_variance(double s1, double s2, double sl, double first, double last, double wd,
+                                                      double rwd, double pairs, double c1)
+{
+    const double mu = s1 * rwd;
+    const double g0 = fmax(__fma_rn(-(wd * mu), mu, s2), 0.0);
+    const double g1 = __fma_rn(pairs * mu, mu, __fma_rn(-mu, (s1 - last) + (s1 - first), sl));
+    const double den = __fma_rn(g0, c1, 1.0e-4);
+    double beta = g1 * rcp_nr(den);
+    beta = fmin(fmax(beta, 0.0), 0.99);
+    return (g0 * rwd) * __fma_rn(-beta, beta, 1.0);
 }
 
 int resolve_spatial_window(long long n, int requested);

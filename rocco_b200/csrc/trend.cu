@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(RV_THREADS) k_rollvar_xhist(const double *__re
     double *v = V + row * row_stride;
     const long long c0 = (long long)blockIdx.x * CHUNK, c1 = min(n, c0 + CHUNK);
     const long long half = w / 2, last = n - w;
-    const double wd = (double)w, pairs = (double)(w - 1), rwd = 1.0 / wd, shrink = 1.0 / (wd + 1.0);
+    const double wd = (double)w, pairs = (double)(w - 1), rwd = 1.0 / wd, shrink = 1.0 + 1.0 / (wd + 1.0) + 1.0e-4;      // c1 of ar1_window_variance
     const int tid = threadIdx.x;
     for (int k = tid; k < NBX; k += RV_THREADS) s_h[k] = 0;
     __syncthreads();

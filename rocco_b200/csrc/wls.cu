@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(256) k_rollvar(const double *__restrict__ C, l
     const long long j0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * RV_ITEMS;
     if (j0 >= n) return;
     const long long half = w / 2, last = n - w;
-    const double wd = (double)w, pairs = (double)(w - 1), rwd = 1.0 / wd, shrink = 1.0 / (wd + 1.0);
+    const double wd = (double)w, pairs = (double)(w - 1), rwd = 1.0 / wd, shrink = 1.0 + 1.0 / (wd + 1.0) + 1.0e-4;      // c1 of ar1_window_variance
     WinSums ws{0.0, 0.0, 0.0};
     long long tprev = -1;
     double cur = 0.0;
@@ -293,8 +293,8 @@ __device__ __forceinline__ double interp_knots(const double *kx, const double *k
     const int hi = lo + 1;
     const double xl = kx[lo], xr = kx[hi];
     if (xr <= xl) return fmax(ky[hi], ky[lo]);
-    const double wgt = div_rcp(__dsub_rn(t, xl), __dsub_rn(xr, xl), krw[lo]);      // krw[lo] = RN(1 / (kx[lo+1] - kx[lo]))
-    return __dadd_rn(ky[lo], __dmul_rn(wgt, __dsub_rn(ky[hi], ky[lo])));
+    const double wgt = (t - xl) * krw[lo];                                          // krw[lo] = 1 / (kx[lo+1] - kx[lo])
+    return __fma_rn(wgt, ky[hi] - ky[lo], ky[lo]);
 }
 
 constexpr int CB_THREADS = 256;
@@ -349,17 +349,15 @@ __global__ void __launch_bounds__(CB_THREADS, 4) k_combine(CombineParams P)
                         pv = fmax(pv, 1.0e-8);
                     }
                     // wls_backend.c:889-911
-                    double post = div_rcp(__dadd_rn(__dmul_rn(P.ldf, ov), __dmul_rn(P.pdf, pv)), tdf1, rtdf1);
-                    const double flo = __dmul_rn(P.pfr, pv);
-                    if (post < flo) post = flo;
-                    post = fmax(post, 1.0e-8);
-                    const double prec = __drcp_rn(post);        // == 1.0 / post (correctly rounded), without the division slow path
+                    double post = __fma_rn(P.ldf, ov, P.pdf * pv) * rtdf1;
+                    post = fmax(fmax(post, P.pfr * pv), 1.0e-8);
+                    const double prec = rcp_nr(post);           // 1 / post to ~1 ulp (hardware seed + two Newton steps)
                     if (want_rq) {                              // only when raw / prior variance outputs are requested
-                        rsum = __dadd_rn(rsum, __drcp_rn(ov));
-                        qsum = __dadd_rn(qsum, __drcp_rn(pv));
+                        rsum += rcp_nr(ov);
+                        qsum += rcp_nr(pv);
                     }
-                    psum = __dadd_rn(psum, prec);
-                    wsum = __dadd_rn(wsum, __dmul_rn(prec, y));
+                    psum += prec;
+                    wsum = __fma_rn(prec, y, wsum);
                 }
             }
         }

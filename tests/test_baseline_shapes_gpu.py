@@ -13,7 +13,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import rel_err
+from tests.conftest import rel_err
 from rocco_b200.synth import HG_PARAMS, chrom_bins, chrom_matrix_numpy, chrom_seed
 
 pytestmark = pytest.mark.gpu
