@@ -53,6 +53,10 @@ def parse_args():
                     help="skip the pinned-input and float32-input end-to-end legs (the pageable float64 leg is the headline)")
     ap.add_argument("--cpu-sample-bins", type=int, default=250_000)
     ap.add_argument("--levels", type=int, default=0, help="bisection levels per launch (0 = library default)")
+    ap.add_argument("--config", type=int, default=4, choices=[4, 5],
+                    help="BASELINE.json config: 4 = hg38 @ 50 bp x 100 samples, chromosome-sharded (default, the metric's config); "
+                         "5 = hg38 @ 20 bp x 1000 samples float32, SAMPLE-sharded scoring + 256-multiplier sweep")
+    ap.add_argument("--multipliers", type=int, default=256)
     return ap.parse_args()
 
 
@@ -189,6 +193,161 @@ def run_reference(args):
     emit(line)
 
 
+
+# ---------------------------------------------------------------------------------------------- config 5
+def run_config5(args):
+    """BASELINE.json config 5: hg38 @ 20 bp x 1000 samples stored float32, the SAMPLES sharded over the ranks.
+
+    Per chromosome: every rank runs the per-sample stages on its rows (-> four per-bin accumulators), ONE all-reduce
+    (sum, float64) of [4, bins] over NVLink, the per-bin finalisation, and on the rank that owns the chromosome (LPT) a
+    sort for the multiplier grid plus a 256-multiplier sweep in one launch set.  The all-reduce / finalise / sweep chain
+    of chromosome c runs on a second stream from a helper thread while the main thread scores chromosome c+1.
+    The matrices stay resident, so at fewer than 8 GPUs the run covers the chromosomes that fit (named in the workload)."""
+    import queue
+    import torch
+    import torch.distributed as dist
+    from rocco_b200 import _lib, pipeline
+    from rocco_b200.synth import chrom_matrix_torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    step_bp = 20 if args.step_bp == 50 else args.step_bp
+    samples = 1000 if args.samples == 100 else args.samples
+    assert samples % world == 0, "samples must divide over the ranks"
+    m_local = samples // world
+    all_names = list(HG38_SIZES) if args.chroms == "all" else args.chroms.split(",")
+    all_bins = {c: chrom_bins(c, step_bp) for c in all_names}
+    # resident inputs <= 80 GB per rank, scratch (centred matrix + variance track, float64) of the largest chromosome <= 80 GB
+    n_max = int(80e9 / (16.0 * m_local))
+    names, used = [], 0.0
+    for c in sorted(all_names, key=lambda c: all_bins[c]):
+        need = all_bins[c] * m_local * 4.0
+        if all_bins[c] <= n_max and used + need <= 80e9:
+            names.append(c)
+            used += need
+    names = [c for c in all_names if c in names]
+    bins = [all_bins[c] for c in names]
+    owner = {}
+    for r, part in enumerate(pipeline.lpt_partition(bins, world)):
+        for k in part:
+            owner[k] = r
+    prm = pipeline.score_params(prior_df=PRIOR_DF)
+    mats = [chrom_matrix_torch(m_local, n, chrom_seed(c), dev, torch.float32, sample_stream=rank + 1) for c, n in zip(names, bins)]
+    comm = torch.cuda.Stream(device=dev)
+    total_bins = int(sum(bins))
+    sweeps = {}
+
+    def tail_worker(q):
+        torch.cuda.set_device(local_rank)
+        with torch.cuda.stream(comm):
+            while True:
+                item = q.get()
+                if item is None:
+                    return
+                k, acc, ready = item
+                comm.wait_event(ready)
+                if world > 1:
+                    dist.all_reduce(acc)
+                scores = pipeline.score_finalize_device(acc, samples, prm)
+                if owner[k] == rank:
+                    n = scores.shape[0]
+                    srt = torch.sort(scores).values
+                    lo, hi = float(srt[int(0.50 * (n - 1))]), float(srt[int(0.999 * (n - 1))])
+                    lam = np.linspace(max(lo, 0.0), hi, args.multipliers)
+                    counts, pen, obj = pipeline.sweep_multipliers(scores, HG_PARAMS[names[k]][1], lam)
+                    sweeps[names[k]] = (int(counts[0]), int(counts[-1]))
+
+    def step():
+        q = queue.Queue()
+        th = threading.Thread(target=tail_worker, args=(q,))
+        th.start()
+        for k, x in enumerate(mats):
+            acc = pipeline.score_partial_device(x, prm)
+            ready = torch.cuda.Event()
+            ready.record()
+            acc.record_stream(comm)
+            q.put((k, acc, ready))
+        q.put(None)
+        th.join()
+        torch.cuda.current_stream().wait_stream(comm)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    sampler = ClockSampler(range(world)) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = _lib.kernel_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_host0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    t_host1 = time.perf_counter()
+    ms = ev0.elapsed_time(ev1)
+    launches = _lib.kernel_launches() - launches0
+    clocks = None
+    if sampler:
+        sampler.mark(t_host0, t_host1)
+        clocks = sampler.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lt)
+    ms = float(t.item())
+    # the collective on its own: [4, bins] float64 of the largest resident chromosome, ranks aligned by a barrier
+    ar = None
+    if world > 1:
+        buf = torch.zeros((4, max(bins)), dtype=torch.float64, device=dev)
+        for _ in range(2):
+            dist.all_reduce(buf)
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(5):
+            dist.all_reduce(buf)
+        a1.record()
+        torch.cuda.synchronize()
+        at = torch.tensor([a0.elapsed_time(a1) / 5.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(at, op=dist.ReduceOp.MAX)
+        nbytes = buf.numel() * 8
+        ar = {"bytes": nbytes, "ms": float(at.item()), "algbw_GBps": nbytes / 1e9 / (float(at.item()) / 1e3),
+              "busbw_GBps": 2.0 * (world - 1) / world * nbytes / 1e9 / (float(at.item()) / 1e3),
+              "reference_busbw_GBps": 725.0, "per_step_bytes": total_bins * 32}
+    if rank == 0:
+        subset = "hg38" if len(names) == 24 else "+".join(names)
+        line = {
+            "metric": METRIC, "value": total_bins * args.steps / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"config 5: synthetic {subset} @ {step_bp} bp x {samples} samples stored float32, scoring "
+                                   f"sample-sharded {m_local} per rank, {args.multipliers}-multiplier sweep per chromosome",
+                       "genome_bins": total_bins, "samples": samples, "chromosomes": len(names),
+                       "resident_input_GB_per_rank": used / 1e9,
+                       "sample_bins_per_sec": total_bins * samples * args.steps / (ms / 1e3),
+                       "l2_policy": "inputs larger than L2", "collective": "one NCCL all-reduce(sum, float64) of [4, bins] per chromosome, "
+                       "overlapped with the scoring of the next chromosome", "all_reduce": ar,
+                       "sweep_counts_first_last": sweeps},
+            "clocks": clocks, "e2e": None, "gpu_launches": int(lt.item()), "roofline": None, "cpu_baseline": None,
+        }
+        emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ---------------------------------------------------------------------------------------------- our arm
 def cpu_baseline_single_core(args):
     from oracle import oracle as orc
@@ -258,6 +417,9 @@ def main():
     if args.impl == "reference":
         run_reference(args)
         return
+    if args.config == 5:
+        run_config5(args)
+        return
 
     import torch
     import torch.distributed as dist
@@ -300,20 +462,32 @@ def main():
     def step():
         shard = pipeline.run_shard(d_mats, budgets, gammas, params=params, levels_per_round=args.levels,
                                    score_streams=args.score_streams) if mine else None
+        # ONE merged BED for the genome in the reference's record order.  Every rank formats the text of its own
+        # chromosomes (one part file each, in parallel, on the node's file system); rank 0 stitches the 24 parts together
+        # once the all-reduce below -- which every rank issues AFTER writing its parts -- has completed.
+        if mine:
+            chrom, starts, ends = shard["runs"]
+            if world == 1:
+                order = np.lexsort((starts, lex_rank[chrom]))
+                pipeline.runs_to_bed_file(os.path.join(tmpdir, "genome.bed"), lex_names,
+                                          (lex_rank[chrom][order].astype(np.int32), starts[order], ends[order]), args.step_bp)
+            else:
+                bounds = np.searchsorted(chrom, np.arange(len(my_names) + 1))          # runs come grouped by chromosome
+                for k, c in enumerate(my_names):
+                    sl = slice(int(bounds[k]), int(bounds[k + 1]))
+                    pipeline.runs_to_bed_file(os.path.join(tmpdir, f"part_{c}.bed"), [c],
+                                              (np.zeros(sl.stop - sl.start, np.int32), starts[sl], ends[sl]), args.step_bp)
         # the one cross-GPU exchange of the path: genome-wide selected-bin count (reporting only)
         count_buf[0] = sum(r["selected_count"] for r in shard["results"]) if mine else 0
         count_buf[1] = sum(my_bins)
         if world > 1:
             dist.all_reduce(count_buf)
-        # ONE merged BED for the genome: every rank's runs go to rank 0 (a few hundred KB), which writes them in the
-        # reference's record order
-        if mine:
-            chrom, starts, ends = shard["runs"]
-            merged = rdist.gather_runs(lex_rank[chrom], starts, ends, device=dev)
-        else:
-            merged = rdist.gather_runs(np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.int64), device=dev)
-        if rank == 0:
-            pipeline.runs_to_bed_file(os.path.join(tmpdir, "genome.bed"), lex_names, (merged[0].astype(np.int32), merged[1], merged[2]), args.step_bp)
+            if rank == 0:
+                torch.cuda.current_stream().synchronize()
+                with open(os.path.join(tmpdir, "genome.bed"), "wb") as out:
+                    for c in lex_names:
+                        with open(os.path.join(tmpdir, f"part_{c}.bed"), "rb") as part:
+                            out.write(part.read())
         return shard
 
     def barrier():

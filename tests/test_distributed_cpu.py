@@ -36,6 +36,14 @@ def _worker(rank, size, port, out_dir):
             bins += sizes[i]
         tot_sel, tot_bins = rd.allreduce_selected(sel, bins)
         merged = rd.gather_bed_records(recs)
+        # the tensor-collective variant: runs as (global chromosome index in record order, first bin, last bin + 1)
+        lex = sorted(names)
+        runs = rd.gather_runs([lex.index(c) for c, _, _ in recs], [a // 50 for _, a, _ in recs], [b // 50 for _, _, b in recs])
+        if rank == 0:
+            with open(os.path.join(out_dir, "merged_runs.bed"), "w") as fh:
+                fh.write("".join(f"{lex[c]}\t{50 * a}\t{50 * b}\n" for c, a, b in zip(*[r.tolist() for r in runs])))
+        else:
+            assert runs is None
         np.save(os.path.join(out_dir, f"tot_{rank}.npy"), np.array([tot_sel, tot_bins]))
         if rank == 0:
             with open(os.path.join(out_dir, "merged.bed"), "w") as fh:
@@ -75,6 +83,7 @@ def test_two_ranks_reproduce_single_rank(tmp_path):
         sel += int(sol.sum())
     want = "".join(f"{c}\t{a}\t{b}\n" for c, a, b in orc.merge_bed_records(recs))
     assert open(tmp_path / "merged.bed").read() == want
+    assert open(tmp_path / "merged_runs.bed").read() == want
     for r in range(2):
         assert np.load(tmp_path / f"tot_{r}.npy").tolist() == [sel, sum(sizes)]
 
