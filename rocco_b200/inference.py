@@ -328,3 +328,100 @@ def estimate_budget_nonnull_fraction_from_empirical_null(centered_matrix, observ
         min_effect=min_effect, precision_floor_ratio=precision_floor_ratio, dependence_lag_hint=dependence_lag_hint,
         num_null_draws=num_null_draws, random_seed=random_seed, progress_label=progress_label,
         num_processes=num_processes, return_details=return_details)
+
+
+# ------------------------------------------------------------------------------------------------
+# empirical-Bayes chromosome budgets (inference.py:1488-1737) -- SURVEY.md 8(f) rank 2
+#
+# Twenty-four numbers per genome: this stays on the host with SciPy exactly as in the reference (the
+# optimiser's iterates decide the last digits, so the same optimiser is used on the same objective).
+# ------------------------------------------------------------------------------------------------
+def _raw_rate_summary(successes: np.ndarray, totals: np.ndarray) -> tuple[float, float, float]:
+    """(pooled rate clipped to [1e-6, 1 - 1e-6], sample variance of the raw rates, binomial floor of that variance)"""
+    trials = np.maximum(totals, 1.0)
+    rates = successes / trials
+    pooled = float(np.clip(np.sum(successes) / max(np.sum(totals), 1.0), 1.0e-6, 1.0 - 1.0e-6))
+    spread = float(np.var(rates, ddof=1)) if rates.size > 1 else 0.0
+    floor = float(pooled * (1.0 - pooled) * np.mean(1.0 / trials))
+    return pooled, spread, floor
+
+
+def fit_beta_prior_mle(successes: np.ndarray, totals: np.ndarray, init_center: float = 0.05,
+                       init_strength: float = 10.0) -> Tuple[float, float]:
+    r"""Maximum-likelihood (alpha, beta) of a beta-binomial over chromosomes, L-BFGS-B on (log alpha, log beta).
+
+    When the raw rates are no more dispersed than binomial sampling alone explains, the fit sits on the boundary
+    rho = 0 and a (practically) infinitely strong prior at the pooled rate is returned (inference.py:1520-1528)."""
+    from scipy import optimize, special
+    x = np.asarray(successes, dtype=np.float64)
+    n = np.asarray(totals, dtype=np.float64)
+    if x.shape != n.shape:
+        raise ValueError("`successes` and `totals` must have the same shape")
+    if x.size == 0:
+        return 1.0, 1.0
+    center = min(max(float(init_center), 1.0e-6), 1.0 - 1.0e-6)
+    pooled, spread, floor = _raw_rate_summary(x, n)
+    if spread <= floor + 1.0e-12:
+        strength = float(max(1.0e12, 100.0 * np.max(n)))
+        return pooled * strength, (1.0 - pooled) * strength
+    weak = (center * float(init_strength), (1.0 - center) * float(init_strength))
+
+    def negative_loglik(theta: np.ndarray) -> float:
+        a, b = float(np.exp(theta[0])), float(np.exp(theta[1]))
+        return float(-np.sum(special.betaln(x + a, n - x + b) - special.betaln(a, b)))
+
+    fit = optimize.minimize(negative_loglik, np.log(np.array(weak, dtype=np.float64)), method="L-BFGS-B")
+    if not fit.success:
+        logger.warning("Falling back to a weak beta prior while fitting EB budgets: %s", fit.message)
+        return weak
+    return float(np.exp(fit.x[0])), float(np.exp(fit.x[1]))
+
+
+def _beta_posterior_budget_quantile(successes: float, total: float, alpha: float, beta: float, posterior_quantile: float,
+                                    min_budget: float, max_budget: float) -> float:
+    from scipy import stats
+    a = float(max(1.0e-12, successes + alpha))
+    b = float(max(1.0e-12, (total - successes) + beta))
+    q = float(np.clip(posterior_quantile, 1.0e-6, 1.0 - 1.0e-6))
+    return float(np.clip(float(stats.beta.ppf(q, a, b)), min_budget, max_budget))
+
+
+def estimate_empirical_bayes_budgets(chrom_candidate_counts: Dict[str, float], chrom_total_counts: Dict[str, float],
+                                     min_budget: float = 1.0e-4, max_budget: float = 0.5, init_center: float = 0.05,
+                                     init_strength: float = 10.0, posterior_quantile: float = 0.01
+                                     ) -> Tuple[Dict[str, float], Dict[str, float]]:
+    r"""Per-chromosome budgets shrunk towards a genome-wide beta prior (inference.py:1593-1737).
+
+    One chromosome: the default prior (init_center, init_strength); two or three: a weak prior at the pooled rate;
+    more: the beta-binomial MLE.  The budget is a LOW quantile of each chromosome's beta posterior, clipped to
+    [min_budget, max_budget].  Returns (budgets, meta) with the reference's meta keys."""
+    chroms = list(chrom_candidate_counts.keys())
+    if chroms != list(chrom_total_counts.keys()):
+        raise ValueError("`chrom_candidate_counts` and `chrom_total_counts` must share keys in the same order")
+    x = np.array([chrom_candidate_counts[c] for c in chroms], dtype=np.float64)
+    n = np.array([chrom_total_counts[c] for c in chroms], dtype=np.float64)
+    pooled, spread, floor = _raw_rate_summary(x, n)
+    q = float(posterior_quantile)
+    if not (0.0 < q < 1.0):
+        raise ValueError("`posterior_quantile` must lie strictly between 0 and 1")
+    at_floor = bool(spread <= floor + 1.0e-12)
+    if len(chroms) <= 1:
+        alpha, beta = float(init_center) * float(init_strength), (1.0 - float(init_center)) * float(init_strength)
+        centre, strength, method, flag = float(init_center), float(init_strength), "single_chrom_default", False
+        dispersion = 1.0 / (1.0 + alpha + beta)
+    elif len(chroms) <= 3:
+        alpha, beta = pooled * float(init_strength), (1.0 - pooled) * float(init_strength)
+        centre, strength, method, flag = pooled, float(alpha + beta), "weak_pooled_prior", at_floor
+        dispersion = max(0.0, 1.0 / (1.0 + strength))
+    else:
+        alpha, beta = fit_beta_prior_mle(x, n, init_center=init_center, init_strength=init_strength)
+        centre, strength, method, flag = float(alpha / (alpha + beta)), float(alpha + beta), "beta_binomial_mle", at_floor
+        dispersion = max(0.0, 1.0 / (1.0 + strength))
+    budgets = {c: _beta_posterior_budget_quantile(x[k], n[k], alpha, beta, q, min_budget, max_budget) for k, c in enumerate(chroms)}
+    meta = {
+        "alpha": float(alpha), "beta": float(beta), "genome_wide_budget": float(centre), "prior_strength": float(strength),
+        "prior_dispersion": float(dispersion), "min_prior_dispersion": 0.0, "observed_raw_budget_var": float(spread),
+        "theoretical_min_raw_budget_var": float(floor), "prior_dispersion_at_floor": bool(flag),
+        "posterior_summary": "beta_quantile", "posterior_quantile": float(q), "prior_fit_method": method,
+    }
+    return budgets, meta

@@ -308,6 +308,25 @@ def _resolve_chrom_gamma(chrom: str, args: dict, chrom_scores: np.ndarray, budge
 
 
 # ------------------------------------------------------------------------------------------------
+# chromosome budgets for the solves (rocco.py:1113-1143) -- SURVEY.md 8(f) rank 2
+# ------------------------------------------------------------------------------------------------
+def _resolve_budgets(chrom_cache: dict, args: dict) -> tuple[dict, dict]:
+    r"""EB-shrunk per-chromosome budgets from the cached budget estimates, rescaled so that the prior centre lands on
+    ``args["budget"]`` when that is given, times ``args["scale_chrom_budgets"]``, clipped to [0.005, 0.1]."""
+    from .inference import estimate_empirical_bayes_budgets
+    candidates = {c: chrom_cache[c]["budget_count_hat"] for c in chrom_cache}
+    totals = {c: chrom_cache[c]["total_count"] for c in chrom_cache}
+    shrunk, budget_meta = estimate_empirical_bayes_budgets(candidates, totals, posterior_quantile=args["budget_posterior_quantile"])
+    centre = budget_meta["genome_wide_budget"]
+    to_target = float(args["budget"]) / centre if (args["budget"] is not None and centre > 0) else 1.0
+    user_scale = float(args["scale_chrom_budgets"])
+    # (budget * rescale) * scale: the reference's association order, kept so the doubles agree
+    chrom_budgets = {c: min(max(b * to_target * user_scale, 0.005), 0.1) for c, b in shrunk.items()}
+    logger.info("Empirical-Bayes budget prior: %s", budget_meta)
+    return chrom_budgets, budget_meta
+
+
+# ------------------------------------------------------------------------------------------------
 # narrowPeak summit offsets (rocco.py:809-872) -- SURVEY.md 8(f) rank 4
 # ------------------------------------------------------------------------------------------------
 def _cpy_narrowpeak_summit_track(chrom: str, intervals: np.ndarray, effect_mean: np.ndarray) -> str | None:
