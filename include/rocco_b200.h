@@ -317,6 +317,41 @@ int rocco_column_stat_f64(const double *matrix, size_t m, size_t n, int stat,
 int rocco_b200_column_stat_dev(const void *d_matrix, int dtype, size_t m, size_t n, int stat,
                                double arg0, double arg1, double power, double *d_out, void *cuda_stream);
 
+/* ------------------------------------------------------------------ matrix assembly / input staging
+ * The step BEFORE the hot path, on the device, so that what crosses PCIe is the decoded alignment records (or the
+ * float32 per-bin coverage), not the float64 samples x bins matrix.  BAM/BGZF decoding itself stays with htslib. */
+typedef struct rocco_b200_count_options {        /* the fields of ccounts_countOptions the coverage loop reads (ccounts_backend.h:59-75) */
+    int32_t flag_include, flag_exclude, min_mapping_quality, paired_end_mode, one_read_per_bin, reserved;
+    int64_t read_length, min_template_length, max_insert_size, shift_forward_strand53, shift_reverse_strand53, extend_bp;
+} rocco_b200_count_options;
+/* ccounts_backend.c:2416-2574: per-read filters, fragment inference, strand shifts / extension, clipping, one-read-per-bin,
+ * delta buffer + prefix sum.  Records are device arrays (struct of arrays of what htslib decodes: bam1_core_t pos,
+ * bam_endpos, flag, qual, isize, mtid == tid); d_counts [count_len] float32, count_len = ceil((end - start) / step). */
+int rocco_b200_count_alignment_region_dev(const int64_t *d_pos, const int64_t *d_endpos, const uint16_t *d_flag,
+                                          const uint8_t *d_mapq, const int64_t *d_isize, const uint8_t *d_mate_same_tid,
+                                          size_t n_reads, const rocco_b200_count_options *options, int64_t start, int64_t end,
+                                          int64_t step, float *d_counts, size_t count_len, void *cuda_stream);
+typedef struct rocco_b200_track {                /* one sample's counted window */
+    const float *d_counts;                       /* device, count_len bins from count_start                        */
+    size_t count_len;
+    int64_t count_start;                         /* multiple of step (readtracks.py:468)                           */
+    double norm_scale;                           /* metadata["norm_scale"] (readtracks.py:495)                     */
+    double const_scale;                          /* applied when >= 0 (readtracks.py:500-503)                      */
+    int32_t scale_by_step;                       /* divide by step (readtracks.py:496-498)                         */
+    int32_t reserved;
+} rocco_b200_track;
+/* readtracks.py:505-516: per track the first and last bin whose SCALED value is > 0 (host outputs; -1, -1: no data). */
+int rocco_b200_track_positive_range_dev(const rocco_b200_track *tracks, int n_tracks, int64_t step, int64_t *first_bin_out,
+                                        int64_t *last_bin_out, void *cuda_stream);
+/* readtracks.py:492-518 + 590-633: rows = the tracks that have data (in order), columns = the sorted union of their
+ * interval starts, given as `n_segments` maximal runs of consecutive bins (segment_start_bp, segment_first_column);
+ * value = np.round(counts * norm_scale [/ step] [* const_scale], round_digits) inside the track's positive range, else 0.
+ * d_matrix: [n_kept][n_columns] float64 (out_f32 = 0) or float32; d_intervals: [n_columns] int64 interval starts. */
+int rocco_b200_assemble_matrix_dev(const rocco_b200_track *tracks, const int64_t *first_bin, const int64_t *last_bin,
+                                   int n_tracks, int64_t step, int round_digits, const int64_t *segment_start_bp,
+                                   const int64_t *segment_first_column, int n_segments, size_t n_columns, int out_f32,
+                                   void *d_matrix, int64_t *d_intervals, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -75,6 +75,22 @@ class BudgetResult(Structure):
                 + [(k, c_int) for k in _BUDGET_INTS])
 
 
+class CountOptions(Structure):
+    _fields_ = [
+        ("flag_include", ctypes.c_int32), ("flag_exclude", ctypes.c_int32), ("min_mapping_quality", ctypes.c_int32),
+        ("paired_end_mode", ctypes.c_int32), ("one_read_per_bin", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("read_length", ctypes.c_int64), ("min_template_length", ctypes.c_int64), ("max_insert_size", ctypes.c_int64),
+        ("shift_forward_strand53", ctypes.c_int64), ("shift_reverse_strand53", ctypes.c_int64), ("extend_bp", ctypes.c_int64),
+    ]
+
+
+class Track(Structure):
+    _fields_ = [
+        ("d_counts", c_void_p), ("count_len", c_size_t), ("count_start", ctypes.c_int64), ("norm_scale", c_double),
+        ("const_scale", c_double), ("scale_by_step", ctypes.c_int32), ("reserved", ctypes.c_int32),
+    ]
+
+
 _lib = None
 
 
@@ -140,6 +156,13 @@ def _declare(lib):
         "rocco_b200_crossfit_baseline_dev": (c_int, [c_void_p, c_size_t, c_size_t, c_double, c_void_p, c_void_p]),
         "rocco_b200_score_centered_wls_dev": (
             c_int, [c_void_p, c_size_t, c_size_t, POINTER(ScoreParams), POINTER(ScoreOutputs), c_void_p]),
+        "rocco_b200_count_alignment_region_dev": (
+            c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, POINTER(CountOptions), ctypes.c_int64,
+                    ctypes.c_int64, ctypes.c_int64, c_void_p, c_size_t, c_void_p]),
+        "rocco_b200_track_positive_range_dev": (c_int, [POINTER(Track), c_int, ctypes.c_int64, c_void_p, c_void_p, c_void_p]),
+        "rocco_b200_assemble_matrix_dev": (
+            c_int, [POINTER(Track), c_void_p, c_void_p, c_int, ctypes.c_int64, c_int, c_void_p, c_void_p, c_int, c_size_t, c_int,
+                    c_void_p, c_void_p, c_void_p]),
         "rocco_column_stat_f64": (c_int, [c_void_p, c_size_t, c_size_t, c_int, c_double, c_double, c_double, c_void_p]),
         "rocco_b200_column_stat_dev": (
             c_int, [c_void_p, c_int, c_size_t, c_size_t, c_int, c_double, c_double, c_double, c_void_p, c_void_p]),
