@@ -47,6 +47,9 @@ int rocco_b200_device_count(void);                /* 0 when no CUDA device is vi
 int rocco_b200_set_device(int device);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 unsigned long long rocco_b200_kernel_launches(void);
+/* Return the scratch the library's stream-ordered memory pools are holding beyond `bytes_to_keep` (per pool) to the
+ * driver, so that other allocators in the process (torch's, a second workload) can use it.  Returns pools trimmed. */
+int rocco_b200_trim_pools(size_t bytes_to_keep);
 
 /* Per-kernel timing with CUDA events on the launching stream (off by default).  report() synchronises,
  * writes "<scope> <total_ms> <launch_sets> <algorithmic_bytes>" lines into buf and clears the log. */

@@ -143,6 +143,7 @@ def _declare(lib):
             c_int, [c_void_p, c_size_t, c_size_t, c_double, c_double, c_double, c_int, c_int, c_double,
                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, dp, ip]),
         "rocco_b200_default_score_params": (None, [POINTER(ScoreParams)]),
+        "rocco_b200_trim_pools": (c_int, [c_size_t]),
         "rocco_b200_trend_set_mode": (c_int, [c_int]),
         "rocco_b200_whittaker_set_mode": (c_int, [c_int]),
         "rocco_b200_trend_fallback_rows": (c_longlong, []),
@@ -226,6 +227,11 @@ def require_device() -> None:
 
 def np_ptr(a: np.ndarray) -> c_void_p:
     return c_void_p(a.ctypes.data)
+
+
+def trim_pools(bytes_to_keep: int = 0) -> int:
+    """Hand the scratch cached in the library's CUDA memory pools (beyond ``bytes_to_keep`` per pool) back to the driver."""
+    return int(load().rocco_b200_trim_pools(int(bytes_to_keep)))
 
 
 def kernel_launches() -> int:

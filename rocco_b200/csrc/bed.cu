@@ -18,17 +18,8 @@ namespace bed {
 constexpr int THREADS = 256;
 constexpr int ITEMS = 16;
 constexpr int TILE = THREADS * ITEMS;
-constexpr int MAX_CHROM_SMEM = 64;
 
 struct Seg { long long offset; long long n; };
-
-// selected(i) over the concatenated array: mask byte non-zero, inside some chromosome, not its last bin
-__device__ __forceinline__ bool in_drop_list(long long g, const long long *drops, int nd)
-{
-    for (int k = 0; k < nd; ++k)
-        if (drops[k] == g) return true;
-    return false;
-}
 
 template <bool WRITE>
 __global__ void __launch_bounds__(THREADS) k_runs(const uint8_t *mask, long long total, const long long *last_bins,
@@ -36,29 +27,18 @@ __global__ void __launch_bounds__(THREADS) k_runs(const uint8_t *mask, long long
                                                   const long long *tile_off_end, long long *starts, long long *ends)
 {
     __shared__ uint8_t s_m[TILE + 2];
-    __shared__ long long s_drop[MAX_CHROM_SMEM];
-    __shared__ int s_nd;
     __shared__ int s_ws[THREADS / 32], s_we[THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const long long t0 = (long long)blockIdx.x * TILE;
-    if (tid == 0) s_nd = 0;
-    __syncthreads();
-    // dropped (last-of-chromosome) positions that touch [t0-1, t0+TILE]
-    for (int k = tid; k < nlast; k += THREADS) {
-        const long long g = last_bins[k];
-        if (g >= t0 - 1 && g <= t0 + TILE) {
-            int slot = atomicAdd(&s_nd, 1);
-            if (slot < MAX_CHROM_SMEM) s_drop[slot] = g;
-        }
-    }
     for (int e = tid; e < TILE + 2; e += THREADS) {
         const long long g = t0 - 1 + e;
         s_m[e] = (g >= 0 && g < total) ? (mask[g] != 0) : 0;
     }
     __syncthreads();
-    const int nd = min(s_nd, MAX_CHROM_SMEM);
-    for (int k = tid; k < nd; k += THREADS) {
-        const long long e = s_drop[k] - (t0 - 1);
+    // dropped (last-of-chromosome) positions that touch [t0-1, t0+TILE] are cleared in place: any number of chromosomes
+    // or contigs per tile (thousands of scaffolds of a few bins each included)
+    for (int k = tid; k < nlast; k += THREADS) {
+        const long long e = last_bins[k] - (t0 - 1);
         if (e >= 0 && e < TILE + 2) s_m[e] = 0;
     }
     __syncthreads();
@@ -134,7 +114,6 @@ int runs_batch(const uint8_t *d_mask, const Seg *segs, int nseg, std::vector<lon
 {
     starts.clear(); ends.clear();
     if (nseg <= 0) return 0;
-    if (nseg > MAX_CHROM_SMEM) return ST_INVALID;
     RB_TRY(ensure_device());
     long long total = 0;
     std::vector<long long> last(nseg);

@@ -1146,6 +1146,13 @@ static int host_chain(const double *scores, const double *costs, size_t n, int m
 {
     if (!scores || !mask_out || n == 0) return ST_INVALID;
     if (n > 1 && !costs) return ST_INVALID;
+    // validate before anything is queued: negative / NaN switch costs are outside the clamp-map form of the DP
+    double csum = 0.0;
+    if (n > 1) {
+        for (size_t i = 0; i + 1 < n; ++i)
+            if (!(costs[i] >= 0.0)) return ST_INVALID;
+        csum = numpy_sum_f64(costs, n - 1);                  // dp.py:110-111 uses numpy.sum; its rounding defines the bracket
+    }
     RB_TRY(ensure_device());
     HostScope lease(true);
     cudaStream_t st = lease.stream();
@@ -1164,13 +1171,9 @@ static int host_chain(const double *scores, const double *costs, size_t n, int m
     if (stage) RB_TRY(pull_from_pinned(d_s, src_s, n * sizeof(double), st));
     else RB_CUDA(cudaMemcpyAsync(d_s, src_s, n * sizeof(double), cudaMemcpyHostToDevice, st));
     RB_CUDA(cudaMemsetAsync(d_c, 0, n * sizeof(double), st));
-    double csum = 0.0;
     if (n > 1) {
         if (stage) RB_TRY(pull_from_pinned(d_c, src_c, (n - 1) * sizeof(double), st));
         else RB_CUDA(cudaMemcpyAsync(d_c, src_c, (n - 1) * sizeof(double), cudaMemcpyHostToDevice, st));
-        for (size_t i = 0; i + 1 < n; ++i)
-            if (!(costs[i] >= 0.0)) return ST_INVALID;      // negative / NaN switch costs are outside the clamp-map form
-        csum = numpy_sum_f64(costs, n - 1);                  // dp.py:110-111 uses numpy.sum; its rounding defines the bracket
     }
     rocco_b200_chain_task t{};
     t.offset = 0; t.n = n; t.gamma = 0.0; t.cost_sum = csum; t.selection_penalty = lam;

@@ -157,18 +157,6 @@ __device__ __forceinline__ int ld_acquire_i32(const int *p) {
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// streaming 128-bit loads (read-once data: do not allocate in L1)
-__device__ __forceinline__ double2 ld_stream_f64x2(const double *p) {
-    double2 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ float4 ld_stream_f32x4(const float *p) {
-    float4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-    return r;
-}
 
 }  // namespace rb
 

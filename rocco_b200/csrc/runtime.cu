@@ -297,6 +297,29 @@ RB_API int rocco_b200_set_device(int device)
 
 RB_API unsigned long long rocco_b200_kernel_launches(void) { return rb::g_launches.load(); }
 
+/* Scratch comes from stream-ordered pools that keep what they have freed (growing a pool costs ~50 ms/GB under driver-wide
+ * locks), so an idle library can sit on tens of GB that neither torch's caching allocator nor another workload in the
+ * process can see.  This hands everything above `bytes_to_keep` per pool back to the driver (all pools of the current
+ * device: the per-call leases, the per-caller-stream pools and the device's default pool).  Call it between workloads, or
+ * after a MemoryError before retrying.  Returns the number of pools trimmed. */
+RB_API int rocco_b200_trim_pools(size_t bytes_to_keep)
+{
+    if (rb::ensure_device() != 0) return 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    cudaDeviceSynchronize();                      // stream-ordered frees still in flight become trimmable
+    int trimmed = 0;
+    std::lock_guard<std::mutex> lk(rb::g_ctx_mu);
+    auto trim = [&](cudaMemPool_t pool) {
+        if (pool && cudaMemPoolTrimTo(pool, bytes_to_keep) == cudaSuccess) ++trimmed; else (void)cudaGetLastError();
+    };
+    for (const rb::HostCtx &c : rb::g_ctx) if (c.dev == dev && !c.busy) trim(c.pool);
+    for (const rb::HostCtx &c : rb::g_user_ctx) if (c.dev == dev) trim(c.pool);
+    cudaMemPool_t def = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&def, dev) == cudaSuccess) trim(def); else (void)cudaGetLastError();
+    return trimmed;
+}
+
 RB_API int rocco_b200_profile_enable(int on)
 {
     return rb::g_prof_on.exchange(on ? 1 : 0);

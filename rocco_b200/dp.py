@@ -17,35 +17,41 @@ from . import _chain_dp, _lib
 logger = logging.getLogger(__name__)
 
 
+def _vector(values, what: str) -> np.ndarray:
+    arr = np.ascontiguousarray(values, dtype=np.float64)
+    if arr.ndim != 1:
+        raise ValueError(f"`{what}` must be a one-dimensional array")
+    return arr
+
+
 def objective_value(solution: np.ndarray, scores: np.ndarray, switch_costs) -> float:
-    solution_ = np.asarray(solution, dtype=np.float64)
-    scores_ = np.asarray(scores, dtype=np.float64)
-    if np.isscalar(switch_costs):
-        switch_costs_ = np.full(max(solution_.shape[0] - 1, 0), float(switch_costs), dtype=np.float64)
-    else:
-        switch_costs_ = np.asarray(switch_costs, dtype=np.float64)
-    penalty = 0.0
-    if solution_.shape[0] > 1:
-        penalty = float(switch_costs_ @ np.abs(np.diff(solution_, 1)))
-    return float(-(scores_ @ solution_) + penalty)
+    r"""-s.z + c.|dz|: the unpenalised objective the reference reports (dp.py:16-34); a scalar cost applies to every
+    adjacent pair."""
+    z = np.asarray(solution, dtype=np.float64)
+    gain = float(np.asarray(scores, dtype=np.float64) @ z)
+    if z.shape[0] < 2:
+        return -gain
+    jumps = np.abs(z[1:] - z[:-1])
+    cost = float(switch_costs) * float(jumps.sum()) if np.isscalar(switch_costs) \
+        else float(np.asarray(switch_costs, dtype=np.float64) @ jumps)
+    return cost - gain
 
 
 def build_switch_costs(scores: np.ndarray, gamma: float = 1.0) -> np.ndarray:
-    scores_ = np.asarray(scores, dtype=np.float64)
-    if scores_.ndim != 1:
-        raise ValueError("`scores` must be a one-dimensional array")
-    if scores_.shape[0] <= 1:
-        return np.zeros(0, dtype=np.float64)
-    return np.full(scores_.shape[0] - 1, float(gamma), dtype=np.float64)
+    r"""The constant fragmentation cost between neighbouring bins, length n - 1 (dp.py:37-46).  The device entries take
+    gamma as a scalar; this vector exists for callers of the reference API."""
+    n = _vector(scores, "scores").shape[0]
+    return np.full(max(n - 1, 0), float(gamma), dtype=np.float64)
 
 
 def solve_penalized_chain(scores, switch_costs, selection_penalty: float) -> Tuple[np.ndarray, float, int]:
-    r"""max_z sum (s_j - lambda) z_j - sum c_j |z_{j+1} - z_j|, ties -> fewer selected (dp.py:49-86)."""
-    scores_ = np.ascontiguousarray(scores, dtype=np.float64)
-    switch_costs_ = np.ascontiguousarray(switch_costs, dtype=np.float64)
-    solution, penalized_objective, selected_count = _chain_dp.solve_penalized_chain(
-        scores_, switch_costs_, float(selection_penalty))
-    return np.asarray(solution, dtype=np.uint8), float(penalized_objective), int(selected_count)
+    r"""max_z sum (s_j - lambda) z_j - sum c_j |z_{j+1} - z_j|, ties -> fewer selected (dp.py:49-86).
+
+    Returns (uint8 mask, penalized objective, selected count) with the reference's Python types."""
+    mask, value, count = _chain_dp.solve_penalized_chain(
+        np.ascontiguousarray(scores, dtype=np.float64), np.ascontiguousarray(switch_costs, dtype=np.float64),
+        float(selection_penalty))
+    return np.asarray(mask, dtype=np.uint8), float(value), int(count)
 
 
 def calibrate_selection_penalty(scores, switch_costs, target_count: int, max_iter: int = 60

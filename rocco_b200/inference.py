@@ -20,93 +20,83 @@ from . import _wls as _wls_native
 logger = logging.getLogger(__name__)
 
 
+def _finite_or_raise(what: str, *arrays) -> None:
+    for a in arrays:
+        if not np.isfinite(a).all():
+            raise ValueError(what)
+
+
 def _log_scale_wls_matrix(chrom_matrix: np.ndarray, pseudocount: float = 1.0) -> np.ndarray:
-    matrix = np.asarray(chrom_matrix, dtype=np.float64)
-    if np.any(~np.isfinite(matrix)):
-        raise ValueError("`chrom_matrix` contains non-finite values")
-    return np.log2(np.clip(matrix, 0.0, None) + float(pseudocount))
+    """log2(max(x, 0) + pseudocount) in float64; non-finite input is an error (inference.py:40-47)."""
+    x = np.asarray(chrom_matrix, dtype=np.float64)
+    _finite_or_raise("`chrom_matrix` contains non-finite values", x)
+    return np.log2(np.maximum(x, 0.0) + float(pseudocount))
 
 
 def _resolve_local_baseline_window(n_loci: int, target_window: int = 101) -> int:
-    n_loci = int(n_loci)
-    if n_loci < 25:
+    """Odd window <= n for the Whittaker baseline, 0 for rows shorter than 25 bins (inference.py:50-62)."""
+    n = int(n_loci)
+    if n < 25:
         return 0
-    window = int(max(3, target_window))
-    if window > n_loci:
-        window = n_loci
-    if (window % 2) == 0:
-        window = window - 1 if window == n_loci else window + 1
-    return int(max(0, window))
+    w = min(max(3, int(target_window)), n)
+    if w % 2 == 0:                      # force odd: shrink only when the window already spans the row
+        w += -1 if w == n else 1
+    return max(0, w)
 
 
 def _consenrich_whittaker_lambda(block_size: int) -> float:
-    block = int(max(3, block_size))
-    if (block % 2) == 0:
-        block += 1
-    w_hat = float(block) * 0.15915494
-    return float(7.0 * (w_hat**4))
+    """lambda = 7 (w / 2 pi)^4 for an odd block w >= 3 (inference.py:65-76; 0.15915494 is the reference's 1 / 2 pi)."""
+    w = max(3, int(block_size))
+    w += 1 - (w % 2)
+    return float(7.0 * (float(w) * 0.15915494) ** 4)
 
 
 def _consenrich_crossfit_whittaker_baseline(y_vals: np.ndarray, block_size: int = 101) -> np.ndarray:
-    y_arr = np.asarray(y_vals, dtype=np.float64)
-    if y_arr.ndim != 1:
+    y = np.asarray(y_vals, dtype=np.float64)
+    if y.ndim != 1:
         raise ValueError("`y_vals` must be one-dimensional")
-    window = _resolve_local_baseline_window(int(y_arr.size), target_window=block_size)
-    if window == 0:
-        return np.zeros_like(y_arr, dtype=np.float64)
-    penalty_lambda = _consenrich_whittaker_lambda(window)
-    return np.asarray(_baseline_native.crossfit_whittaker_baseline(y_arr, penalty_lambda=penalty_lambda), dtype=np.float64)
+    w = _resolve_local_baseline_window(y.size, target_window=block_size)
+    if w == 0:
+        return np.zeros_like(y)
+    return np.asarray(_baseline_native.crossfit_whittaker_baseline(y, penalty_lambda=_consenrich_whittaker_lambda(w)), dtype=np.float64)
 
 
 def _estimate_local_background_matrix(centered_matrix: np.ndarray, target_window: int = 101) -> tuple[np.ndarray, int, float]:
-    matrix = np.asarray(centered_matrix, dtype=np.float64)
-    if matrix.ndim != 2:
+    """Row-wise cross-fit Whittaker baseline: (baselines, resolved window, lambda) (inference.py:185-228)."""
+    rows = np.asarray(centered_matrix, dtype=np.float64)
+    if rows.ndim != 2:
         raise ValueError("`centered_matrix` must be two-dimensional")
-    window = _resolve_local_baseline_window(matrix.shape[1], target_window=target_window)
-    if window == 0:
-        return np.zeros_like(matrix, dtype=np.float64), 0, 0.0
-    penalty_lambda = _consenrich_whittaker_lambda(window)
-    local_baselines = np.asarray(
-        _baseline_native.crossfit_whittaker_baseline(matrix, penalty_lambda=penalty_lambda), dtype=np.float64)
-    if not np.all(np.isfinite(local_baselines)):
-        raise ValueError("Local baseline fit produced non-finite values")
-    return local_baselines, window, penalty_lambda
+    w = _resolve_local_baseline_window(rows.shape[1], target_window=target_window)
+    if w == 0:
+        return np.zeros_like(rows), 0, 0.0
+    lam = _consenrich_whittaker_lambda(w)
+    base = np.asarray(_baseline_native.crossfit_whittaker_baseline(rows, penalty_lambda=lam), dtype=np.float64)
+    _finite_or_raise("Local baseline fit produced non-finite values", base)
+    return base, w, lam
+
+
+_WLS_FIELDS = ("mean", "raw_variance", "prior_variance", "moderated_variance", "standard_error")
 
 
 def _score_centered_wls_matrix(centered_matrix: np.ndarray, lower_bound_z: float = 1.0, prior_df: float = 5.0,
                                min_effect: float | None = None, spatial_window: int | None = None,
                                precision_floor_ratio: float = 0.01) -> tuple[np.ndarray, Dict[str, np.ndarray | float]]:
-    centered = np.asarray(centered_matrix, dtype=np.float64)
-    if centered.ndim != 2:
+    """EB-moderated WLS scores of a centred matrix plus the reference's details dict (inference.py:231-299)."""
+    c = np.asarray(centered_matrix, dtype=np.float64)
+    if c.ndim != 2:
         raise ValueError("`centered_matrix` must be two-dimensional")
-    if centered.shape[0] == 0 or centered.shape[1] == 0:
+    if 0 in c.shape:
         raise ValueError("`centered_matrix` must be non-empty")
-    precision_floor_ratio_ = float(max(precision_floor_ratio, 0.0))
-    (scores_arr, mean_arr, raw_var_arr, prior_var_arr, moderated_var_arr, se_arr, total_df, resolved_window,
-     ) = _wls_native.score_centered_wls(
-        centered, lower_bound_z=float(lower_bound_z), prior_df=float(prior_df), min_effect=min_effect,
-        spatial_window=31 if spatial_window is None else int(spatial_window),
-        precision_floor_ratio=precision_floor_ratio_)
-    se = np.asarray(se_arr, dtype=np.float64)
-    mean = np.asarray(mean_arr, dtype=np.float64)
-    scores = np.asarray(scores_arr, dtype=np.float64)
-    details = {
-        "mean": mean,
-        "raw_variance": np.asarray(raw_var_arr, dtype=np.float64),
-        "prior_variance": np.asarray(prior_var_arr, dtype=np.float64),
-        "moderated_variance": np.asarray(moderated_var_arr, dtype=np.float64),
-        "standard_error": se,
-        "z_scores": mean / np.maximum(se, 1.0e-8),
-        "min_effect": float(0.0 if min_effect is None else max(min_effect, 0.0)),
-        "precision_floor_ratio": float(precision_floor_ratio_),
-        "degrees_of_freedom": np.full(centered.shape[1], float(total_df), dtype=np.float64),
-        "prior_spatial_window": float(resolved_window),
-    }
-    if (not np.all(np.isfinite(scores)) or not np.all(np.isfinite(details["mean"]))
-            or not np.all(np.isfinite(details["raw_variance"])) or not np.all(np.isfinite(details["prior_variance"]))
-            or not np.all(np.isfinite(details["moderated_variance"])) or not np.all(np.isfinite(details["standard_error"]))
-            or not np.all(np.isfinite(details["z_scores"]))):
-        raise ValueError("EB scoring produced non-finite values")
+    floor_ratio = float(max(precision_floor_ratio, 0.0))
+    out = _wls_native.score_centered_wls(
+        c, lower_bound_z=float(lower_bound_z), prior_df=float(prior_df), min_effect=min_effect,
+        spatial_window=31 if spatial_window is None else int(spatial_window), precision_floor_ratio=floor_ratio)
+    scores = np.asarray(out[0], dtype=np.float64)
+    details: Dict[str, np.ndarray | float] = {k: np.asarray(v, dtype=np.float64) for k, v in zip(_WLS_FIELDS, out[1:6])}
+    details["z_scores"] = details["mean"] / np.maximum(details["standard_error"], 1.0e-8)
+    _finite_or_raise("EB scoring produced non-finite values", scores, *(details[k] for k in _WLS_FIELDS), details["z_scores"])
+    details.update(min_effect=float(0.0 if min_effect is None else max(min_effect, 0.0)), precision_floor_ratio=floor_ratio,
+                   degrees_of_freedom=np.full(c.shape[1], float(out[6]), dtype=np.float64), prior_spatial_window=float(out[7]))
     return scores, details
 
 

@@ -21,42 +21,39 @@ logger = logging.getLogger(__name__)
 
 
 def _read_bed_records(bed_file: str) -> tuple[list[tuple[str, int, int]], bool]:
-    records: list[tuple[str, int, int]] = []
-    saw_extra_columns = False
-    with open(bed_file, "r", encoding="utf-8") as handle:
-        for line_num, line in enumerate(handle, start=1):
-            line_ = line.strip()
-            if line_ == "":
+    """(chrom, start, end) of every non-blank line; the flag says whether any line carried more than three columns.
+    Lines are stripped, split on tabs, and the coordinates must parse as integers (rocco.py:53-71)."""
+    out: list[tuple[str, int, int]] = []
+    wide = False
+    with open(bed_file, "r", encoding="utf-8") as fh:
+        for number, raw in enumerate(fh, start=1):
+            cols = raw.strip().split("\t") if raw.strip() else None
+            if cols is None:
                 continue
-            fields = line_.split("\t")
-            if len(fields) < 3:
-                raise ValueError(f"BED row {line_num} in {bed_file} has fewer than 3 columns.")
-            if len(fields) > 3:
-                saw_extra_columns = True
-            records.append((str(fields[0]), int(fields[1]), int(fields[2])))
-    return records, saw_extra_columns
+            if len(cols) < 3:
+                raise ValueError(f"BED row {number} in {bed_file} has fewer than 3 columns.")
+            wide |= len(cols) > 3
+            out.append((str(cols[0]), int(cols[1]), int(cols[2])))
+    return out, wide
 
 
 def _merge_bed_records(records, min_length_bp: int | None = None):
-    """Sort by (chrom string, start, end) and merge records with start <= previous end."""
-    if len(records) == 0:
-        return []
-    merged: list[list] = []
-    for chrom, start, end in sorted(records, key=lambda x: (x[0], x[1], x[2])):
-        if merged and chrom == merged[-1][0] and int(start) <= int(merged[-1][2]):
-            merged[-1][2] = max(int(merged[-1][2]), int(end))
-            continue
-        merged.append([chrom, int(start), int(end)])
-    return [(str(c), int(s), int(e)) for c, s, e in merged
-            if min_length_bp is None or (int(e) - int(s)) >= int(min_length_bp)]
+    """Sort by (chrom STRING, start, end), fuse records that touch or overlap the running interval, then drop the ones
+    shorter than ``min_length_bp`` (rocco.py:74-95)."""
+    fused: list[list] = []
+    for chrom, start, end in sorted(((c, int(s), int(e)) for c, s, e in records), key=lambda r: (r[0], r[1], r[2])):
+        if fused and fused[-1][0] == chrom and start <= fused[-1][2]:
+            fused[-1][2] = max(fused[-1][2], end)
+        else:
+            fused.append([chrom, start, end])
+    keep = (lambda s, e: True) if min_length_bp is None else (lambda s, e: e - s >= int(min_length_bp))
+    return [(str(c), s, e) for c, s, e in fused if keep(s, e)]
 
 
 def _write_bed_records(records, output_file: str, name_features: bool = False) -> str:
-    with open(output_file, "w", encoding="utf-8") as handle:
-        if name_features:
-            handle.write("".join(f"{c}\t{s}\t{e}\t{c}_{s}_{e}\n" for c, s, e in records))
-        else:
-            handle.write("".join(f"{c}\t{s}\t{e}\n" for c, s, e in records))
+    row = (lambda c, s, e: f"{c}\t{s}\t{e}\t{c}_{s}_{e}\n") if name_features else (lambda c, s, e: f"{c}\t{s}\t{e}\n")
+    with open(output_file, "w", encoding="utf-8") as fh:
+        fh.write("".join(row(c, s, e) for c, s, e in records))
     return output_file
 
 
@@ -116,91 +113,39 @@ def chrom_solution_to_bed(chromosome, intervals, solution, ID=None, check_gaps_i
     return _lib.write_bed_arrays(output_file, [str(chromosome)], None, starts, ends)
 
 
-def _merge_bed_arrays(chrom_rank: np.ndarray, start: np.ndarray, end: np.ndarray):
-    """Vectorised restatement of _merge_bed_records on (chromosome rank, start, end) arrays: sort lexicographically
-    and merge records with start <= running end.  Returns the merged (rank, start, end)."""
-    if len(start) == 0:
-        return chrom_rank, start, end
-    order = np.lexsort((end, start, chrom_rank))
-    rk, start, end = chrom_rank[order], start[order], end[order]
-    # running maximum of `end` restarted at every chromosome change: offset each chromosome by a stride larger than any coordinate
-    stride = np.int64(max(int(end.max()), 0) + 1)
-    shifted_end = end + rk.astype(np.int64) * stride
-    run_end = np.maximum.accumulate(shifted_end)
-    shifted_start = start + rk.astype(np.int64) * stride
-    new_grp = np.concatenate(([True], (shifted_start[1:] > run_end[:-1]) | (rk[1:] != rk[:-1])))
-    first = np.flatnonzero(new_grp)
-    last = np.concatenate((first[1:] - 1, [len(start) - 1]))
-    return rk[first], start[first], run_end[last] - rk[last].astype(np.int64) * stride
-
-
-def _read_bed_fast(bed_file: str):
-    """(chrom object array, start int64, end int64, saw_extra_columns) via the C parser; None when the file needs the
-    line-by-line reader (ragged rows, non-integer coordinates, ...)."""
-    import pandas as pd
-    try:
-        df = pd.read_csv(bed_file, sep="\t", header=None, dtype={0: str}, keep_default_na=False, na_values=[""],
-                         skip_blank_lines=True)
-    except pd.errors.EmptyDataError:
-        return np.zeros(0, dtype=object), np.zeros(0, np.int64), np.zeros(0, np.int64), False
-    except Exception:
-        return None
-    if df.shape[1] < 3 or df[1].dtype != np.int64 or df[2].dtype != np.int64:
-        return None
-    return df[0].to_numpy(dtype=object), df[1].to_numpy(), df[2].to_numpy(), df.shape[1] > 3
-
-
 def combine_chrom_results(chrom_bed_files: list, output_file: str, name_features: bool = False) -> str:
-    r"""Concatenate per-chromosome BED files, sort by (chrom string, start, end), merge, write
-    (rocco.py:194-240).  Same records as the reference; parsing, sorting and merging are vectorised."""
-    import pandas as pd
+    r"""Concatenate per-chromosome BED files, sort by (chrom string, start, end), merge, write (rocco.py:194-240).
 
-    printed_colct_msg = False
+    Canonical BED text (what this package and the reference write) is read, sorted, merged and written in one native
+    pass; anything the native parser declines (ragged rows, stray whitespace, non-integer coordinates, ...) goes through
+    the line-by-line reader above, whose tolerance and error messages are the reference's."""
     if os.path.exists(output_file):
         logger.info(f"Removing existing output file: {output_file}")
         try:
             os.remove(output_file)
         except OSError:
             logger.info(f"Could not remove existing output file: {output_file}.")
-    chroms, starts, ends = [], [], []
-    for chrom_bed_file in chrom_bed_files:
-        if not os.path.exists(chrom_bed_file):
-            raise FileNotFoundError(f"File does not exist: {chrom_bed_file}")
+    for f in chrom_bed_files:
+        if not os.path.exists(f):
+            raise FileNotFoundError(f"File does not exist: {f}")
+    extra_msg = "More than 3 columns detected in the input BED files. Extra columns will be ignored."
     native = _lib.combine_bed_files(list(chrom_bed_files), output_file, name_features) if len(chrom_bed_files) else None
-    if native is not None:                       # canonical BED text everywhere: read, sort, merge, write in one native pass
+    if native is not None:
         if native[1]:
-            logger.info("More than 3 columns detected in the input BED files. Extra columns will be ignored.")
+            logger.info(extra_msg)
         return output_file
-    for chrom_bed_file in chrom_bed_files:
-        fast = _read_bed_fast(chrom_bed_file)
-        if fast is None:
-            try:
-                recs, saw_extra_columns = _read_bed_records(chrom_bed_file)      # the reference's reader (and its errors)
-            except Exception as e:
-                logger.info(f"Could not read BED file: {chrom_bed_file}\n{e}\n")
-                raise
-            c = np.array([r[0] for r in recs], dtype=object)
-            a = np.array([r[1] for r in recs], dtype=np.int64)
-            b = np.array([r[2] for r in recs], dtype=np.int64)
-        else:
-            c, a, b, saw_extra_columns = fast
-        if saw_extra_columns and not printed_colct_msg:
-            logger.info("More than 3 columns detected in the input BED files. Extra columns will be ignored.")
-            printed_colct_msg = True
-        chroms.append(c); starts.append(a); ends.append(b)
-    chrom = np.concatenate(chroms) if chroms else np.zeros(0, dtype=object)
-    start = np.concatenate(starts) if starts else np.zeros(0, np.int64)
-    end = np.concatenate(ends) if ends else np.zeros(0, np.int64)
-    if len(start):
-        codes, uniques = pd.factorize(chrom)
-        names = sorted(str(u) for u in uniques)                      # Python string order, as sorted() in the reference
-        rank_of = {nm: k for k, nm in enumerate(names)}
-        rank = np.array([rank_of[str(u)] for u in uniques], dtype=np.int64)[codes]
-        rk, start, end = _merge_bed_arrays(rank, start.astype(np.int64), end.astype(np.int64))
-    if len(start):
-        return _lib.write_bed_arrays(output_file, names, rk.astype(np.int32), start, end, name_features=name_features)
-    open(output_file, "w").close()
-    return output_file
+    records, told = [], False
+    for f in chrom_bed_files:
+        try:
+            recs, wide = _read_bed_records(f)
+        except Exception as e:
+            logger.info(f"Could not read BED file: {f}\n{e}\n")
+            raise
+        if wide and not told:
+            logger.info(extra_msg)
+            told = True
+        records.extend(recs)
+    return _write_bed_records(_merge_bed_records(records), output_file, name_features=name_features)
 
 
 # ------------------------------------------------------------------------------------------------

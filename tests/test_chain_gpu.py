@@ -278,3 +278,23 @@ def test_budget_search_many_seeds_masks_identical(rb, oracle, gamma):
         assert abs(got[k]["objective"] - want_obj) <= 1e-6 * abs(want_obj)
         exact += got[k]["selection_penalty"] == want["selection_penalty"]
     print(f"gamma={gamma}: multiplier bit-identical in {exact}/8 cases")
+
+
+def test_mask_to_runs_with_hundreds_of_tiny_contigs(rb, oracle):
+    """more than 64 chromosomes / contigs per launch (alt and unplaced scaffolds of a few bins each, many per tile)"""
+    import torch
+    from rocco_b200 import pipeline
+    rng = np.random.default_rng(4)
+    lengths = [int(v) for v in rng.integers(1, 60, size=700)] + [5000, 1, 2, 9000]
+    offsets, total = pipeline.layout_offsets(lengths)
+    masks = [(rng.random(n) < 0.4).astype(np.uint8) for n in lengths]
+    buf = np.zeros(total, dtype=np.uint8)
+    for off, m in zip(offsets, masks):
+        buf[off:off + len(m)] = m
+    chrom, starts, ends = pipeline.masks_to_runs(torch.from_numpy(buf).cuda(), offsets, lengths)
+    got = list(zip(chrom.tolist(), starts.tolist(), ends.tolist()))
+    want = []
+    for c, m in enumerate(masks):
+        for _, a, b in oracle.solution_to_records("c", np.arange(len(m)), m):
+            want.append((c, a, b))
+    assert got == want
