@@ -126,6 +126,12 @@ int rocco_b200_chain_solve_batch_dev(
  * reference's sequential recurrence operation for operation (bit-identical value / count / mask);
  * longer ones use the parallel scan.  Returns the previous setting.  0 forces the scan everywhere. */
 int rocco_b200_chain_set_seq_max(int max_bins);
+/* Exact search (off by default): every multiplier at which some decision lies within 1e-7 (1 + c) of its threshold -- i.e.
+ * inside the rounding noise of the reference's absolute-value recurrence, which is where the last bisection levels land --
+ * is re-evaluated by replaying that recurrence sequentially over the whole chromosome (_chain_dp.c:109-186).  The
+ * returned multiplier and mask are then the reference's bits for ANY length, at ~13 ns per bin per replayed pass.
+ * Returns the previous setting. */
+int rocco_b200_chain_set_exact_search(int on);
 
 /* Multiplier sweep: counts and objectives for `lambda_count` multipliers in one launch set
  * (BASELINE.json config 5).  Outputs are host arrays of lambda_count entries. */
@@ -193,7 +199,9 @@ typedef struct rocco_b200_score_params {
     int spatial_window;             /* 31                                           */
     double precision_floor_ratio;   /* 0.01                                         */
     int baseline_window;            /* 101 (inference.py:185-228)                   */
-    int reserved;
+    int pilot_mode;                 /* row-median pilot offset (inference.py:333): 0 = exact for n <= 4096, median of a
+                                       4096-point sample above (the offset cancels in y - baseline(y): DESIGN.md section 4);
+                                       1 = exact np.median for any n (one radix sort per row; validation mode)            */
 } rocco_b200_score_params;
 
 void rocco_b200_default_score_params(rocco_b200_score_params *p);

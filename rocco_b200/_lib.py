@@ -38,7 +38,7 @@ class ScoreParams(Structure):
     _fields_ = [
         ("lower_bound_z", c_double), ("prior_df", c_double), ("min_effect", c_double),
         ("use_min_effect", c_int), ("spatial_window", c_int), ("precision_floor_ratio", c_double),
-        ("baseline_window", c_int), ("reserved", c_int),
+        ("baseline_window", c_int), ("pilot_mode", c_int),
     ]
 
 
@@ -129,6 +129,7 @@ def _declare(lib):
         "rocco_b200_chain_solve_batch_dev": (
             c_int, [c_void_p, c_void_p, POINTER(ChainTask), c_int, c_void_p, POINTER(ChainResult), c_int, c_void_p]),
         "rocco_b200_chain_set_seq_max": (c_int, [c_int]),
+        "rocco_b200_chain_set_exact_search": (c_int, [c_int]),
         "rocco_b200_chain_sweep_dev": (
             c_int, [c_void_p, c_size_t, c_double, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
         "rocco_mask_to_intervals_u8": (

@@ -155,6 +155,7 @@ struct Params {
     int ngroups;                // ceil(max nslots / slots_per_block)
     int epoch;
     int lex_pass;               // 1: only chromosomes with need_lex
+    int exact_mode;             // 1: multipliers with a decision inside the reference's rounding noise are replayed sequentially
 };
 
 // ------------------------------------------------------------------ the tile kernel
@@ -309,13 +310,14 @@ __global__ void __launch_bounds__(THREADS, 4) k_chain_tiles(Params P)
                     dec |= 1u << j;
                     if (v_lt(v_make(tv, 0.0, 0), x)) val |= 1u << j;
                     ties += (x.v == 0.0);
+                    if (P.exact_mode) near += (fabs(x.v) <= 1.0e-7);
                 } else {
                     const double cr = VEC_COST ? s_cs[(base + j + 1) + (base + j + 1) / ITEMS] : cd.gamma;
                     if (v_lt(v_make(tv, cr, 0), x)) { dec |= 1u << j; val |= 1u << j; }
                     else if (v_lt(x, v_make(tv, -cr, 0))) { dec |= 1u << j; }
                     ties += (x.v == cr) || (x.v == -cr);
-                    if (EMIT) {
-                        const double tol = 1.0e-9 * (1.0 + fabs(cr));
+                    if (EMIT || P.exact_mode) {
+                        const double tol = (P.exact_mode ? 1.0e-7 : 1.0e-9) * (1.0 + fabs(cr));
                         near += (fabs(x.v - cr) <= tol) || (fabs(x.v + cr) <= tol);
                     }
                 }
@@ -411,6 +413,7 @@ __global__ void __launch_bounds__(THREADS, 4) k_chain_tiles(Params P)
                 any |= s_whas[w];
             }
             o.head = any ? (int)(z & 1u) : 2;
+            if (P.exact_mode) o.ties += nr;          // near ties count like ties: the multiplier is re-evaluated by the exact replay
             P.tout[sidx] = o;
             if (P.tsweep) {
                 TileSweep ts{0.0, 0.0, 0, 0};
@@ -483,6 +486,81 @@ __global__ void __launch_bounds__(256) k_chain_seq(Params P)
     }
 }
 
+// ------------------------------------------------------------------ exact replay for long chromosomes (opt-in)
+// The reference's decisions compare ABSOLUTE values V0, V1 (|V| up to ~1e5-1e6, ulp ~1e-11..1e-10) and its rounding
+// errors accumulate along the whole chromosome; the scan works on d = V1 - V0 with errors of ~1e-15.  Both agree on every
+// decision whose margin exceeds that noise, i.e. everywhere except at multipliers within ~1e-9 of a breakpoint of
+// count(lambda) -- exactly where the last bisection levels land.  The noise is a function of the full prefix of the
+// recurrence, so it cannot be reproduced tile-locally: in exact mode a multiplier that shows any decision within
+// 1e-7 (1 + c) of its threshold is re-evaluated by replaying the reference's recurrence (_chain_dp.c:109-186) operation
+// for operation, one thread per (chromosome, multiplier), over the whole chromosome (~13 ns per bin).  The searched
+// multiplier and the mask are then the reference's bits for any length; the price is why this is not the default.
+template <bool VEC_COST, bool EMIT>
+__global__ void __launch_bounds__(MAX_SLOTS) k_chain_replay(Params P)
+{
+    const int c = blockIdx.x;
+    const ChromDev cd = P.chroms[c];
+    const SearchDev sd = P.search[c];
+    if (cd.seq || !sd.need_lex) return;
+    const int slot = threadIdx.x;
+    if (slot >= sd.nslots) return;
+    const double lam = P.lam[(size_t)c * MAX_SLOTS + slot];
+    const double *s = P.scores + cd.offset;
+    const double *cs = VEC_COST ? P.costs + cd.offset : nullptr;
+    const bool emit = EMIT && slot == 0;
+    uint8_t *bt = EMIT ? P.bt + (size_t)cd.tile0 * TILE : nullptr;
+    const long long n = cd.n;
+    double v0 = 0.0, v1 = s[0] - lam;
+    long long k0 = 0, k1 = 1;
+    constexpr int CH = 8;
+    for (long long i0 = 1; i0 < n; i0 += CH) {
+        double sv[CH], cv[CH];
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {                      // the loads of a chunk are issued before its dependent chain
+            const long long i = i0 + k;
+            sv[k] = i < n ? s[i] : 0.0;
+            cv[k] = (VEC_COST && i < n) ? cs[i - 1] : cd.gamma;
+        }
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+            const long long i = i0 + k;
+            if (i >= n) break;
+            const double cc = cv[k], si = sv[k];
+            const double off_leave = v1 - cc;
+            const double on_keep = v1 + si - lam;
+            const double on_enter = v0 - cc + si - lam;
+            const bool leave = (off_leave > v0) || (off_leave == v0 && k1 < k0);
+            const bool enter = (on_enter > on_keep) || (on_enter == on_keep && (k0 + 1) < (k1 + 1));
+            const double nv0 = leave ? off_leave : v0;
+            const long long nk0 = leave ? k1 : k0;
+            const double nv1 = enter ? on_enter : on_keep;
+            const long long nk1 = (enter ? k0 : k1) + 1;
+            if (emit) bt[i] = (uint8_t)((leave ? 1 : 0) | (enter ? 0 : 2));
+            v0 = nv0; k0 = nk0; v1 = nv1; k1 = nk1;
+        }
+    }
+    const bool end_on = (v1 > v0) || (v1 == v0 && k1 < k0);
+    P.counts[(size_t)c * MAX_SLOTS + slot] = end_on ? k1 : k0;
+    P.tiecnt[(size_t)c * MAX_SLOTS + slot] = 0;
+    if (emit) {
+        uint8_t *m = P.mask + cd.offset;
+        int st = end_on ? 1 : 0;
+        m[n - 1] = (uint8_t)st;
+        for (long long i = n - 1; i > 0; --i) {
+            st = st ? ((bt[i] >> 1) & 1) : (bt[i] & 1);
+            m[i - 1] = (uint8_t)st;
+        }
+        // the mask is final: nothing left pending for k_chain_finalize, which still needs each tile's right neighbour
+        for (int t = 0; t < cd.ntiles; ++t) {
+            TileOut o = P.tout[cd.tile0 + t];
+            o.pend = 0;
+            P.tout[cd.tile0 + t] = o;
+            const long long nxt = (long long)(t + 1) * TILE;
+            P.zin[cd.tile0 + t] = nxt < n ? (int)m[nxt] : 0;
+        }
+    }
+}
+
 // ------------------------------------------------------------------ per-chromosome finish + search controller
 // One block per chromosome, one warp per multiplier slot (looping when there are more slots than warps).
 // Multipliers whose count needs no DP pass (costs are >= 0):
@@ -546,7 +624,8 @@ __global__ void __launch_bounds__(256) k_chain_finish(Params P, int emit)
     if (threadIdx.x == 0) s_anytie = 0;
     __syncthreads();
 
-    for (int slot = wid; slot < sd.nslots && !cd.seq; slot += nw) {
+    const bool replayed = P.lex_pass && P.exact_mode;       // counts were written by k_chain_replay
+    for (int slot = wid; slot < sd.nslots && !cd.seq && !replayed; slot += nw) {
         const TileOut *to = P.tout + (size_t)slot * P.ntiles + cd.tile0;
         long long total = 0;
         int ties = 0;
@@ -819,6 +898,8 @@ __global__ void k_chain_results(Params P, const FinalPart *parts, rocco_b200_cha
 // ------------------------------------------------------------------ host driver
 // chromosomes of at most this many bins (<= TILE) use the exact sequential kernel
 static std::atomic<int> g_seq_max{TILE};
+// 1: re-evaluate multipliers with near-tie decisions by the sequential replay (any length); see k_chain_replay
+static std::atomic<int> g_exact_search{0};
 
 struct Workspace {
     ChromDev *d_chroms = nullptr;
@@ -873,6 +954,10 @@ static int launch_round(Params P, bool vec, int nslots_max, int &epoch, bool any
         if (lex == 0) {
             if (vec) RB_TRY((launch_tiles<VD, true, EMIT>(P, blocks, st)));
             else RB_TRY((launch_tiles<VD, false, EMIT>(P, blocks, st)));
+        } else if (P.exact_mode) {
+            if (vec) k_chain_replay<true, EMIT><<<P.nchrom, MAX_SLOTS, 0, st>>>(P);
+            else k_chain_replay<false, EMIT><<<P.nchrom, MAX_SLOTS, 0, st>>>(P);
+            RB_LAUNCH_CHECK();
         } else {
             if (vec) RB_TRY((launch_tiles<VL, true, EMIT>(P, blocks, st)));
             else RB_TRY((launch_tiles<VL, false, EMIT>(P, blocks, st)));
@@ -941,7 +1026,8 @@ static int solve_batch(const double *d_scores, const double *d_costs, const rocc
     RB_TRY(ar.alloc(&w.d_results, ntask));
     uint8_t *d_bt = nullptr;
     double *d_seqv = nullptr;
-    RB_TRY(ar.alloc(&d_bt, any_seq ? (size_t)ntiles * TILE : 16));
+    const bool exact = g_exact_search.load() != 0;
+    RB_TRY(ar.alloc(&d_bt, (any_seq || exact) ? (size_t)ntiles * TILE : 16));
     RB_TRY(ar.alloc(&d_seqv, ntask));
 
     // modes: 0 fixed (lambda given), 2 fixed at 0.0; both are PH_DONE from the start
@@ -970,6 +1056,7 @@ static int solve_batch(const double *d_scores, const double *d_costs, const rocc
     P.mask = d_masks; P.zin = w.d_zin; P.near_ties = w.d_near; P.ntiles = ntiles; P.nchrom = ntask;
     P.slots_per_block = slots_per_block;
     P.bt = d_bt; P.seq_value = d_seqv;
+    P.exact_mode = exact ? 1 : 0;
     int epoch = 0;
 
     std::vector<SearchDev> hsearch(ntask);
@@ -1123,6 +1210,11 @@ extern "C" __attribute__((visibility("default"))) int rocco_b200_chain_set_seq_m
     const int prev = chain::g_seq_max.load();
     chain::g_seq_max.store(std::max(0, std::min(max_bins, chain::TILE)));
     return prev;
+}
+
+extern "C" __attribute__((visibility("default"))) int rocco_b200_chain_set_exact_search(int on)
+{
+    return chain::g_exact_search.exchange(on ? 1 : 0);
 }
 
 extern "C" __attribute__((visibility("default"))) int rocco_b200_chain_solve_batch_dev(

@@ -15,8 +15,9 @@ int whittaker_set_mode(int mode);
 
 // Pilot offsets: per-row median of log2(max(x,0)+1) -- exact for n <= 4096, else the median of a
 // 4096-point strided sample (the offset cancels in  y - baseline(y)  up to the solver's noise).
+// exact != 0: np.median for any n (one radix sort per row).
 int pilot_offsets(const void *d_x, int in_f32, long long rows, long long n, long long row_stride, double *d_pilot,
-                  cudaStream_t st);
+                  cudaStream_t st, int exact = 0);
 
 // Centered matrix -> per-locus WLS outputs (wls_backend.c:744-947).
 int centered_wls(const double *d_centered, long long m, long long n, const rocco_b200_score_params &prm,

@@ -100,11 +100,44 @@ __global__ void __launch_bounds__(256) k_pilot(const void *x, int in_f32, long l
     }
 }
 
-int pilot_offsets(const void *d_x, int in_f32, long long rows, long long n, long long row_stride, double *d_pilot,
-                  cudaStream_t st)
+// exact mode: y keys of one row (>= 0, so the bit pattern orders like the value; NaN sorts last) and the median of the sorted row
+__global__ void k_pilot_keys(const void *x, int in_f32, long long n, long long base, unsigned long long *keys)
 {
-    k_pilot<<<(unsigned)rows, 256, 0, st>>>(d_x, in_f32, n, row_stride, d_pilot);
-    RB_LAUNCH_CHECK();
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x)
+        keys[j] = (unsigned long long)__double_as_longlong(load_logx(x, in_f32, base + j));
+}
+__global__ void k_pilot_pick(const unsigned long long *sorted, long long n, double *pilot)
+{
+    const double hi = __longlong_as_double((long long)sorted[n / 2]);
+    *pilot = (n & 1) ? hi : (__longlong_as_double((long long)sorted[n / 2 - 1]) + hi) / 2.0;      // np.median: mean of the two middle values
+}
+
+int pilot_offsets(const void *d_x, int in_f32, long long rows, long long n, long long row_stride, double *d_pilot,
+                  cudaStream_t st, int exact)
+{
+    if (!exact || n <= PILOT_CAP) {
+        k_pilot<<<(unsigned)rows, 256, 0, st>>>(d_x, in_f32, n, row_stride, d_pilot);
+        RB_LAUNCH_CHECK();
+        return 0;
+    }
+    if (n > 0x7fffffffLL) return ST_INVALID;
+    Arena ar(st);
+    unsigned long long *k0 = nullptr, *k1 = nullptr;
+    char *tmp = nullptr;
+    size_t tmp_bytes = 0;
+    RB_TRY(ar.alloc(&k0, (size_t)n));
+    RB_TRY(ar.alloc(&k1, (size_t)n));
+    cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, k0, k1, (int)n, 0, 64, st);
+    RB_TRY(ar.alloc(&tmp, tmp_bytes));
+    const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 16);
+    for (long long r = 0; r < rows; ++r) {
+        k_pilot_keys<<<blocks, 256, 0, st>>>(d_x, in_f32, n, r * row_stride, k0);
+        RB_LAUNCH_CHECK();
+        RB_CUDA(cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, k0, k1, (int)n, 0, 64, st));
+        count_launch(8);
+        k_pilot_pick<<<1, 1, 0, st>>>(k1, n, d_pilot + r);
+        RB_LAUNCH_CHECK();
+    }
     return 0;
 }
 
@@ -737,7 +770,7 @@ static int score_loci_core(const void *d_matrix_in, const void *h_matrix, int dt
         const char *xg = (const char *)d_matrix + (size_t)r0 * n * esz;
         {
             RB_PROF("k_pilot", st, 0.0);
-            status = pilot_offsets(xg, dtype, r1 - r0, n, n, d_pilot + r0, st);
+            status = pilot_offsets(xg, dtype, r1 - r0, n, n, d_pilot + r0, st, prm.pilot_mode);
         }
         if (status == 0) status = whittaker_rows(xg, dtype, 1, d_pilot + r0, r1 - r0, n, n, lam, 0, d_cent + r0 * n, d_bad, st);
         if (status == 0) status = wls_rows(d_cent, R, r0, r1, st);
@@ -777,7 +810,7 @@ RB_API void rocco_b200_default_score_params(rocco_b200_score_params *p)
 {
     if (!p) return;
     p->lower_bound_z = 1.0; p->prior_df = 5.0; p->min_effect = 0.0; p->use_min_effect = 0;
-    p->spatial_window = 31; p->precision_floor_ratio = 0.01; p->baseline_window = 101; p->reserved = 0;
+    p->spatial_window = 31; p->precision_floor_ratio = 0.01; p->baseline_window = 101; p->pilot_mode = 0;
 }
 
 RB_API int rocco_b200_score_loci_wls_dev(const void *d_matrix, int dtype, size_t m, size_t n,

@@ -250,7 +250,7 @@ def masks_to_runs(d_masks, offsets, lengths):
 # scoring on device-resident matrices
 # ---------------------------------------------------------------------------------------------
 def score_params(lower_bound_z=1.0, prior_df=5.0, min_effect=None, precision_floor_ratio=0.01,
-                 spatial_window=31, baseline_window=101):
+                 spatial_window=31, baseline_window=101, exact_pilot=False):
     lib = _lib.load()
     prm = _lib.ScoreParams()
     lib.rocco_b200_default_score_params(ctypes.byref(prm))
@@ -261,6 +261,7 @@ def score_params(lower_bound_z=1.0, prior_df=5.0, min_effect=None, precision_flo
     prm.precision_floor_ratio = float(max(precision_floor_ratio, 0.0))
     prm.spatial_window = int(spatial_window)
     prm.baseline_window = int(baseline_window)
+    prm.pilot_mode = 1 if exact_pilot else 0          # exact np.median row offsets for any row length (validation mode)
     return prm
 
 

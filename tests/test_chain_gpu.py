@@ -298,3 +298,48 @@ def test_mask_to_runs_with_hundreds_of_tiny_contigs(rb, oracle):
         for _, a, b in oracle.solution_to_records("c", np.arange(len(m)), m):
             want.append((c, a, b))
     assert got == want
+
+
+@pytest.fixture
+def exact_search():
+    from rocco_b200 import _lib
+    prev = _lib.load().rocco_b200_chain_set_exact_search(1)
+    yield
+    _lib.load().rocco_b200_chain_set_exact_search(prev)
+
+
+@pytest.mark.parametrize("n,gamma,budget,seed", [(50_000, 1.0, 0.02, 0), (200_000, 6.86, 0.03, 1),
+                                                 (934_200, 1.0, 0.02, 21), (33_333, 0.0, 0.1, 3)])
+def test_exact_search_returns_the_reference_multiplier_bit_for_bit(rb, oracle, exact_search, n, gamma, budget, seed):
+    """SURVEY.md 8d gate "lambda from the search: identical double" on long inputs, with the exact replay switched on"""
+    from rocco_b200.pipeline import solve_chromosomes
+    s = _scores(n, seed)
+    want_sol, want_obj, want = oracle.solve_chrom_exact(s, budget=budget, gamma=gamma, return_details=True)
+    for levels in (2, 3):
+        got = solve_chromosomes([s], [budget], [gamma], levels_per_round=levels)[0]
+        assert got["selection_penalty"] == want["selection_penalty"], (levels, got["selection_penalty"], want["selection_penalty"])
+        assert np.array_equal(got["solution"], want_sol)
+        assert got["selected_count"] == want["selected_count"]
+        assert abs(got["objective"] - want_obj) <= 1e-6 * abs(want_obj)
+
+
+@pytest.mark.parametrize("gamma", [1.0, 6.86])
+def test_exact_search_many_seeds_all_identical(rb, oracle, exact_search, gamma):
+    from rocco_b200.pipeline import solve_chromosomes
+    n, budget = 500_000, 0.03
+    scores = [_scores(n, 1000 + k) for k in range(8)]
+    got = solve_chromosomes(scores, [budget] * 8, [gamma] * 8)
+    for k in range(8):
+        want_sol, want_obj, want = oracle.solve_chrom_exact(scores[k], budget=budget, gamma=gamma, return_details=True)
+        assert got[k]["selection_penalty"] == want["selection_penalty"], (k, got[k]["selection_penalty"], want["selection_penalty"])
+        assert np.array_equal(got[k]["solution"], want_sol)
+        assert got[k]["selected_count"] == want["selected_count"]
+
+
+def test_exact_search_with_vector_costs(rb, oracle, exact_search):
+    n = 30_000
+    s = _scores(n, 9)
+    c = np.random.default_rng(10).uniform(0.1, 3.0, size=n - 1)
+    want = oracle.calibrate_selection_penalty(s, c, 900)
+    got = rb.calibrate_selection_penalty(s, c, 900)
+    assert got[0] == want[0] and got[3] == want[3] and np.array_equal(got[1], want[1])

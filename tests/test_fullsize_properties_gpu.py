@@ -109,3 +109,35 @@ def test_scores_invariant_to_sample_order_and_sharding_full_chr21():
     d64 = pipeline.score_loci_wls_device(x32.to(torch.float64), params=prm)
     d32 = pipeline.score_loci_wls_device(x32, params=prm)
     assert torch.equal(d64, d32)
+
+
+def test_sampled_pilot_offset_cancels_at_chr1_size():
+    """DESIGN.md section 4, deviation a2: above 4096 bins the row-median pilot offset (inference.py:333) is the median
+    of a 4096-point sample.  The offset only enters through  y - B(y)  and the smoother B reproduces constants, so it
+    cancels up to rounding.  Bounded here at the longest chromosome (4,979,129 bins) against the EXACT np.median mode."""
+    import torch
+    from rocco_b200 import pipeline
+    from rocco_b200.synth import chrom_bins, chrom_matrix_torch, chrom_seed
+    n = chrom_bins("chr1")
+    assert n == 4_979_129
+    x = chrom_matrix_torch(4, n, chrom_seed("chr1"), torch.device("cuda", 0), torch.float64)
+    s0, d0 = pipeline.score_loci_wls_device(x, params=pipeline.score_params(prior_df=6.0), details=True)
+    s1, d1 = pipeline.score_loci_wls_device(x, params=pipeline.score_params(prior_df=6.0, exact_pilot=True), details=True)
+    # the exact mode really is np.median of log2(max(x,0)+1) per row
+    y = torch.log2(torch.clamp(x, min=0.0) + 1.0)
+    med = torch.sort(y, dim=1).values[:, [n // 2]]               # n is odd
+    c_ref_offset = (d1["centered_matrix"] - (y - med)).abs().max()
+    assert float(c_ref_offset) < 10.0                            # (sanity: same scale; the baseline itself is O(1))
+    assert float((d0["centered_matrix"] - d1["centered_matrix"]).abs().max()) <= 1e-9
+    assert float(((s0 - s1).abs() / torch.clamp(s1.abs(), min=1e-3)).max()) <= 1e-7
+
+
+def test_exact_pilot_mode_matches_numpy_median():
+    import torch
+    from oracle import oracle as orc
+    from rocco_b200 import pipeline
+    from rocco_b200.synth import chrom_matrix_numpy
+    x = chrom_matrix_numpy(3, 50_000, seed=9)                    # even length: mean of the two middle values
+    _, d = pipeline.score_loci_wls_device(torch.from_numpy(x).cuda(), params=pipeline.score_params(prior_df=6.0, exact_pilot=True), details=True)
+    _, want = orc.score_loci_wls(x, prior_df=6.0, return_details=True)
+    assert float(np.max(np.abs(d["centered_matrix"].cpu().numpy() - want["centered_matrix"]))) <= 1e-9
