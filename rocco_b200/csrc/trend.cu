@@ -86,7 +86,10 @@ struct RowPlan {
     int slot_bucket[MAXSLOT];
     int slot_prefix[MAXSLOT];          // rank of the first pair of the bucket
     int slot_count[MAXSLOT];
-    int slot_boundary[MAXSLOT];        // bucket contains a bin boundary
+    int slot_boundary[MAXSLOT];        // number of bin boundaries inside the bucket
+    int slot_brank[MAXSLOT];           // rank inside the slot of its (last) boundary: pairs below it belong to the lower bin
+    int slot_done[MAXSLOT];            // resolved by the selection kernel (the sort kernels skip it)
+    int ybin_done[MAXB];               // bin's variance medians resolved by the selection kernel
     // x medians: per bin up to two ranks -> (slot, rank inside slot)
     int xm_slot[MAXB][2];
     int xm_rank[MAXB][2];
@@ -108,6 +111,7 @@ struct TrendBuffers {
     int *yhist;            // [m][MAXB][NBY]
     double *ycand;         // [m][MAXB][2][CAPY]
     int *ycand_cnt;        // [m][MAXB][2]
+    unsigned long long *yover_min, *yover_max;   // [m][MAXB][2]  bit-pattern range of the variances that did not fit their slot
     long long rows;
     BucketGeom geom;
     int capy;              // capacity of a ycand slot
@@ -320,40 +324,53 @@ __global__ void __launch_bounds__(256) k_xplan(TrendBuffers T, const double *__r
             T.plan[row].yb0 = (int)((unsigned long long)__double_as_longlong(med) >> T.geom.yshift) - NBY / 2;
         }
     }
-    if (threadIdx.x != 0) return;
+    // the <= 3B wanted ranks (bin boundary, upper median, lower median) are located in parallel, one thread each; slots
+    // are then handed out by one thread in the fixed order boundary, median 1, median 0 per bin (deterministic slot ids)
+    __shared__ int s_req_bucket[3 * MAXB];
+    __shared__ int s_req_rank[3 * MAXB];
     RowPlan &P = T.plan[row];
-    P.nslot = 0; P.fallback = 0;
-    auto bucket_of = [&](long long r) {                 // largest b with pre[b] <= r
-        int lo = 0, hi = NBX;
-        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if ((long long)s_pre[mid] <= r) lo = mid; else hi = mid; }
-        return lo;
-    };
-    auto slot_for = [&](int b, int boundary) {
-        int s = lut[b];
-        if (s == 0xFF) {
-            s = P.nslot++;
-            lut[b] = (unsigned char)s;
-            P.slot_bucket[s] = b; P.slot_prefix[s] = s_pre[b]; P.slot_count[s] = s_pre[b + 1] - s_pre[b];
-            P.slot_boundary[s] = 0;
-            if (P.slot_count[s] > CAPX) P.fallback |= FB_XSLOT;
-        }
-        if (boundary) P.slot_boundary[s] = 1;
-        return s;
-    };
-    for (int b = 0; b < B; ++b) {
+    for (int q = threadIdx.x; q < 3 * B; q += 256) {
+        const int b = q / 3, kind = q % 3;                  // 0: boundary at the bin's first rank, 1: upper median, 2: lower median
         const long long lo = ((long long)b * n) / B, hi = ((long long)(b + 1) * n) / B;
         const long long w = hi - lo;
-        for (int k = 0; k < 2; ++k) { P.xm_slot[b][k] = -1; P.xm_rank[b][k] = 0; P.ym_bucket[b][k] = -1; }
-        if (w <= 0) continue;
-        if (b > 0) slot_for(bucket_of(lo), 1);
-        const long long r1 = lo + w / 2;
-        const int b1 = bucket_of(r1);
-        P.xm_slot[b][1] = slot_for(b1, 0); P.xm_rank[b][1] = (int)(r1 - s_pre[b1]);
-        if ((w & 1) == 0) {
-            const long long r0 = r1 - 1;
-            const int b0 = bucket_of(r0);
-            P.xm_slot[b][0] = slot_for(b0, 0); P.xm_rank[b][0] = (int)(r0 - s_pre[b0]);
+        long long r = -1;
+        if (w > 0) {
+            if (kind == 0) r = b > 0 ? lo : -1;
+            else if (kind == 1) r = lo + w / 2;
+            else r = (w & 1) == 0 ? lo + w / 2 - 1 : -1;
         }
+        int bucket = -1;
+        if (r >= 0) {                                       // largest bucket with pre[bucket] <= r
+            int l = 0, h = NBX;
+            while (h - l > 1) { const int mid = (l + h) >> 1; if ((long long)s_pre[mid] <= r) l = mid; else h = mid; }
+            bucket = l;
+        }
+        s_req_bucket[q] = bucket;
+        s_req_rank[q] = bucket >= 0 ? (int)(r - s_pre[bucket]) : 0;
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    P.nslot = 0; P.fallback = 0;
+    auto slot_for = [&](int b) {
+        int sl = lut[b];
+        if (sl == 0xFF) {
+            sl = P.nslot++;
+            lut[b] = (unsigned char)sl;
+            P.slot_bucket[sl] = b; P.slot_prefix[sl] = s_pre[b]; P.slot_count[sl] = s_pre[b + 1] - s_pre[b];
+            P.slot_boundary[sl] = 0; P.slot_brank[sl] = 0; P.slot_done[sl] = 0;
+            if (P.slot_count[sl] > CAPX) P.fallback |= FB_XSLOT;
+        }
+        return sl;
+    };
+    for (int b = 0; b < B; ++b) {
+        for (int k = 0; k < 2; ++k) { P.xm_slot[b][k] = -1; P.xm_rank[b][k] = 0; P.ym_bucket[b][k] = -1; }
+        P.ybin_done[b] = 0;
+        if (s_req_bucket[3 * b] >= 0) {
+            const int sl = slot_for(s_req_bucket[3 * b]);
+            P.slot_boundary[sl] += 1; P.slot_brank[sl] = s_req_rank[3 * b];
+        }
+        if (s_req_bucket[3 * b + 1] >= 0) { P.xm_slot[b][1] = slot_for(s_req_bucket[3 * b + 1]); P.xm_rank[b][1] = s_req_rank[3 * b + 1]; }
+        if (s_req_bucket[3 * b + 2] >= 0) { P.xm_slot[b][0] = slot_for(s_req_bucket[3 * b + 2]); P.xm_rank[b][0] = s_req_rank[3 * b + 2]; }
     }
 }
 
@@ -412,6 +429,219 @@ __global__ void __launch_bounds__(XC_THREADS) k_xcollect(const double *__restric
     }
 }
 
+// ------------------------------------------------------------------ T4 by selection
+// Only one or two order statistics of a slot are ever wanted, so the slot is not sorted: an MSB-first radix SELECT over
+// the keys in shared memory (11 bits per pass, starting at the highest bit in which the keys differ) finds the key of a
+// given rank in two or three passes of `cnt / THREADS` elements per thread, where the bitonic sort needs ~log2(cnt)^2 / 2.
+constexpr int SEL_BITS = 11, SEL_BINS = 1 << SEL_BITS;
+
+struct SelScratch { int hist[SEL_BINS]; unsigned long long res[4]; int ires[4]; };
+
+// Key of 0-based `rank` among the keys[i], i < cnt, that pass the filter (fkeys == nullptr, or fkeys[i] == fval).  All
+// THREADS threads call it; the result is uniform.  *below = number of filtered keys smaller than the result, *equal =
+// number equal to it.  The filtered set must hold more than `rank` keys.
+template <int THREADS>
+__device__ unsigned long long block_select(const unsigned long long *keys, int cnt, int rank, const unsigned long long *fkeys,
+                                           unsigned long long fval, SelScratch &S, int *below, int *equal)
+{
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    // highest differing bit of the filtered keys
+    unsigned long long kmin = ~0ULL, kmax = 0ULL;
+    for (int i = tid; i < cnt; i += THREADS)
+        if (!fkeys || fkeys[i] == fval) { const unsigned long long k = keys[i]; kmin = min(kmin, k); kmax = max(kmax, k); }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, d));
+        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, d));
+    }
+    __syncthreads();                                       // S may still be read by a previous call
+    if (tid == 0) { S.res[0] = ~0ULL; S.res[1] = 0ULL; }
+    __syncthreads();
+    if (lane == 0) { atomicMin(&S.res[0], kmin); atomicMax(&S.res[1], kmax); }
+    __syncthreads();
+    kmin = S.res[0]; kmax = S.res[1];
+    int top = 64 - __clzll((long long)(kmin ^ kmax));      // number of low bits that can differ (0: all keys equal)
+    unsigned long long prefix = (top >= 64) ? 0ULL : (kmin >> top) << top, mask = (top >= 64) ? 0ULL : ~((1ULL << top) - 1ULL);
+    int r = rank, nbelow = 0, nequal = 0;
+    bool found = false;
+    unsigned long long result = kmin;
+    if (top == 0) {                                        // every filtered key is the same value
+        int c = 0;
+        for (int i = tid; i < cnt; i += THREADS) c += (!fkeys || fkeys[i] == fval);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+        __syncthreads();
+        if (tid == 0) S.ires[0] = 0;
+        __syncthreads();
+        if (lane == 0) atomicAdd(&S.ires[0], c);
+        __syncthreads();
+        nequal = S.ires[0];
+        found = true;
+    }
+    while (!found) {
+        const int width = min(SEL_BITS, top), shift = top - width;
+        for (int k = tid; k < SEL_BINS; k += THREADS) S.hist[k] = 0;
+        __syncthreads();
+        for (int i = tid; i < cnt; i += THREADS) {
+            const unsigned long long k = keys[i];
+            if ((!fkeys || fkeys[i] == fval) && (k & mask) == prefix) atomicAdd(&S.hist[(int)((k >> shift) & (unsigned long long)((1 << width) - 1))], 1);
+        }
+        __syncthreads();
+        if (wid == 0) {                                    // digit whose cumulative count passes r: 64 bins per lane
+            int sum = 0;
+            for (int k = 0; k < SEL_BINS / 32; ++k) sum += S.hist[lane * (SEL_BINS / 32) + k];
+            int inc = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+            const int exc = inc - sum;
+            if (exc <= r && r < inc) {
+                int acc = exc, k = 0;
+                for (; k < SEL_BINS / 32; ++k) { const int h = S.hist[lane * (SEL_BINS / 32) + k]; if (r < acc + h) break; acc += h; }
+                S.ires[0] = lane * (SEL_BINS / 32) + k; S.ires[1] = acc; S.ires[2] = S.hist[lane * (SEL_BINS / 32) + k];
+            }
+        }
+        __syncthreads();
+        const int digit = S.ires[0], before = S.ires[1], inside = S.ires[2];
+        nbelow += before; r -= before;
+        prefix |= (unsigned long long)digit << shift;
+        mask |= (unsigned long long)((1 << width) - 1) << shift;
+        top = shift;
+        if (top == 0) { result = prefix; nequal = inside; found = true; }
+        else if (inside == 1) {                            // a single candidate left: fetch it
+            for (int i = tid; i < cnt; i += THREADS) {
+                const unsigned long long k = keys[i];
+                if ((!fkeys || fkeys[i] == fval) && (k & mask) == prefix) S.res[2] = k;
+            }
+            __syncthreads();
+            result = S.res[2]; nequal = 1; found = true;
+        }
+        __syncthreads();
+    }
+    if (below) *below = nbelow;
+    if (equal) *equal = nequal;
+    return result;
+}
+
+// (row, slot) CTAs for the slots the selection handles: at most two median ranks and no boundary, or exactly one
+// boundary and no median rank.  Everything else (short rows where a bucket spans several bins) is left to the sort
+// kernels below.  A boundary slot is PARTITIONED in place around its boundary pair -- lexicographic (|signal|, variance)
+// order, like the reference's comparator (wls_backend.c:207-230) -- which is all T6 needs: the first slot_brank pairs
+// belong to the lower bin, the rest to the upper one.
+template <int THREADS, int CAP_LO, int CAP_HI>
+__global__ void __launch_bounds__(THREADS) k_xselect(TrendBuffers T, long long n, int B)
+{
+    extern __shared__ unsigned long long s_sel[];         // x keys [cap], then y keys [cap] for boundary slots
+    __shared__ SelScratch S;
+    __shared__ int s_want[4], s_nwant, s_cursor[2];
+    const long long row = blockIdx.y;
+    const int s = blockIdx.x;
+    RowPlan &P = T.plan[row];
+    if (P.fallback || s >= P.nslot) return;
+    const int total = P.slot_count[s];
+    if (total <= CAP_LO || total > CAP_HI) return;                               // not this tier
+    const int cnt = min(T.cand_cnt[row * MAXSLOT + s], CAPX);
+    if (cnt != total) return;                                                    // the sort kernel reports the mismatch
+    const int nb = P.slot_boundary[s];
+    if (threadIdx.x == 0) s_nwant = 0;
+    __syncthreads();
+    for (int q = threadIdx.x; q < 2 * B; q += THREADS)
+        if (P.xm_slot[q >> 1][q & 1] == s) { const int w = atomicAdd(&s_nwant, 1); if (w < 4) s_want[w] = q; }
+    __syncthreads();
+    const int nwant = s_nwant;
+    const bool median_only = (nb == 0 && nwant >= 1 && nwant <= 2);
+    const bool boundary_only = (nb == 1 && nwant == 0);
+    if (!median_only && !boundary_only) return;
+    double2 *cand = T.cand + ((size_t)row * MAXSLOT + s) * CAPX;
+    unsigned long long *kx = s_sel, *ky = s_sel + CAP_HI;
+    for (int k = threadIdx.x; k < cnt; k += THREADS) {
+        const double2 pr = cand[k];
+        kx[k] = (unsigned long long)__double_as_longlong(pr.x);                  // |signal| >= 0, variance > 0: the bit patterns order like the values
+        if (boundary_only) ky[k] = (unsigned long long)__double_as_longlong(pr.y);
+    }
+    __syncthreads();
+    if (median_only) {
+        for (int w = 0; w < nwant; ++w) {
+            const int q = s_want[w];
+            const unsigned long long key = block_select<THREADS>(kx, cnt, P.xm_rank[q >> 1][q & 1], nullptr, 0ULL, S, nullptr, nullptr);
+            if (threadIdx.x == 0) P.xm_val[q >> 1][q & 1] = __longlong_as_double((long long)key);
+        }
+        if (threadIdx.x == 0) P.slot_done[s] = 1;
+        return;
+    }
+    // boundary slot: the pair of rank rb is the first pair of the upper bin
+    const int rb = P.slot_brank[s];
+    int xbelow = 0, xequal = 0, ybelow = 0;
+    const unsigned long long px = block_select<THREADS>(kx, cnt, rb, nullptr, 0ULL, S, &xbelow, &xequal);
+    unsigned long long py = 0ULL;
+    if (xequal > 1) py = block_select<THREADS>(ky, cnt, rb - xbelow, kx, px, S, &ybelow, nullptr);
+    // lower bin: pairs lexicographically below the pivot, plus as many pivot-equal pairs as are needed to reach rb
+    const int n_less = xbelow + ybelow;
+    if (threadIdx.x == 0) { s_cursor[0] = 0; s_cursor[1] = 0; s_want[0] = rb - n_less; }
+    __syncthreads();
+    const long long pre = P.slot_prefix[s];
+    const int bin_hi = bin_of_rank(pre + rb, n, B), bin_lo = bin_hi - 1;
+    int *g = T.yhist + (size_t)row * MAXB * NBY;
+    for (int k = threadIdx.x; k < cnt; k += THREADS) {
+        const unsigned long long x = kx[k], y = ky[k];
+        bool lower;
+        if (x != px) lower = x < px;
+        else if (xequal == 1) lower = false;                                     // the pivot itself
+        else if (y != py) lower = y < py;
+        else lower = atomicSub(&s_want[0], 1) > 0;                                // identical pairs are interchangeable
+        const int pos = lower ? atomicAdd(&s_cursor[0], 1) : rb + atomicAdd(&s_cursor[1], 1);
+        const double yv = __longlong_as_double((long long)y);
+        cand[pos] = make_double2(__longlong_as_double((long long)x), yv);
+        atomicAdd(&g[(lower ? bin_lo : bin_hi) * NBY + ybucket(yv, P.yb0, T.geom)], 1);
+    }
+    if (threadIdx.x == 0) P.slot_done[s] = 1;
+}
+
+// (bin, row) CTAs: the one or two median ranks of the bin's variances, selected from the collected bucket(s).  A bucket
+// that outgrew its slot is still exact when every value in it is the same (variances sitting on the 1e-8 floor): the
+// overflow's min / max were tracked by T6.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_yselect(TrendBuffers T, long long n, int B)
+{
+    extern __shared__ unsigned long long s_sel[];
+    __shared__ SelScratch S;
+    const long long row = blockIdx.y;
+    const int b = blockIdx.x;
+    RowPlan &P = T.plan[row];
+    if (P.fallback) return;
+    const long long lo = ((long long)b * n) / B, hi = ((long long)(b + 1) * n) / B;
+    if (hi <= lo) return;
+    double ym[2] = {0.0, 0.0};
+    bool ok = true;
+    for (int k = 1; k >= 0 && ok; --k) {
+        if (P.ym_bucket[b][k] < 0) continue;
+        if (k == 0 && P.ym_bucket[b][0] == P.ym_bucket[b][1]) continue;                 // resolved together with k = 1
+        const size_t slot = ((size_t)row * MAXB + b) * 2 + k;
+        const int total = T.ycand_cnt[slot];
+        if (total != P.ym_count[b][k]) { ok = false; break; }                           // the sort kernel reports it
+        const int cnt = min(total, T.capy);
+        const double *src = T.ycand + slot * T.capy;
+        for (int q = threadIdx.x; q < cnt; q += THREADS) s_sel[q] = (unsigned long long)__double_as_longlong(src[q]);
+        __syncthreads();
+        const bool same_bucket = (k == 1 && P.ym_bucket[b][0] == P.ym_bucket[b][1]);
+        if (total > T.capy) {
+            // over capacity: exact only if stored values and overflow are all one value
+            int below = 0, equal = 0;
+            const unsigned long long v = block_select<THREADS>(s_sel, cnt, 0, nullptr, 0ULL, S, &below, &equal);
+            if (equal == cnt && T.yover_min[slot] == v && T.yover_max[slot] == v) {
+                ym[k] = __longlong_as_double((long long)v);
+                if (same_bucket) ym[0] = ym[k];
+            } else ok = false;
+        } else {
+            ym[k] = __longlong_as_double((long long)block_select<THREADS>(s_sel, cnt, P.ym_rank[b][k], nullptr, 0ULL, S, nullptr, nullptr));
+            if (same_bucket) ym[0] = __longlong_as_double((long long)block_select<THREADS>(s_sel, cnt, P.ym_rank[b][0], nullptr, 0ULL, S, nullptr, nullptr));
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (ok) { P.ym_val[b][0] = ym[0]; P.ym_val[b][1] = ym[1]; P.ybin_done[b] = 1; }
+    }
+}
+
 // ------------------------------------------------------------------ T4
 __device__ __forceinline__ bool pair_gt(const double2 &a, const double2 &b) { return a.x > b.x || (a.x == b.x && a.y > b.y); }
 
@@ -428,6 +658,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 256) ? 4 : (CAP_HI <= 409
     if (P.fallback || s >= P.nslot) return;
     const int cnt = min(T.cand_cnt[row * MAXSLOT + s], CAPX);
     if (P.slot_count[s] <= CAP_LO || P.slot_count[s] > CAP_HI) return;          // not this tier
+    if (P.slot_done[s]) return;                                                 // resolved by k_xselect
     if (cnt != P.slot_count[s]) { if (threadIdx.x == 0) atomicOr(&P.fallback, FB_XCOUNT); return; }
     int len = 1;
     while (len < cnt) len <<= 1;
@@ -521,7 +752,6 @@ __global__ void __launch_bounds__(256) k_yplan(TrendBuffers T, long long n, int 
                 const int b0 = bucket_of(r0);
                 P.ym_bucket[b][0] = b0; P.ym_rank[b][0] = (int)(r0 - s_pre[b0]); P.ym_count[b][0] = s_pre[b0 + 1] - s_pre[b0];
             }
-            if (P.ym_count[b][1] > T.capy || P.ym_count[b][0] > T.capy) atomicOr(&P.fallback, FB_YSLOT);
         }
     }
 }
@@ -533,8 +763,14 @@ __device__ __forceinline__ void ycollect_one(TrendBuffers &T, long long row, con
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         if (s_yb[bin][k] == yb && (k == 1 || s_yb[bin][1] != yb)) {
-            const int pos = atomicAdd(&T.ycand_cnt[(row * MAXB + bin) * 2 + k], 1);
-            if (pos < T.capy) T.ycand[(((size_t)row * MAXB + bin) * 2 + k) * T.capy + pos] = y;
+            const size_t slot = ((size_t)row * MAXB + bin) * 2 + k;
+            const int pos = atomicAdd(&T.ycand_cnt[slot], 1);
+            if (pos < T.capy) T.ycand[slot * T.capy + pos] = y;
+            else {                                                   // massive ties (variances on their floor): remember the range
+                const unsigned long long key = (unsigned long long)__double_as_longlong(y);
+                atomicMin(&T.yover_min[slot], key);
+                atomicMax(&T.yover_max[slot], key);
+            }
         }
     }
 }
@@ -597,7 +833,7 @@ __global__ void __launch_bounds__(256) k_yresolve(TrendBuffers T, long long n, i
     const long long row = blockIdx.y;
     const int b = blockIdx.x;
     RowPlan &P = T.plan[row];
-    if (P.fallback) return;
+    if (P.fallback || P.ybin_done[b]) return;
     const long long lo = ((long long)b * n) / B, hi = ((long long)(b + 1) * n) / B;
     if (hi <= lo) return;
     if (threadIdx.x == 0) s_fail = 0;
@@ -608,6 +844,7 @@ __global__ void __launch_bounds__(256) k_yresolve(TrendBuffers T, long long n, i
         if (k == 0 && P.ym_bucket[b][0] == P.ym_bucket[b][1]) continue;       // same bucket: resolved with k = 1
         const int cnt = T.ycand_cnt[(row * MAXB + b) * 2 + k];
         if (cnt != P.ym_count[b][k]) { if (threadIdx.x == 0) s_fail = FB_YCOUNT; }
+        else if (cnt > T.capy) { if (threadIdx.x == 0) s_fail = FB_YSLOT; }
         __syncthreads();
         if (s_fail) break;
         int len = 1;
@@ -706,7 +943,7 @@ int trend_knots_select(const double *d_C, double *d_V, long long m, long long n,
     TrendBuffers T{};
     T.rows = m;
     T.geom = bucket_geometry(n);
-    T.capy = n <= 6000000LL ? CAPY : CAPY_MAX;
+    T.capy = CAPY_MAX;          // 16384 variances per (bin, median) slot: 8 MB per row of scratch
     RB_TRY(ar.alloc(&T.xhist, (size_t)m * NBX));
     RB_TRY(ar.alloc(&T.lut, (size_t)m * NBX));
     RB_TRY(ar.alloc(&T.binlo, (size_t)m * NBX));
@@ -720,6 +957,10 @@ int trend_knots_select(const double *d_C, double *d_V, long long m, long long n,
     RB_CUDA(cudaMemsetAsync(T.cand_cnt, 0, sizeof(int) * (size_t)m * MAXSLOT, st));
     RB_CUDA(cudaMemsetAsync(T.yhist, 0, sizeof(int) * (size_t)m * MAXB * NBY, st));
     RB_CUDA(cudaMemsetAsync(T.ycand_cnt, 0, sizeof(int) * (size_t)m * MAXB * 2, st));
+    RB_TRY(ar.alloc(&T.yover_min, (size_t)m * MAXB * 2));
+    RB_TRY(ar.alloc(&T.yover_max, (size_t)m * MAXB * 2));
+    RB_CUDA(cudaMemsetAsync(T.yover_min, 0xFF, sizeof(unsigned long long) * (size_t)m * MAXB * 2, st));
+    RB_CUDA(cudaMemsetAsync(T.yover_max, 0, sizeof(unsigned long long) * (size_t)m * MAXB * 2, st));
 
     static bool attr_dev[64] = {false};
     int attr_d = 0;
@@ -736,6 +977,8 @@ int trend_knots_select(const double *d_C, double *d_V, long long m, long long n,
         RB_CUDA(cudaFuncSetAttribute(k_xresolve<512, 2048, 4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double2) * 4096)));
         RB_CUDA(cudaFuncSetAttribute(k_xplan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_plan));
         RB_CUDA(cudaFuncSetAttribute(k_yresolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * CAPY_MAX)));
+        RB_CUDA(cudaFuncSetAttribute(k_xselect<512, 2048, CAPX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(unsigned long long) * 2 * CAPX)));
+        RB_CUDA(cudaFuncSetAttribute(k_yselect<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(unsigned long long) * CAPY_MAX)));
         attr = true;
     }
     const unsigned chunks = (unsigned)((n + CHUNK - 1) / CHUNK);
@@ -774,6 +1017,12 @@ int trend_knots_select(const double *d_C, double *d_V, long long m, long long n,
     {
         RB_PROF("trend_plan_resolve", st, 0.0);
         const unsigned nslot_max = (unsigned)std::min(MAXSLOT, 3 * B);
+        // selection first (one or two ranks per slot, or one boundary to partition around); the sort kernels then only see
+        // what it left: short rows whose buckets span several bins
+        k_xselect<256, -1, 2048><<<dim3(nslot_max, (unsigned)m), 256, sizeof(unsigned long long) * 2 * 2048, st>>>(T, n, B);
+        RB_LAUNCH_CHECK();
+        k_xselect<512, 2048, CAPX><<<dim3(nslot_max, (unsigned)m), 512, sizeof(unsigned long long) * 2 * CAPX, st>>>(T, n, B);
+        RB_LAUNCH_CHECK();
         k_xresolve<256, -1, 2048><<<dim3(nslot_max, (unsigned)m), 256, sizeof(double2) * 2048, st>>>(T, n, B);
         RB_LAUNCH_CHECK();
         k_xresolve<512, 2048, 4096><<<dim3(nslot_max, (unsigned)m), 512, sizeof(double2) * 4096, st>>>(T, n, B);
@@ -790,6 +1039,8 @@ int trend_knots_select(const double *d_C, double *d_V, long long m, long long n,
     }
     {
         RB_PROF("trend_plan_resolve", st, 0.0);
+        k_yselect<256><<<dim3((unsigned)B, (unsigned)m), 256, sizeof(unsigned long long) * T.capy, st>>>(T, n, B);
+        RB_LAUNCH_CHECK();
         k_yresolve<<<dim3((unsigned)B, (unsigned)m), 256, sizeof(double) * T.capy, st>>>(T, n, B);
         RB_LAUNCH_CHECK();
         k_row_knots<<<(unsigned)((m + 63) / 64), 64, 0, st>>>(T, n, B, d_knots, d_row_fallback);

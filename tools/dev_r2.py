@@ -115,5 +115,22 @@ def cmd_scopes():
     json.dump(sp, open(os.path.join(OUT, "dev_scopes.json"), "w"), indent=1)
 
 
+
+
+def cmd_fallback():
+    """which rows of a chromosome take the sort fallback, and why"""
+    import ctypes
+    name = sys.argv[2] if len(sys.argv) > 2 else "chr1"
+    m = int(sys.argv[3]) if len(sys.argv) > 3 else 100
+    x = chrom_matrix_torch(m, chrom_bins(name), chrom_seed(name), DEV, torch.float64)
+    lib = _lib.load()
+    r0 = (ctypes.c_longlong * 8)(); r1 = (ctypes.c_longlong * 8)()
+    lib.rocco_b200_trend_fallback_reasons(r0)
+    f0 = lib.rocco_b200_trend_fallback_rows()
+    pipeline.score_loci_wls_device(x, params=pipeline.score_params(prior_df=6.0))
+    lib.rocco_b200_trend_fallback_reasons(r1)
+    print(name, "fallback rows", lib.rocco_b200_trend_fallback_rows() - f0, "reasons [xslot,xcount,ytotal,yslot,ycount]", [r1[k] - r0[k] for k in range(5)])
+
+
 if __name__ == "__main__":
-    {"whit": cmd_whit, "scopes": cmd_scopes}[sys.argv[1]]()
+    {"whit": cmd_whit, "scopes": cmd_scopes, "fallback": cmd_fallback}[sys.argv[1]]()
