@@ -541,6 +541,35 @@ def main():
         dist.all_gather_object(parts_, by_chrom)
         by_chrom = {k: v for p_ in parts_ for k, v in p_.items()}
 
+    # ---- the column statistics kernel (not on the default CLI path, measured on its own)
+    colstat = None
+    if rank == 0 and mine:
+        k_small = min(range(len(d_mats)), key=lambda k: my_bins[k])
+        xm = d_mats[k_small]
+        out_cs = torch.empty(xm.shape[1], dtype=torch.float64, device=dev)
+        lib = _lib.load()
+
+        def colstat_once(stat):
+            st_ = lib.rocco_b200_column_stat_dev(ctypes.c_void_p(xm.data_ptr()), 0 if xm.dtype == torch.float64 else 1, xm.shape[0], xm.shape[1],
+                                                 stat, 0.0, 0.0, 1.0, ctypes.c_void_p(out_cs.data_ptr()),
+                                                 ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+            _lib.check(st_, "column_stat")
+
+        colstat = {"workload": f"{my_names[k_small]} x {xm.shape[0]} samples ({xm.shape[1]} bins), {args.dtype}", "kernels": {}}
+        for nm, code in (("median", 0), ("mad", 4)):
+            for _ in range(3):
+                colstat_once(code)
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(5):
+                colstat_once(code)
+            c1.record()
+            torch.cuda.synchronize()
+            ms_cs = c0.elapsed_time(c1) / 5.0
+            nbytes = xm.numel() * xm.element_size() + 8 * xm.shape[1]
+            colstat["kernels"][nm] = {"ms": ms_cs, "algorithmic_bytes": nbytes, "GBps": nbytes / 1e9 / (ms_cs / 1e3),
+                                      "bins_per_sec": xm.shape[1] / (ms_cs / 1e3)}
+
     # ---- end-to-end through the reference-facing host API (NumPy in, BED files out)
     e2e = None
     e2e_steps = min(args.steps, 2) if args.e2e_steps < 0 else args.e2e_steps
@@ -659,6 +688,9 @@ def main():
                     "all_scopes": {k: {"ms": round(v[0], 3), "launch_sets": v[1],
                                        "GBps_algorithmic": round((v[2] / 1e9) / (v[0] / 1e3), 1) if v[0] > 0 else 0.0}
                                    for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}}
+        if colstat:
+            for v in colstat["kernels"].values():
+                v["frac_of_peak"] = v["GBps"] / peak
         cpu, parity = None, None
         if world == 1 and not args.no_cpu_baseline:
             cpu, parity = cpu_baseline_single_core(args)
@@ -673,7 +705,7 @@ def main():
                        "selected_by_chrom": {c: by_chrom[c][0] for c in names if c in by_chrom},
                        "lambda_by_chrom": {c: by_chrom[c][1] for c in names if c in by_chrom}, "trend_sort_fallback_rows": fb_rows,
                        "trend_fallback_reason_counts": list(reasons)[:5], "collective": "one NCCL all-reduce of [selected, bins] per step"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(lt.item()), "roofline": roof, "cpu_baseline": cpu, "parity": parity,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(lt.item()), "roofline": roof, "cpu_baseline": cpu, "parity": parity, "column_stat": colstat,
         }
         emit(line)
     if world > 1:

@@ -1,4 +1,5 @@
 // Library plumbing: error text, device selection, launch counter, numpy-compatible summation.
+#include <nvtx3/nvToolsExt.h>
 #include "common.cuh"
 
 #include <stdarg.h>
@@ -201,6 +202,7 @@ static std::vector<cudaEvent_t> g_prof_pool;      // recycled events: creating t
 
 ProfScope::ProfScope(const char *name, cudaStream_t st, double bytes) : idx_(-1), st_(st)
 {
+    nvtxRangePushA(name);                         // every scope is also an NVTX range (a no-op unless a tool is attached)
     if (!g_prof_on.load(std::memory_order_relaxed)) return;
     ProfEntry e;
     e.name = name; e.bytes = bytes;
@@ -216,6 +218,7 @@ ProfScope::ProfScope(const char *name, cudaStream_t st, double bytes) : idx_(-1)
 
 ProfScope::~ProfScope()
 {
+    nvtxRangePop();
     if (idx_ < 0) return;
     std::lock_guard<std::mutex> lk(g_prof_mu);
     if (idx_ < (int)g_prof.size()) cudaEventRecord(g_prof[idx_].b, st_);
