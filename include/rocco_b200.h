@@ -132,6 +132,9 @@ int rocco_b200_chain_set_seq_max(int max_bins);
  * returned multiplier and mask are then the reference's bits for ANY length, at ~13 ns per bin per replayed pass.
  * Returns the previous setting. */
 int rocco_b200_chain_set_exact_search(int on);
+/* Search rounds skip tiles whose decisions provably cannot change inside the remaining bracket (default on; 0 evaluates every
+ * tile in every round -- same counts, used for A/B checks).  Returns the previous setting. */
+int rocco_b200_chain_set_tile_freezing(int on);
 
 /* Multiplier sweep: counts and objectives for `lambda_count` multipliers in one launch set
  * (BASELINE.json config 5).  Outputs are host arrays of lambda_count entries. */

@@ -130,6 +130,7 @@ def _declare(lib):
             c_int, [c_void_p, c_void_p, POINTER(ChainTask), c_int, c_void_p, POINTER(ChainResult), c_int, c_void_p]),
         "rocco_b200_chain_set_seq_max": (c_int, [c_int]),
         "rocco_b200_chain_set_exact_search": (c_int, [c_int]),
+        "rocco_b200_chain_set_tile_freezing": (c_int, [c_int]),
         "rocco_b200_chain_sweep_dev": (
             c_int, [c_void_p, c_size_t, c_double, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
         "rocco_mask_to_intervals_u8": (

@@ -156,6 +156,12 @@ struct Params {
     int epoch;
     int lex_pass;               // 1: only chromosomes with need_lex
     int exact_mode;             // 1: multipliers with a decision inside the reference's rounding noise are replayed sequentially
+    // tile freezing (search rounds; nullptr: off).  state bit 0: every decision of the tile is stable over the whole current
+    // bracket and its last bin is saturated; read buffer = previous round, write buffer = this round
+    const int *fz_read;
+    int *fz_write;
+    TileOut *fz_out;            // [tile] the tile's fixed outputs
+    double *fz_incl;            // [tile] +-HUGE: the saturated value it hands to its successor
 };
 
 // ------------------------------------------------------------------ the tile kernel
@@ -194,6 +200,36 @@ __global__ void __launch_bounds__(THREADS, 4) k_chain_tiles(Params P)
     const bool first_tile = (tile == cd.tile0);
     const bool last_tile = (s0 + len == cd.n);
     const double *gsc = P.scores + cd.offset + s0;
+
+    // ---- frozen tiles.  d_i(lambda) moves by at most len_i |dlambda|, len_i = 1 + the number of unsaturated bins
+    // right before i, so a bin whose distance to both thresholds exceeds len_i x (bracket width) keeps its decision class
+    // for every multiplier the bisection can still visit (the bracket only shrinks).  A tile all of whose bins are that
+    // stable, whose last bin is saturated and whose predecessor ends saturated and stable, contributes the same
+    // (count, pending, head) to every later round and hands the same clamp value on: it is answered from the values
+    // stored when that was established (previous round's buffer) without touching its scores again.
+    const bool fz_on = !EMIT && P.fz_read != nullptr && sd.phase == PH_BISECT;
+    if (fz_on) {
+        const bool frozen = (P.fz_read[tile] & 1) && (first_tile || (P.fz_read[tile - 1] & 1));
+        if (frozen) {
+            if (tid == 0) {
+                V *gincl = reinterpret_cast<V *>(P.incl);
+                V *tv0 = nullptr;
+                const TileOut o = P.fz_out[tile];
+                for (int slot = slot0; slot < slot1; ++slot) {
+                    const size_t sidx = (size_t)slot * P.ntiles + tile;
+                    P.tout[sidx] = o;
+                    gincl[sidx] = v_make(tv0, P.fz_incl[tile], 0);
+                    st_release_i32(P.flags + sidx, (P.epoch << 2) | 2);
+                }
+                if (group == 0 && !P.lex_pass) P.fz_write[tile] = P.fz_read[tile];
+            }
+            return;
+        }
+    }
+    const bool fz_eval = fz_on && !P.lex_pass && group == 0;       // this CTA establishes the tile's state for the next round
+    const double fz_width = sd.upper - sd.lower;
+    __shared__ int s_fzlen[WARPS];
+    __shared__ int s_fzlast;
 
     // stage scores (coalesced) into the padded blocked layout
     for (int e = tid; e < TILE; e += THREADS) {
@@ -295,6 +331,9 @@ __global__ void __launch_bounds__(THREADS, 4) k_chain_tiles(Params P)
         V x = map_apply<V>(excl, s_din);
         unsigned dec = 0, val = 0;
         int ties = 0, near = 0;
+        const bool fz_track = fz_eval && slot == slot0;
+        int fz_run = 0, fz_sat = 0, fz_lastok = 0;       // bins since the last saturated one in this chunk; any saturated bin; last bin of the tile stable
+        double fz_a = INFINITY, fz_b = INFINITY;         // min slack of the bins before / after the chunk's first saturated bin
 #pragma unroll
         for (int j = 0; j < ITEMS; ++j) {
             if (j < cnt) {
@@ -305,6 +344,17 @@ __global__ void __launch_bounds__(THREADS, 4) k_chain_tiles(Params P)
                 } else {
                     const double cc = VEC_COST ? s_cs[(base + j) + (base + j) / ITEMS] : cd.gamma;
                     x = v_add(v_clamp(x, v_make(tv, -cc, 0), v_make(tv, cc, 0)), a);
+                }
+                if (fz_track) {
+                    const bool term = (gi == cd.n - 1);
+                    const double cr_ = term ? 0.0 : (VEC_COST ? s_cs[(base + j + 1) + (base + j + 1) / ITEMS] : cd.gamma);
+                    const double margin = term ? fabs(x.v) : fmin(fabs(x.v - cr_), fabs(x.v + cr_));
+                    fz_run += 1;
+                    const double slack = margin - (double)fz_run * fz_width;
+                    if (fz_sat) fz_b = fmin(fz_b, slack); else fz_a = fmin(fz_a, slack);
+                    const bool sat = term || x.v > cr_ || x.v < -cr_;
+                    if (base + j == len - 1) fz_lastok = sat ? 1 : 0;
+                    if (sat) { fz_sat = 1; fz_run = 0; }
                 }
                 if (gi == cd.n - 1) {                 // terminal choice (_chain_dp.c:167-179)
                     dec |= 1u << j;
@@ -425,6 +475,43 @@ __global__ void __launch_bounds__(THREADS, 4) k_chain_tiles(Params P)
             if (EMIT && nr) atomicAdd(reinterpret_cast<unsigned long long *>(P.near_ties + c), (unsigned long long)nr);
         }
         __syncthreads();
+        if (fz_track) {
+            // bins since the last saturated bin BEFORE this thread's chunk: scan of (saturated seen, run length) over the threads
+            const int SATBIT = 1 << 30;
+            int st = fz_sat ? (SATBIT | fz_run) : cnt;
+            int inc = st;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d && !(inc & SATBIT)) inc = (o & SATBIT) | ((o & ~SATBIT) + inc);
+            }
+            int before = __shfl_up_sync(0xffffffffu, inc, 1);
+            if (lane == 0) before = 0;
+            if (lane == 31) s_fzlen[wid] = inc;
+            if (tid == 0) s_fzlast = 0;
+            __syncthreads();
+            // the tile's first bin follows a saturated bin (checked below) or is bin 0 of the chromosome: run length 0 there
+            int wpre = 0;
+            for (int w = 0; w < wid; ++w) { const int t = s_fzlen[w]; wpre = (t & SATBIT) ? t : ((wpre & SATBIT) | ((wpre & ~SATBIT) + t)); }
+            if (!(before & SATBIT)) before = (wpre & SATBIT) | ((wpre & ~SATBIT) + before);
+            const int in_len = before & ~SATBIT;
+            const double eps = 1.0e-9 * (1.0 + fabs(cd.gamma));
+            int ok = (cnt == 0) || ((fz_a - (double)in_len * fz_width > eps) && (fz_b > eps));
+            if (fz_lastok && cnt > 0 && base + cnt == len) s_fzlast = 1;
+            ok = __syncthreads_and(ok);
+            if (tid == 0) {
+                const V din_ = s_din;
+                const bool in_sat = first_tile || fabs(din_.v) > (VEC_COST ? s_cs[0] : cd.gamma) + eps;   // the clamp of the first step saturates
+                const bool own = ok && s_fzlast && in_sat && P.tout[sidx].ties == 0;
+                P.fz_write[tile] = own ? 1 : 0;
+                if (own) {
+                    P.fz_out[tile] = P.tout[sidx];
+                    P.fz_incl[tile] = 0.0;               // set by the owner of the last bin below
+                }
+            }
+            __syncthreads();
+            if (cnt > 0 && base + cnt == len) P.fz_incl[tile] = x.v > 0.0 ? 1.0e300 : -1.0e300;
+        }
     }
     (void)last_tile;
 }
@@ -900,6 +987,8 @@ __global__ void k_chain_results(Params P, const FinalPart *parts, rocco_b200_cha
 static std::atomic<int> g_seq_max{TILE};
 // 1: re-evaluate multipliers with near-tie decisions by the sequential replay (any length); see k_chain_replay
 static std::atomic<int> g_exact_search{0};
+// 1 (default): search rounds answer tiles whose decisions cannot change any more from stored outputs; 0: evaluate every tile
+static std::atomic<int> g_freeze{1};
 
 struct Workspace {
     ChromDev *d_chroms = nullptr;
@@ -1058,6 +1147,22 @@ static int solve_batch(const double *d_scores, const double *d_costs, const rocc
     P.bt = d_bt; P.seq_value = d_seqv;
     P.exact_mode = exact ? 1 : 0;
     int epoch = 0;
+    // tile freezing: two state buffers (read = previous round, write = this round), the frozen outputs and hand-on values
+    int *d_fz[2] = {nullptr, nullptr};
+    const bool freeze = any_search && !exact && g_freeze.load() != 0;
+    if (freeze) {
+        RB_TRY(ar.alloc(&d_fz[0], (size_t)ntiles));
+        RB_TRY(ar.alloc(&d_fz[1], (size_t)ntiles));
+        RB_TRY(ar.alloc(&P.fz_out, (size_t)ntiles));
+        RB_TRY(ar.alloc(&P.fz_incl, (size_t)ntiles));
+        RB_CUDA(cudaMemsetAsync(d_fz[0], 0, sizeof(int) * (size_t)ntiles, st));
+        RB_CUDA(cudaMemsetAsync(d_fz[1], 0, sizeof(int) * (size_t)ntiles, st));
+    }
+    int fz_round = 0;
+    auto search_round = [&](int nslots) -> int {
+        if (freeze) { P.fz_read = d_fz[fz_round & 1]; P.fz_write = d_fz[(fz_round & 1) ^ 1]; ++fz_round; }
+        return launch_round<false>(P, vec, nslots, epoch, any_seq, st);
+    };
 
     std::vector<SearchDev> hsearch(ntask);
     if (any_search) {
@@ -1072,9 +1177,9 @@ static int solve_batch(const double *d_scores, const double *d_costs, const rocc
             if (hsearch[c].phase == PH_BRACKET) { need_bracket = true; rounds = std::max(rounds, (chroms[c].max_iter + levels - 1) / levels); }
             else if (hsearch[c].phase == PH_BISECT) rounds = std::max(rounds, (hsearch[c].iters_left + levels - 1) / levels);
         }
-        if (need_bracket) RB_TRY((launch_round<false>(P, vec, 2, epoch, any_seq, st)));     // bracket ends
+        if (need_bracket) RB_TRY(search_round(2));     // bracket ends
         // PH_BRACKET -> PH_BISECT generates the first tree in the same finish kernel
-        for (int r = 0; r < rounds; ++r) RB_TRY((launch_round<false>(P, vec, max_slots, epoch, any_seq, st)));
+        for (int r = 0; r < rounds; ++r) RB_TRY(search_round(max_slots));
         // rare: bracket expansion (dp.py:119-125, 132-138) is driven from the host with single solves
         RB_CUDA(cudaMemcpyAsync(hsearch.data(), w.d_search, sizeof(SearchDev) * ntask, cudaMemcpyDeviceToHost, st));
         RB_CUDA(cudaStreamSynchronize(st));
@@ -1130,6 +1235,7 @@ static int solve_batch(const double *d_scores, const double *d_costs, const rocc
     }
 
     // final solve at the chosen multiplier, mask emitted
+    P.fz_read = nullptr; P.fz_write = nullptr;
     RB_TRY((launch_round<true>(P, vec, 1, epoch, any_seq, st)));
     {
         RB_PROF("k_chain_finalize", st, (double)ntiles * TILE * 9.0);
@@ -1210,6 +1316,11 @@ extern "C" __attribute__((visibility("default"))) int rocco_b200_chain_set_seq_m
     const int prev = chain::g_seq_max.load();
     chain::g_seq_max.store(std::max(0, std::min(max_bins, chain::TILE)));
     return prev;
+}
+
+extern "C" __attribute__((visibility("default"))) int rocco_b200_chain_set_tile_freezing(int on)
+{
+    return chain::g_freeze.exchange(on ? 1 : 0);
 }
 
 extern "C" __attribute__((visibility("default"))) int rocco_b200_chain_set_exact_search(int on)

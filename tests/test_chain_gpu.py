@@ -343,3 +343,25 @@ def test_exact_search_with_vector_costs(rb, oracle, exact_search):
     want = oracle.calibrate_selection_penalty(s, c, 900)
     got = rb.calibrate_selection_penalty(s, c, 900)
     assert got[0] == want[0] and got[3] == want[3] and np.array_equal(got[1], want[1])
+
+
+def test_tile_freezing_changes_nothing_but_the_time(rb, oracle):
+    """search rounds answer tiles whose decisions cannot change inside the remaining bracket from stored outputs: counts,
+    multipliers and masks must be those of the run that evaluates every tile in every round (and the oracle's)"""
+    from rocco_b200 import _lib
+    from rocco_b200.pipeline import solve_chromosomes
+    rng = np.random.default_rng(12)
+    sc = [_scores(300_000, 41), _scores(70_001, 42), rng.normal(size=120_000) + 3.0 * (rng.random(120_000) < 0.2)]   # the last: many unsaturated tile boundaries
+    budgets, gammas = [0.02, 0.05, 0.1], [1.0, 2.5, 0.7]
+    runs = {}
+    for on in (1, 0):
+        prev = _lib.load().rocco_b200_chain_set_tile_freezing(on)
+        try:
+            runs[on] = solve_chromosomes(sc, budgets, gammas)
+        finally:
+            _lib.load().rocco_b200_chain_set_tile_freezing(prev)
+    for a, b, s, bud, g in zip(runs[1], runs[0], sc, budgets, gammas):
+        assert a["selection_penalty"] == b["selection_penalty"] and a["selected_count"] == b["selected_count"]
+        assert np.array_equal(a["solution"], b["solution"])
+        want_sol, _, want = oracle.solve_chrom_exact(s, budget=bud, gamma=g, return_details=True)
+        assert np.array_equal(a["solution"], want_sol) and a["selected_count"] == want["selected_count"]
