@@ -1,4 +1,5 @@
 // Library plumbing: error text, device selection, launch counter, numpy-compatible summation.
+#include <thread>
 #include <nvtx3/nvToolsExt.h>
 #include "common.cuh"
 
@@ -390,14 +391,21 @@ RB_API int rocco_b200_write_bed3(const char *path, const char *const *names, int
     size_t maxlen = 0;
     for (int k = 0; k < n_names; ++k) { len[k] = strlen(names[k]); maxlen = std::max(maxlen, len[k]); }
     const size_t per = 2 * maxlen + 4 * 21 + 8;
-    const size_t chunk = 1 << 16;
-    std::vector<char> buf(per * chunk);
-    for (size_t i0 = 0; i0 < n; i0 += chunk) {
-        char *p = buf.data();
-        const size_t i1 = std::min(n, i0 + chunk);
+    // records are formatted in parallel (a few host threads, one contiguous slice each) and written in order
+    for (size_t i = 0; i < n; ++i) {
+        const int c = name_idx ? name_idx[i] : 0;
+        if (c < 0 || c >= n_names) { fclose(fh); return rb::ST_INVALID; }
+    }
+    const unsigned hw = std::thread::hardware_concurrency();
+    const size_t nthreads = std::max<size_t>(1, std::min<size_t>({(size_t)4, (size_t)(hw ? hw : 1), n / 8192 + 1}));
+    std::vector<std::vector<char>> bufs(nthreads);
+    std::vector<size_t> used(nthreads, 0);
+    auto work = [&](size_t t) {
+        const size_t i0 = n * t / nthreads, i1 = n * (t + 1) / nthreads;
+        bufs[t].resize(per * (i1 - i0) + 1);
+        char *p = bufs[t].data();
         for (size_t i = i0; i < i1; ++i) {
             const int c = name_idx ? name_idx[i] : 0;
-            if (c < 0 || c >= n_names) { fclose(fh); return rb::ST_INVALID; }
             memcpy(p, names[c], len[c]); p += len[c];
             *p++ = '\t'; p = put_ll(p, starts[i]);
             *p++ = '\t'; p = put_ll(p, ends[i]);
@@ -409,8 +417,14 @@ RB_API int rocco_b200_write_bed3(const char *path, const char *const *names, int
             }
             *p++ = '\n';
         }
-        if (fwrite(buf.data(), 1, (size_t)(p - buf.data()), fh) != (size_t)(p - buf.data())) { fclose(fh); return rb::ST_INVALID; }
-    }
+        used[t] = (size_t)(p - bufs[t].data());
+    };
+    std::vector<std::thread> pool;
+    for (size_t t = 1; t < nthreads; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto &th : pool) th.join();
+    for (size_t t = 0; t < nthreads; ++t)
+        if (used[t] && fwrite(bufs[t].data(), 1, used[t], fh) != used[t]) { fclose(fh); return rb::ST_INVALID; }
     fclose(fh);
     return 0;
 }
