@@ -302,9 +302,63 @@ static std::atomic<int> g_trend_mode{0};
 static std::atomic<long long> g_trend_fallback_rows{0};
 static std::atomic<long long> g_trend_fb_reason[8];
 
+// ------------------------------------------------------------------ knot tables for the combine
+// The trend of a row as the combine reads it: knots as {x, y} pairs, the slope of every segment, a 64-entry bucket -> first
+// candidate segment table keyed by the exponent and the top two mantissa bits of |signal| (16 octaves from 2^-12), and the
+// clamp range.  lin-interp with flat extrapolation (wls_backend.c:341-391) is then: clamp t to [x_0, x_last], start at
+// lut[bucket(t)], step forward while the next knot is <= t (the knots are quantiles of |signal|: a bucket rarely holds
+// more than one), y_lo + (t - x_lo) * slope_lo.
+constexpr int KT_KNOTS = 32, KT_LUT = 64, KT_BASE = (1023 - 12) << 2;
+struct KnotTable {
+    double2 xy[KT_KNOTS];
+    double slope[KT_KNOTS];
+    unsigned char lut[KT_LUT];
+    double xlo, xhi;
+    int top;                      // last segment index (nk - 2, at least 0)
+    int pad;
+};
+static_assert(sizeof(KnotTable) % 16 == 0, "KnotTable is staged with 128-bit copies");
+
+__device__ __forceinline__ int knot_bucket(double t)
+{
+    const int key = (__double2hiint(t) >> 18) - KT_BASE;              // t >= 0: sign bit clear
+    return min(max(key, 0), KT_LUT - 1);
+}
+
+__global__ void __launch_bounds__(64) k_knot_tables(const Knots *knots, KnotTable *tables)
+{
+    const Knots &K = knots[blockIdx.x];
+    KnotTable &T = tables[blockIdx.x];
+    const int k = threadIdx.x;
+    // a constant trend (one knot, or none) is a single flat segment at x = 0
+    const bool flat = K.constant || K.nk <= 0;
+    const int nk = flat ? 1 : K.nk;
+    const double yflat = K.constant ? K.cval : 1.0e-8;
+    if (k < KT_KNOTS) {
+        const bool in = k < nk;
+        T.xy[k] = make_double2(in ? (flat ? 0.0 : K.x[k]) : INFINITY, in ? (flat ? yflat : K.y[k]) : 0.0);
+        double sl = 0.0;
+        if (!flat && k + 1 < nk && K.x[k + 1] > K.x[k]) sl = (K.y[k + 1] - K.y[k]) / (K.x[k + 1] - K.x[k]);
+        T.slope[k] = sl;
+    }
+    const int top = max(nk - 2, 0);
+    if (k == 0) {
+        T.top = top;
+        T.xlo = flat ? 0.0 : K.x[0];
+        T.xhi = flat ? 0.0 : K.x[nk - 1];
+        T.pad = 0;
+    }
+    // lut[b] = last segment whose left knot is <= the bucket's lower edge (bucket 0 also takes everything below it)
+    const double edge = (k == 0) ? 0.0 : ldexp(1.0 + 0.25 * (double)(k & 3), (k >> 2) - 12);
+    int lo = 0;
+    if (!flat)
+        for (int q = 1; q <= top; ++q) if (K.x[q] <= edge) lo = q;
+    T.lut[k] = (unsigned char)lo;
+}
+
 // ------------------------------------------------------------------ fused posterior + column reduction over samples
 struct CombineParams {
-    const double *C; const double *V; const Knots *knots; const double *row_const;
+    const double *C; const double *V; const KnotTable *tables; const double *row_const;
     long long m, n, row_stride;
     double ldf, pdf, tdf, pfr, lower_bound_z, min_effect;
     int use_min_effect; int const_rows;
@@ -313,84 +367,75 @@ struct CombineParams {
     int *bad;
 };
 
-__device__ __forceinline__ double interp_knots(const double *kx, const double *ky, const double *krw, int nk, double t)
+constexpr int CB_THREADS = 256;
+constexpr int CB_ROWS_SMEM = 24;          // knot tables staged per batch of sample rows
+
+// posterior precision of one sample-bin and its accumulation (wls_backend.c:889-911)
+template <bool WANT_RQ>
+__device__ __forceinline__ void combine_one(double y, double ov, double pv, double ldf, double pdf, double rtdf1, double pfr,
+                                            double &wsum, double &psum, double &rsum, double &qsum)
 {
-    // wls_backend.c:341-391
-    if (nk == 0) return 1.0e-8;
-    if (nk == 1 || t <= kx[0]) return ky[0];
-    if (t >= kx[nk - 1]) return ky[nk - 1];
-    // kx is padded with +inf up to 32 entries: five branch-free steps find the last knot <= t
-    int lo = 0;
-#pragma unroll
-    for (int step = 16; step > 0; step >>= 1) lo += (kx[lo + step] <= t) ? step : 0;
-    const int hi = lo + 1;
-    const double xl = kx[lo], xr = kx[hi];
-    if (xr <= xl) return fmax(ky[hi], ky[lo]);
-    const double wgt = (t - xl) * krw[lo];                                          // krw[lo] = 1 / (kx[lo+1] - kx[lo])
-    return __fma_rn(wgt, ky[hi] - ky[lo], ky[lo]);
+    double post = __fma_rn(ldf, ov, pdf * pv) * rtdf1;
+    post = fmax(fmax(post, pfr * pv), 1.0e-8);
+    const double prec = rcp_nr(post);                 // 1 / post to ~1 ulp (hardware seed + two Newton steps)
+    if (WANT_RQ) { rsum += rcp_nr(ov); qsum += rcp_nr(pv); }
+    psum += prec;
+    wsum = __fma_rn(prec, y, wsum);
 }
 
-constexpr int CB_THREADS = 256;
-constexpr int CB_ROWS_SMEM = 25;          // knot tables staged per batch of sample rows
-
+template <bool CONST_ROWS, bool WANT_RQ>
 __global__ void __launch_bounds__(CB_THREADS, 4) k_combine(CombineParams P)
 {
-    __shared__ double s_kx[CB_ROWS_SMEM][32], s_ky[CB_ROWS_SMEM][32], s_kr[CB_ROWS_SMEM][32];
-    __shared__ int s_nk[CB_ROWS_SMEM];
-    __shared__ double s_cv[CB_ROWS_SMEM];
+    __shared__ __align__(16) KnotTable s_t[CONST_ROWS ? 1 : CB_ROWS_SMEM];
     const long long j = (long long)blockIdx.x * CB_THREADS + threadIdx.x;
     const bool live = j < P.n;
     double wsum = 0.0, psum = 0.0, rsum = 0.0, qsum = 0.0;
-    const double tdf1 = fmax(P.tdf, 1.0), rtdf1 = 1.0 / tdf1;
-    const bool want_rq = (P.raw != nullptr) || (P.prior != nullptr) || (P.acc != nullptr);
-    for (long long r0 = 0; r0 < P.m; r0 += CB_ROWS_SMEM) {
-        const int nr = (int)min((long long)CB_ROWS_SMEM, P.m - r0);
-        __syncthreads();
-        if (!P.const_rows) {
-            for (int e = threadIdx.x; e < nr * 32; e += CB_THREADS) {
-                const int rr = e >> 5, k = e & 31;
-                const Knots &K = P.knots[r0 + rr];
-                s_kx[rr][k] = (k < K.nk) ? K.x[k] : INFINITY;
-                s_ky[rr][k] = (k < K.nk) ? K.y[k] : 0.0;
-                s_kr[rr][k] = (k + 1 < K.nk && K.x[k + 1] > K.x[k]) ? __drcp_rn(__dsub_rn(K.x[k + 1], K.x[k])) : 0.0;
-                if (k == 0) { s_nk[rr] = K.constant ? -1 : K.nk; s_cv[rr] = K.cval; }
+    const double rtdf1 = 1.0 / fmax(P.tdf, 1.0);
+    const double ldf = P.ldf, pdf = P.pdf, pfr = P.pfr;
+    const long long stride = P.row_stride;
+    if (CONST_ROWS) {
+        if (live) {
+            const double *pc = P.C + j;
+            for (long long r = 0; r < P.m; ++r, pc += stride) {
+                const double v = P.row_const[r];
+                combine_one<WANT_RQ>(*pc, v, v, ldf, pdf, rtdf1, pfr, wsum, psum, rsum, qsum);
             }
         }
-        __syncthreads();
-        if (live) {
-            const double *pc = P.C + r0 * P.row_stride + j;
-            const double *pv_ = P.const_rows ? nullptr : P.V + r0 * P.row_stride + j;
-            // rows in groups of four: the eight loads of a group are issued before any of its arithmetic
-            for (int rb = 0; rb < nr; rb += 4) {
-                double ys[4], vs[4];
+    } else {
+        const double *pc = P.C + (live ? j : 0), *pv_ = P.V + (live ? j : 0);
+        for (long long r0 = 0; r0 < P.m; r0 += CB_ROWS_SMEM) {
+            const int nr = (int)min((long long)CB_ROWS_SMEM, P.m - r0);
+            __syncthreads();
+            {
+                const uint4 *src = reinterpret_cast<const uint4 *>(P.tables + r0);
+                uint4 *dst = reinterpret_cast<uint4 *>(s_t);
+                for (int e = threadIdx.x; e < nr * (int)(sizeof(KnotTable) / 16); e += CB_THREADS) dst[e] = src[e];
+            }
+            __syncthreads();
+            if (live) {
+                // rows in groups of four: the eight loads of a group are issued before any of its arithmetic
+                for (int rb = 0; rb < nr; rb += 4) {
+                    double ys[4], vs[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int rr = rb + u;
-                    ys[u] = (rr < nr) ? pc[(long long)rr * P.row_stride] : 0.0;
-                    vs[u] = (rr < nr && pv_) ? pv_[(long long)rr * P.row_stride] : 1.0;
-                }
+                    for (int u = 0; u < 4; ++u) {
+                        const bool in = rb + u < nr;
+                        ys[u] = in ? pc[(long long)u * stride] : 0.0;
+                        vs[u] = in ? pv_[(long long)u * stride] : 1.0;
+                    }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int rr = rb + u;
-                    if (rr >= nr) break;
-                    const double y = ys[u];
-                    double ov, pv;
-                    if (P.const_rows) { ov = pv = P.row_const[r0 + rr]; }
-                    else {
-                        ov = fmax(vs[u], 1.0e-8);
-                        pv = (s_nk[rr] < 0) ? s_cv[rr] : fmax(interp_knots(s_kx[rr], s_ky[rr], s_kr[rr], s_nk[rr], fabs(y)), 1.0e-8);
-                        pv = fmax(pv, 1.0e-8);
+                    for (int u = 0; u < 4; ++u) {
+                        if (rb + u >= nr) break;
+                        const KnotTable &T = s_t[rb + u];
+                        const double tt = fmin(fmax(fabs(ys[u]), T.xlo), T.xhi);
+                        int lo = T.lut[knot_bucket(tt)];
+                        const int top = T.top;
+                        while (lo < top && T.xy[lo + 1].x <= tt) ++lo;
+                        const double2 k = T.xy[lo];
+                        const double pv = fmax(__fma_rn(tt - k.x, T.slope[lo], k.y), 1.0e-8);
+                        combine_one<WANT_RQ>(ys[u], vs[u], pv, ldf, pdf, rtdf1, pfr, wsum, psum, rsum, qsum);     // V is floored at 1e-8 by its producer
                     }
-                    // wls_backend.c:889-911
-                    double post = __fma_rn(P.ldf, ov, P.pdf * pv) * rtdf1;
-                    post = fmax(fmax(post, P.pfr * pv), 1.0e-8);
-                    const double prec = rcp_nr(post);           // 1 / post to ~1 ulp (hardware seed + two Newton steps)
-                    if (want_rq) {                              // only when raw / prior variance outputs are requested
-                        rsum += rcp_nr(ov);
-                        qsum += rcp_nr(pv);
-                    }
-                    psum += prec;
-                    wsum = __fma_rn(prec, y, wsum);
+                    const int adv = min(4, nr - rb);
+                    pc += (long long)adv * stride; pv_ += (long long)adv * stride;
                 }
             }
         }
@@ -450,6 +495,7 @@ struct WlsRun {
     bool const_rows = false, fused = false, sort_all = false;
     double *d_V = nullptr, *d_rc = nullptr;
     Knots *d_knots = nullptr;
+    KnotTable *d_tables = nullptr;
     int *d_fb = nullptr, *d_bad = nullptr;
 };
 
@@ -471,6 +517,7 @@ static int wls_prepare(Arena &ar, long long m, long long n, const rocco_b200_sco
     } else {
         RB_TRY(ar.alloc(&R.d_V, (size_t)m * n));
         RB_TRY(ar.alloc(&R.d_knots, (size_t)m));
+        RB_TRY(ar.alloc(&R.d_tables, (size_t)m));
         RB_TRY(ar.alloc(&R.d_fb, (size_t)m));
         R.sort_all = g_trend_mode.load() == 1;
         R.fused = !R.sort_all && (R.w <= trend_fused_max_window());
@@ -530,11 +577,19 @@ static int wls_finish(const double *d_centered, WlsRun &R, const rocco_b200_scor
             RB_PROF("trend_sort_fallback", st, (double)rows.size() * (double)n * 16.0);
             RB_TRY(trend_knots_sorted(d_centered, R.d_V, rows, n, n, R.d_knots, st));
         }
-        P.const_rows = 0; P.V = R.d_V; P.knots = R.d_knots;
+        P.const_rows = 0; P.V = R.d_V; P.tables = R.d_tables;
+        k_knot_tables<<<(unsigned)m, 64, 0, st>>>(R.d_knots, R.d_tables);
+        RB_LAUNCH_CHECK();
     }
     {
         RB_PROF("k_combine", st, (double)m * (double)n * (P.const_rows ? 8.0 : 16.0) + 48.0 * (double)n);
-        k_combine<<<(unsigned)((n + CB_THREADS - 1) / CB_THREADS), CB_THREADS, 0, st>>>(P);
+        const unsigned grid = (unsigned)((n + CB_THREADS - 1) / CB_THREADS);
+        const bool want_rq = (P.raw != nullptr) || (P.prior != nullptr) || (P.acc != nullptr);   // raw / prior variance sums only when asked for
+        if (P.const_rows) {
+            if (want_rq) k_combine<true, true><<<grid, CB_THREADS, 0, st>>>(P); else k_combine<true, false><<<grid, CB_THREADS, 0, st>>>(P);
+        } else {
+            if (want_rq) k_combine<false, true><<<grid, CB_THREADS, 0, st>>>(P); else k_combine<false, false><<<grid, CB_THREADS, 0, st>>>(P);
+        }
         RB_LAUNCH_CHECK();
     }
     int bad = 0;
