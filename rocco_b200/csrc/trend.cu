@@ -375,50 +375,57 @@ __global__ void __launch_bounds__(256) k_xplan(TrendBuffers T, const double *__r
 }
 
 // ------------------------------------------------------------------ T3
+// One 16-bit entry per |signal| bucket for the two streaming passes: the bucket's bin (5 bits), whether it holds a bin
+// boundary (bit 7), and its slot (0xFF: none) -- a single shared-memory load per pair.
+__device__ __forceinline__ void bucket_table(unsigned short *s_tab, const unsigned char *lut, const unsigned char *binlo, const RowPlan &P,
+                                             int threads)
+{
+    for (int k = threadIdx.x; k < NBX; k += threads) {
+        const unsigned sl = lut[k];
+        const unsigned bnd = (sl != 0xFFu && P.slot_boundary[sl] != 0) ? 0x80u : 0u;
+        s_tab[k] = (unsigned short)((unsigned)binlo[k] | bnd | (sl << 8));
+    }
+}
 constexpr int XC_THREADS = 1024;          // one CTA per SM (160 KB of histograms + LUTs): 32 warps hide the LUT/atomic chain
 __global__ void __launch_bounds__(XC_THREADS) k_xcollect(const double *__restrict__ C, const double *__restrict__ V, long long n,
                                                          long long row_stride, TrendBuffers T, int B)
 {
     extern __shared__ int s_raw[];
     int *s_yh = s_raw;                                              // [B][NBY]
-    unsigned char *s_lut = reinterpret_cast<unsigned char *>(s_raw + B * NBY);
-    unsigned char *s_bin = s_lut + NBX;
+    unsigned short *s_tab = reinterpret_cast<unsigned short *>(s_raw + B * NBY);    // per |signal| bucket: bin | boundary << 7 | slot << 8
     const long long row = blockIdx.y;
-    if (T.plan[row].fallback) return;
+    const RowPlan &P = T.plan[row];
+    if (P.fallback) return;
     const long long c0 = (long long)blockIdx.x * CHUNK, c1 = min(n, c0 + CHUNK);
     for (int k = threadIdx.x; k < B * NBY; k += XC_THREADS) s_yh[k] = 0;
-    for (int k = threadIdx.x; k < NBX / 4; k += XC_THREADS) {
-        reinterpret_cast<unsigned *>(s_lut)[k] = reinterpret_cast<const unsigned *>(T.lut + row * NBX)[k];
-        reinterpret_cast<unsigned *>(s_bin)[k] = reinterpret_cast<const unsigned *>(T.binlo + row * NBX)[k];
-    }
+    bucket_table(s_tab, T.lut + row * NBX, T.binlo + row * NBX, P, XC_THREADS);
     __syncthreads();
     const double *c = C + row * row_stride, *v = V + row * row_stride;
     double2 *cand = T.cand + (size_t)row * MAXSLOT * CAPX;
     int *ccnt = T.cand_cnt + row * MAXSLOT;
-    const RowPlan &P = T.plan[row];
     const int yb0 = P.yb0;
-    // four independent loads in flight per thread before the dependent LUT / atomic chain
-    for (long long jb = c0; jb < c1; jb += 4 * XC_THREADS) {
-        double xs[4], ys[4];
+    // eight independent loads in flight per thread before the dependent table / atomic chain
+    constexpr int U = 8;
+    for (long long jb = c0; jb < c1; jb += U * XC_THREADS) {
+        double xs[U], ys[U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
             const long long j = jb + u * XC_THREADS + threadIdx.x;
             xs[u] = (j < c1) ? fabs(c[j]) : -1.0;
             ys[u] = (j < c1) ? v[j] : 0.0;
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
             if (xs[u] < 0.0) continue;
             const double x = xs[u], y = ys[u];
-            const int b = xbucket(x, T.geom);
-            const int s = s_lut[b];
-            bool boundary = false;
-            if (s != 0xFF) {
-                const int pos = atomicAdd(&ccnt[s], 1);
-                if (pos < CAPX) cand[(size_t)s * CAPX + pos] = make_double2(x, y);
-                boundary = P.slot_boundary[s] != 0;
+            const unsigned e = s_tab[xbucket(x, T.geom)];
+            if (e < 0xFF00u) {                                      // slot bucket (~2 % of the pairs): keep the pair
+                const int sl = (int)(e >> 8);
+                const int pos = atomicAdd(&ccnt[sl], 1);
+                if (pos < CAPX) cand[(size_t)sl * CAPX + pos] = make_double2(x, y);
+                if (e & 0x80u) continue;                            // boundary bucket: its bin is settled by T4
             }
-            if (!boundary) atomicAdd(&s_yh[(int)s_bin[b] * NBY + ybucket(y, yb0, T.geom)], 1);
+            atomicAdd(&s_yh[(int)(e & 31u) * NBY + ybucket(y, yb0, T.geom)], 1);
         }
     }
     __syncthreads();
@@ -757,67 +764,64 @@ __global__ void __launch_bounds__(256) k_yplan(TrendBuffers T, long long n, int 
 }
 
 // ------------------------------------------------------------------ T6
-__device__ __forceinline__ void ycollect_one(TrendBuffers &T, long long row, const int (*s_yb)[2], int bin, double y, int yb0)
+__device__ __forceinline__ void ycollect_append(TrendBuffers &T, long long row, int bin, int k, double y)
+{
+    const size_t slot = ((size_t)row * MAXB + bin) * 2 + k;
+    const int pos = atomicAdd(&T.ycand_cnt[slot], 1);
+    if (pos < T.capy) T.ycand[slot * T.capy + pos] = y;
+    else {                                                   // massive ties (variances on their floor): remember the range
+        const unsigned long long key = (unsigned long long)__double_as_longlong(y);
+        atomicMin(&T.yover_min[slot], key);
+        atomicMax(&T.yover_max[slot], key);
+    }
+}
+
+// the variance belongs to slot 1 (upper median bucket) or 0 (lower median bucket, when it is a different bucket) of its bin
+__device__ __forceinline__ void ycollect_one(TrendBuffers &T, long long row, const int2 *s_yb, int bin, double y, int yb0)
 {
     const int yb = ybucket(y, yb0, T.geom);
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        if (s_yb[bin][k] == yb && (k == 1 || s_yb[bin][1] != yb)) {
-            const size_t slot = ((size_t)row * MAXB + bin) * 2 + k;
-            const int pos = atomicAdd(&T.ycand_cnt[slot], 1);
-            if (pos < T.capy) T.ycand[slot * T.capy + pos] = y;
-            else {                                                   // massive ties (variances on their floor): remember the range
-                const unsigned long long key = (unsigned long long)__double_as_longlong(y);
-                atomicMin(&T.yover_min[slot], key);
-                atomicMax(&T.yover_max[slot], key);
-            }
-        }
-    }
+    const int2 t = s_yb[bin];
+    if (yb == t.y) ycollect_append(T, row, bin, 1, y);
+    else if (yb == t.x) ycollect_append(T, row, bin, 0, y);
 }
 
 __global__ void __launch_bounds__(ST_THREADS) k_ycollect(const double *__restrict__ C, const double *__restrict__ V, long long n,
                                                          long long row_stride, TrendBuffers T, int B)
 {
-    __shared__ unsigned char s_lut[NBX];
-    __shared__ unsigned char s_bin[NBX];
-    __shared__ int s_yb[MAXB][2];
-    __shared__ unsigned char s_bnd[MAXSLOT];
+    __shared__ unsigned short s_tab[NBX];
+    __shared__ int2 s_yb[MAXB];
     const long long row = blockIdx.y;
     const RowPlan &P = T.plan[row];
     if (P.fallback) return;
-    for (int k = threadIdx.x; k < NBX / 4; k += ST_THREADS) {
-        reinterpret_cast<unsigned *>(s_lut)[k] = reinterpret_cast<const unsigned *>(T.lut + row * NBX)[k];
-        reinterpret_cast<unsigned *>(s_bin)[k] = reinterpret_cast<const unsigned *>(T.binlo + row * NBX)[k];
-    }
-    for (int k = threadIdx.x; k < MAXB * 2; k += ST_THREADS) s_yb[k >> 1][k & 1] = (k >> 1) < B ? P.ym_bucket[k >> 1][k & 1] : -1;
-    for (int k = threadIdx.x; k < MAXSLOT; k += ST_THREADS) s_bnd[k] = (k < P.nslot && P.slot_boundary[k]) ? 1 : 0;
+    bucket_table(s_tab, T.lut + row * NBX, T.binlo + row * NBX, P, ST_THREADS);
+    for (int k = threadIdx.x; k < MAXB; k += ST_THREADS) s_yb[k] = k < B ? make_int2(P.ym_bucket[k][0], P.ym_bucket[k][1]) : make_int2(-1, -1);
     __syncthreads();
     const long long c0 = (long long)blockIdx.x * CHUNK, c1 = min(n, c0 + CHUNK);
     const double *c = C + row * row_stride, *v = V + row * row_stride;
     const int yb0 = P.yb0;
-    for (long long jb = c0; jb < c1; jb += 4 * ST_THREADS) {
-        double xs[4], ys[4];
+    constexpr int U = 8;
+    for (long long jb = c0; jb < c1; jb += U * ST_THREADS) {
+        double xs[U], ys[U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
             const long long j = jb + u * ST_THREADS + threadIdx.x;
             xs[u] = (j < c1) ? fabs(c[j]) : -1.0;
             ys[u] = (j < c1) ? v[j] : 0.0;
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
             if (xs[u] < 0.0) continue;
-            const int b = xbucket(xs[u], T.geom);
-            const int s = s_lut[b];
-            if (s != 0xFF && s_bnd[s]) continue;                    // boundary buckets: handled from the sorted slot below
-            ycollect_one(T, row, s_yb, (int)s_bin[b], ys[u], yb0);
+            const unsigned e = s_tab[xbucket(xs[u], T.geom)];
+            if (e < 0xFF00u && (e & 0x80u)) continue;               // boundary buckets: handled from the partitioned slot below
+            ycollect_one(T, row, s_yb, (int)(e & 31u), ys[u], yb0);
         }
     }
     if (blockIdx.x == 0) {
-        for (int s = 0; s < P.nslot; ++s) {
-            if (!s_bnd[s]) continue;
-            const double2 *cand = T.cand + ((size_t)row * MAXSLOT + s) * CAPX;
-            const long long pre = P.slot_prefix[s];
-            for (int k = threadIdx.x; k < P.slot_count[s]; k += ST_THREADS)
+        for (int sl = 0; sl < P.nslot; ++sl) {
+            if (!P.slot_boundary[sl]) continue;
+            const double2 *cand = T.cand + ((size_t)row * MAXSLOT + sl) * CAPX;
+            const long long pre = P.slot_prefix[sl];
+            for (int k = threadIdx.x; k < P.slot_count[sl]; k += ST_THREADS)
                 ycollect_one(T, row, s_yb, bin_of_rank(pre + k, n, B), cand[k].y, P.yb0);
         }
     }
@@ -967,7 +971,7 @@ int trend_knots_select(const double *d_C, double *d_V, long long m, long long n,
     cudaGetDevice(&attr_d);
     bool &attr = attr_dev[attr_d & 63];
     const size_t sm_xhist = sizeof(int) * NBX;
-    const size_t sm_collect = sizeof(int) * (size_t)B * NBY + 2 * NBX;
+    const size_t sm_collect = sizeof(int) * (size_t)B * NBY + 2 * NBX;      // histograms + the 16-bit bucket table
     const size_t sm_resolve = sizeof(double2) * CAPX;
     const size_t sm_plan = sizeof(int) * (NBX + 258) + sizeof(double) * YSAMPLE;
     if (!attr) {
