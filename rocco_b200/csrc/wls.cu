@@ -5,6 +5,8 @@
 //   394-608  monotone variance-vs-|signal| trend -> exact order statistics per sample row, PAVA on <= 32 knots
 //   744-947  posterior precision + combine       -> k_combine   (fused column reduction over the sample axis)
 // and the Python driver inference.py:302-379.
+#include <stdlib.h>
+
 #include <condition_variable>
 #include <deque>
 #include <mutex>
@@ -664,8 +666,13 @@ class StageCopier {
     struct Job { char *dst; const char *src; size_t n; };
     StageCopier()
     {
+        // the copy is bound by what one core can move (4-10 GB/s), so it takes most of the cores this process may claim: all
+        // but one of the host's, divided by the ranks that share the host (torchrun's LOCAL_WORLD_SIZE), at most 15 helpers
         unsigned hw = std::thread::hardware_concurrency();
-        nthreads_ = (int)std::max(1u, std::min(7u, hw > 2 ? hw / 2 - 1 : 1u));
+        unsigned ranks = 1;
+        if (const char *e = getenv("ROCCO_B200_STAGE_THREADS")) { nthreads_ = std::max(0, std::min(63, atoi(e))); ranks = 0; }
+        else if (const char *e = getenv("LOCAL_WORLD_SIZE")) ranks = (unsigned)std::max(1, atoi(e));
+        if (ranks) nthreads_ = (int)std::max(1u, std::min(15u, (hw ? hw : 2u) / ranks > 1 ? (hw ? hw : 2u) / ranks - 1 : 1u));
         for (int t = 0; t < nthreads_; ++t) std::thread([this] { worker(); }).detach();
     }
     void finish_one()
