@@ -376,6 +376,13 @@ def parity_against(ref, budget, gamma, kind):
     wdet = ref["details"]
     # the multiplier search on identical scores: the searched double itself
     sol2, obj2, det2 = rocco_b200.solve_chrom_exact(want, budget=budget, gamma=gamma, return_details=True)
+    # ... and with the opt-in exact search (decisions replayed in the reference's own operation order near ties)
+    from rocco_b200 import _lib
+    prev = _lib.load().rocco_b200_chain_set_exact_search(1)
+    try:
+        sol3, obj3, det3 = rocco_b200.solve_chrom_exact(want, budget=budget, gamma=gamma, return_details=True)
+    finally:
+        _lib.load().rocco_b200_chain_set_exact_search(prev)
     return {
         "against": f"oracle kind={kind}, same input bytes ({x.shape[0]} x {n})",
         "scores_max_rel_err": rel, "scores_tolerance": 1e-5,
@@ -387,6 +394,9 @@ def parity_against(ref, budget, gamma, kind):
         "same_scores_search": {"mask_identical": bool(np.array_equal(sol2, ref["solution"])),
                                "lambda_identical": bool(det2["selection_penalty"] == wdet["selection_penalty"]),
                                "lambda_abs_diff": float(abs(det2["selection_penalty"] - wdet["selection_penalty"]))},
+        "same_scores_exact_search": {"mask_identical": bool(np.array_equal(sol3, ref["solution"])),
+                                     "lambda_identical": bool(det3["selection_penalty"] == wdet["selection_penalty"]),
+                                     "objective_identical": bool(obj3 == ref["objective"])},
     }
 
 
@@ -457,7 +467,7 @@ def main():
     count_buf = torch.zeros(2, dtype=torch.int64, device=dev)
     # record order of the reference's combined BED (rocco.py:74-95 sorts by the chromosome STRING: chr1 < chr10 < chr2)
     lex_names = sorted(names)
-    lex_rank = np.array([lex_names.index(c) for c in my_names], dtype=np.int64)
+    lex_order = sorted(range(len(my_names)), key=lambda k: my_names[k])      # shard-local chromosome indices in that order
 
     def step():
         shard = pipeline.run_shard(d_mats, budgets, gammas, params=params, levels_per_round=args.levels,
@@ -468,9 +478,8 @@ def main():
         if mine:
             chrom, starts, ends = shard["runs"]
             if world == 1:
-                order = np.lexsort((starts, lex_rank[chrom]))
                 pipeline.runs_to_bed_file(os.path.join(tmpdir, "genome.bed"), lex_names,
-                                          (lex_rank[chrom][order].astype(np.int32), starts[order], ends[order]), args.step_bp)
+                                          pipeline.reorder_runs(shard["runs"], lex_order), args.step_bp)
             else:
                 bounds = np.searchsorted(chrom, np.arange(len(my_names) + 1))          # runs come grouped by chromosome
                 for k, c in enumerate(my_names):

@@ -55,6 +55,8 @@ int rocco_b200_trim_pools(size_t bytes_to_keep);
  * writes "<scope> <total_ms> <launch_sets> <algorithmic_bytes>" lines into buf and clears the log. */
 int rocco_b200_profile_enable(int on);
 int rocco_b200_profile_report(char *buf, size_t capacity);
+/* "<scope> <start_ms> <duration_ms>" per recorded scope in record order (start relative to the first scope); keeps the log. */
+int rocco_b200_profile_timeline(char *buf, size_t capacity);
 
 /* ------------------------------------------------------------------ reference-named host entries */
 int rocco_crossfit_whittaker_baseline_f64(

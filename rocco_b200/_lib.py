@@ -104,6 +104,7 @@ def _declare(lib):
         "rocco_b200_kernel_launches": (c_ulonglong, []),
         "rocco_b200_profile_enable": (c_int, [c_int]),
         "rocco_b200_profile_report": (c_int, [c_char_p, c_size_t]),
+        "rocco_b200_profile_timeline": (c_int, [c_char_p, c_size_t]),
         "rocco_b200_uniform_step_i64": (c_int, [c_void_p, c_size_t]),
         "rocco_b200_write_bed3": (c_int, [c_char_p, POINTER(c_char_p), c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int]),
         "rocco_b200_combine_bed3": (ctypes.c_longlong, [POINTER(c_char_p), c_int, c_char_p, c_int, POINTER(c_int)]),
@@ -258,6 +259,13 @@ def profile_report() -> dict:
         name, ms, cnt, nbytes = line.split()
         out[name] = (float(ms), int(cnt), float(nbytes))
     return out
+
+
+def profile_timeline() -> list:
+    """[(scope, start_ms, duration_ms)] of the scopes recorded since the last report, in record order."""
+    buf = ctypes.create_string_buffer(1 << 22)
+    load().rocco_b200_profile_timeline(buf, len(buf))
+    return [(a, float(b), float(c)) for a, b, c in (line.split() for line in buf.value.decode().splitlines())]
 
 
 def write_bed_arrays(path: str, names, name_idx, starts: np.ndarray, ends: np.ndarray, name_features: bool = False) -> str:

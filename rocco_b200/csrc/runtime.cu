@@ -357,6 +357,26 @@ RB_API int rocco_b200_profile_report(char *buf, size_t cap)
     return (int)off;
 }
 
+/* Writes one line per recorded scope in record order: "<name> <start_ms> <duration_ms>\n", start relative to the first
+   scope's start (all scopes must be on one stream for the offsets to mean anything); does not clear the log. */
+RB_API int rocco_b200_profile_timeline(char *buf, size_t cap)
+{
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lk(rb::g_prof_mu);
+    size_t off = 0;
+    for (auto &e : rb::g_prof) {
+        float t0 = 0.f, ms = 0.f;
+        if (cudaEventElapsedTime(&t0, rb::g_prof[0].a, e.a) != cudaSuccess || cudaEventElapsedTime(&ms, e.a, e.b) != cudaSuccess) continue;
+        int w = snprintf(buf ? buf + off : nullptr, buf && cap > off ? cap - off : 0, "%s %.4f %.4f\n", e.name.c_str(), t0, ms);
+        if (w < 0) break;
+        off += (size_t)w;
+        if (buf && off >= cap) { off = cap ? cap - 1 : 0; break; }
+    }
+    (void)cudaGetLastError();
+    if (buf && cap) buf[off < cap ? off : cap - 1] = 0;
+    return (int)off;
+}
+
 /* 1 when v[i+1]-v[i] is the same for all i (the reference's `len(set(np.diff(intervals))) > 1` test, rocco.py:170-172,
  * without materialising the differences); host helper. */
 RB_API int rocco_b200_uniform_step_i64(const long long *v, size_t n)

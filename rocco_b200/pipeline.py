@@ -384,6 +384,19 @@ def runs_to_bed_file(path: str, chrom_names, runs, step: int, first_start: int =
     return _lib.write_bed_arrays(path, list(chrom_names), chrom, first_start + starts * step, first_start + ends * step)
 
 
+def reorder_runs(runs, chrom_order):
+    """Runs regrouped so that chromosome index `chrom_order[0]` comes first, then `chrom_order[1]`, ...  The runs of a
+    shard arrive grouped by chromosome and sorted by start inside each group (`mask_to_runs`), so putting a genome into
+    the reference's record order (rocco.py:74-95: chromosome STRINGS ascending, then start) is a permutation of
+    blocks -- no sort.  Returns (position in chrom_order as int32, starts, ends)."""
+    chrom, starts, ends = runs
+    order = np.asarray(chrom_order, dtype=np.int64)
+    bounds = np.searchsorted(chrom, np.arange(int(order.max(initial=-1)) + 2))
+    take = np.concatenate([np.arange(bounds[c], bounds[c + 1]) for c in order] or [np.zeros(0, np.int64)])
+    sizes = bounds[order + 1] - bounds[order]
+    return np.repeat(np.arange(order.shape[0], dtype=np.int32), sizes), starts[take], ends[take]
+
+
 def runs_to_bed_text(chrom_names, runs, step: int, first_start: int = 0) -> str:
     """BED3 text of all runs (per chromosome in the given order; coordinates = first_start + bin*step)."""
     chrom, starts, ends = runs

@@ -129,3 +129,23 @@ def test_forked_child_gets_a_named_error(monkeypatch):
     monkeypatch.setattr(_lib, "_CUDA_PID", os.getpid() + 1)          # as if the context had been created by a parent
     with pytest.raises(RuntimeError, match="forked child"):
         _lib.require_device()
+
+
+def test_reorder_runs_equals_a_lexsort_of_the_records():
+    from rocco_b200 import pipeline
+    """the genome BED's record order (chromosome strings ascending, then start) from a block permutation of the shard's runs"""
+    rng = np.random.default_rng(3)
+    names = ["chr1", "chr2", "chr10", "chrX", "chr21", "chr3"]
+    chrom, starts = [], []
+    for k in range(len(names)):
+        cnt = 0 if k == 2 else int(rng.integers(0, 40))
+        chrom += [k] * cnt
+        starts += sorted(rng.choice(10000, cnt, replace=False).tolist())
+    runs = (np.array(chrom, np.int32), np.array(starts, np.int64), np.array(starts, np.int64) + 3)
+    lex_order = sorted(range(len(names)), key=lambda k: names[k])
+    got = pipeline.reorder_runs(runs, lex_order)
+    lex_rank = np.array([sorted(names).index(c) for c in names])
+    o = np.lexsort((runs[1], lex_rank[runs[0]]))
+    assert np.array_equal(got[0], lex_rank[runs[0]][o]) and np.array_equal(got[1], runs[1][o]) and np.array_equal(got[2], runs[2][o])
+    empty = pipeline.reorder_runs((np.zeros(0, np.int32), np.zeros(0, np.int64), np.zeros(0, np.int64)), lex_order)
+    assert all(a.shape == (0,) for a in empty)

@@ -132,5 +132,39 @@ def cmd_fallback():
     print(name, "fallback rows", lib.rocco_b200_trend_fallback_rows() - f0, "reasons [xslot,xcount,ytotal,yslot,ycount]", [r1[k] - r0[k] for k in range(5)])
 
 
+def cmd_timeline():
+    """device-side gaps between the profile scopes of one run_shard call"""
+    names = sys.argv[2].split(",") if len(sys.argv) > 2 else ["chr21"]
+    m = int(sys.argv[3]) if len(sys.argv) > 3 else 100
+    mats = [chrom_matrix_torch(m, chrom_bins(c), chrom_seed(c), DEV, torch.float64) for c in names]
+    budgets = [HG_PARAMS[c][0] for c in names]
+    gammas = [HG_PARAMS[c][1] for c in names]
+    prm = pipeline.score_params(prior_df=6.0)
+    for _ in range(2):
+        pipeline.run_shard(mats, budgets, gammas, params=prm)
+    torch.cuda.synchronize()
+    _lib.profile_enable(True)
+    _lib.profile_report()
+    pipeline.run_shard(mats, budgets, gammas, params=prm)
+    torch.cuda.synchronize()
+    tl = _lib.profile_timeline()
+    _lib.profile_enable(False)
+    _lib.profile_report()
+    end_prev, gaps = None, {}
+    busy = 0.0
+    for name, t0, ms in tl:
+        if end_prev is not None:
+            key = f"{prev_name}->{name}"
+            g = gaps.setdefault(key, [0, 0.0])
+            g[0] += 1; g[1] += t0 - end_prev
+        end_prev, prev_name = t0 + ms, name
+        busy += ms
+    span = tl[-1][1] + tl[-1][2] - tl[0][1]
+    print("search rounds ms:", " ".join(f"{ms:.3f}" for name, t0, ms in tl if name == "chain_search_round"))
+    print(f"span {span:.3f} ms, inside scopes {busy:.3f} ms, gaps {span - busy:.3f} ms over {len(tl)} scopes")
+    for k, (c, g) in sorted(gaps.items(), key=lambda kv: -kv[1][1])[:25]:
+        print(f"{k:55s} n={c:4d} gap {g:8.3f} ms ({1e3 * g / c:7.1f} us each)")
+
+
 if __name__ == "__main__":
-    {"whit": cmd_whit, "scopes": cmd_scopes, "fallback": cmd_fallback}[sys.argv[1]]()
+    {"whit": cmd_whit, "scopes": cmd_scopes, "fallback": cmd_fallback, "timeline": cmd_timeline}[sys.argv[1]]()
