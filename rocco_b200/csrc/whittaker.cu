@@ -86,6 +86,7 @@ struct PairTab {
     double cf[2][3][2];                            // [chain][dinv, l1, l2][position parity]
     double trans[2][2][WP_LEVELS][4];              // [chain][fwd/bwd][level]: transition over ITEMS * 2^level bins
     double g[2][16][2];                            // [chain][j]: response of the zero-state backward sweep of a chunk to z_j = 1: (x_0, x_1)
+    double il2[2][2];                              // [chain][position parity]: 1 / l2 (the forward recurrence run right to left)
 };
 struct PairPow {
     double lane[2][2][2][32][2];                   // [chain][dir][matrix row][k]: row of T^k chunks (k = 0: identity); 16-byte lane stride
@@ -188,6 +189,7 @@ static void build_factor(long long n, double lam, FactorHost &F)
             const int p = ch ^ ap;                                  // parity mask served by this chain
             for (int k = 0; k < 3; ++k)
                 for (int q = 0; q < 2; ++q) T.cf[ch][k][q] = F.steady[p][k][q ^ ap];
+            for (int q = 0; q < 2; ++q) T.il2[ch][q] = 1.0 / T.cf[ch][2][q];
             double Tf[4] = {1, 0, 0, 1}, Tb[4] = {1, 0, 0, 1};
             for (int j = 0; j < WP_ITEMS; ++j) {                    // position j of a chunk (chunks start on even positions)
                 const double S[4] = {-T.cf[ch][1][(j + 1) & 1], -T.cf[ch][2][j & 1], 1.0, 0.0};
@@ -706,6 +708,7 @@ struct PairParams {
     int tile_offset, span_tiles;
     int shift;
     int log_transform, write_baseline;
+    int total_pairs;            // streaming form: (row, tile) pairs of this launch
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -766,7 +769,8 @@ __device__ __forceinline__ void warp_entry_state(double (&E)[4], int target, int
 
 template <bool REV, int WP_WARPS>
 __device__ __forceinline__ void pair_scan(double (&v)[4], double (&in)[4], const PairParams &P, double (*s_wex)[4],
-                                          const double *s_pow, double (*s_nbr)[4], unsigned long long *s_cbar, int rank)
+                                          const double *s_pow, double (*s_nbr)[4], unsigned long long *s_cbar, int rank,
+                                          unsigned cpar = 0)
 {
     constexpr int D = REV ? 1 : 0;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -816,7 +820,7 @@ __device__ __forceinline__ void pair_scan(double (&v)[4], double (&in)[4], const
         }
     }
     const bool use_peer = receiver && wpos < 4;
-    if (use_peer) mbar_wait(smem_u32(&s_cbar[D]), 0);
+    if (use_peer) mbar_wait(smem_u32(&s_cbar[D]), cpar);
     double E[4];
     warp_entry_state<WP_WARPS>(E, wpos, D, use_peer, s_wex, s_pow, s_nbr);
     {
@@ -993,6 +997,203 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WP_THREADS, 2) k_whi
     }
 }
 
+// ------------------------------------------------------------------ steady tiles, streaming cluster-pair form
+// The pair kernel above made PERSISTENT: 148 clusters walk the (row, tile) list, and the raw input of a cluster's next tile
+// is in flight (bulk async copy into the second of two landing buffers) while the current one is solved, so that neither
+// the load latency at the start of a tile nor the drain of its bulk store at the end is exposed; the scan tables are
+// loaded once per CTA.  Shared memory has room for the second buffer because the forward solution is no longer stored:
+// the backward sweep re-derives it by running the forward recurrence right to left from the chunk's final state
+// (n_{j-2} = (r_j - n_j - l1 n_{j-1}) / l2; twelve steps of a recurrence whose reverse growth is 1/0.9775 per bin, i.e.
+// ~1e-16 relative).  y stays in registers, the result is written over the thread's own slots of the landing buffer and
+// leaves from there as one bulk store.
+template <bool F32, int WP_THREADS, int WP_ITEMS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WP_THREADS, 2) k_whittaker_stream(const __grid_constant__ PairParams P)
+{
+    namespace cg = cooperative_groups;
+    static_assert(WP_THREADS * WP_ITEMS == WP_HALF && WP_ITEMS % 4 == 0 && WP_ITEMS <= 16, "pair geometry");
+    constexpr int WP_WARPS = WP_THREADS / 32;
+    extern __shared__ __align__(128) double smem_pair[];
+    double *s_buf0 = smem_pair, *s_buf1 = smem_pair + WP_HALF;        // landing buffers (raw in, result out)
+    double *s_pow = smem_pair + 2 * WP_HALF;
+    const double2 *s_log = reinterpret_cast<const double2 *>(s_pow + sizeof(PairPow) / sizeof(double));
+    __shared__ __align__(8) unsigned long long s_full[2]; // raw input of buffer b has landed
+    __shared__ __align__(8) unsigned long long s_tabbar;  // tables
+    __shared__ __align__(8) unsigned long long s_cbar[2]; // carry from the peer CTA: [forward, backward]
+    __shared__ __align__(16) double s_nbr[2][4];
+    __shared__ __align__(16) double s_wex[2][WP_MAXWARPS][4];
+
+    const int rank = (int)cg::this_cluster().block_rank();
+    const int tid = threadIdx.x;
+    const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+    const int total = P.total_pairs;
+    constexpr unsigned BYTES = WP_HALF * (F32 ? 4u : 8u);
+    constexpr unsigned LOG_BYTES = 16u * LOG2_V2_ENTRIES;
+    const int recv = (rank == 1) ? 0 : 1;                 // the carry this CTA receives: forward (right half) / backward (left half)
+
+    auto half_base = [&](int pair_idx) -> long long {
+        const long long row = P.row0 + (long long)(pair_idx / P.span_tiles) * P.row_step;
+        const int tile = P.tile_offset + pair_idx % P.span_tiles;
+        const long long r0 = (long long)tile * WT_OUT - WT_HALO - P.shift;
+        return row * P.row_stride + r0 + (long long)rank * WP_HALF;
+    };
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_full[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_full[1])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_tabbar)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_cbar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_cbar[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&s_tabbar)), "r"((unsigned)sizeof(PairPow) + LOG_BYTES) : "memory");
+        bulk_load(smem_u32(s_pow), P.pow_tab, (unsigned)sizeof(PairPow), smem_u32(&s_tabbar));
+        bulk_load(smem_u32(s_log), P.log2tab, LOG_BYTES, smem_u32(&s_tabbar));
+        if (cid < total) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&s_full[0])), "r"(BYTES) : "memory");
+            bulk_load(smem_u32(s_buf0), reinterpret_cast<const char *>(P.x) + half_base(cid) * (F32 ? 4 : 8), BYTES, smem_u32(&s_full[0]));
+        }
+    }
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.aligned;" ::: "memory");      // the peer's barriers exist (once per CTA)
+    mbar_wait(smem_u32(&s_tabbar), 0);
+
+    const double (*cfA)[2] = P.tab.cf[0];
+    const double (*cfB)[2] = P.tab.cf[1];
+    const int p0 = rank * WP_HALF + tid * WP_ITEMS;
+    const int o_lo = WT_HALO + P.shift, o_hi = o_lo + WT_OUT;
+    const bool dead = (p0 + WP_ITEMS <= o_lo);            // left-halo threads only feed the forward scan
+    const int q0 = max(o_lo, rank * WP_HALF) - rank * WP_HALF, q1 = min(o_hi, (rank + 1) * WP_HALF) - rank * WP_HALF;   // own bins in half positions
+    int bad = 0;
+
+#pragma unroll 1
+    for (int it = 0, pair_idx = cid; pair_idx < total; ++it, pair_idx += ncl) {
+        const int b = it & 1;
+        double *buf = b ? s_buf1 : s_buf0;
+        const long long row = P.row0 + (long long)(pair_idx / P.span_tiles) * P.row_step;
+        const long long hbase = half_base(pair_idx);
+        if (tid == 0)          // this tile's carry (the previous phase of the barrier was completed and observed one tile ago)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 32;" ::"r"(smem_u32(&s_cbar[recv])) : "memory");
+        const double pil = (P.log_transform && P.pilot) ? P.pilot[row] : 0.0;
+        mbar_wait(smem_u32(&s_full[b]), (unsigned)(it >> 1) & 1u);
+
+        // ---- this thread's bins: raw -> y (registers)
+        double y[WP_ITEMS];
+        if (F32) {
+            const float4 *rp = reinterpret_cast<const float4 *>(buf) + tid * (WP_ITEMS / 4);
+#pragma unroll
+            for (int u = 0; u < WP_ITEMS / 4; ++u) {
+                const float4 q = rp[u];
+                y[4 * u + 0] = (double)q.x; y[4 * u + 1] = (double)q.y; y[4 * u + 2] = (double)q.z; y[4 * u + 3] = (double)q.w;
+            }
+        } else {
+            const double2 *rp = reinterpret_cast<const double2 *>(buf) + tid * (WP_ITEMS / 2);
+#pragma unroll
+            for (int u = 0; u < WP_ITEMS / 2; ++u) { const double2 q = rp[u]; y[2 * u] = q.x; y[2 * u + 1] = q.y; }
+        }
+        int expmax = 0;                                   // inference.py:45-46: non-finite input is an error
+#pragma unroll
+        for (int j = 0; j < WP_ITEMS; ++j) expmax = max(expmax, __double2hiint(y[j]) & 0x7FF00000);
+        bad |= (expmax == 0x7FF00000);
+        if (P.log_transform) {
+#pragma unroll
+            for (int j = 0; j < WP_ITEMS; ++j) y[j] = fast_log2_ge1_v2(fmax(y[j], 0.0) + 1.0, s_log) - pil;
+        }
+
+        double v[4], in[4];
+        // ================= forward substitution: zero-state sweep, carry scan, true sweep
+        {
+            double a1 = 0.0, a2 = 0.0, b1 = 0.0, b2 = 0.0;
+#pragma unroll
+            for (int j = 0; j < WP_ITEMS; ++j) {
+                const double ra = (j & 1) ? 0.0 : y[j], rb_ = (j & 1) ? y[j] : 0.0;
+                const double na = fma(-cfA[2][j & 1], a2, fma(-cfA[1][(j + 1) & 1], a1, ra));
+                const double nb = fma(-cfB[2][j & 1], b2, fma(-cfB[1][(j + 1) & 1], b1, rb_));
+                a2 = a1; a1 = na; b2 = b1; b1 = nb;
+            }
+            v[0] = a1; v[1] = a2; v[2] = b1; v[3] = b2;
+        }
+        pair_scan<false, WP_WARPS>(v, in, P, s_wex[0], s_pow, s_nbr, s_cbar, rank, (unsigned)it & 1u);
+        // (the scan's CTA barrier: every thread has its raw bins in registers, and the other buffer's previous store was
+        // issued a whole tile phase ago)  -> start the next tile's input
+        if (tid == 0 && pair_idx + ncl < total) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");          // the other buffer's result has left
+            const unsigned fb = smem_u32(&s_full[b ^ 1]);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(BYTES) : "memory");
+            bulk_load(smem_u32(b ? s_buf0 : s_buf1), reinterpret_cast<const char *>(P.x) + half_base(pair_idx + ncl) * (F32 ? 4 : 8), BYTES, fb);
+        }
+        double fa1 = 0.0, fa2 = 0.0, fb1 = 0.0, fb2 = 0.0;       // final forward state of the chunk: n_{last}, n_{last-1}
+        v[0] = v[1] = v[2] = v[3] = 0.0;
+        if (!dead) {
+            double a1 = in[0], a2 = in[1], b1 = in[2], b2 = in[3];
+#pragma unroll
+            for (int j = 0; j < WP_ITEMS; ++j) {
+                const double ra = (j & 1) ? 0.0 : y[j], rb_ = (j & 1) ? y[j] : 0.0;
+                const double na = fma(-cfA[2][j & 1], a2, fma(-cfA[1][(j + 1) & 1], a1, ra));
+                const double nb = fma(-cfB[2][j & 1], b2, fma(-cfB[1][(j + 1) & 1], b1, rb_));
+                a2 = a1; a1 = na; b2 = b1; b1 = nb;
+                const double za = na * cfA[0][j & 1], zb = nb * cfB[0][j & 1];
+                v[0] = fma(P.tab.g[0][j][0], za, v[0]); v[1] = fma(P.tab.g[0][j][1], za, v[1]);
+                v[2] = fma(P.tab.g[1][j][0], zb, v[2]); v[3] = fma(P.tab.g[1][j][1], zb, v[3]);
+            }
+            fa1 = a1; fa2 = a2; fb1 = b1; fb2 = b2;
+        }
+        // ================= backward substitution (right to left), the forward solution re-derived on the way
+        pair_scan<true, WP_WARPS>(v, in, P, s_wex[1], s_pow, s_nbr, s_cbar, rank, (unsigned)it & 1u);
+        if (!dead) {
+            double a1 = in[0], a2 = in[1], b1 = in[2], b2 = in[3];
+#pragma unroll
+            for (int j = WP_ITEMS - 1; j >= 0; --j) {
+                const double za = fa1 * cfA[0][j & 1], zb = fb1 * cfB[0][j & 1];
+                const double na = fma(-cfA[2][j & 1], a2, fma(-cfA[1][j & 1], a1, za));
+                const double nb = fma(-cfB[2][j & 1], b2, fma(-cfB[1][j & 1], b1, zb));
+                a2 = a1; a1 = na; b2 = b1; b1 = nb;
+                if (j >= 2) {
+                    const double ra = (j & 1) ? 0.0 : y[j], rb_ = (j & 1) ? y[j] : 0.0;
+                    const double pa = fma(-cfA[1][(j + 1) & 1], fa2, ra - fa1) * P.tab.il2[0][j & 1];
+                    const double pb = fma(-cfB[1][(j + 1) & 1], fb2, rb_ - fb1) * P.tab.il2[1][j & 1];
+                    fa1 = fa2; fa2 = pa; fb1 = fb2; fb2 = pb;
+                } else {
+                    fa1 = fa2; fb1 = fb2;
+                }
+                const double bsl = 0.5 * (na + nb);                   // cross-fit average (baseline_backend.c:296-299)
+                y[j] = P.write_baseline ? bsl : y[j] - bsl;
+            }
+            if (!P.log_transform) {                       // (log2 of a finite count cannot overflow the solve)
+                expmax = 0;
+#pragma unroll
+                for (int j = 0; j < WP_ITEMS; ++j) expmax = max(expmax, __double2hiint(y[j]) & 0x7FF00000);
+                bad |= (expmax == 0x7FF00000);
+            }
+        }
+        // ---- epilogue: results over this thread's own slots of the landing buffer, own bins out in bulk
+        // (float input: other threads' raw slots overlap these double slots -- all raw reads precede the scans' barriers)
+        if (!dead) {
+            double2 *sp = reinterpret_cast<double2 *>(buf) + tid * (WP_ITEMS / 2);
+#pragma unroll
+            for (int u = 0; u < WP_ITEMS / 2; ++u) sp[u] = make_double2(y[2 * u], y[2 * u + 1]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        double *outp = P.out + hbase;
+        if ((reinterpret_cast<uintptr_t>(outp) & 15) == 0) {
+            if (tid == 0) {
+                const int b0 = (q0 + 1) & ~1, b1 = q1 & ~1;
+                if (q0 < b0) outp[q0] = buf[q0];
+                if (b1 < q1) outp[b1] = buf[b1];
+                if (b1 > b0) {
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 ::"l"(outp + b0), "r"(smem_u32(buf + b0)), "r"((unsigned)(b1 - b0) * 8u) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
+        } else {
+            for (int q = q0 + tid; q < q1; q += WP_THREADS) outp[q] = buf[q];          // coalesced fallback
+            __syncthreads();                              // before the buffer is handed to the next bulk load
+        }
+    }
+    if (bad) *P.bad = 1;
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");    // shared memory must outlive the last read
+}
+
 // n < 25: the reference returns a zero baseline (baseline_backend.c:266-273) -> centered = y
 __global__ void k_small_rows(WhitParams P)
 {
@@ -1108,7 +1309,7 @@ static int get_factor(long long n, double lam, FactorRef *out)
 // steady tiles: 0 = cluster-pair kernel 512 x 12 (default), 2 = cluster-pair kernel 384 x 16, 1 = the single-CTA kernel
 // (kept for A/B checks)
 static std::atomic<int> g_whit_mode{0};
-int whittaker_set_mode(int mode) { return g_whit_mode.exchange((mode >= 0 && mode <= 2) ? mode : 0); }
+int whittaker_set_mode(int mode) { return g_whit_mode.exchange((mode >= 0 && mode <= 3) ? mode : 0); }
 
 template <bool F32, int THREADS, int ITEMS>
 static int launch_pair(const PairParams &R, unsigned grid, cudaStream_t st)
@@ -1124,6 +1325,43 @@ static int launch_pair(const PairParams &R, unsigned grid, cudaStream_t st)
         attr = true;
     }
     k_whittaker_pair<F32, THREADS, ITEMS><<<grid, THREADS, sm, st>>>(R);
+    RB_LAUNCH_CHECK();
+    return 0;
+}
+
+template <bool F32, int THREADS, int ITEMS>
+static int launch_stream(PairParams R, long long pairs, cudaStream_t st)
+{
+    constexpr size_t sm = sizeof(double) * 2 * WP_HALF + sizeof(PairPow) + 16 * LOG2_V2_ENTRIES;
+    static bool attr_dev[64] = {false};
+    int d = 0;
+    cudaGetDevice(&d);
+    bool &attr = attr_dev[d & 63];
+    if (!attr) {
+        RB_CUDA(cudaFuncSetAttribute(k_whittaker_stream<F32, THREADS, ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        RB_CUDA(cudaFuncSetAttribute(k_whittaker_stream<F32, THREADS, ITEMS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        attr = true;
+    }
+    // persistent grid: as many clusters as are co-resident (two CTAs per SM -> about one cluster per SM)
+    static int resident_dev[64] = {0};
+    int &resident = resident_dev[d & 63];
+    if (resident == 0) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(2 * (unsigned)sm_count()); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = sm;
+        cudaLaunchAttribute at{};
+        at.id = cudaLaunchAttributeClusterDimension;
+        at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+        cfg.attrs = &at; cfg.numAttrs = 1;
+        int nc = 0;
+        if (cudaOccupancyMaxActiveClusters(&nc, k_whittaker_stream<F32, THREADS, ITEMS>, &cfg) != cudaSuccess || nc <= 0) {
+            (void)cudaGetLastError();
+            nc = sm_count();
+        }
+        resident = nc;
+    }
+    R.total_pairs = (int)pairs;
+    const long long clusters = std::min<long long>(pairs, resident);
+    k_whittaker_stream<F32, THREADS, ITEMS><<<(unsigned)(clusters * 2), THREADS, sm, st>>>(R);
     RB_LAUNCH_CHECK();
     return 0;
 }
@@ -1215,7 +1453,8 @@ int whittaker_rows(const void *d_x, int in_f32, int log_transform, const double 
                 R.log2tab = F->d_log2i;
                 const long long nrows = (rows - p + period - 1) / period;
                 const unsigned grid = (unsigned)(nrows * Q.span_tiles * 2);
-                if (gm == 0) RB_TRY(in_f32 ? (launch_pair<true, 512, 12>(R, grid, st)) : (launch_pair<false, 512, 12>(R, grid, st)));
+                if (mode == 3) RB_TRY(in_f32 ? (launch_stream<true, 512, 12>(R, nrows * Q.span_tiles, st)) : (launch_stream<false, 512, 12>(R, nrows * Q.span_tiles, st)));
+                else if (gm == 0) RB_TRY(in_f32 ? (launch_pair<true, 512, 12>(R, grid, st)) : (launch_pair<false, 512, 12>(R, grid, st)));
                 else RB_TRY(in_f32 ? (launch_pair<true, 384, 16>(R, grid, st)) : (launch_pair<false, 384, 16>(R, grid, st)));
             }
         } else if (sp.steady) {
