@@ -78,10 +78,11 @@ static void host_factor(long long n_true, long long len, int parity, double lam,
 constexpr int WP_HALF = 6144;                      // bins per CTA, two CTAs per region
 constexpr int WP_MAXWARPS = 16;
 constexpr int WP_LEVELS = 9;                       // 5 in-warp levels + 4 across the warps of a CTA
-// thread geometries of the pair kernel (threads x bins per thread = WP_HALF): 0 = 512 x 12, 1 = 384 x 16
-constexpr int WP_NGEOM = 2;
-constexpr int WP_GEOM_THREADS[WP_NGEOM] = {512, 384};
-constexpr int WP_GEOM_ITEMS[WP_NGEOM] = {12, 16};
+// thread geometry of the pair kernels (threads x bins per thread = WP_HALF): 512 x 12 (384 x 16 and a cluster of four
+// 256-thread CTAs were measured slower: fewer resident warps / no gain from the finer phases)
+constexpr int WP_NGEOM = 1;
+constexpr int WP_GEOM_THREADS[WP_NGEOM] = {512};
+constexpr int WP_GEOM_ITEMS[WP_NGEOM] = {12};
 struct PairTab {
     double cf[2][3][2];                            // [chain][dinv, l1, l2][position parity]
     double trans[2][2][WP_LEVELS][4];              // [chain][fwd/bwd][level]: transition over ITEMS * 2^level bins
@@ -767,7 +768,7 @@ __device__ __forceinline__ void warp_entry_state(double (&E)[4], int target, int
     }
 }
 
-template <bool REV, int WP_WARPS>
+template <bool REV, int WP_WARPS, int CL = 2>
 __device__ __forceinline__ void pair_scan(double (&v)[4], double (&in)[4], const PairParams &P, double (*s_wex)[4],
                                           const double *s_pow, double (*s_nbr)[4], unsigned long long *s_cbar, int rank,
                                           unsigned cpar = 0)
@@ -802,8 +803,12 @@ __device__ __forceinline__ void pair_scan(double (&v)[4], double (&in)[4], const
         *reinterpret_cast<double2 *>(&s_wex[wpos][2]) = make_double2(v[2], v[3]);
     }
     __syncthreads();
-    const bool sender = REV ? (rank == 1) : (rank == 0);
-    const bool receiver = !sender;
+    // scan order over the cluster's CTAs: ascending rank forward, descending backward.  A CTA's total leaves for the next
+    // CTA in scan order WITHOUT the contribution of the CTA before it: a transition over a whole CTA (>= 3072 bins) is
+    // below 1e-30, so the chain over more than two CTAs has no serial dependency.
+    const bool sender = REV ? (rank > 0) : (rank < CL - 1);
+    const bool receiver = REV ? (rank < CL - 1) : (rank > 0);
+    const int dest = REV ? rank - 1 : rank + 1;
     if (sender && wpos == WP_WARPS - 1) {
         // this CTA's total = the state that would enter a warp after the last one; 32 bytes into the peer's shared memory,
         // completing on the peer's mbarrier
@@ -811,8 +816,8 @@ __device__ __forceinline__ void pair_scan(double (&v)[4], double (&in)[4], const
         warp_entry_state<WP_WARPS>(N, WP_WARPS, D, false, s_wex, s_pow, s_nbr);
         if (lane == 0) {
             unsigned rdst, rbar;
-            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rdst) : "r"(smem_u32(&s_nbr[D][0])), "r"(rank ^ 1));
-            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(smem_u32(&s_cbar[D])), "r"(rank ^ 1));
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rdst) : "r"(smem_u32(&s_nbr[D][0])), "r"(dest));
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(smem_u32(&s_cbar[D])), "r"(dest));
             asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];"
                          ::"r"(rdst), "d"(N[0]), "d"(N[1]), "r"(rbar) : "memory");
             asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];"
@@ -1006,15 +1011,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WP_THREADS, 2) k_whi
 // (n_{j-2} = (r_j - n_j - l1 n_{j-1}) / l2; twelve steps of a recurrence whose reverse growth is 1/0.9775 per bin, i.e.
 // ~1e-16 relative).  y stays in registers, the result is written over the thread's own slots of the landing buffer and
 // leaves from there as one bulk store.
-template <bool F32, int WP_THREADS, int WP_ITEMS>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WP_THREADS, 2) k_whittaker_stream(const __grid_constant__ PairParams P)
+template <bool F32, int WP_THREADS, int WP_ITEMS, int CL>
+__global__ void __launch_bounds__(WP_THREADS, 1024 / WP_THREADS) k_whittaker_stream(const __grid_constant__ PairParams P)
 {
     namespace cg = cooperative_groups;
-    static_assert(WP_THREADS * WP_ITEMS == WP_HALF && WP_ITEMS % 4 == 0 && WP_ITEMS <= 16, "pair geometry");
+    constexpr int CTA_BINS = WP_THREADS * WP_ITEMS;       // cluster of CL CTAs (launch attribute) = one 12288-bin region
+    static_assert(CL * CTA_BINS == 2 * WP_HALF && WP_ITEMS % 4 == 0 && WP_ITEMS <= 16 && CTA_BINS >= 3072, "stream geometry");
     constexpr int WP_WARPS = WP_THREADS / 32;
     extern __shared__ __align__(128) double smem_pair[];
-    double *s_buf0 = smem_pair, *s_buf1 = smem_pair + WP_HALF;        // landing buffers (raw in, result out)
-    double *s_pow = smem_pair + 2 * WP_HALF;
+    double *s_buf0 = smem_pair, *s_buf1 = smem_pair + CTA_BINS;       // landing buffers (raw in, result out)
+    double *s_pow = smem_pair + 2 * CTA_BINS;
     const double2 *s_log = reinterpret_cast<const double2 *>(s_pow + sizeof(PairPow) / sizeof(double));
     __shared__ __align__(8) unsigned long long s_full[2]; // raw input of buffer b has landed
     __shared__ __align__(8) unsigned long long s_tabbar;  // tables
@@ -1024,17 +1030,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WP_THREADS, 2) k_whi
 
     const int rank = (int)cg::this_cluster().block_rank();
     const int tid = threadIdx.x;
-    const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+    const int cid = blockIdx.x / CL, ncl = gridDim.x / CL;
     const int total = P.total_pairs;
-    constexpr unsigned BYTES = WP_HALF * (F32 ? 4u : 8u);
+    constexpr unsigned BYTES = CTA_BINS * (F32 ? 4u : 8u);
     constexpr unsigned LOG_BYTES = 16u * LOG2_V2_ENTRIES;
-    const int recv = (rank == 1) ? 0 : 1;                 // the carry this CTA receives: forward (right half) / backward (left half)
+    const bool recv_fwd = rank > 0, recv_bwd = rank < CL - 1;     // carries this CTA receives (from its left / right neighbour)
 
     auto half_base = [&](int pair_idx) -> long long {
         const long long row = P.row0 + (long long)(pair_idx / P.span_tiles) * P.row_step;
         const int tile = P.tile_offset + pair_idx % P.span_tiles;
         const long long r0 = (long long)tile * WT_OUT - WT_HALO - P.shift;
-        return row * P.row_stride + r0 + (long long)rank * WP_HALF;
+        return row * P.row_stride + r0 + (long long)rank * CTA_BINS;
     };
 
     if (tid == 0) {
@@ -1058,10 +1064,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WP_THREADS, 2) k_whi
 
     const double (*cfA)[2] = P.tab.cf[0];
     const double (*cfB)[2] = P.tab.cf[1];
-    const int p0 = rank * WP_HALF + tid * WP_ITEMS;
+    const int p0 = rank * CTA_BINS + tid * WP_ITEMS;
     const int o_lo = WT_HALO + P.shift, o_hi = o_lo + WT_OUT;
     const bool dead = (p0 + WP_ITEMS <= o_lo);            // left-halo threads only feed the forward scan
-    const int q0 = max(o_lo, rank * WP_HALF) - rank * WP_HALF, q1 = min(o_hi, (rank + 1) * WP_HALF) - rank * WP_HALF;   // own bins in half positions
+    const int q0 = max(o_lo, rank * CTA_BINS) - rank * CTA_BINS, q1 = min(o_hi, (rank + 1) * CTA_BINS) - rank * CTA_BINS;   // own bins in CTA positions
     int bad = 0;
 
 #pragma unroll 1
@@ -1070,8 +1076,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WP_THREADS, 2) k_whi
         double *buf = b ? s_buf1 : s_buf0;
         const long long row = P.row0 + (long long)(pair_idx / P.span_tiles) * P.row_step;
         const long long hbase = half_base(pair_idx);
-        if (tid == 0)          // this tile's carry (the previous phase of the barrier was completed and observed one tile ago)
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 32;" ::"r"(smem_u32(&s_cbar[recv])) : "memory");
+        if (tid == 0) {        // this tile's carries (the previous phase of each barrier was completed and observed one tile ago)
+            if (recv_fwd) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 32;" ::"r"(smem_u32(&s_cbar[0])) : "memory");
+            if (recv_bwd) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 32;" ::"r"(smem_u32(&s_cbar[1])) : "memory");
+        }
         const double pil = (P.log_transform && P.pilot) ? P.pilot[row] : 0.0;
         mbar_wait(smem_u32(&s_full[b]), (unsigned)(it >> 1) & 1u);
 
@@ -1111,7 +1119,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WP_THREADS, 2) k_whi
             }
             v[0] = a1; v[1] = a2; v[2] = b1; v[3] = b2;
         }
-        pair_scan<false, WP_WARPS>(v, in, P, s_wex[0], s_pow, s_nbr, s_cbar, rank, (unsigned)it & 1u);
+        pair_scan<false, WP_WARPS, CL>(v, in, P, s_wex[0], s_pow, s_nbr, s_cbar, rank, (unsigned)it & 1u);
         // (the scan's CTA barrier: every thread has its raw bins in registers, and the other buffer's previous store was
         // issued a whole tile phase ago)  -> start the next tile's input
         if (tid == 0 && pair_idx + ncl < total) {
@@ -1137,7 +1145,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WP_THREADS, 2) k_whi
             fa1 = a1; fa2 = a2; fb1 = b1; fb2 = b2;
         }
         // ================= backward substitution (right to left), the forward solution re-derived on the way
-        pair_scan<true, WP_WARPS>(v, in, P, s_wex[1], s_pow, s_nbr, s_cbar, rank, (unsigned)it & 1u);
+        pair_scan<true, WP_WARPS, CL>(v, in, P, s_wex[1], s_pow, s_nbr, s_cbar, rank, (unsigned)it & 1u);
         if (!dead) {
             double a1 = in[0], a2 = in[1], b1 = in[2], b2 = in[3];
 #pragma unroll
@@ -1218,7 +1226,7 @@ struct FactorDev {
     double *d_lanepow = nullptr;
     double *d_log2 = nullptr;
     double *d_log2i = nullptr;                       // the same tables interleaved {inv[i], tab[i]} (pair kernel)
-    double *d_pairpow[WP_NGEOM][2] = {{nullptr, nullptr}, {nullptr, nullptr}};       // PairPow per geometry and shift parity
+    double *d_pairpow[WP_NGEOM][2] = {};       // PairPow per geometry and shift parity
     int device = 0;
     unsigned long long last_use = 0;
     FactorDev() = default;
@@ -1306,8 +1314,9 @@ static int get_factor(long long n, double lam, FactorRef *out)
     return 0;
 }
 
-// steady tiles: 0 = cluster-pair kernel 512 x 12 (default), 2 = cluster-pair kernel 384 x 16, 1 = the single-CTA kernel
-// (kept for A/B checks)
+// steady tiles: 0 = automatic (float64 input: streaming cluster-pair kernel; float32 input: one-shot cluster-pair kernel,
+// whose shorter input copy leaves nothing for the streaming form to hide), 1 = the single-CTA kernel, 2 = one-shot pair
+// kernel, 3 = streaming pair kernel (1-3 kept for A/B checks)
 static std::atomic<int> g_whit_mode{0};
 int whittaker_set_mode(int mode) { return g_whit_mode.exchange((mode >= 0 && mode <= 3) ? mode : 0); }
 
@@ -1329,40 +1338,42 @@ static int launch_pair(const PairParams &R, unsigned grid, cudaStream_t st)
     return 0;
 }
 
-template <bool F32, int THREADS, int ITEMS>
+template <bool F32, int THREADS, int ITEMS, int CL>
 static int launch_stream(PairParams R, long long pairs, cudaStream_t st)
 {
-    constexpr size_t sm = sizeof(double) * 2 * WP_HALF + sizeof(PairPow) + 16 * LOG2_V2_ENTRIES;
+    constexpr size_t sm = sizeof(double) * 2 * THREADS * ITEMS + sizeof(PairPow) + 16 * LOG2_V2_ENTRIES;
+    auto kern = k_whittaker_stream<F32, THREADS, ITEMS, CL>;
     static bool attr_dev[64] = {false};
+    static int resident_dev[64] = {0};
     int d = 0;
     cudaGetDevice(&d);
     bool &attr = attr_dev[d & 63];
     if (!attr) {
-        RB_CUDA(cudaFuncSetAttribute(k_whittaker_stream<F32, THREADS, ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        RB_CUDA(cudaFuncSetAttribute(k_whittaker_stream<F32, THREADS, ITEMS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        RB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        RB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr = true;
     }
-    // persistent grid: as many clusters as are co-resident (two CTAs per SM -> about one cluster per SM)
-    static int resident_dev[64] = {0};
+    cudaLaunchAttribute at{};
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = CL; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = sm; cfg.stream = st; cfg.attrs = &at; cfg.numAttrs = 1;
+    // persistent grid: as many clusters as are co-resident (1024 threads per SM)
     int &resident = resident_dev[d & 63];
     if (resident == 0) {
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(2 * (unsigned)sm_count()); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = sm;
-        cudaLaunchAttribute at{};
-        at.id = cudaLaunchAttributeClusterDimension;
-        at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
-        cfg.attrs = &at; cfg.numAttrs = 1;
+        cfg.gridDim = dim3((unsigned)(CL * sm_count()));
         int nc = 0;
-        if (cudaOccupancyMaxActiveClusters(&nc, k_whittaker_stream<F32, THREADS, ITEMS>, &cfg) != cudaSuccess || nc <= 0) {
+        if (cudaOccupancyMaxActiveClusters(&nc, kern, &cfg) != cudaSuccess || nc <= 0) {
             (void)cudaGetLastError();
-            nc = sm_count();
+            nc = sm_count() * (1024 / THREADS) / CL;
         }
         resident = nc;
     }
     R.total_pairs = (int)pairs;
     const long long clusters = std::min<long long>(pairs, resident);
-    k_whittaker_stream<F32, THREADS, ITEMS><<<(unsigned)(clusters * 2), THREADS, sm, st>>>(R);
-    RB_LAUNCH_CHECK();
+    cfg.gridDim = dim3((unsigned)(clusters * CL));
+    RB_CUDA(cudaLaunchKernelEx(&cfg, kern, R));
+    count_launch();
     return 0;
 }
 
@@ -1426,7 +1437,8 @@ int whittaker_rows(const void *d_x, int in_f32, int log_transform, const double 
     }
     const size_t esz = in_f32 ? 4 : 8;
     const int mode = g_whit_mode.load();
-    const int gm = mode == 2 ? 1 : 0;
+    const int gm = 0;
+    const bool stream = mode == 3 || (mode == 0 && !in_f32);
     const bool pair_ok = mode != 1 && (reinterpret_cast<uintptr_t>(d_x) % esz) == 0;
     for (const Span &sp : spans) {
         WhitParams Q = P;
@@ -1453,9 +1465,8 @@ int whittaker_rows(const void *d_x, int in_f32, int log_transform, const double 
                 R.log2tab = F->d_log2i;
                 const long long nrows = (rows - p + period - 1) / period;
                 const unsigned grid = (unsigned)(nrows * Q.span_tiles * 2);
-                if (mode == 3) RB_TRY(in_f32 ? (launch_stream<true, 512, 12>(R, nrows * Q.span_tiles, st)) : (launch_stream<false, 512, 12>(R, nrows * Q.span_tiles, st)));
-                else if (gm == 0) RB_TRY(in_f32 ? (launch_pair<true, 512, 12>(R, grid, st)) : (launch_pair<false, 512, 12>(R, grid, st)));
-                else RB_TRY(in_f32 ? (launch_pair<true, 384, 16>(R, grid, st)) : (launch_pair<false, 384, 16>(R, grid, st)));
+                if (stream) RB_TRY(in_f32 ? (launch_stream<true, 512, 12, 2>(R, nrows * Q.span_tiles, st)) : (launch_stream<false, 512, 12, 2>(R, nrows * Q.span_tiles, st)));
+                else RB_TRY(in_f32 ? (launch_pair<true, 512, 12>(R, grid, st)) : (launch_pair<false, 512, 12>(R, grid, st)));
             }
         } else if (sp.steady) {
             k_whittaker<true, WT_THREADS_S, WT_ITEMS_S><<<(unsigned)blocks, WT_THREADS_S, sm_steady, st>>>(Q);

@@ -47,20 +47,20 @@ def cmd_whit():
     for m, n, dt, use_oracle in shapes:
         x = chrom_matrix_torch(m, n, 11 + n % 7, DEV, dt)
         out = {}
-        for mode in (1, 0, 3):
+        for mode in (1, 2, 3):
             prev = lib.rocco_b200_whittaker_set_mode(mode)
             s, d = pipeline.score_loci_wls_device(x, params=prm, details=True)
             torch.cuda.synchronize()
             out[mode] = (s.clone(), d["centered_matrix"].clone())
             lib.rocco_b200_whittaker_set_mode(prev)
         row = {"m": m, "n": n, "dtype": str(dt)}
-        for mode in (0, 3):
+        for mode in (2, 3):
             row[f"centered_maxabs_mode{mode}_vs_old"] = float((out[mode][1] - out[1][1]).abs().max())
             row[f"scores_maxabs_mode{mode}_vs_old"] = float((out[mode][0] - out[1][0]).abs().max())
         if use_oracle:
             want_s, want_d = orc.score_loci_wls(x.cpu().numpy(), prior_df=6.0, return_details=True,
                                                 kind="reference" if orc.reference_available() else "port")
-            for mode in (1, 0, 3):
+            for mode in (1, 2, 3):
                 row[f"centered_maxabs_mode{mode}_vs_oracle"] = float(np.max(np.abs(out[mode][1].cpu().numpy() - want_d["centered_matrix"])))
                 ref = np.maximum(np.abs(want_s), 1e-3)
                 row[f"scores_maxrel_mode{mode}_vs_oracle"] = float(np.max(np.abs(out[mode][0].cpu().numpy() - want_s) / ref))
@@ -81,7 +81,7 @@ def cmd_whit():
         n = chrom_bins(name)
         x = chrom_matrix_torch(m, n, chrom_seed(name), DEV, dt)
         sc = torch.empty(n, dtype=torch.float64, device=DEV)
-        for mode in (1, 0, 3):
+        for mode in (1, 2, 3):
             prev = lib.rocco_b200_whittaker_set_mode(mode)
             sp = scopes_of(lambda: pipeline.score_loci_wls_device(x, out_scores=sc, params=prm))
             lib.rocco_b200_whittaker_set_mode(prev)
