@@ -390,15 +390,25 @@ RB_API int rocco_b200_uniform_step_i64(const long long *v, size_t n)
 
 /* BED3 (or BED4 with chrom_start_end names) text of n records straight to a file: the host half of rocco.py:98-110
  * (_write_bed_records) without a Python loop per record.  names[name_idx[i]] (name_idx == NULL: names[0]). */
+static const char kDigitPairs[201] =
+    "00010203040506070809101112131415161718192021222324252627282930313233343536373839404142434445464748495051525354555657585960616263646566676869707172737475767778798081828384858687888990919293949596979899";
 static inline char *put_ll(char *p, long long v)
 {
-    char tmp[24];
-    int k = 0;
-    unsigned long long u = v < 0 ? (unsigned long long)(-(v + 1)) + 1ULL : (unsigned long long)v;
-    if (v < 0) *p++ = '-';
-    do { tmp[k++] = (char)('0' + (u % 10)); u /= 10; } while (u);
-    while (k) *p++ = tmp[--k];
-    return p;
+    unsigned long long u;
+    if (v < 0) { *p++ = '-'; u = 0ULL - (unsigned long long)v; } else u = (unsigned long long)v;
+    // digit count first, then two digits at a time from the back (genomic coordinates: 32-bit arithmetic almost always)
+    int nd = 1;
+    for (unsigned long long t = u; t >= 10; t /= 10) ++nd;
+    char *q = p + nd;
+    if (u <= 0xFFFFFFFFULL) {
+        unsigned w = (unsigned)u;
+        while (w >= 100) { const unsigned r = w % 100; w /= 100; q -= 2; q[0] = kDigitPairs[2 * r]; q[1] = kDigitPairs[2 * r + 1]; }
+        if (w >= 10) { q -= 2; q[0] = kDigitPairs[2 * w]; q[1] = kDigitPairs[2 * w + 1]; } else *--q = (char)('0' + w);
+    } else {
+        while (u >= 100) { const unsigned r = (unsigned)(u % 100); u /= 100; q -= 2; q[0] = kDigitPairs[2 * r]; q[1] = kDigitPairs[2 * r + 1]; }
+        if (u >= 10) { q -= 2; q[0] = kDigitPairs[2 * u]; q[1] = kDigitPairs[2 * u + 1]; } else *--q = (char)('0' + u);
+    }
+    return p + nd;
 }
 
 RB_API int rocco_b200_write_bed3(const char *path, const char *const *names, int n_names, const int *name_idx,
@@ -410,20 +420,30 @@ RB_API int rocco_b200_write_bed3(const char *path, const char *const *names, int
     std::vector<size_t> len((size_t)n_names);
     size_t maxlen = 0;
     for (int k = 0; k < n_names; ++k) { len[k] = strlen(names[k]); maxlen = std::max(maxlen, len[k]); }
-    const size_t per = 2 * maxlen + 4 * 21 + 8;
+    const size_t per = (name_features ? 2 : 1) * (maxlen + 2 * 20 + 2) + 2;      // upper bound of one record's text
     // records are formatted in parallel (a few host threads, one contiguous slice each) and written in order
     for (size_t i = 0; i < n; ++i) {
         const int c = name_idx ? name_idx[i] : 0;
         if (c < 0 || c >= n_names) { fclose(fh); return rb::ST_INVALID; }
     }
     const unsigned hw = std::thread::hardware_concurrency();
-    const size_t nthreads = std::max<size_t>(1, std::min<size_t>({(size_t)4, (size_t)(hw ? hw : 1), n / 8192 + 1}));
-    std::vector<std::vector<char>> bufs(nthreads);
+    const size_t nthreads = std::max<size_t>(1, std::min<size_t>({(size_t)8, (size_t)(hw ? hw : 1), n / 8192 + 1}));
+    // one text buffer kept between calls (touching fresh pages costs more than the formatting itself)
+    static std::mutex text_mu;
+    static char *text = nullptr;
+    static size_t text_cap = 0;
+    std::lock_guard<std::mutex> text_lock(text_mu);
+    if (per * n + 1 > text_cap) {
+        free(text);
+        text_cap = per * n + 1 + (per * n) / 4;
+        text = (char *)malloc(text_cap);
+        if (!text) { text_cap = 0; fclose(fh); return rb::ST_NOMEM; }
+    }
     std::vector<size_t> used(nthreads, 0);
     auto work = [&](size_t t) {
         const size_t i0 = n * t / nthreads, i1 = n * (t + 1) / nthreads;
-        bufs[t].resize(per * (i1 - i0) + 1);
-        char *p = bufs[t].data();
+        char *const base = text + per * i0;
+        char *p = base;
         for (size_t i = i0; i < i1; ++i) {
             const int c = name_idx ? name_idx[i] : 0;
             memcpy(p, names[c], len[c]); p += len[c];
@@ -437,14 +457,14 @@ RB_API int rocco_b200_write_bed3(const char *path, const char *const *names, int
             }
             *p++ = '\n';
         }
-        used[t] = (size_t)(p - bufs[t].data());
+        used[t] = (size_t)(p - base);
     };
     std::vector<std::thread> pool;
     for (size_t t = 1; t < nthreads; ++t) pool.emplace_back(work, t);
     work(0);
     for (auto &th : pool) th.join();
     for (size_t t = 0; t < nthreads; ++t)
-        if (used[t] && fwrite(bufs[t].data(), 1, used[t], fh) != used[t]) { fclose(fh); return rb::ST_INVALID; }
+        if (used[t] && fwrite(text + per * (n * t / nthreads), 1, used[t], fh) != used[t]) { fclose(fh); return rb::ST_INVALID; }
     fclose(fh);
     return 0;
 }
