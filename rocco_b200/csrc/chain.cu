@@ -48,6 +48,9 @@ __device__ __forceinline__ bool v_eq(VD a, VD b) { return a.v == b.v; }
 __device__ __forceinline__ bool v_eq(VL a, VL b) { return a.v == b.v && a.k == b.k; }
 template <typename V> __device__ __forceinline__ V v_max(V a, V b) { return v_lt(a, b) ? b : a; }
 template <typename V> __device__ __forceinline__ V v_min(V a, V b) { return v_lt(b, a) ? b : a; }
+// plain doubles: the same selections as one compare + select (rb::dmax / rb::dmin; ties keep a, as above)
+template <> __device__ __forceinline__ VD v_max<VD>(VD a, VD b) { return VD{dmax(b.v, a.v)}; }
+template <> __device__ __forceinline__ VD v_min<VD>(VD a, VD b) { return VD{dmin(b.v, a.v)}; }
 template <typename V> __device__ __forceinline__ V v_clamp(V x, V lo, V hi) { return v_min(v_max(x, lo), hi); }
 __device__ __forceinline__ VD v_shfl_up(VD a, int d) { return VD{__shfl_up_sync(0xffffffffu, a.v, d)}; }
 __device__ __forceinline__ VL v_shfl_up(VL a, int d) {
@@ -348,10 +351,10 @@ __global__ void __launch_bounds__(THREADS, 4) k_chain_tiles(Params P)
                 if (fz_track) {
                     const bool term = (gi == cd.n - 1);
                     const double cr_ = term ? 0.0 : (VEC_COST ? s_cs[(base + j + 1) + (base + j + 1) / ITEMS] : cd.gamma);
-                    const double margin = term ? fabs(x.v) : fmin(fabs(x.v - cr_), fabs(x.v + cr_));
+                    const double margin = term ? fabs(x.v) : dmin(fabs(x.v - cr_), fabs(x.v + cr_));
                     fz_run += 1;
                     const double slack = margin - (double)fz_run * fz_width;
-                    if (fz_sat) fz_b = fmin(fz_b, slack); else fz_a = fmin(fz_a, slack);
+                    if (fz_sat) fz_b = dmin(slack, fz_b); else fz_a = dmin(slack, fz_a);
                     const bool sat = term || x.v > cr_ || x.v < -cr_;
                     if (base + j == len - 1) fz_lastok = sat ? 1 : 0;
                     if (sat) { fz_sat = 1; fz_run = 0; }

@@ -13,6 +13,25 @@
 
 namespace rb {
 
+// max / min of two doubles as ONE compare and a select.  fmax()/fmin() cost about eight instructions each on sm_100
+// (DSETP.MAX + FSEL + SEL + NaN quieting + moves); these keep fmax/fmin's result whenever `b` is not NaN -- a NaN in
+// `a` gives b, exactly like fmax/fmin -- which is how every call site uses them (b is a constant or an already clamped value).
+#ifdef __CUDACC__
+// (inline PTX: written as `a > b ? a : b` the compiler recognises the idiom and emits the fmax sequence again)
+__device__ __forceinline__ double dmax(double a, double b)
+{
+    double r;
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %1, %2;\n\tselp.f64 %0, %1, %2, p;\n\t}" : "=d"(r) : "d"(a), "d"(b));
+    return r;
+}
+__device__ __forceinline__ double dmin(double a, double b)
+{
+    double r;
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.f64 p, %1, %2;\n\tselp.f64 %0, %1, %2, p;\n\t}" : "=d"(r) : "d"(a), "d"(b));
+    return r;
+}
+#endif
+
 constexpr int ST_OK = 0, ST_NOMEM = -1, ST_INVALID = -2, ST_CUDA = -3, ST_NONFINITE = -4;
 
 void set_error(const char *fmt, ...);

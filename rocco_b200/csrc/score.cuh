@@ -55,11 +55,11 @@ __device__ __forceinline__ double ar1_window_variance(double s1, double s2, doub
                                                       double rwd, double pairs, double c1)
 {
     const double mu = s1 * rwd;
-    const double g0 = fmax(__fma_rn(-(wd * mu), mu, s2), 0.0);
+    const double g0 = dmax(__fma_rn(-(wd * mu), mu, s2), 0.0);
     const double g1 = __fma_rn(pairs * mu, mu, __fma_rn(-mu, (s1 - last) + (s1 - first), sl));
     const double den = __fma_rn(g0, c1, 1.0e-4);
     double beta = g1 * rcp_nr(den);
-    beta = fmin(fmax(beta, 0.0), 0.99);
+    beta = dmin(dmax(beta, 0.0), 0.99);
     return (g0 * rwd) * __fma_rn(-beta, beta, 1.0);
 }
 

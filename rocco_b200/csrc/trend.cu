@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(RV_THREADS) k_rollvar_xhist(const double *__re
                     sl = __fma_rn(y[k - 2 + W], nx, __fma_rn(-out_v, y[k], sl));
                 }
                 const double cur = ar1_window_variance(s1, s2, sl, y[k], y[k + W - 1], wd, rwd, pairs, shrink);
-                ob[k] = fmax(cur, 1.0e-8);                                         // wls_backend.c:869
+                ob[k] = dmax(cur, 1.0e-8);                                         // wls_backend.c:869
             }
         } else {
             const long long jt = j0 + (long long)tid * RV_K;
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(RV_THREADS) k_rollvar_xhist(const double *__re
                     cur = ar1_window_variance(s1, s2, sl, s_in[padpos(r)], s_in[padpos(r + w - 1)], wd, rwd, pairs, shrink);
                     tprev = t;
                 }
-                s_out[padpos(tid * RV_K + k)] = fmax(cur, 1.0e-8);
+                s_out[padpos(tid * RV_K + k)] = dmax(cur, 1.0e-8);
             }
         }
         __syncthreads();

@@ -911,7 +911,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WP_THREADS, 2) k_whi
     int bad = (expmax == 0x7FF00000);
     if (P.log_transform) {
 #pragma unroll
-        for (int j = 0; j < WP_ITEMS; ++j) y[j] = fast_log2_ge1_v2(fmax(y[j], 0.0) + 1.0, s_log) - pil;
+        for (int j = 0; j < WP_ITEMS; ++j) y[j] = fast_log2_ge1_v2(dmax(y[j], 0.0) + 1.0, s_log) - pil;
     }
 
     const double (*cfA)[2] = P.tab.cf[0];                 // [dinv, l1, l2][position parity]
@@ -1103,7 +1103,7 @@ __global__ void __launch_bounds__(WP_THREADS, 1024 / WP_THREADS) k_whittaker_str
         bad |= (expmax == 0x7FF00000);
         if (P.log_transform) {
 #pragma unroll
-            for (int j = 0; j < WP_ITEMS; ++j) y[j] = fast_log2_ge1_v2(fmax(y[j], 0.0) + 1.0, s_log) - pil;
+            for (int j = 0; j < WP_ITEMS; ++j) y[j] = fast_log2_ge1_v2(dmax(y[j], 0.0) + 1.0, s_log) - pil;
         }
 
         double v[4], in[4];

@@ -378,7 +378,7 @@ __device__ __forceinline__ void combine_one(double y, double ov, double pv, doub
                                             double &wsum, double &psum, double &rsum, double &qsum)
 {
     double post = __fma_rn(ldf, ov, pdf * pv) * rtdf1;
-    post = fmax(fmax(post, pfr * pv), 1.0e-8);
+    post = dmax(dmax(post, pfr * pv), 1.0e-8);
     const double prec = rcp_nr(post);                 // 1 / post to ~1 ulp (hardware seed + two Newton steps)
     if (WANT_RQ) { rsum += rcp_nr(ov); qsum += rcp_nr(pv); }
     psum += prec;
@@ -428,12 +428,12 @@ __global__ void __launch_bounds__(CB_THREADS, 4) k_combine(CombineParams P)
                     for (int u = 0; u < 4; ++u) {
                         if (rb + u >= nr) break;
                         const KnotTable &T = s_t[rb + u];
-                        const double tt = fmin(fmax(fabs(ys[u]), T.xlo), T.xhi);
+                        const double tt = dmin(dmax(fabs(ys[u]), T.xlo), T.xhi);
                         int lo = T.lut[knot_bucket(tt)];
                         const int top = T.top;
                         while (lo < top && T.xy[lo + 1].x <= tt) ++lo;
                         const double2 k = T.xy[lo];
-                        const double pv = fmax(__fma_rn(tt - k.x, T.slope[lo], k.y), 1.0e-8);
+                        const double pv = dmax(__fma_rn(tt - k.x, T.slope[lo], k.y), 1.0e-8);
                         combine_one<WANT_RQ>(ys[u], vs[u], pv, ldf, pdf, rtdf1, pfr, wsum, psum, rsum, qsum);     // V is floored at 1e-8 by its producer
                     }
                     const int adv = min(4, nr - rb);
