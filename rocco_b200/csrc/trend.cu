@@ -141,23 +141,24 @@ __global__ void __launch_bounds__(ST_THREADS) k_xhist(const double *__restrict__
 // produces 8 consecutive variances (direct 31-term window sums for the first, sliding updates for the next 7 --
 // far less drift than the reference's whole-row slide), results go back through shared memory for coalesced
 // stores, and the same pass feeds the |C| histogram.  Replaces wls_backend.c:610-742 + the T1 pass.
-constexpr int RV_T = 8192;                   // bins per CTA iteration
+constexpr int RV_T = 4096;                   // bins per CTA iteration
 constexpr int RV_K = 8;
-constexpr int RV_THREADS = RV_T / RV_K;      // 1024: one CTA per SM, 32 warps (the 64 KB histogram is shared)
+constexpr int RV_THREADS = RV_T / RV_K;      // 512: two CTAs per SM (64 KB histogram + 37 KB tile each), so that the staging
+                                             // loads of one overlap the window arithmetic of the other
 constexpr int RV_MAXW = 1025;
 
 __host__ __device__ __forceinline__ int padpos(int i) { return i + (i >> 3); }
 
 // W > 0: compile-time window (31 = the reference default): interior tiles run fully unrolled from registers.
 template <int W>
-__global__ void __launch_bounds__(RV_THREADS) k_rollvar_xhist(const double *__restrict__ C, long long n, long long row_stride, int w_rt,
+__global__ void __launch_bounds__(RV_THREADS, 2) k_rollvar_xhist(const double *__restrict__ C, long long n, long long row_stride, int w_rt,
                                                                double *__restrict__ V, int *xhist, BucketGeom G)
 {
     extern __shared__ int s_dyn[];
     const int w = W > 0 ? W : w_rt;
     int *s_h = s_dyn;                                              // NBX
     double *s_in = reinterpret_cast<double *>(s_dyn + NBX);        // padpos(RV_T + w)
-    double *s_out = s_in + padpos(RV_T + w) + 8;                   // padpos(RV_T)
+    double *s_out = s_in;                                          // the results reuse the tile's slots (after a barrier)
     const long long row = blockIdx.y;
     const double *c = C + row * row_stride;
     double *v = V + row * row_stride;
@@ -189,6 +190,7 @@ __global__ void __launch_bounds__(RV_THREADS) k_rollvar_xhist(const double *__re
         }
         __syncthreads();
         const bool interior = (j0 - half >= 0) && ((j1 - 1) - half <= last) && (j1 - j0 == RV_T);
+        double res[RV_K];
         if (W > 0 && interior) {
             // window of output k starts at staged position tid*8 + k; padded address = tid*9 + q + (q >> 3)
             const double *base = s_in + tid * 9;
@@ -202,7 +204,6 @@ __global__ void __launch_bounds__(RV_THREADS) k_rollvar_xhist(const double *__re
                 s2 = __fma_rn(y[q], y[q], s2);
                 if (q + 1 < W) sl = __fma_rn(y[q], y[q + 1], sl);
             }
-            double *ob = s_out + tid * 9;
 #pragma unroll
             for (int k = 0; k < RV_K; ++k) {
                 if (k > 0) {
@@ -212,16 +213,17 @@ __global__ void __launch_bounds__(RV_THREADS) k_rollvar_xhist(const double *__re
                     sl = __fma_rn(y[k - 2 + W], nx, __fma_rn(-out_v, y[k], sl));
                 }
                 const double cur = ar1_window_variance(s1, s2, sl, y[k], y[k + W - 1], wd, rwd, pairs, shrink);
-                ob[k] = dmax(cur, 1.0e-8);                                         // wls_backend.c:869
+                res[k] = dmax(cur, 1.0e-8);                                        // wls_backend.c:869
             }
         } else {
             const long long jt = j0 + (long long)tid * RV_K;
             double s1 = 0.0, s2 = 0.0, sl = 0.0, cur = 0.0;
             long long tprev = -1;
-#pragma unroll 1
+#pragma unroll
             for (int k = 0; k < RV_K; ++k) {
                 const long long j = jt + k;
-                if (j >= j1) break;
+                res[k] = 0.0;
+                if (j >= j1) continue;
                 long long t = j - half;
                 if (t < 0) t = 0; else if (t > last) t = last;
                 const int r = (int)(t - tlo);
@@ -246,8 +248,14 @@ __global__ void __launch_bounds__(RV_THREADS) k_rollvar_xhist(const double *__re
                     cur = ar1_window_variance(s1, s2, sl, s_in[padpos(r)], s_in[padpos(r + w - 1)], wd, rwd, pairs, shrink);
                     tprev = t;
                 }
-                s_out[padpos(tid * RV_K + k)] = dmax(cur, 1.0e-8);
+                res[k] = dmax(cur, 1.0e-8);
             }
+        }
+        __syncthreads();                                           // every window has been read: the slots can take the results
+        {
+            double *ob = s_out + tid * 9;                          // padpos(tid * 8 + k) = tid * 9 + k
+#pragma unroll
+            for (int k = 0; k < RV_K; ++k) ob[k] = res[k];
         }
         __syncthreads();
         double *dst = v + j0;
@@ -988,13 +996,13 @@ int trend_knots_select(const double *d_C, double *d_V, long long m, long long n,
     const unsigned chunks = (unsigned)((n + CHUNK - 1) / CHUNK);
     const dim3 gstream(chunks, (unsigned)m);
     if (fused_window > 0) {
-        const size_t sm_fused = sizeof(int) * NBX + sizeof(double) * (padpos(RV_T + fused_window) + 8 + padpos(RV_T) + 8);
+        const size_t sm_fused = sizeof(int) * NBX + sizeof(double) * (padpos(RV_T + fused_window) + 8);
         static bool attr2_dev[64] = {false};
     int attr2_d = 0;
     cudaGetDevice(&attr2_d);
     bool &attr2 = attr2_dev[attr2_d & 63];
         if (!attr2) {
-            const int mx = (int)(sizeof(int) * NBX + sizeof(double) * (padpos(RV_T + RV_MAXW) + 8 + padpos(RV_T) + 8));
+            const int mx = (int)(sizeof(int) * NBX + sizeof(double) * (padpos(RV_T + RV_MAXW) + 8));
             RB_CUDA(cudaFuncSetAttribute(k_rollvar_xhist<31>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
             RB_CUDA(cudaFuncSetAttribute(k_rollvar_xhist<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
             attr2 = true;
