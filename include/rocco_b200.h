@@ -217,10 +217,9 @@ int rocco_b200_trend_set_mode(int mode);
 long long rocco_b200_trend_fallback_rows(void);   /* rows that took the sort path since load */
 void rocco_b200_trend_fallback_reasons(long long *out8);   /* per-reason counts (diagnostics) */
 
-/* Kernel used for the interior ("steady") tiles of the Whittaker baseline: 0 = automatic (default: the streaming
- * cluster-pair kernel for float64 input, the one-shot cluster-pair kernel for float32 input); 1 = the round-1 single-CTA
- * kernel; 2 = one-shot pair kernel; 3 = streaming pair kernel.  All solve the same regions; results agree to rounding.
- * Returns the previous mode. */
+/* Kernel used for the interior ("steady") tiles of the Whittaker baseline: 0 = the streaming cluster-pair kernel
+ * (default); 1 = the round-1 single-CTA kernel; 2 = one-shot pair kernel; 3 = same as 0.  All solve the same regions;
+ * results agree to rounding.  Returns the previous mode. */
 int rocco_b200_whittaker_set_mode(int mode);
 
 /* Optional per-locus detail outputs (device or host according to the entry point); any may be NULL. */

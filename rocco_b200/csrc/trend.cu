@@ -135,6 +135,21 @@ __global__ void __launch_bounds__(ST_THREADS) k_xhist(const double *__restrict__
     }
 }
 
+// T3 runs on a PERSISTENT grid: the rows of the matrix, each padded to a multiple of 1024 pairs and laid end to end, are
+// cut into gridDim.x equal contiguous ranges (multiples of 1024), so that a CTA sets up the per-row table and clears and
+// flushes its 128 KB of histograms once per row it touches (one or two) instead of once per 131072 pairs, and no wave of
+// CTAs is left partly filled.  (T1 and T6, whose per-CTA setup is small, were measured slower in this form -- 296
+// separate streams instead of neighbouring chunks -- and keep one CTA per 131072-element chunk.)
+__device__ __forceinline__ long long padded_row(long long n) { return (n + 1023) & ~1023LL; }
+__device__ __forceinline__ void cta_range(long long rows, long long n, long long *g0, long long *g1)
+{
+    const long long total = rows * padded_row(n);
+    long long per = (total + gridDim.x - 1) / gridDim.x;
+    per = (per + 1023) & ~1023LL;
+    *g0 = min(total, per * blockIdx.x);
+    *g1 = min(total, *g0 + per);
+}
+
 // ------------------------------------------------------------------ T1 fused with the rolling AR(1) variance
 // One CTA streams a CHUNK of one row in tiles of RV_T bins: the tile (+ w-1 halo) is staged in shared memory in a
 // padded layout (position i + i/8, so that 8-bin-per-thread accesses are bank-conflict free), every thread
@@ -395,52 +410,63 @@ __device__ __forceinline__ void bucket_table(unsigned short *s_tab, const unsign
     }
 }
 constexpr int XC_THREADS = 1024;          // one CTA per SM (160 KB of histograms + LUTs): 32 warps hide the LUT/atomic chain
+
 __global__ void __launch_bounds__(XC_THREADS) k_xcollect(const double *__restrict__ C, const double *__restrict__ V, long long n,
                                                          long long row_stride, TrendBuffers T, int B)
 {
     extern __shared__ int s_raw[];
     int *s_yh = s_raw;                                              // [B][NBY]
     unsigned short *s_tab = reinterpret_cast<unsigned short *>(s_raw + B * NBY);    // per |signal| bucket: bin | boundary << 7 | slot << 8
-    const long long row = blockIdx.y;
-    const RowPlan &P = T.plan[row];
-    if (P.fallback) return;
-    const long long c0 = (long long)blockIdx.x * CHUNK, c1 = min(n, c0 + CHUNK);
-    for (int k = threadIdx.x; k < B * NBY; k += XC_THREADS) s_yh[k] = 0;
-    bucket_table(s_tab, T.lut + row * NBX, T.binlo + row * NBX, P, XC_THREADS);
-    __syncthreads();
-    const double *c = C + row * row_stride, *v = V + row * row_stride;
-    double2 *cand = T.cand + (size_t)row * MAXSLOT * CAPX;
-    int *ccnt = T.cand_cnt + row * MAXSLOT;
-    const int yb0 = P.yb0;
-    // eight independent loads in flight per thread before the dependent table / atomic chain
-    constexpr int U = 8;
-    for (long long jb = c0; jb < c1; jb += U * XC_THREADS) {
-        double xs[U], ys[U];
+    long long g0, g1;
+    cta_range(T.rows, n, &g0, &g1);
+    const long long np = padded_row(n);
+    for (long long g = g0; g < g1;) {
+        const long long row = g / np, c0 = g - row * np, seg = min(np - c0, g1 - g), c1 = min(n, c0 + seg);
+        g += seg;
+        const RowPlan &P = T.plan[row];
+        if (P.fallback || c0 >= c1) continue;
+        __syncthreads();                                            // the previous row's flush is done
+        for (int k = threadIdx.x; k < B * NBY; k += XC_THREADS) s_yh[k] = 0;
+        bucket_table(s_tab, T.lut + row * NBX, T.binlo + row * NBX, P, XC_THREADS);
+        __syncthreads();
+        const double *c = C + row * row_stride, *v = V + row * row_stride;
+        double2 *cand = T.cand + (size_t)row * MAXSLOT * CAPX;
+        int *ccnt = T.cand_cnt + row * MAXSLOT;
+        const int yb0 = P.yb0;
+        // eight independent loads in flight per thread, then the table lookups, then the slot counters (independent global
+        // atomics, all in flight together), and only then the stores and histogram updates that depend on them
+        constexpr int U = 8;
+        for (long long jb = c0; jb < c1; jb += U * XC_THREADS) {
+            double xs[U], ys[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const long long j = jb + u * XC_THREADS + threadIdx.x;
-            xs[u] = (j < c1) ? fabs(c[j]) : -1.0;
-            ys[u] = (j < c1) ? v[j] : 0.0;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (xs[u] < 0.0) continue;
-            const double x = xs[u], y = ys[u];
-            const unsigned e = s_tab[xbucket(x, T.geom)];
-            if (e < 0xFF00u) {                                      // slot bucket (~2 % of the pairs): keep the pair
-                const int sl = (int)(e >> 8);
-                const int pos = atomicAdd(&ccnt[sl], 1);
-                if (pos < CAPX) cand[(size_t)sl * CAPX + pos] = make_double2(x, y);
-                if (e & 0x80u) continue;                            // boundary bucket: its bin is settled by T4
+            for (int u = 0; u < U; ++u) {
+                const long long j = jb + u * XC_THREADS + threadIdx.x;
+                xs[u] = (j < c1) ? fabs(c[j]) : -1.0;
+                ys[u] = (j < c1) ? v[j] : 0.0;
             }
-            atomicAdd(&s_yh[(int)(e & 31u) * NBY + ybucket(y, yb0, T.geom)], 1);
+            unsigned es[U];
+            int pos[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) es[u] = (xs[u] < 0.0) ? 0xFFFFFFFFu : (unsigned)s_tab[xbucket(xs[u], T.geom)];
+#pragma unroll
+            for (int u = 0; u < U; ++u) pos[u] = (es[u] < 0xFF00u) ? atomicAdd(&ccnt[es[u] >> 8], 1) : CAPX;   // slot bucket (~2 % of the pairs)
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const unsigned e = es[u];
+                if (e == 0xFFFFFFFFu) continue;
+                if (e < 0xFF00u) {
+                    if (pos[u] < CAPX) cand[(size_t)(e >> 8) * CAPX + pos[u]] = make_double2(xs[u], ys[u]);
+                    if (e & 0x80u) continue;                        // boundary bucket: its bin is settled by T4
+                }
+                atomicAdd(&s_yh[(int)(e & 31u) * NBY + ybucket(ys[u], yb0, T.geom)], 1);
+            }
         }
-    }
-    __syncthreads();
-    int *g = T.yhist + (size_t)row * MAXB * NBY;
-    for (int k = threadIdx.x; k < B * NBY; k += XC_THREADS) {
-        const int val = s_yh[k];
-        if (val) atomicAdd(&g[k], val);
+        __syncthreads();
+        int *gh = T.yhist + (size_t)row * MAXB * NBY;
+        for (int k = threadIdx.x; k < B * NBY; k += XC_THREADS) {
+            const int val = s_yh[k];
+            if (val) atomicAdd(&gh[k], val);
+        }
     }
 }
 
@@ -1023,7 +1049,7 @@ int trend_knots_select(const double *d_C, double *d_V, long long m, long long n,
     }
     {
         RB_PROF("trend_xcollect", st, (double)m * n * 16.0);
-        k_xcollect<<<gstream, XC_THREADS, sm_collect, st>>>(d_C, d_V, n, row_stride, T, B);
+        k_xcollect<<<(unsigned)sm_count(), XC_THREADS, sm_collect, st>>>(d_C, d_V, n, row_stride, T, B);
         RB_LAUNCH_CHECK();
     }
     {

@@ -1314,9 +1314,9 @@ static int get_factor(long long n, double lam, FactorRef *out)
     return 0;
 }
 
-// steady tiles: 0 = automatic (float64 input: streaming cluster-pair kernel; float32 input: one-shot cluster-pair kernel,
-// whose shorter input copy leaves nothing for the streaming form to hide), 1 = the single-CTA kernel, 2 = one-shot pair
-// kernel, 3 = streaming pair kernel (1-3 kept for A/B checks)
+// steady tiles: 0 = the streaming cluster-pair kernel (default, both input types: float32 storage of the same values
+// must give the same bits as float64 storage, so both take the same arithmetic), 1 = the single-CTA kernel, 2 = one-shot
+// pair kernel, 3 = streaming pair kernel (1-3 kept for A/B checks)
 static std::atomic<int> g_whit_mode{0};
 int whittaker_set_mode(int mode) { return g_whit_mode.exchange((mode >= 0 && mode <= 3) ? mode : 0); }
 
@@ -1438,7 +1438,7 @@ int whittaker_rows(const void *d_x, int in_f32, int log_transform, const double 
     const size_t esz = in_f32 ? 4 : 8;
     const int mode = g_whit_mode.load();
     const int gm = 0;
-    const bool stream = mode == 3 || (mode == 0 && !in_f32);
+    const bool stream = mode == 3 || mode == 0;
     const bool pair_ok = mode != 1 && (reinterpret_cast<uintptr_t>(d_x) % esz) == 0;
     for (const Span &sp : spans) {
         WhitParams Q = P;

@@ -12,7 +12,7 @@ COLS = [
     ("time us", "gpu__time_duration.sum", 1.0),
     ("dram rd MB", "dram__bytes_read.sum", None),
     ("dram wr MB", "dram__bytes_write.sum", None),
-    ("dram %", "dram__throughput.avg.pct_of_peak_sustained_elapsed", 1.0),
+    ("dram %", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", 1.0),
     ("issue %", "smsp__issue_active.avg.pct_of_peak_sustained_active", 1.0),
     ("fp64 %", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", 1.0),
     ("occ %", "sm__warps_active.avg.pct_of_peak_sustained_active", 1.0),
