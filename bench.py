@@ -469,9 +469,14 @@ def main():
     lex_names = sorted(names)
     lex_order = sorted(range(len(my_names)), key=lambda k: my_names[k])      # shard-local chromosome indices in that order
 
+    host_phase = {}
+
     def step():
+        t_a = time.perf_counter()
         shard = pipeline.run_shard(d_mats, budgets, gammas, params=params, levels_per_round=args.levels,
                                    score_streams=args.score_streams) if mine else None
+        host_phase["run_shard_ms"] = 1e3 * (time.perf_counter() - t_a)     # returns once the runs are on the host
+        t_a = time.perf_counter()
         # ONE merged BED for the genome in the reference's record order.  Every rank formats the text of its own
         # chromosomes (one part file each, in parallel, on the node's file system); rank 0 stitches the 24 parts together
         # once the all-reduce below -- which every rank issues AFTER writing its parts -- has completed.
@@ -486,6 +491,7 @@ def main():
                     sl = slice(int(bounds[k]), int(bounds[k + 1]))
                     pipeline.runs_to_bed_file(os.path.join(tmpdir, f"part_{c}.bed"), [c],
                                               (np.zeros(sl.stop - sl.start, np.int32), starts[sl], ends[sl]), args.step_bp)
+        host_phase["bed_ms"] = 1e3 * (time.perf_counter() - t_a)
         # the one cross-GPU exchange of the path: genome-wide selected-bin count (reporting only)
         count_buf[0] = sum(r["selected_count"] for r in shard["results"]) if mine else 0
         count_buf[1] = sum(my_bins)
@@ -713,7 +719,8 @@ def main():
                        "selected_bins": selected_total,
                        "selected_by_chrom": {c: by_chrom[c][0] for c in names if c in by_chrom},
                        "lambda_by_chrom": {c: by_chrom[c][1] for c in names if c in by_chrom}, "trend_sort_fallback_rows": fb_rows,
-                       "trend_fallback_reason_counts": list(reasons)[:5], "collective": "one NCCL all-reduce of [selected, bins] per step"},
+                       "trend_fallback_reason_counts": list(reasons)[:5], "collective": "one NCCL all-reduce of [selected, bins] per step",
+                       "host_phases_last_step_ms": {k: round(v, 2) for k, v in host_phase.items()}},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(lt.item()), "roofline": roof, "cpu_baseline": cpu, "parity": parity, "column_stat": colstat,
         }
         emit(line)

@@ -305,29 +305,29 @@ static std::atomic<long long> g_trend_fallback_rows{0};
 static std::atomic<long long> g_trend_fb_reason[8];
 
 // ------------------------------------------------------------------ knot tables for the combine
-// The trend of a row as the combine reads it: knots as {x, y} pairs, the slope of every segment, a 64-entry bucket -> first
-// candidate segment table keyed by the exponent and the top two mantissa bits of |signal| (16 octaves from 2^-12), and the
+// The trend of a row as the combine reads it: knots as {x, y} pairs, the slope of every segment, a 256-entry bucket -> first
+// candidate segment table keyed by the exponent and the top four mantissa bits of |signal| (16 octaves from 2^-12), and the
 // clamp range.  lin-interp with flat extrapolation (wls_backend.c:341-391) is then: clamp t to [x_0, x_last], start at
-// lut[bucket(t)], step forward while the next knot is <= t (the knots are quantiles of |signal|: a bucket rarely holds
-// more than one), y_lo + (t - x_lo) * slope_lo.
-constexpr int KT_KNOTS = 32, KT_LUT = 64, KT_BASE = (1023 - 12) << 2;
+// lut[bucket(t)], step forward while the next knot is <= t (the knots are quantiles of |signal|, at most ~6 per octave:
+// with 16 buckets per octave a warp rarely needs a step), y_lo + (t - x_lo) * slope_lo.
+constexpr int KT_KNOTS = 32, KT_LUT = 256, KT_BASE = (1023 - 12) << 4;
 struct KnotTable {
     double2 xy[KT_KNOTS];
     double slope[KT_KNOTS];
     unsigned char lut[KT_LUT];
     double xlo, xhi;
     int top;                      // last segment index (nk - 2, at least 0)
-    int pad;
+    int pad[3];
 };
 static_assert(sizeof(KnotTable) % 16 == 0, "KnotTable is staged with 128-bit copies");
 
 __device__ __forceinline__ int knot_bucket(double t)
 {
-    const int key = (__double2hiint(t) >> 18) - KT_BASE;              // t >= 0: sign bit clear
+    const int key = (__double2hiint(t) >> 16) - KT_BASE;              // t >= 0: sign bit clear
     return min(max(key, 0), KT_LUT - 1);
 }
 
-__global__ void __launch_bounds__(64) k_knot_tables(const Knots *knots, KnotTable *tables)
+__global__ void __launch_bounds__(KT_LUT) k_knot_tables(const Knots *knots, KnotTable *tables)
 {
     const Knots &K = knots[blockIdx.x];
     KnotTable &T = tables[blockIdx.x];
@@ -348,10 +348,10 @@ __global__ void __launch_bounds__(64) k_knot_tables(const Knots *knots, KnotTabl
         T.top = top;
         T.xlo = flat ? 0.0 : K.x[0];
         T.xhi = flat ? 0.0 : K.x[nk - 1];
-        T.pad = 0;
+        T.pad[0] = T.pad[1] = T.pad[2] = 0;
     }
     // lut[b] = last segment whose left knot is <= the bucket's lower edge (bucket 0 also takes everything below it)
-    const double edge = (k == 0) ? 0.0 : ldexp(1.0 + 0.25 * (double)(k & 3), (k >> 2) - 12);
+    const double edge = (k == 0) ? 0.0 : ldexp(1.0 + 0.0625 * (double)(k & 15), (k >> 4) - 12);
     int lo = 0;
     if (!flat)
         for (int q = 1; q <= top; ++q) if (K.x[q] <= edge) lo = q;
@@ -369,8 +369,8 @@ struct CombineParams {
     int *bad;
 };
 
-constexpr int CB_THREADS = 256;
-constexpr int CB_ROWS_SMEM = 24;          // knot tables staged per batch of sample rows
+constexpr int CB_THREADS = 512;           // two CTAs per SM: one stages its tables while the other computes
+constexpr int CB_ROWS_SMEM = 40;          // knot tables staged per batch of sample rows (41 KB)
 
 // posterior precision of one sample-bin and its accumulation (wls_backend.c:889-911)
 template <bool WANT_RQ>
@@ -386,7 +386,7 @@ __device__ __forceinline__ void combine_one(double y, double ov, double pv, doub
 }
 
 template <bool CONST_ROWS, bool WANT_RQ>
-__global__ void __launch_bounds__(CB_THREADS, 4) k_combine(CombineParams P)
+__global__ void __launch_bounds__(CB_THREADS, 2) k_combine(CombineParams P)
 {
     __shared__ __align__(16) KnotTable s_t[CONST_ROWS ? 1 : CB_ROWS_SMEM];
     const long long j = (long long)blockIdx.x * CB_THREADS + threadIdx.x;
@@ -580,7 +580,7 @@ static int wls_finish(const double *d_centered, WlsRun &R, const rocco_b200_scor
             RB_TRY(trend_knots_sorted(d_centered, R.d_V, rows, n, n, R.d_knots, st));
         }
         P.const_rows = 0; P.V = R.d_V; P.tables = R.d_tables;
-        k_knot_tables<<<(unsigned)m, 64, 0, st>>>(R.d_knots, R.d_tables);
+        k_knot_tables<<<(unsigned)m, KT_LUT, 0, st>>>(R.d_knots, R.d_tables);
         RB_LAUNCH_CHECK();
     }
     {
