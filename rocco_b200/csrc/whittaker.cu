@@ -710,6 +710,7 @@ struct PairParams {
     int shift;
     int log_transform, write_baseline;
     int total_pairs;            // streaming form: (row, tile) pairs of this launch
+    double w_y, w_b;            // streaming form: output = w_b * (b_even + b_odd) + w_y * y  ((1, -0.5) centred, (0, 0.5) baseline)
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -1036,10 +1037,14 @@ __global__ void __launch_bounds__(WP_THREADS, 1024 / WP_THREADS) k_whittaker_str
     constexpr unsigned LOG_BYTES = 16u * LOG2_V2_ENTRIES;
     const bool recv_fwd = rank > 0, recv_bwd = rank < CL - 1;     // carries this CTA receives (from its left / right neighbour)
 
-    auto half_base = [&](int pair_idx) -> long long {
+    // (row, first element of this CTA's part) of a tile: worked out by the thread that issues the tile's bulk load and left in
+    // shared memory for the others (the load's mbarrier orders the two), so that nobody else pays the index divisions
+    __shared__ long long s_meta[2][2];
+    auto tile_meta = [&](int pair_idx, long long *row_out) -> long long {
         const long long row = P.row0 + (long long)(pair_idx / P.span_tiles) * P.row_step;
         const int tile = P.tile_offset + pair_idx % P.span_tiles;
         const long long r0 = (long long)tile * WT_OUT - WT_HALO - P.shift;
+        *row_out = row;
         return row * P.row_stride + r0 + (long long)rank * CTA_BINS;
     };
 
@@ -1054,8 +1059,11 @@ __global__ void __launch_bounds__(WP_THREADS, 1024 / WP_THREADS) k_whittaker_str
         bulk_load(smem_u32(s_pow), P.pow_tab, (unsigned)sizeof(PairPow), smem_u32(&s_tabbar));
         bulk_load(smem_u32(s_log), P.log2tab, LOG_BYTES, smem_u32(&s_tabbar));
         if (cid < total) {
+            long long row0;
+            const long long hb0 = tile_meta(cid, &row0);
+            s_meta[0][0] = row0; s_meta[0][1] = hb0;
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&s_full[0])), "r"(BYTES) : "memory");
-            bulk_load(smem_u32(s_buf0), reinterpret_cast<const char *>(P.x) + half_base(cid) * (F32 ? 4 : 8), BYTES, smem_u32(&s_full[0]));
+            bulk_load(smem_u32(s_buf0), reinterpret_cast<const char *>(P.x) + hb0 * (F32 ? 4 : 8), BYTES, smem_u32(&s_full[0]));
         }
     }
     asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
@@ -1074,14 +1082,13 @@ __global__ void __launch_bounds__(WP_THREADS, 1024 / WP_THREADS) k_whittaker_str
     for (int it = 0, pair_idx = cid; pair_idx < total; ++it, pair_idx += ncl) {
         const int b = it & 1;
         double *buf = b ? s_buf1 : s_buf0;
-        const long long row = P.row0 + (long long)(pair_idx / P.span_tiles) * P.row_step;
-        const long long hbase = half_base(pair_idx);
         if (tid == 0) {        // this tile's carries (the previous phase of each barrier was completed and observed one tile ago)
             if (recv_fwd) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 32;" ::"r"(smem_u32(&s_cbar[0])) : "memory");
             if (recv_bwd) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 32;" ::"r"(smem_u32(&s_cbar[1])) : "memory");
         }
-        const double pil = (P.log_transform && P.pilot) ? P.pilot[row] : 0.0;
         mbar_wait(smem_u32(&s_full[b]), (unsigned)(it >> 1) & 1u);
+        const long long row = s_meta[b][0];
+        const double pil = (P.log_transform && P.pilot) ? P.pilot[row] : 0.0;
 
         // ---- this thread's bins: raw -> y (registers)
         double y[WP_ITEMS];
@@ -1125,8 +1132,11 @@ __global__ void __launch_bounds__(WP_THREADS, 1024 / WP_THREADS) k_whittaker_str
         if (tid == 0 && pair_idx + ncl < total) {
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");          // the other buffer's result has left
             const unsigned fb = smem_u32(&s_full[b ^ 1]);
+            long long rown;
+            const long long hbn = tile_meta(pair_idx + ncl, &rown);
+            s_meta[b ^ 1][0] = rown; s_meta[b ^ 1][1] = hbn;          // (read one tile ago for the last time: barriers in between)
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(BYTES) : "memory");
-            bulk_load(smem_u32(b ? s_buf0 : s_buf1), reinterpret_cast<const char *>(P.x) + half_base(pair_idx + ncl) * (F32 ? 4 : 8), BYTES, fb);
+            bulk_load(smem_u32(b ? s_buf0 : s_buf1), reinterpret_cast<const char *>(P.x) + hbn * (F32 ? 4 : 8), BYTES, fb);
         }
         double fa1 = 0.0, fa2 = 0.0, fb1 = 0.0, fb2 = 0.0;       // final forward state of the chunk: n_{last}, n_{last-1}
         v[0] = v[1] = v[2] = v[3] = 0.0;
@@ -1162,8 +1172,9 @@ __global__ void __launch_bounds__(WP_THREADS, 1024 / WP_THREADS) k_whittaker_str
                 } else {
                     fa1 = fa2; fb1 = fb2;
                 }
-                const double bsl = 0.5 * (na + nb);                   // cross-fit average (baseline_backend.c:296-299)
-                y[j] = P.write_baseline ? bsl : y[j] - bsl;
+                // cross-fit average (baseline_backend.c:296-299) and the output in one fused step: 0.5 * (na + nb) is exact,
+                // so fma(-0.5, na + nb, y) rounds once, like y - baseline; (w_y, w_b) = (1, -0.5) centred, (0, 0.5) baseline
+                y[j] = fma(P.w_b, na + nb, P.w_y * y[j]);
             }
             if (!P.log_transform) {                       // (log2 of a finite count cannot overflow the solve)
                 expmax = 0;
@@ -1181,7 +1192,7 @@ __global__ void __launch_bounds__(WP_THREADS, 1024 / WP_THREADS) k_whittaker_str
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
-        double *outp = P.out + hbase;
+        double *outp = P.out + s_meta[b][1];
         if ((reinterpret_cast<uintptr_t>(outp) & 15) == 0) {
             if (tid == 0) {
                 const int b0 = (q0 + 1) & ~1, b1 = q1 & ~1;
@@ -1370,6 +1381,8 @@ static int launch_stream(PairParams R, long long pairs, cudaStream_t st)
         resident = nc;
     }
     R.total_pairs = (int)pairs;
+    R.w_y = R.write_baseline ? 0.0 : 1.0;
+    R.w_b = R.write_baseline ? 0.5 : -0.5;
     const long long clusters = std::min<long long>(pairs, resident);
     cfg.gridDim = dim3((unsigned)(clusters * CL));
     RB_CUDA(cudaLaunchKernelEx(&cfg, kern, R));
