@@ -285,6 +285,12 @@ __global__ void __launch_bounds__(RV_THREADS, 2) k_rollvar_xhist(const double *_
 }
 
 // ------------------------------------------------------------------ T2
+struct SelScratch;
+template <int THREADS>
+__device__ unsigned long long block_select(const unsigned long long *keys, int cnt, int rank, const unsigned long long *fkeys,
+                                           unsigned long long fval, SelScratch &S, int *below, int *equal);
+__device__ SelScratch &plan_scratch(void *raw);
+
 __global__ void __launch_bounds__(256) k_xplan(TrendBuffers T, const double *__restrict__ V, long long row_stride, long long n, int B)
 {
     extern __shared__ int s_plan[];
@@ -310,42 +316,31 @@ __global__ void __launch_bounds__(256) k_xplan(TrendBuffers T, const double *__r
     }
     __syncthreads();
     unsigned char *lut = T.lut + row * NBX, *binlo = T.binlo + row * NBX;
+    // bin of every bucket's first rank = number of bin boundaries floor(b n / B), b = 1..B-1, at or below it
+    __shared__ long long s_lo[MAXB];
+    if (threadIdx.x < B) s_lo[threadIdx.x] = ((long long)threadIdx.x * n) / B;
+    __syncthreads();
     for (int k = threadIdx.x; k < NBX; k += 256) {
         lut[k] = 0xFF;
-        binlo[k] = (unsigned char)bin_of_rank(min((long long)s_pre[k], n - 1), n, B);
+        const long long r = min((long long)s_pre[k], n - 1);
+        int bin = 0;
+        for (int b = 1; b < B; ++b) bin += (s_lo[b] <= r);
+        binlo[k] = (unsigned char)bin;
     }
     __syncthreads();
-    // centre the variance buckets on the median of a strided sample of this row's variances
+    // centre the variance buckets on the median of a strided sample of this row's variances (a radix select: the bit
+    // patterns of positive doubles order like the values)
     {
-        double *s_smp = reinterpret_cast<double *>(s_plan + NBX + 1 + 256 + 1);   // 8-byte aligned: NBX+258 ints
+        unsigned long long *s_smp = reinterpret_cast<unsigned long long *>(s_plan + NBX + 1 + 256 + 1);   // 8-byte aligned: NBX+258 ints
         const int take = (int)min((long long)YSAMPLE, n);
-        int len = 1;
-        while (len < take) len <<= 1;
-        for (int k = threadIdx.x; k < len; k += 256) {
-            double v = INFINITY;
-            if (k < take) {
-                const long long i = (n <= YSAMPLE) ? k : (long long)(((double)k + 0.5) * ((double)n / (double)YSAMPLE));
-                v = V[row * row_stride + min(i, n - 1)];
-            }
-            s_smp[k] = v;
+        for (int k = threadIdx.x; k < take; k += 256) {
+            const long long i = (n <= YSAMPLE) ? k : (long long)(((double)k + 0.5) * ((double)n / (double)YSAMPLE));
+            s_smp[k] = (unsigned long long)__double_as_longlong(V[row * row_stride + min(i, n - 1)]);
         }
         __syncthreads();
-        for (int kk = 2; kk <= len; kk <<= 1)
-            for (int j = kk >> 1; j > 0; j >>= 1) {
-                for (int i = threadIdx.x; i < len; i += 256) {
-                    const int ixj = i ^ j;
-                    if (ixj > i) {
-                        const double a = s_smp[i], c = s_smp[ixj];
-                        const bool up = ((i & kk) == 0);
-                        if ((a > c) == up) { s_smp[i] = c; s_smp[ixj] = a; }
-                    }
-                }
-                __syncthreads();
-            }
-        if (threadIdx.x == 0) {
-            const double med = s_smp[take / 2];
-            T.plan[row].yb0 = (int)((unsigned long long)__double_as_longlong(med) >> T.geom.yshift) - NBY / 2;
-        }
+        const unsigned long long med = block_select<256>(s_smp, take, take / 2, nullptr, 0ULL, plan_scratch(s_smp + YSAMPLE), nullptr, nullptr);
+        if (threadIdx.x == 0) T.plan[row].yb0 = (int)(med >> T.geom.yshift) - NBY / 2;
+        __syncthreads();
     }
     // the <= 3B wanted ranks (bin boundary, upper median, lower median) are located in parallel, one thread each; slots
     // are then handed out by one thread in the fixed order boundary, median 1, median 0 per bin (deterministic slot ids)
@@ -477,6 +472,7 @@ __global__ void __launch_bounds__(XC_THREADS) k_xcollect(const double *__restric
 constexpr int SEL_BITS = 11, SEL_BINS = 1 << SEL_BITS;
 
 struct SelScratch { int hist[SEL_BINS]; unsigned long long res[4]; int ires[4]; };
+__device__ SelScratch &plan_scratch(void *raw) { return *reinterpret_cast<SelScratch *>(raw); }
 
 // Key of 0-based `rank` among the keys[i], i < cnt, that pass the filter (fkeys == nullptr, or fkeys[i] == fval).  All
 // THREADS threads call it; the result is uniform.  *below = number of filtered keys smaller than the result, *equal =
@@ -640,7 +636,7 @@ __global__ void __launch_bounds__(THREADS) k_xselect(TrendBuffers T, long long n
 // (bin, row) CTAs: the one or two median ranks of the bin's variances, selected from the collected bucket(s).  A bucket
 // that outgrew its slot is still exact when every value in it is the same (variances sitting on the 1e-8 floor): the
 // overflow's min / max were tracked by T6.
-template <int THREADS>
+template <int THREADS, int CAP_LO, int CAP_HI>
 __global__ void __launch_bounds__(THREADS) k_yselect(TrendBuffers T, long long n, int B)
 {
     extern __shared__ unsigned long long s_sel[];
@@ -651,6 +647,12 @@ __global__ void __launch_bounds__(THREADS) k_yselect(TrendBuffers T, long long n
     if (P.fallback) return;
     const long long lo = ((long long)b * n) / B, hi = ((long long)(b + 1) * n) / B;
     if (hi <= lo) return;
+    {   // two launches share the bins by the size of their candidate lists: the small tier keeps several CTAs per SM
+        int mx = 0;
+        for (int k = 0; k < 2; ++k)
+            if (P.ym_bucket[b][k] >= 0) mx = max(mx, min(T.ycand_cnt[((size_t)row * MAXB + b) * 2 + k], T.capy));
+        if (mx <= CAP_LO || mx > CAP_HI) return;
+    }
     double ym[2] = {0.0, 0.0};
     bool ok = true;
     for (int k = 1; k >= 0 && ok; --k) {
@@ -773,10 +775,26 @@ __global__ void __launch_bounds__(256) k_yplan(TrendBuffers T, long long n, int 
     const long long w = hi - lo;
     if (w <= 0) return;
     const int *h = T.yhist + ((size_t)row * MAXB + b) * NBY;
+    {   // exclusive prefix over the NBY buckets: four per thread, warp scan, eight warp totals
+        static_assert(NBY == 4 * 256, "k_yplan: four buckets per thread");
+        __shared__ int s_wsum[8];
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        const int4 v = reinterpret_cast<const int4 *>(h)[threadIdx.x];
+        const int mine = v.x + v.y + v.z + v.w;
+        int inc = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+        if (lane == 31) s_wsum[wid] = inc;
+        __syncthreads();
+        int base = inc - mine;
+        for (int q = 0; q < wid; ++q) base += s_wsum[q];
+        s_pre[4 * threadIdx.x + 0] = base; s_pre[4 * threadIdx.x + 1] = base + v.x;
+        s_pre[4 * threadIdx.x + 2] = base + v.x + v.y; s_pre[4 * threadIdx.x + 3] = base + v.x + v.y + v.z;
+        if (threadIdx.x == 255) s_pre[NBY] = base + mine;
+        __syncthreads();
+    }
     if (threadIdx.x == 0) {
-        int acc = 0;
-        for (int k = 0; k < NBY; ++k) { s_pre[k] = acc; acc += h[k]; }
-        s_pre[NBY] = acc;
+        const int acc = s_pre[NBY];
         if (acc != (int)w) { atomicOr(&P.fallback, FB_YTOTAL); }
         else {
             auto bucket_of = [&](long long r) {
@@ -1007,7 +1025,7 @@ int trend_knots_select(const double *d_C, double *d_V, long long m, long long n,
     const size_t sm_xhist = sizeof(int) * NBX;
     const size_t sm_collect = sizeof(int) * (size_t)B * NBY + 2 * NBX;      // histograms + the 16-bit bucket table
     const size_t sm_resolve = sizeof(double2) * CAPX;
-    const size_t sm_plan = sizeof(int) * (NBX + 258) + sizeof(double) * YSAMPLE;
+    const size_t sm_plan = sizeof(int) * (NBX + 258) + sizeof(double) * YSAMPLE + sizeof(SelScratch);
     if (!attr) {
         RB_CUDA(cudaFuncSetAttribute(k_xhist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_xhist));
         RB_CUDA(cudaFuncSetAttribute(k_xcollect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(int) * MAXB * NBY + 2 * NBX)));
@@ -1016,7 +1034,7 @@ int trend_knots_select(const double *d_C, double *d_V, long long m, long long n,
         RB_CUDA(cudaFuncSetAttribute(k_xplan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_plan));
         RB_CUDA(cudaFuncSetAttribute(k_yresolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * CAPY_MAX)));
         RB_CUDA(cudaFuncSetAttribute(k_xselect<512, 2048, CAPX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(unsigned long long) * 2 * CAPX)));
-        RB_CUDA(cudaFuncSetAttribute(k_yselect<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(unsigned long long) * CAPY_MAX)));
+        RB_CUDA(cudaFuncSetAttribute(k_yselect<256, 4096, CAPY_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(unsigned long long) * CAPY_MAX)));
         attr = true;
     }
     const unsigned chunks = (unsigned)((n + CHUNK - 1) / CHUNK);
@@ -1077,7 +1095,9 @@ int trend_knots_select(const double *d_C, double *d_V, long long m, long long n,
     }
     {
         RB_PROF("trend_plan_resolve", st, 0.0);
-        k_yselect<256><<<dim3((unsigned)B, (unsigned)m), 256, sizeof(unsigned long long) * T.capy, st>>>(T, n, B);
+        k_yselect<256, -1, 4096><<<dim3((unsigned)B, (unsigned)m), 256, sizeof(unsigned long long) * 4096, st>>>(T, n, B);
+        RB_LAUNCH_CHECK();
+        k_yselect<256, 4096, CAPY_MAX><<<dim3((unsigned)B, (unsigned)m), 256, sizeof(unsigned long long) * T.capy, st>>>(T, n, B);
         RB_LAUNCH_CHECK();
         k_yresolve<<<dim3((unsigned)B, (unsigned)m), 256, sizeof(double) * T.capy, st>>>(T, n, B);
         RB_LAUNCH_CHECK();
