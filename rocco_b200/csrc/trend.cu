@@ -691,14 +691,11 @@ __device__ __forceinline__ bool pair_gt(const double2 &a, const double2 &b) { re
 // Two tiers over the same slots: <256 threads, slots of <= 2048 pairs> (32 KB of shared memory, several CTAs per SM --
 // almost every slot) and <512 threads, up to CAPX pairs> for the rare large ones; a CTA exits if the slot is not its tier.
 template <int THREADS, int CAP_LO, int CAP_HI>
-__global__ void __launch_bounds__(THREADS, (THREADS == 256) ? 4 : (CAP_HI <= 4096 ? 2 : 1)) k_xresolve(TrendBuffers T, long long n, int B)
+__device__ void xresolve_slot(TrendBuffers &T, long long n, int B, long long row, int s, double2 *s_p)
 {
     constexpr int ST_THREADS = THREADS;
-    extern __shared__ double2 s_p[];
-    const long long row = blockIdx.y;
-    const int s = blockIdx.x;
     RowPlan &P = T.plan[row];
-    if (P.fallback || s >= P.nslot) return;
+    if (s >= P.nslot) return;
     const int cnt = min(T.cand_cnt[row * MAXSLOT + s], CAPX);
     if (P.slot_count[s] <= CAP_LO || P.slot_count[s] > CAP_HI) return;          // not this tier
     if (P.slot_done[s]) return;                                                 // resolved by k_xselect
@@ -760,6 +757,22 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 256) ? 4 : (CAP_HI <= 409
             cand[k] = pr;
             atomicAdd(&g[bin_of_rank(pre + k, n, B) * NBY + ybucket(pr.y, P.yb0, T.geom)], 1);
         }
+    }
+}
+
+// a CTA walks the slots blockIdx.x, blockIdx.x + gridDim.x, ... of its row: almost all of them were settled by k_xselect,
+// so a thin grid keeps the (usually empty) launches cheap
+template <int THREADS, int CAP_LO, int CAP_HI>
+__global__ void __launch_bounds__(THREADS, (THREADS == 256) ? 4 : (CAP_HI <= 4096 ? 2 : 1)) k_xresolve(TrendBuffers T, long long n, int B, int nslot_max)
+{
+    extern __shared__ double2 s_p[];
+    __shared__ int s_skip;                       // the row's fallback flag, read once for the whole CTA (other CTAs may set it meanwhile)
+    if (threadIdx.x == 0) s_skip = T.plan[blockIdx.y].fallback;
+    __syncthreads();
+    if (s_skip) return;
+    for (int s = blockIdx.x; s < nslot_max; s += gridDim.x) {
+        xresolve_slot<THREADS, CAP_LO, CAP_HI>(T, n, B, blockIdx.y, s, s_p);
+        __syncthreads();
     }
 }
 
@@ -881,15 +894,12 @@ __global__ void __launch_bounds__(ST_THREADS) k_ycollect(const double *__restric
 
 // ------------------------------------------------------------------ T7
 
-__global__ void __launch_bounds__(256) k_yresolve(TrendBuffers T, long long n, int B)
+__device__ void yresolve_bin(TrendBuffers &T, long long n, int B, long long row, int b, double *s_v)
 {
-    // one CTA per (bin, row): sort the collected variances of the bin's target bucket(s), pick the median rank(s)
-    extern __shared__ double s_v[];              // CAPY
+    // sort the collected variances of the bin's target bucket(s), pick the median rank(s)
     __shared__ int s_fail;
-    const long long row = blockIdx.y;
-    const int b = blockIdx.x;
     RowPlan &P = T.plan[row];
-    if (P.fallback || P.ybin_done[b]) return;
+    if (P.ybin_done[b]) return;
     const long long lo = ((long long)b * n) / B, hi = ((long long)(b + 1) * n) / B;
     if (hi <= lo) return;
     if (threadIdx.x == 0) s_fail = 0;
@@ -927,6 +937,20 @@ __global__ void __launch_bounds__(256) k_yresolve(TrendBuffers T, long long n, i
     if (threadIdx.x == 0) {
         if (s_fail) atomicOr(&P.fallback, s_fail);
         else { P.ym_val[b][0] = ym[0]; P.ym_val[b][1] = ym[1]; }
+    }
+}
+
+// (bins blockIdx.x, blockIdx.x + gridDim.x, ... of row blockIdx.y: k_yselect leaves almost nothing, so the grid is thin)
+__global__ void __launch_bounds__(256) k_yresolve(TrendBuffers T, long long n, int B)
+{
+    extern __shared__ double s_v[];              // CAPY
+    __shared__ int s_skip;
+    if (threadIdx.x == 0) s_skip = T.plan[blockIdx.y].fallback;
+    __syncthreads();
+    if (s_skip) return;
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        yresolve_bin(T, n, B, blockIdx.y, b, s_v);
+        __syncthreads();
     }
 }
 
@@ -1079,11 +1103,11 @@ int trend_knots_select(const double *d_C, double *d_V, long long m, long long n,
         RB_LAUNCH_CHECK();
         k_xselect<512, 2048, CAPX><<<dim3(nslot_max, (unsigned)m), 512, sizeof(unsigned long long) * 2 * CAPX, st>>>(T, n, B);
         RB_LAUNCH_CHECK();
-        k_xresolve<256, -1, 2048><<<dim3(nslot_max, (unsigned)m), 256, sizeof(double2) * 2048, st>>>(T, n, B);
+        k_xresolve<256, -1, 2048><<<dim3(std::min(nslot_max, 8u), (unsigned)m), 256, sizeof(double2) * 2048, st>>>(T, n, B, (int)nslot_max);
         RB_LAUNCH_CHECK();
-        k_xresolve<512, 2048, 4096><<<dim3(nslot_max, (unsigned)m), 512, sizeof(double2) * 4096, st>>>(T, n, B);
+        k_xresolve<512, 2048, 4096><<<dim3(std::min(nslot_max, 8u), (unsigned)m), 512, sizeof(double2) * 4096, st>>>(T, n, B, (int)nslot_max);
         RB_LAUNCH_CHECK();
-        k_xresolve<512, 4096, CAPX><<<dim3(nslot_max, (unsigned)m), 512, sm_resolve, st>>>(T, n, B);
+        k_xresolve<512, 4096, CAPX><<<dim3(std::min(nslot_max, 8u), (unsigned)m), 512, sm_resolve, st>>>(T, n, B, (int)nslot_max);
         RB_LAUNCH_CHECK();
         k_yplan<<<dim3((unsigned)B, (unsigned)m), 256, 0, st>>>(T, n, B);
         RB_LAUNCH_CHECK();
@@ -1099,7 +1123,7 @@ int trend_knots_select(const double *d_C, double *d_V, long long m, long long n,
         RB_LAUNCH_CHECK();
         k_yselect<256, 4096, CAPY_MAX><<<dim3((unsigned)B, (unsigned)m), 256, sizeof(unsigned long long) * T.capy, st>>>(T, n, B);
         RB_LAUNCH_CHECK();
-        k_yresolve<<<dim3((unsigned)B, (unsigned)m), 256, sizeof(double) * T.capy, st>>>(T, n, B);
+        k_yresolve<<<dim3((unsigned)std::min(B, 4), (unsigned)m), 256, sizeof(double) * T.capy, st>>>(T, n, B);
         RB_LAUNCH_CHECK();
         k_row_knots<<<(unsigned)((m + 63) / 64), 64, 0, st>>>(T, n, B, d_knots, d_row_fallback);
         RB_LAUNCH_CHECK();
