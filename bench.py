@@ -477,32 +477,25 @@ def main():
                                    score_streams=args.score_streams) if mine else None
         host_phase["run_shard_ms"] = 1e3 * (time.perf_counter() - t_a)     # returns once the runs are on the host
         t_a = time.perf_counter()
-        # ONE merged BED for the genome in the reference's record order.  Every rank formats the text of its own
-        # chromosomes (one part file each, in parallel, on the node's file system); rank 0 stitches the 24 parts together
-        # once the all-reduce below -- which every rank issues AFTER writing its parts -- has completed.
-        if mine:
-            chrom, starts, ends = shard["runs"]
-            if world == 1:
-                pipeline.runs_to_bed_file(os.path.join(tmpdir, "genome.bed"), lex_names,
-                                          pipeline.reorder_runs(shard["runs"], lex_order), args.step_bp)
-            else:
-                bounds = np.searchsorted(chrom, np.arange(len(my_names) + 1))          # runs come grouped by chromosome
-                for k, c in enumerate(my_names):
-                    sl = slice(int(bounds[k]), int(bounds[k + 1]))
-                    pipeline.runs_to_bed_file(os.path.join(tmpdir, f"part_{c}.bed"), [c],
-                                              (np.zeros(sl.stop - sl.start, np.int32), starts[sl], ends[sl]), args.step_bp)
-        host_phase["bed_ms"] = 1e3 * (time.perf_counter() - t_a)
-        # the one cross-GPU exchange of the path: genome-wide selected-bin count (reporting only)
-        count_buf[0] = sum(r["selected_count"] for r in shard["results"]) if mine else 0
-        count_buf[1] = sum(my_bins)
-        if world > 1:
-            dist.all_reduce(count_buf)
-            if rank == 0:
-                torch.cuda.current_stream().synchronize()
-                with open(os.path.join(tmpdir, "genome.bed"), "wb") as out:
-                    for c in lex_names:
-                        with open(os.path.join(tmpdir, f"part_{c}.bed"), "rb") as part:
-                            out.write(part.read())
+        # ONE merged BED for the genome in the reference's record order.  world == 1: the runs are regrouped and written in
+        # one call.  world > 1: every rank announces the text size of each of its chromosomes in the step's one collective
+        # (an all-gather of [selected, bins, 24 sizes] per rank), derives every chromosome's byte offset in the genome file,
+        # and writes its own chromosomes there with positioned writes -- no part files, no gather pass on rank 0.
+        genome_bed = os.path.join(tmpdir, "genome.bed")
+        sel_mine = sum(r["selected_count"] for r in shard["results"]) if mine else 0
+        if world == 1:
+            if mine:
+                pipeline.runs_to_bed_file(genome_bed, lex_names, pipeline.reorder_runs(shard["runs"], lex_order), args.step_bp)
+            host_phase["bed_ms"] = 1e3 * (time.perf_counter() - t_a)
+            count_buf[0] = sel_mine
+            count_buf[1] = sum(my_bins)
+        else:
+            empty = (np.zeros(0, np.int32), np.zeros(0, np.int64), np.zeros(0, np.int64))
+            tot = rdist.write_genome_bed(genome_bed, lex_names, my_names, shard["runs"] if mine else empty, args.step_bp,
+                                         extras=(sel_mine, sum(my_bins)), device=dev)
+            count_buf[0] = tot[0]
+            count_buf[1] = tot[1]
+            host_phase["bed_ms"] = 1e3 * (time.perf_counter() - t_a)
         return shard
 
     def barrier():
@@ -719,7 +712,7 @@ def main():
                        "selected_bins": selected_total,
                        "selected_by_chrom": {c: by_chrom[c][0] for c in names if c in by_chrom},
                        "lambda_by_chrom": {c: by_chrom[c][1] for c in names if c in by_chrom}, "trend_sort_fallback_rows": fb_rows,
-                       "trend_fallback_reason_counts": list(reasons)[:5], "collective": "one NCCL all-reduce of [selected, bins] per step",
+                       "trend_fallback_reason_counts": list(reasons)[:5], "collective": "one NCCL all-gather of [selected, bins, per-chromosome BED text sizes] per step",
                        "host_phases_last_step_ms": {k: round(v, 2) for k, v in host_phase.items()}},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(lt.item()), "roofline": roof, "cpu_baseline": cpu, "parity": parity, "column_stat": colstat,
         }

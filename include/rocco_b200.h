@@ -182,6 +182,12 @@ int rocco_b200_summit_offsets_dev(const long long *d_track_starts, const long lo
  * (rocco.py:98-110 _write_bed_records).  Record i uses names[name_idx[i]] (name_idx == NULL: names[0]). */
 int rocco_b200_write_bed3(const char *path, const char *const *names, int n_names, const int *name_idx,
                           const long long *starts, const long long *ends, size_t n, int name_features);
+/* The same text written into `path` at byte `offset` without truncating the file (created if missing): processes that
+ * know each other's text sizes assemble ONE BED file without a gather pass (the multi-rank form of rocco.py:194-240's
+ * output).  *bytes_written (may be NULL) returns the size of the text. */
+int rocco_b200_write_bed3_at(const char *path, long long offset, const char *const *names, int n_names, const int *name_idx,
+                             const long long *starts, const long long *ends, size_t n, int name_features,
+                             long long *bytes_written);
 /* Host helper: combine_chrom_results (rocco.py:194-240) over canonical BED text -- read `n_paths` files, order the
  * records by (chrom, start, end), merge overlapping/abutting records per chrom, write BED3 (BED4 when name_features).
  * Returns the number of records written, or -1 when a file is not canonical BED (the caller falls back to the

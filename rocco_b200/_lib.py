@@ -107,6 +107,8 @@ def _declare(lib):
         "rocco_b200_profile_timeline": (c_int, [c_char_p, c_size_t]),
         "rocco_b200_uniform_step_i64": (c_int, [c_void_p, c_size_t]),
         "rocco_b200_write_bed3": (c_int, [c_char_p, POINTER(c_char_p), c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int]),
+        "rocco_b200_write_bed3_at": (c_int, [c_char_p, c_longlong, POINTER(c_char_p), c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int,
+                                     POINTER(c_longlong)]),
         "rocco_b200_combine_bed3": (ctypes.c_longlong, [POINTER(c_char_p), c_int, c_char_p, c_int, POINTER(c_int)]),
         "rocco_b200_default_budget_params": (None, [POINTER(BudgetParams)]),
         "rocco_b200_budget_bandwidth": (c_int, [c_size_t, c_int]),
@@ -280,6 +282,21 @@ def write_bed_arrays(path: str, names, name_idx, starts: np.ndarray, ends: np.nd
     if st != 0:
         raise OSError(f"could not write BED file {path}: {last_error()}")
     return path
+
+
+def write_bed_arrays_at(path: str, offset: int, names, name_idx, starts: np.ndarray, ends: np.ndarray, name_features: bool = False) -> int:
+    """The text of write_bed_arrays placed at byte `offset` of `path` (no truncation); returns the number of bytes written."""
+    lib = load()
+    starts = np.ascontiguousarray(starts, dtype=np.int64)
+    ends = np.ascontiguousarray(ends, dtype=np.int64)
+    arr = (c_char_p * len(names))(*[str(x).encode("utf-8") for x in names])
+    idx = None if name_idx is None else np.ascontiguousarray(name_idx, dtype=np.int32)
+    written = c_longlong(0)
+    st = lib.rocco_b200_write_bed3_at(str(path).encode("utf-8"), int(offset), arr, len(names), None if idx is None else np_ptr(idx),
+                                      np_ptr(starts), np_ptr(ends), len(starts), 1 if name_features else 0, ctypes.byref(written))
+    if st != 0:
+        raise OSError(f"could not write BED file {path}: {last_error()}")
+    return int(written.value)
 
 
 def combine_bed_files(paths, output_file: str, name_features: bool = False):

@@ -411,24 +411,25 @@ static inline char *put_ll(char *p, long long v)
     return p + nd;
 }
 
-RB_API int rocco_b200_write_bed3(const char *path, const char *const *names, int n_names, const int *name_idx,
-                                 const long long *starts, const long long *ends, size_t n, int name_features)
+}  // extern "C"
+namespace {
+// BED text of n records, formatted by a few host threads (one contiguous slice of records each) into one buffer kept
+// between calls (touching fresh pages costs more than the formatting itself).  `emit(ptr, bytes)` is called for the
+// slices in record order while the buffer is held.
+template <typename Emit>
+static int format_bed3(const char *const *names, int n_names, const int *name_idx, const long long *starts, const long long *ends,
+                       size_t n, int name_features, Emit emit)
 {
-    if (!path || !names || n_names <= 0 || (n && (!starts || !ends))) return rb::ST_INVALID;
-    FILE *fh = fopen(path, "wb");
-    if (!fh) { rb::set_error("cannot open %s for writing", path); return rb::ST_INVALID; }
     std::vector<size_t> len((size_t)n_names);
     size_t maxlen = 0;
     for (int k = 0; k < n_names; ++k) { len[k] = strlen(names[k]); maxlen = std::max(maxlen, len[k]); }
     const size_t per = (name_features ? 2 : 1) * (maxlen + 2 * 20 + 2) + 2;      // upper bound of one record's text
-    // records are formatted in parallel (a few host threads, one contiguous slice each) and written in order
     for (size_t i = 0; i < n; ++i) {
         const int c = name_idx ? name_idx[i] : 0;
-        if (c < 0 || c >= n_names) { fclose(fh); return rb::ST_INVALID; }
+        if (c < 0 || c >= n_names) return rb::ST_INVALID;
     }
     const unsigned hw = std::thread::hardware_concurrency();
     const size_t nthreads = std::max<size_t>(1, std::min<size_t>({(size_t)8, (size_t)(hw ? hw : 1), n / 8192 + 1}));
-    // one text buffer kept between calls (touching fresh pages costs more than the formatting itself)
     static std::mutex text_mu;
     static char *text = nullptr;
     static size_t text_cap = 0;
@@ -437,7 +438,7 @@ RB_API int rocco_b200_write_bed3(const char *path, const char *const *names, int
         free(text);
         text_cap = per * n + 1 + (per * n) / 4;
         text = (char *)malloc(text_cap);
-        if (!text) { text_cap = 0; fclose(fh); return rb::ST_NOMEM; }
+        if (!text) { text_cap = 0; return rb::ST_NOMEM; }
     }
     std::vector<size_t> used(nthreads, 0);
     auto work = [&](size_t t) {
@@ -464,9 +465,45 @@ RB_API int rocco_b200_write_bed3(const char *path, const char *const *names, int
     work(0);
     for (auto &th : pool) th.join();
     for (size_t t = 0; t < nthreads; ++t)
-        if (used[t] && fwrite(text + per * (n * t / nthreads), 1, used[t], fh) != used[t]) { fclose(fh); return rb::ST_INVALID; }
-    fclose(fh);
+        if (used[t] && !emit(text + per * (n * t / nthreads), used[t])) return rb::ST_INVALID;
     return 0;
+}
+}  // namespace
+extern "C" {
+
+RB_API int rocco_b200_write_bed3(const char *path, const char *const *names, int n_names, const int *name_idx,
+                                 const long long *starts, const long long *ends, size_t n, int name_features)
+{
+    if (!path || !names || n_names <= 0 || (n && (!starts || !ends))) return rb::ST_INVALID;
+    FILE *fh = fopen(path, "wb");
+    if (!fh) { rb::set_error("cannot open %s for writing", path); return rb::ST_INVALID; }
+    const int st = format_bed3(names, n_names, name_idx, starts, ends, n, name_features,
+                               [&](const char *p, size_t bytes) { return fwrite(p, 1, bytes, fh) == bytes; });
+    fclose(fh);
+    return st;
+}
+
+/* The same text written INTO an existing (or new) file at byte `offset`, without truncating it: several processes that
+ * know each other's text sizes assemble one BED file with no gather pass.  *bytes_written returns the text size. */
+RB_API int rocco_b200_write_bed3_at(const char *path, long long offset, const char *const *names, int n_names, const int *name_idx,
+                                    const long long *starts, const long long *ends, size_t n, int name_features,
+                                    long long *bytes_written)
+{
+    if (!path || offset < 0 || !names || n_names <= 0 || (n && (!starts || !ends))) return rb::ST_INVALID;
+    const int fd = open(path, O_WRONLY | O_CREAT, 0644);
+    if (fd < 0) { rb::set_error("cannot open %s for writing", path); return rb::ST_INVALID; }
+    long long pos = offset;
+    const int st = format_bed3(names, n_names, name_idx, starts, ends, n, name_features, [&](const char *p, size_t bytes) {
+        while (bytes) {
+            const ssize_t w = pwrite(fd, p, bytes, (off_t)pos);
+            if (w <= 0) return false;
+            p += w; bytes -= (size_t)w; pos += w;
+        }
+        return true;
+    });
+    close(fd);
+    if (bytes_written) *bytes_written = pos - offset;
+    return st;
 }
 
 /* combine_chrom_results (rocco.py:194-240) for canonical BED text, without a Python object per record: read every file,

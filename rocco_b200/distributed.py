@@ -85,3 +85,43 @@ def gather_runs(chrom_index, starts, ends, device=None):
         rec = np.concatenate([p[:, :k].cpu().numpy() for p, k in zip(parts, counts)], axis=1)
     order = np.lexsort((rec[1], rec[0]))
     return rec[0][order], rec[1][order], rec[2][order]
+
+
+def write_genome_bed(path: str, genome_names, my_names, runs, step: int, extras=(), device=None, first_start: int = 0):
+    """ONE BED file for the genome, written by all ranks together without a gather pass.
+
+    `genome_names`: every chromosome of the genome in the file's record order (the reference's combined BED sorts by the
+    chromosome STRING, rocco.py:74-95); `my_names`: this rank's chromosomes, `runs` their (local chromosome index, first
+    bin, last bin + 1) arrays as `pipeline.masks_to_runs` returns them.  One all-gather carries every rank's per-chromosome
+    text sizes (plus the integers in `extras`, which come back summed over ranks: e.g. selected bins and bins); each
+    rank then writes its chromosomes at their byte offsets (`pipeline.write_genome_bed_part`) and rank 0 fixes the file
+    length.  The file is complete once every rank has returned (callers synchronise before reading it).
+    Returns the list of summed extras."""
+    import numpy as np
+    import torch
+    from . import pipeline
+    dist = _dist()
+    rank, size = world()
+    genome_names = list(genome_names)
+    pos = np.array([genome_names.index(c) for c in my_names], dtype=np.int64)
+    sizes = np.zeros(len(genome_names), dtype=np.int64)
+    if len(my_names):
+        sizes[pos] = pipeline.bed_text_sizes(my_names, runs, step, first_start)
+    msg = np.concatenate([np.asarray(list(extras), dtype=np.int64), sizes])
+    if size > 1:
+        dev = device or "cpu"
+        mine = torch.from_numpy(msg).to(dev)
+        parts = [torch.zeros_like(mine) for _ in range(size)]
+        dist.all_gather(parts, mine)
+        allv = torch.stack(parts).cpu().numpy()
+    else:
+        allv = msg[None, :]
+    k = len(list(extras))
+    total_sizes = allv[:, k:].sum(axis=0)                      # one rank owns each chromosome
+    offsets = np.concatenate([[0], np.cumsum(total_sizes)[:-1]])
+    if len(my_names):
+        pipeline.write_genome_bed_part(path, list(my_names), runs, step, offsets[pos], first_start)
+    if rank == 0:
+        with open(path, "ab") as fh:                           # exact length, whatever an earlier file left behind
+            fh.truncate(int(total_sizes.sum()))
+    return [int(v) for v in allv[:, :k].sum(axis=0)]

@@ -384,6 +384,41 @@ def runs_to_bed_file(path: str, chrom_names, runs, step: int, first_start: int =
     return _lib.write_bed_arrays(path, list(chrom_names), chrom, first_start + starts * step, first_start + ends * step)
 
 
+_POW10 = np.array([10 ** k for k in range(1, 19)], dtype=np.int64)
+
+
+def bed_text_sizes(chrom_names, runs, step: int, first_start: int = 0) -> np.ndarray:
+    """Bytes of BED3 text each chromosome of `runs` will take (name, two tabs, newline, the digits of both coordinates) --
+    what a rank announces to the others before a genome BED is assembled with positioned writes (`write_genome_bed_part`)."""
+    chrom, starts, ends = runs
+    k = len(chrom_names)
+    if chrom.shape[0] == 0:
+        return np.zeros(k, dtype=np.int64)
+    s = first_start + starts * step
+    e = first_start + ends * step
+    if int(s.min(initial=0)) < 0:
+        raise ValueError("negative coordinates")
+    digits = (np.searchsorted(_POW10, s, side="right") + 1) + (np.searchsorted(_POW10, e, side="right") + 1)
+    name_len = np.array([len(str(c).encode("utf-8")) for c in chrom_names], dtype=np.int64)
+    per_chrom_digits = np.bincount(chrom, weights=digits, minlength=k).astype(np.int64)
+    counts = np.bincount(chrom, minlength=k).astype(np.int64)
+    return per_chrom_digits + counts * (name_len + 3)
+
+
+def write_genome_bed_part(path: str, chrom_names, runs, step: int, offsets, first_start: int = 0) -> int:
+    """This rank's chromosomes written into the shared genome BED at their byte offsets (`offsets[c]` for chromosome index c
+    of `chrom_names`; chromosomes without records are skipped).  Returns the bytes written."""
+    chrom, starts, ends = runs
+    bounds = np.searchsorted(chrom, np.arange(len(chrom_names) + 1))
+    total = 0
+    for c, name in enumerate(chrom_names):
+        a, b = int(bounds[c]), int(bounds[c + 1])
+        if b > a:
+            total += _lib.write_bed_arrays_at(path, int(offsets[c]), [name], None, first_start + starts[a:b] * step,
+                                              first_start + ends[a:b] * step)
+    return total
+
+
 def reorder_runs(runs, chrom_order):
     """Runs regrouped so that chromosome index `chrom_order[0]` comes first, then `chrom_order[1]`, ...  The runs of a
     shard arrive grouped by chromosome and sorted by start inside each group (`mask_to_runs`), so putting a genome into

@@ -44,6 +44,19 @@ def _worker(rank, size, port, out_dir):
                 fh.write("".join(f"{lex[c]}\t{50 * a}\t{50 * b}\n" for c, a, b in zip(*[r.tolist() for r in runs])))
         else:
             assert runs is None
+        # the positioned-write variant: every rank writes its chromosomes straight into ONE file (a stale, longer file is there)
+        shared = os.path.join(out_dir, "genome_positioned.bed")
+        if rank == 0:
+            with open(shared, "wb") as fh:
+                fh.write(b"#" * 200000)
+        dist.barrier()
+        my_names = [names[i] for i in mine]
+        local = {c: k for k, c in enumerate(my_names)}
+        my_runs = (np.array([local[c] for c, _, _ in recs], dtype=np.int32), np.array([a // 50 for _, a, _ in recs], dtype=np.int64),
+                   np.array([b // 50 for _, _, b in recs], dtype=np.int64))
+        tot = rd.write_genome_bed(shared, lex, my_names, my_runs, 50, extras=(sel, bins))
+        assert tot == [tot_sel, tot_bins]
+        dist.barrier()
         np.save(os.path.join(out_dir, f"tot_{rank}.npy"), np.array([tot_sel, tot_bins]))
         if rank == 0:
             with open(os.path.join(out_dir, "merged.bed"), "w") as fh:
@@ -84,6 +97,7 @@ def test_two_ranks_reproduce_single_rank(tmp_path):
     want = "".join(f"{c}\t{a}\t{b}\n" for c, a, b in orc.merge_bed_records(recs))
     assert open(tmp_path / "merged.bed").read() == want
     assert open(tmp_path / "merged_runs.bed").read() == want
+    assert open(tmp_path / "genome_positioned.bed").read() == want
     for r in range(2):
         assert np.load(tmp_path / f"tot_{r}.npy").tolist() == [sel, sum(sizes)]
 
