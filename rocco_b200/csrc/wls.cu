@@ -13,6 +13,7 @@
 #include <thread>
 
 #include "common.cuh"
+#include "select.cuh"
 #include "score.cuh"
 #include "trend.cuh"
 
@@ -58,51 +59,30 @@ __device__ __forceinline__ double load_logx(const void *x, int in_f32, long long
     return log2(fmax(v, 0.0) + 1.0);
 }
 
-// in-place bitonic sort of `len` (power of two) doubles in shared memory
-__device__ void bitonic_sort(double *s, int len)
-{
-    for (int k = 2; k <= len; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < len; i += blockDim.x) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const double a = s[i], b = s[ixj];
-                    const bool up = ((i & k) == 0);
-                    if ((a > b) == up) { s[i] = b; s[ixj] = a; }
-                }
-            }
-            __syncthreads();
-        }
-    }
-}
-
 constexpr int PILOT_CAP = 4096;
 
 // inference.py:333  np.median(matrix, axis=1): exact for n <= 4096, sampled above (see score.cuh)
 __global__ void __launch_bounds__(256) k_pilot(const void *x, int in_f32, long long n, long long row_stride, double *pilot)
 {
-    __shared__ double s[PILOT_CAP];
+    // the values are log2(max(x, 0) + 1) >= 0 (NaN -> +inf): their bit patterns order like the values, so the one or two
+    // middle ranks come from a radix select instead of a sort
+    __shared__ unsigned long long s[PILOT_CAP];
+    __shared__ SelScratch S;
     const long long row = blockIdx.x;
     const int take = (int)min((long long)PILOT_CAP, n);
-    int len = 1;
-    while (len < take) len <<= 1;
-    for (int k = threadIdx.x; k < len; k += blockDim.x) {
-        double v = INFINITY;
-        if (k < take) {
-            const long long i = (n <= PILOT_CAP) ? k : (long long)(((double)k + 0.5) * ((double)n / (double)PILOT_CAP));
-            v = load_logx(x, in_f32, row * row_stride + min(i, n - 1));
-            if (!(v == v)) v = INFINITY;
-        }
-        s[k] = v;
+    for (int k = threadIdx.x; k < take; k += 256) {
+        const long long i = (n <= PILOT_CAP) ? k : (long long)(((double)k + 0.5) * ((double)n / (double)PILOT_CAP));
+        double v = load_logx(x, in_f32, row * row_stride + min(i, n - 1));
+        if (!(v == v)) v = INFINITY;
+        s[k] = (unsigned long long)__double_as_longlong(v);
     }
     __syncthreads();
-    bitonic_sort(s, len);
-    if (threadIdx.x == 0) {
-        pilot[row] = (take & 1) ? s[take / 2] : (s[take / 2 - 1] + s[take / 2]) / 2.0;
-    }
+    const double hi = __longlong_as_double((long long)block_select<256>(s, take, take / 2, nullptr, 0ULL, S, nullptr, nullptr));
+    double lo = hi;
+    if (!(take & 1)) lo = __longlong_as_double((long long)block_select<256>(s, take, take / 2 - 1, nullptr, 0ULL, S, nullptr, nullptr));
+    if (threadIdx.x == 0) pilot[row] = (take & 1) ? hi : (lo + hi) / 2.0;
 }
 
-// exact mode: y keys of one row (>= 0, so the bit pattern orders like the value; NaN sorts last) and the median of the sorted row
 __global__ void k_pilot_keys(const void *x, int in_f32, long long n, long long base, unsigned long long *keys)
 {
     for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x)
