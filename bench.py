@@ -682,7 +682,7 @@ def main():
             d_ms, d_cnt, d_bytes = prof[dom]
             achieved = (d_bytes / 1e9) / (d_ms / 1e3) if d_ms > 0 else 0.0
             traffic, traffic_src = None, None
-            tpath = os.path.join(REPO, "profiles", "r1_traffic.json")
+            tpath = os.path.join(REPO, "profiles", "r2_traffic.json")
             if os.path.exists(tpath):
                 tj = json.load(open(tpath))
                 if dom in tj["kernels"]:
