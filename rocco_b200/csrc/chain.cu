@@ -165,6 +165,13 @@ struct Params {
     int *fz_write;
     TileOut *fz_out;            // [tile] the tile's fixed outputs
     double *fz_incl;            // [tile] +-HUGE: the saturated value it hands to its successor
+    // adaptive tree depth (nullptr: off): tiles that did real work in round r are counted in live_cnt[r & 1]; while that
+    // stays above live_threshold the rounds are throughput-bound and the controller asks for ONE level per round (a deeper
+    // tree evaluates 2^L - 1 multipliers to advance L levels); below it rounds are latency-bound and take levels_base
+    int *live_cnt;
+    int round_id;
+    int levels_base;
+    int live_threshold;
 };
 
 // ------------------------------------------------------------------ the tile kernel
@@ -229,15 +236,21 @@ __global__ void __launch_bounds__(THREADS, 4) k_chain_tiles(Params P)
             return;
         }
     }
+    if (!EMIT && P.live_cnt && !P.lex_pass && group == 0 && tid == 0) atomicAdd(&P.live_cnt[P.round_id & 1], 1);
     const bool fz_eval = fz_on && !P.lex_pass && group == 0;       // this CTA establishes the tile's state for the next round
     const double fz_width = sd.upper - sd.lower;
     __shared__ int s_fzlen[WARPS];
     __shared__ int s_fzlast;
 
-    // stage scores (coalesced) into the padded blocked layout
-    for (int e = tid; e < TILE; e += THREADS) {
-        double v = (e < len) ? __ldg(gsc + e) : 0.0;
-        s_sc[e + e / ITEMS] = v;
+    // stage scores (coalesced) into the padded blocked layout: all of a thread's loads are issued before the first store
+    // (eight at a time; sixteen dependent round trips to DRAM per thread otherwise: a third of a search round)
+#pragma unroll
+    for (int k0 = 0; k0 < ITEMS; k0 += 8) {
+        double v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const int e = tid + (k0 + k) * THREADS; v[k] = (e < len) ? __ldg(gsc + e) : 0.0; }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const int e = tid + (k0 + k) * THREADS; s_sc[e + e / ITEMS] = v[k]; }
     }
     if (VEC_COST) {
         // s_cs[e] = cost between bins (s0+e-1) and (s0+e);  e in [0, TILE]
@@ -704,7 +717,10 @@ __global__ void __launch_bounds__(256) k_chain_finish(Params P, int emit)
     const int c = blockIdx.x;
     const ChromDev cd = P.chroms[c];
     SearchDev sd = P.search[c];
-    if (blockIdx.x == 0 && threadIdx.x == 0) *P.ticket = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *P.ticket = 0;
+        if (P.live_cnt && !P.lex_pass) P.live_cnt[(P.round_id + 1) & 1] = 0;       // the next round's counter
+    }
     const bool active = P.lex_pass ? (sd.need_lex != 0)
                                    : !((sd.phase == PH_DONE && !emit) || sd.phase == PH_HOST);
     // (sequential-kernel chromosomes never set need_lex: their counts are already the reference's)
@@ -802,7 +818,9 @@ __global__ void __launch_bounds__(256) k_chain_finish(Params P, int emit)
             sd.nslots = 1;
             lam[0] = sd.upper;                            // dp.py:164 returns the upper end
         } else {
-            const int lv = min(sd.levels > 0 ? sd.levels : 1, sd.iters_left);
+            int pref = sd.levels > 0 ? sd.levels : 1;
+            if (P.live_cnt) pref = (P.live_cnt[P.round_id & 1] >= P.live_threshold) ? 1 : P.levels_base;
+            const int lv = min(pref, sd.iters_left);
             sd.levels = lv;
             sd.nslots = (1 << lv) - 1;
             gen_tree(sd, lam, lv);
@@ -1065,8 +1083,12 @@ static int solve_batch(const double *d_scores, const double *d_costs, const rocc
 {
     if (ntask <= 0) return 0;
     if (!d_scores || !tasks || !d_masks || !results) return ST_INVALID;
+    // levels <= 0 (default): two levels per round, dropping to ONE while more than LIVE_THRESHOLD tiles still do real work
+    // (throughput-bound rounds: a 2-level tree evaluates 3 multipliers to advance 2 levels).  An explicit value is used as is.
+    const bool adaptive = levels <= 0;
     if (levels <= 0) levels = 2;      // measured on B200: 1 GPU, hg38 x 100: L=2 49 ms, L=3 57 ms, L=4 84 ms per genome search
     levels = std::min(levels, MAX_LEVELS);
+    constexpr int LIVE_THRESHOLD = 1536;   // tiles: ~28 ns per tile and multiplier against a ~66 us floor per round (B200)
     RB_TRY(ensure_device());
 
     std::vector<ChromDev> chroms(ntask);
@@ -1138,7 +1160,8 @@ static int solve_batch(const double *d_scores, const double *d_costs, const rocc
 
     k_chain_minmax<<<dim3(ntask, nparts), 256, 0, st>>>(d_scores, w.d_chroms, w.d_search, w.d_partial);
     RB_LAUNCH_CHECK();
-    k_chain_init<<<(ntask + 63) / 64, 64, 0, st>>>(w.d_chroms, w.d_search, w.d_lam, w.d_partial, nparts, levels, ntask, vec ? 1 : 0);
+    const int init_levels = (adaptive && ntiles >= LIVE_THRESHOLD) ? 1 : levels;
+    k_chain_init<<<(ntask + 63) / 64, 64, 0, st>>>(w.d_chroms, w.d_search, w.d_lam, w.d_partial, nparts, init_levels, ntask, vec ? 1 : 0);
     RB_LAUNCH_CHECK();
 
     Params P{};
@@ -1161,8 +1184,15 @@ static int solve_batch(const double *d_scores, const double *d_costs, const rocc
         RB_CUDA(cudaMemsetAsync(d_fz[0], 0, sizeof(int) * (size_t)ntiles, st));
         RB_CUDA(cudaMemsetAsync(d_fz[1], 0, sizeof(int) * (size_t)ntiles, st));
     }
-    int fz_round = 0;
+    if (adaptive && any_search) {
+        RB_TRY(ar.alloc(&P.live_cnt, (size_t)2));
+        RB_CUDA(cudaMemsetAsync(P.live_cnt, 0, sizeof(int) * 2, st));
+        P.levels_base = levels;
+        P.live_threshold = LIVE_THRESHOLD;
+    }
+    int fz_round = 0, round_id = 0;
     auto search_round = [&](int nslots) -> int {
+        P.round_id = round_id++;
         if (freeze) { P.fz_read = d_fz[fz_round & 1]; P.fz_write = d_fz[(fz_round & 1) ^ 1]; ++fz_round; }
         return launch_round<false>(P, vec, nslots, epoch, any_seq, st);
     };
@@ -1182,10 +1212,30 @@ static int solve_batch(const double *d_scores, const double *d_costs, const rocc
         }
         if (need_bracket) RB_TRY(search_round(2));     // bracket ends
         // PH_BRACKET -> PH_BISECT generates the first tree in the same finish kernel
-        for (int r = 0; r < rounds; ++r) RB_TRY(search_round(max_slots));
+        if (!P.live_cnt) {
+            for (int r = 0; r < rounds; ++r) RB_TRY(search_round(max_slots));
+            RB_CUDA(cudaMemcpyAsync(hsearch.data(), w.d_search, sizeof(SearchDev) * ntask, cudaMemcpyDeviceToHost, st));
+            RB_CUDA(cudaStreamSynchronize(st));
+        } else {
+            // the depth of each round is chosen on the device, so the number of rounds is not known here: launch them in
+            // batches and look at the controllers' state (a few hundred bytes) after each; a round launched for chromosomes
+            // that are already done costs ~20 us
+            int upper = 0;                             // rounds still needed if every one of them took a single level
+            for (int c = 0; c < ntask; ++c)
+                if (chroms[c].mode == 1 && (hsearch[c].phase == PH_BRACKET || hsearch[c].phase == PH_BISECT))
+                    upper = std::max(upper, hsearch[c].phase == PH_BRACKET ? chroms[c].max_iter : hsearch[c].iters_left);
+            for (;;) {
+                const int batch = std::min(upper, 12);
+                for (int r = 0; r < batch; ++r) RB_TRY(search_round(max_slots));
+                RB_CUDA(cudaMemcpyAsync(hsearch.data(), w.d_search, sizeof(SearchDev) * ntask, cudaMemcpyDeviceToHost, st));
+                RB_CUDA(cudaStreamSynchronize(st));
+                upper = 0;
+                for (int c = 0; c < ntask; ++c)
+                    if (chroms[c].mode == 1 && hsearch[c].phase == PH_BISECT) upper = std::max(upper, hsearch[c].iters_left);
+                if (upper <= 0) break;
+            }
+        }
         // rare: bracket expansion (dp.py:119-125, 132-138) is driven from the host with single solves
-        RB_CUDA(cudaMemcpyAsync(hsearch.data(), w.d_search, sizeof(SearchDev) * ntask, cudaMemcpyDeviceToHost, st));
-        RB_CUDA(cudaStreamSynchronize(st));
         bool any_host = false;
         for (int c = 0; c < ntask; ++c) any_host |= (hsearch[c].phase == PH_HOST);
         if (any_host) {
