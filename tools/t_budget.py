@@ -1,6 +1,6 @@
 """Timing of the device-resident budget null at BASELINE config sizes (scratch tool)."""
-import sys, time, torch
-sys.path.insert(0, '/root/repo')
+import os, sys, time, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from rocco_b200 import pipeline, _lib
 from rocco_b200.synth import chrom_matrix_torch, chrom_bins, chrom_seed
 dev = torch.device('cuda', 0)

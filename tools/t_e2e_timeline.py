@@ -1,7 +1,7 @@
 """Timeline of the e2e leg: per-thread start/end of each public-API call (scratch tool, not part of the product)."""
 import sys, time, os, numpy as np, torch, threading
 from concurrent.futures import ThreadPoolExecutor
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import rocco_b200
 from rocco_b200.synth import chrom_matrix_torch, chrom_bins, HG38_SIZES, HG_PARAMS, chrom_seed
 dev = torch.device('cuda', 0)

@@ -1,6 +1,6 @@
 """H2D rate from pinned memory alone vs while scoring kernels run on another stream (scratch tool)."""
-import sys, time, threading, torch
-sys.path.insert(0, '/root/repo')
+import os, sys, time, threading, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from rocco_b200 import pipeline
 from rocco_b200.synth import chrom_matrix_torch, chrom_bins, chrom_seed
 dev = torch.device('cuda', 0)
