@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(XC_THREADS) k_xcollect(const double *__restric
 // order, like the reference's comparator (wls_backend.c:207-230) -- which is all T6 needs: the first slot_brank pairs
 // belong to the lower bin, the rest to the upper one.
 template <int THREADS, int CAP_LO, int CAP_HI>
-__global__ void __launch_bounds__(THREADS) k_xselect(TrendBuffers T, long long n, int B)
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_xselect(TrendBuffers T, long long n, int B)
 {
     extern __shared__ unsigned long long s_sel[];         // x keys [cap], then y keys [cap] for boundary slots
     __shared__ SelScratch S;
@@ -540,7 +540,7 @@ __global__ void __launch_bounds__(THREADS) k_xselect(TrendBuffers T, long long n
 // that outgrew its slot is still exact when every value in it is the same (variances sitting on the 1e-8 floor): the
 // overflow's min / max were tracked by T6.
 template <int THREADS, int CAP_LO, int CAP_HI>
-__global__ void __launch_bounds__(THREADS) k_yselect(TrendBuffers T, long long n, int B)
+__global__ void __launch_bounds__(THREADS, CAP_HI <= 4096 ? 1024 / THREADS : 1) k_yselect(TrendBuffers T, long long n, int B)
 {
     extern __shared__ unsigned long long s_sel[];
     __shared__ SelScratch S;
