@@ -176,6 +176,22 @@ def test_every_steady_tile_kernel_matches_the_oracle(rb, oracle, mode, rows, n):
     assert np.max(np.abs(got - want)) <= 2e-9, float(np.max(np.abs(got - want)))
 
 
+@pytest.mark.parametrize("n", [250001, 250002, 250003])
+def test_float32_rows_of_every_alignment_class_give_the_float64_bits(rb, n):
+    """float32 storage: four row-alignment classes for the 16-byte bulk copies (row length mod 4); the scores must equal, bit
+    for bit, those of the same values stored as float64 (the reference widens to float64 first, inference.py:40-47)"""
+    import torch
+    from rocco_b200 import pipeline
+    from rocco_b200.synth import chrom_matrix_torch
+    dev = torch.device("cuda", 0)
+    x32 = chrom_matrix_torch(5, n, 7 + n % 5, dev, torch.float32)
+    prm = pipeline.score_params(prior_df=6.0)
+    s32, d32 = pipeline.score_loci_wls_device(x32, params=prm, details=True)
+    s64, d64 = pipeline.score_loci_wls_device(x32.to(torch.float64), params=prm, details=True)
+    assert torch.equal(d32["centered_matrix"], d64["centered_matrix"])
+    assert torch.equal(s32, s64)
+
+
 def test_baseline_small_n_is_zero(rb):
     from rocco_b200 import _baseline
     assert np.array_equal(_baseline.crossfit_whittaker_baseline(np.arange(24.0), 5.0), np.zeros(24))
