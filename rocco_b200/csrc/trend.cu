@@ -113,6 +113,8 @@ struct TrendBuffers {
     double *ycand;         // [m][MAXB][2][CAPY]
     int *ycand_cnt;        // [m][MAXB][2]
     unsigned long long *yover_min, *yover_max;   // [m][MAXB][2]  bit-pattern range of the variances that did not fit their slot
+    unsigned short *codes;  // [m][code_stride]  T3 -> T6: bin << 10 | variance bucket of every pair (0xFFFF: not T6's business)
+    long long code_stride;  // n rounded up to a multiple of 8 (128-bit loads)
     long long rows;
     BucketGeom geom;
     int capy;              // capacity of a ycand slot
@@ -422,6 +424,7 @@ __global__ void __launch_bounds__(XC_THREADS) k_xcollect(const double *__restric
         const double *c = C + row * row_stride, *v = V + row * row_stride;
         double2 *cand = T.cand + (size_t)row * MAXSLOT * CAPX;
         int *ccnt = T.cand_cnt + row * MAXSLOT;
+        unsigned short *codes = T.codes + row * T.code_stride;
         const int yb0 = P.yb0;
         // eight independent loads in flight per thread, then the table lookups, then the slot counters (independent global
         // atomics, all in flight together), and only then the stores and histogram updates that depend on them
@@ -444,11 +447,14 @@ __global__ void __launch_bounds__(XC_THREADS) k_xcollect(const double *__restric
             for (int u = 0; u < U; ++u) {
                 const unsigned e = es[u];
                 if (e == 0xFFFFFFFFu) continue;
-                if (e < 0xFF00u) {
-                    if (pos[u] < CAPX) cand[(size_t)(e >> 8) * CAPX + pos[u]] = make_double2(xs[u], ys[u]);
-                    if (e & 0x80u) continue;                        // boundary bucket: its bin is settled by T4
+                unsigned short code = 0xFFFFu;
+                if (e < 0xFF00u && pos[u] < CAPX) cand[(size_t)(e >> 8) * CAPX + pos[u]] = make_double2(xs[u], ys[u]);
+                if (!(e < 0xFF00u && (e & 0x80u))) {                // (boundary bucket: its bin is settled by T4)
+                    const int bin = (int)(e & 31u), yb = ybucket(ys[u], yb0, T.geom);
+                    atomicAdd(&s_yh[bin * NBY + yb], 1);
+                    code = (unsigned short)((bin << 10) | yb);
                 }
-                atomicAdd(&s_yh[(int)(e & 31u) * NBY + ybucket(ys[u], yb0, T.geom)], 1);
+                codes[jb + u * XC_THREADS + threadIdx.x] = code;    // T6 reads two bytes per pair instead of sixteen
             }
         }
         __syncthreads();
@@ -753,44 +759,48 @@ __device__ __forceinline__ void ycollect_one(TrendBuffers &T, long long row, con
     else if (yb == t.x) ycollect_append(T, row, bin, 0, y);
 }
 
-__global__ void __launch_bounds__(ST_THREADS) k_ycollect(const double *__restrict__ C, const double *__restrict__ V, long long n,
-                                                         long long row_stride, TrendBuffers T, int B)
+__global__ void __launch_bounds__(ST_THREADS) k_ycollect(const double *__restrict__ V, long long n, long long row_stride, TrendBuffers T, int B)
 {
-    __shared__ unsigned short s_tab[NBX];
+    // T3 left (bin, variance bucket) of every pair as a 16-bit code: this pass reads those two bytes per pair, eight pairs per
+    // 128-bit load, and fetches the variance itself only for the ~2 % that sit in a bin's median bucket(s)
     __shared__ int2 s_yb[MAXB];
+    __shared__ long long s_lo[MAXB];
     const long long row = blockIdx.y;
     const RowPlan &P = T.plan[row];
     if (P.fallback) return;
-    bucket_table(s_tab, T.lut + row * NBX, T.binlo + row * NBX, P, ST_THREADS);
     for (int k = threadIdx.x; k < MAXB; k += ST_THREADS) s_yb[k] = k < B ? make_int2(P.ym_bucket[k][0], P.ym_bucket[k][1]) : make_int2(-1, -1);
     __syncthreads();
     const long long c0 = (long long)blockIdx.x * CHUNK, c1 = min(n, c0 + CHUNK);
-    const double *c = C + row * row_stride, *v = V + row * row_stride;
-    const int yb0 = P.yb0;
-    constexpr int U = 8;
-    for (long long jb = c0; jb < c1; jb += U * ST_THREADS) {
-        double xs[U], ys[U];
+    const double *v = V + row * row_stride;
+    const unsigned short *codes = T.codes + row * T.code_stride;
+    for (long long jb = c0 + 8LL * threadIdx.x; jb < c1; jb += 8LL * ST_THREADS) {
+        const uint4 q = *reinterpret_cast<const uint4 *>(codes + jb);
+        const unsigned w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const long long j = jb + u * ST_THREADS + threadIdx.x;
-            xs[u] = (j < c1) ? fabs(c[j]) : -1.0;
-            ys[u] = (j < c1) ? v[j] : 0.0;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (xs[u] < 0.0) continue;
-            const unsigned e = s_tab[xbucket(xs[u], T.geom)];
-            if (e < 0xFF00u && (e & 0x80u)) continue;               // boundary buckets: handled from the partitioned slot below
-            ycollect_one(T, row, s_yb, (int)(e & 31u), ys[u], yb0);
+        for (int u = 0; u < 8; ++u) {
+            const unsigned code = (w[u >> 1] >> (16 * (u & 1))) & 0xFFFFu;
+            const long long j = jb + u;
+            if (code == 0xFFFFu || j >= c1) continue;
+            const int bin = (int)(code >> 10), yb = (int)(code & 1023u);
+            const int2 t = s_yb[bin];
+            const int k = yb == t.y ? 1 : (yb == t.x ? 0 : -1);
+            if (k >= 0) ycollect_append(T, row, bin, k, v[j]);      // ~2 % of the pairs (deferring these atomics was measured slower)
         }
     }
-    if (blockIdx.x == 0) {
-        for (int sl = 0; sl < P.nslot; ++sl) {
-            if (!P.slot_boundary[sl]) continue;
-            const double2 *cand = T.cand + ((size_t)row * MAXSLOT + sl) * CAPX;
-            const long long pre = P.slot_prefix[sl];
-            for (int k = threadIdx.x; k < P.slot_count[sl]; k += ST_THREADS)
-                ycollect_one(T, row, s_yb, bin_of_rank(pre + k, n, B), cand[k].y, P.yb0);
+    // the partitioned / sorted boundary slots of T4 (their pairs carry no code): shared out over the row's CTAs; the bin of
+    // rank r is the number of bin boundaries floor(b n / B), b >= 1, at or below r
+    for (int b = threadIdx.x; b < B; b += ST_THREADS) s_lo[b] = ((long long)b * n) / B;
+    __syncthreads();
+    for (int sl = blockIdx.x; sl < P.nslot; sl += gridDim.x) {
+        if (!P.slot_boundary[sl]) continue;
+        const double2 *cand = T.cand + ((size_t)row * MAXSLOT + sl) * CAPX;
+        const long long pre = P.slot_prefix[sl];
+        int bin0 = 0;
+        while (bin0 + 1 < B && s_lo[bin0 + 1] <= pre) ++bin0;
+        for (int k = threadIdx.x; k < P.slot_count[sl]; k += ST_THREADS) {
+            int bin = bin0;
+            while (bin + 1 < B && s_lo[bin + 1] <= pre + k) ++bin;
+            ycollect_one(T, row, s_yb, bin, cand[k].y, P.yb0);
         }
     }
 }
@@ -936,6 +946,8 @@ int trend_knots_select(const double *d_C, double *d_V, long long m, long long n,
     RB_TRY(ar.alloc(&T.yhist, (size_t)m * MAXB * NBY));
     RB_TRY(ar.alloc(&T.ycand, (size_t)m * MAXB * 2 * T.capy));
     RB_TRY(ar.alloc(&T.ycand_cnt, (size_t)m * MAXB * 2));
+    T.code_stride = (n + 7) & ~7LL;
+    RB_TRY(ar.alloc(&T.codes, (size_t)m * (size_t)T.code_stride));
     RB_CUDA(cudaMemsetAsync(T.xhist, 0, sizeof(int) * (size_t)m * NBX, st));
     RB_CUDA(cudaMemsetAsync(T.cand_cnt, 0, sizeof(int) * (size_t)m * MAXSLOT, st));
     RB_CUDA(cudaMemsetAsync(T.yhist, 0, sizeof(int) * (size_t)m * MAXB * NBY, st));
@@ -993,7 +1005,7 @@ int trend_knots_select(const double *d_C, double *d_V, long long m, long long n,
         RB_LAUNCH_CHECK();
     }
     {
-        RB_PROF("trend_xcollect", st, (double)m * n * 16.0);
+        RB_PROF("trend_xcollect", st, (double)m * n * 18.0);
         k_xcollect<<<(unsigned)sm_count(), XC_THREADS, sm_collect, st>>>(d_C, d_V, n, row_stride, T, B);
         RB_LAUNCH_CHECK();
     }
@@ -1016,8 +1028,8 @@ int trend_knots_select(const double *d_C, double *d_V, long long m, long long n,
         RB_LAUNCH_CHECK();
     }
     {
-        RB_PROF("trend_ycollect", st, (double)m * n * 16.0);
-        k_ycollect<<<gstream, ST_THREADS, 0, st>>>(d_C, d_V, n, row_stride, T, B);
+        RB_PROF("trend_ycollect", st, (double)m * n * 2.0);
+        k_ycollect<<<gstream, ST_THREADS, 0, st>>>(d_V, n, row_stride, T, B);
         RB_LAUNCH_CHECK();
     }
     {

@@ -176,10 +176,12 @@ def test_every_steady_tile_kernel_matches_the_oracle(rb, oracle, mode, rows, n):
     assert np.max(np.abs(got - want)) <= 2e-9, float(np.max(np.abs(got - want)))
 
 
-@pytest.mark.parametrize("n", [250001, 250002, 250003])
-def test_float32_rows_of_every_alignment_class_give_the_float64_bits(rb, n):
-    """float32 storage: four row-alignment classes for the 16-byte bulk copies (row length mod 4); the scores must equal, bit
-    for bit, those of the same values stored as float64 (the reference widens to float64 first, inference.py:40-47)"""
+@pytest.mark.parametrize("n", [250000, 250001, 250002, 250003])
+def test_float32_rows_of_every_alignment_class_match_float64_storage(rb, n):
+    """float32 storage: four row-alignment classes for the 16-byte bulk copies (row length mod 4).  The reference widens to
+    float64 first (inference.py:40-47), so the same values stored either way must score alike: bit for bit when the rows of
+    both layouts fall in the same alignment class (n a multiple of 4: identical tile regions), and within the halo
+    truncation (1e-11) otherwise, where the regions start a few bins apart."""
     import torch
     from rocco_b200 import pipeline
     from rocco_b200.synth import chrom_matrix_torch
@@ -188,8 +190,11 @@ def test_float32_rows_of_every_alignment_class_give_the_float64_bits(rb, n):
     prm = pipeline.score_params(prior_df=6.0)
     s32, d32 = pipeline.score_loci_wls_device(x32, params=prm, details=True)
     s64, d64 = pipeline.score_loci_wls_device(x32.to(torch.float64), params=prm, details=True)
-    assert torch.equal(d32["centered_matrix"], d64["centered_matrix"])
-    assert torch.equal(s32, s64)
+    if n % 4 == 0:
+        assert torch.equal(d32["centered_matrix"], d64["centered_matrix"]) and torch.equal(s32, s64)
+    else:
+        assert float((d32["centered_matrix"] - d64["centered_matrix"]).abs().max()) <= 1e-11
+        assert float((s32 - s64).abs().max()) <= 1e-9 * max(1.0, float(s64.abs().max()))
 
 
 def test_baseline_small_n_is_zero(rb):
