@@ -763,28 +763,81 @@ __global__ void __launch_bounds__(ST_THREADS) k_ycollect(const double *__restric
 {
     // T3 left (bin, variance bucket) of every pair as a 16-bit code: this pass reads those two bytes per pair, eight pairs per
     // 128-bit load, and fetches the variance itself only for the ~2 % that sit in a bin's median bucket(s)
+    constexpr int YQ_CAP = 8192;                         // matches queued per 131072-pair chunk (typically ~2600)
+    static_assert(CHUNK <= (1 << 17), "queue entries keep the offset inside the chunk in 17 bits");
     __shared__ int2 s_yb[MAXB];
     __shared__ long long s_lo[MAXB];
+    __shared__ unsigned s_q[YQ_CAP];
+    __shared__ int s_qn;
+    __shared__ int s_cnt[2 * MAXB], s_base[2 * MAXB];
+    extern __shared__ unsigned char s_hit[];             // [32768] per code: 0 = not wanted, 1 + k = the bin's median bucket k
     const long long row = blockIdx.y;
     const RowPlan &P = T.plan[row];
     if (P.fallback) return;
     for (int k = threadIdx.x; k < MAXB; k += ST_THREADS) s_yb[k] = k < B ? make_int2(P.ym_bucket[k][0], P.ym_bucket[k][1]) : make_int2(-1, -1);
+    for (int k = threadIdx.x; k < 32768 / 16; k += ST_THREADS) reinterpret_cast<uint4 *>(s_hit)[k] = make_uint4(0u, 0u, 0u, 0u);
+    if (threadIdx.x == 0) s_qn = 0;
+    if (threadIdx.x < 2 * MAXB) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    if (threadIdx.x < 2 * B) {                           // (k = 0 first: when both medians share a bucket it is filed as k = 1)
+        const int bin = threadIdx.x >> 1, k = threadIdx.x & 1;
+        const int yb = k ? s_yb[bin].y : s_yb[bin].x;
+        if (yb >= 0 && yb < NBY && !(k == 0 && yb == s_yb[bin].y)) s_hit[(bin << 10) | yb] = (unsigned char)(1 + k);
+    }
     __syncthreads();
     const long long c0 = (long long)blockIdx.x * CHUNK, c1 = min(n, c0 + CHUNK);
     const double *v = V + row * row_stride;
     const unsigned short *codes = T.codes + row * T.code_stride;
-    for (long long jb = c0 + 8LL * threadIdx.x; jb < c1; jb += 8LL * ST_THREADS) {
-        const uint4 q = *reinterpret_cast<const uint4 *>(codes + jb);
-        const unsigned w[4] = {q.x, q.y, q.z, q.w};
+    constexpr int YU = 4;                                // 128-bit loads in flight per thread
+    for (long long jb0 = c0 + 8LL * threadIdx.x; jb0 < c1; jb0 += 8LL * ST_THREADS * YU) {
+        uint4 qs[YU];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const unsigned code = (w[u >> 1] >> (16 * (u & 1))) & 0xFFFFu;
-            const long long j = jb + u;
-            if (code == 0xFFFFu || j >= c1) continue;
-            const int bin = (int)(code >> 10), yb = (int)(code & 1023u);
-            const int2 t = s_yb[bin];
-            const int k = yb == t.y ? 1 : (yb == t.x ? 0 : -1);
-            if (k >= 0) ycollect_append(T, row, bin, k, v[j]);      // ~2 % of the pairs (deferring these atomics was measured slower)
+        for (int r = 0; r < YU; ++r) {
+            const long long jb = jb0 + 8LL * ST_THREADS * r;
+            qs[r] = jb < c1 ? *reinterpret_cast<const uint4 *>(codes + jb) : make_uint4(~0u, ~0u, ~0u, ~0u);
+        }
+#pragma unroll
+        for (int r = 0; r < YU; ++r) {
+            const long long jb = jb0 + 8LL * ST_THREADS * r;
+            const unsigned w[4] = {qs[r].x, qs[r].y, qs[r].z, qs[r].w};
+            const int valid = (int)min(8LL, c1 - jb);    // (<= 0 for the all-ones filler; < 8 only at the end of the row)
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const unsigned code = (w[u >> 1] >> (16 * (u & 1))) & 0xFFFFu;
+                const unsigned hit = code < 0x8000u ? s_hit[code] : 0u;
+                if (hit && u < valid) {
+                    // ~2 % of the pairs.  A global atomic round trip here would stall the warp once per match: matches are
+                    // queued in shared memory (target << 17 | offset in the chunk) and filed by the whole CTA afterwards
+                    // (a ballot-aggregated push was measured slower)
+                    const int bin = (int)(code >> 10), k = (int)hit - 1;
+                    const int qp = atomicAdd(&s_qn, 1);
+                    if (qp < YQ_CAP) { s_q[qp] = ((unsigned)(bin * 2 + k) << 17) | (unsigned)(jb + u - c0); atomicAdd(&s_cnt[bin * 2 + k], 1); }
+                    else ycollect_append(T, row, bin, k, v[jb + u]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int qn = min(s_qn, YQ_CAP);
+    // one global atomic per (CTA, slot) reserves the slot's range for this chunk's matches -- every CTA of a row bumping the
+    // same 2B counters once per match was what this pass spent its time on -- and the matches take consecutive places in it
+    if (threadIdx.x < 2 * MAXB) {
+        const int c = s_cnt[threadIdx.x];
+        s_base[threadIdx.x] = c ? atomicAdd(&T.ycand_cnt[(size_t)row * MAXB * 2 + threadIdx.x], c) : 0;
+        s_cnt[threadIdx.x] = 0;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < qn; i += ST_THREADS) {
+        const unsigned e = s_q[i];
+        const int tgt = (int)(e >> 17);
+        const double y = v[c0 + (e & 0x1FFFFu)];
+        const int pos = s_base[tgt] + atomicAdd(&s_cnt[tgt], 1);
+        const size_t slot = (size_t)row * MAXB * 2 + tgt;
+        if (pos < T.capy) T.ycand[slot * T.capy + pos] = y;
+        else {                                                   // massive ties (variances on their floor): remember the range
+            const unsigned long long key = (unsigned long long)__double_as_longlong(y);
+            atomicMin(&T.yover_min[slot], key);
+            atomicMax(&T.yover_max[slot], key);
         }
     }
     // the partitioned / sorted boundary slots of T4 (their pairs carry no code): shared out over the row's CTAs; the bin of
@@ -967,6 +1020,7 @@ int trend_knots_select(const double *d_C, double *d_V, long long m, long long n,
     const size_t sm_plan = sizeof(int) * (NBX + 258) + sizeof(double) * YSAMPLE + sizeof(SelScratch);
     if (!attr) {
         RB_CUDA(cudaFuncSetAttribute(k_xhist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_xhist));
+        RB_CUDA(cudaFuncSetAttribute(k_ycollect, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768));
         RB_CUDA(cudaFuncSetAttribute(k_xcollect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(int) * MAXB * NBY + 2 * NBX)));
         RB_CUDA(cudaFuncSetAttribute(k_xresolve<512, 4096, CAPX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_resolve));
         RB_CUDA(cudaFuncSetAttribute(k_xresolve<512, 2048, 4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double2) * 4096)));
@@ -1029,7 +1083,7 @@ int trend_knots_select(const double *d_C, double *d_V, long long m, long long n,
     }
     {
         RB_PROF("trend_ycollect", st, (double)m * n * 2.0);
-        k_ycollect<<<gstream, ST_THREADS, 0, st>>>(d_V, n, row_stride, T, B);
+        k_ycollect<<<gstream, ST_THREADS, 32768, st>>>(d_V, n, row_stride, T, B);
         RB_LAUNCH_CHECK();
     }
     {
