@@ -47,8 +47,7 @@ constexpr int YSAMPLE = 2048;
 constexpr int MAXB = 32;                // bins per row (n < 2^31)
 constexpr int MAXSLOT = 3 * MAXB;
 constexpr int CAPX = 8192;              // pairs per x slot
-constexpr int CAPY = 8192;              // variances per (bin, k) slot (rows > 6 M bins: 2x, see TrendBuffers::capy)
-constexpr int CAPY_MAX = 16384;
+constexpr int CAPY_MAX = 16384;         // variances per (bin, k) slot (TrendBuffers::capy)
 constexpr int CHUNK = 131072;           // elements streamed per CTA
 constexpr int ST_THREADS = 512;
 int trend_fused_max_window() { return 1025; }
@@ -110,7 +109,7 @@ struct TrendBuffers {
     double2 *cand;         // [m][MAXSLOT][CAPX]
     int *cand_cnt;         // [m][MAXSLOT]
     int *yhist;            // [m][MAXB][NBY]
-    double *ycand;         // [m][MAXB][2][CAPY]
+    double *ycand;         // [m][MAXB][2][capy]
     int *ycand_cnt;        // [m][MAXB][2]
     unsigned long long *yover_min, *yover_max;   // [m][MAXB][2]  bit-pattern range of the variances that did not fit their slot
     unsigned short *codes;  // [m][code_stride]  T3 -> T6: bin << 10 | variance bucket of every pair (0xFFFF: not T6's business)
@@ -909,7 +908,7 @@ __device__ void yresolve_bin(TrendBuffers &T, long long n, int B, long long row,
 // (bins blockIdx.x, blockIdx.x + gridDim.x, ... of row blockIdx.y: k_yselect leaves almost nothing, so the grid is thin)
 __global__ void __launch_bounds__(256) k_yresolve(TrendBuffers T, long long n, int B)
 {
-    extern __shared__ double s_v[];              // CAPY
+    extern __shared__ double s_v[];              // capy
     __shared__ int s_skip;
     if (threadIdx.x == 0) s_skip = T.plan[blockIdx.y].fallback;
     __syncthreads();
