@@ -1088,7 +1088,7 @@ static int solve_batch(const double *d_scores, const double *d_costs, const rocc
     const bool adaptive = levels <= 0;
     if (levels <= 0) levels = 2;      // measured on B200: 1 GPU, hg38 x 100: L=2 49 ms, L=3 57 ms, L=4 84 ms per genome search
     levels = std::min(levels, MAX_LEVELS);
-    constexpr int LIVE_THRESHOLD = 1536;   // tiles: ~28 ns per tile and multiplier against a ~66 us floor per round (B200)
+    constexpr int LIVE_THRESHOLD = 3072;   // tiles: ~28 ns per tile and multiplier against a ~66 us floor per round (B200); 1950-tile shards measured better at 2 levels
     RB_TRY(ensure_device());
 
     std::vector<ChromDev> chroms(ntask);
