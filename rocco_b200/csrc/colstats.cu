@@ -4,9 +4,11 @@
 // np.quantile(method="nearest") / scipy.stats.tmean in a Python loop over bins / np.mean) and
 // rocco.py:307-355 (score_dispersion_chrom: scipy median_abs_deviation / iqr / np.std / tstd).
 //
-// One thread per bin.  Loads are coalesced along the bin axis (thread j reads X[i, j] for every sample i);
-// the column is kept in shared memory as [sample][thread] (conflict-free) and insertion-sorted there, so all
-// order statistics are exact.  Sums follow NumPy's own association order -- sequential over rows for axis-0
+// One thread per bin.  Loads are coalesced along the bin axis (thread j reads X[i, j] for every sample i).  Median,
+// nearest-rank quantile, MAD and IQR read one to four ranks of the column: the thread keeps just the smallest (and / or
+// largest) values needed to reach them in a short sorted list in shared memory, [slot][thread] (conflict-free)
+// (k_colstat_ranks).  Trimmed mean / std need the whole column: it is insertion-sorted in shared memory (k_colstat).
+// All order statistics are exact.  Sums follow NumPy's own association order -- sequential over rows for axis-0
 // reductions of a C-contiguous matrix, pairwise (8 accumulators, blocks of 128) for the 1-D reductions that
 // scipy's tmean/tstd perform per column -- so means and standard deviations reproduce the reference's bits.
 #include "common.cuh"
@@ -190,6 +192,74 @@ __global__ void k_colstat(Params P)
     P.out[j] = np_power(result, P.power);
 }
 
+// ---- order statistics that need only a few ranks: MEDIAN, QUANTILE, MAD, IQR
+// Instead of sorting the whole column, a thread keeps the `cap` smallest (ascending list) and / or the `cap` largest
+// (descending list) values seen so far -- half the shared memory per column (twice the resident warps) and fewer than half
+// the compare-and-shift steps for a median.  Lists live in shared memory as [slot][thread] (conflict-free).
+struct PartialLists { int cap_lo, cap_hi; };
+
+template <bool SMALLEST>
+__device__ __forceinline__ void partial_insert(double *L, int tb, int cap, int &len, double v)
+{
+    auto before = [](double a, double b) { return SMALLEST ? a < b : a > b; };      // a sorts before b
+    if (len == cap) {
+        if (!before(v, L[(cap - 1) * tb])) return;       // not among the kept ones
+        --len;                                           // the last kept value drops out
+    }
+    int q = len;
+    while (q > 0 && before(v, L[(q - 1) * tb])) { L[q * tb] = L[(q - 1) * tb]; --q; }
+    L[q * tb] = v;
+    ++len;
+}
+
+__global__ void k_colstat_ranks(Params P, PartialLists C)
+{
+    extern __shared__ double s_col[];                 // [cap_lo + cap_hi][tb]
+    const int tb = P.tb;
+    const long long j = (long long)blockIdx.x * tb + threadIdx.x;
+    if (j >= P.n) return;
+    const long long m = P.m;
+    double *lo = s_col + threadIdx.x;                 // ascending: the cap_lo smallest
+    double *hi = s_col + (size_t)C.cap_lo * tb + threadIdx.x;      // descending: the cap_hi largest
+    int nlo = 0, nhi = 0;
+    for (long long i = 0; i < m; ++i) {
+        const double v = ldx(P, i, j);
+        if (C.cap_lo) partial_insert<true>(lo, tb, C.cap_lo, nlo, v);
+        if (C.cap_hi) partial_insert<false>(hi, tb, C.cap_hi, nhi, v);
+    }
+    // ascending rank r of the column (the caller sized the lists so that every rank asked for is covered)
+    auto rank = [&](long long r) { return r < C.cap_lo ? lo[r * tb] : hi[(m - 1 - r) * tb]; };
+    auto median_of = [&]() { return (m & 1) ? rank(m / 2) : __dadd_rn(rank(m / 2 - 1), rank(m / 2)) / 2.0; };
+    double result = 0.0;
+    const int stat = P.stat;
+    if (stat == ROCCO_STAT_MEDIAN) {
+        result = median_of();
+    } else if (stat == ROCCO_STAT_QUANTILE) {
+        long long k = round_half_even((double)(m - 1) * P.arg0);
+        k = k < 0 ? 0 : (k >= m ? m - 1 : k);
+        result = rank(k);
+    } else if (stat == ROCCO_STAT_MAD) {
+        const double med = median_of();
+        nlo = 0;                                       // second pass: the smallest |x - med| (same list, same capacity)
+        for (long long i = 0; i < m; ++i) partial_insert<true>(lo, tb, C.cap_lo, nlo, fabs(__dsub_rn(ldx(P, i, j), med)));
+        result = median_of();
+    } else {                                           // IQR (scipy.stats.iqr, linear interpolation)
+        double pv[2];
+        for (int k = 0; k < 2; ++k) {
+            const double q = (k == 0 ? P.arg0 : P.arg1) / 100.0;
+            const double vi = (double)(m - 1) * q;
+            double prev = floor(vi);
+            long long ip = (long long)prev, in = ip + 1;
+            if (vi >= (double)(m - 1)) { ip = m - 1; in = m - 1; }
+            if (vi < 0) { ip = 0; in = 0; }
+            const double gamma = __dsub_rn(vi, prev);
+            pv[k] = lerp_np(rank(ip), rank(in), gamma);
+        }
+        result = __dsub_rn(pv[1], pv[0]);
+    }
+    P.out[j] = np_power(result, P.power);
+}
+
 __global__ void k_single_row(Params P)
 {
     // m == 1: central tendency = row ** power; dispersion = zeros ** power (rocco.py:254-255, 318-319)
@@ -211,6 +281,59 @@ static int run(const void *d_x, int dtype, size_t m, size_t n, int stat, double 
     P.arg0 = arg0; P.arg1 = arg1; P.power = power;
     if (m == 1) {
         k_single_row<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P);
+        RB_LAUNCH_CHECK();
+        return 0;
+    }
+    // ranks wanted by the order-statistic modes -> list capacities (ascending ranks below cap_lo, the rest from the top)
+    if (stat == ROCCO_STAT_MEDIAN || stat == ROCCO_STAT_QUANTILE || stat == ROCCO_STAT_MAD || stat == ROCCO_STAT_IQR) {
+        long long r_min = 0, r_max = 0;                    // smallest and largest 0-based rank read
+        const long long mm = (long long)m;
+        auto clampr = [&](long long r) { return r < 0 ? 0 : (r >= mm ? mm - 1 : r); };
+        if (stat == ROCCO_STAT_MEDIAN || stat == ROCCO_STAT_MAD) { r_min = (mm & 1) ? mm / 2 : mm / 2 - 1; r_max = mm / 2; }
+        else if (stat == ROCCO_STAT_QUANTILE) { r_min = r_max = clampr((long long)nearbyint((double)(mm - 1) * arg0)); }
+        else {
+            long long lo_r = mm, hi_r = -1;
+            for (int k = 0; k < 2; ++k) {
+                const double vi = (double)(mm - 1) * ((k == 0 ? arg0 : arg1) / 100.0);
+                long long ip = (long long)floor(vi), in = ip + 1;
+                if (vi >= (double)(mm - 1)) { ip = mm - 1; in = mm - 1; }
+                if (vi < 0) { ip = 0; in = 0; }
+                lo_r = std::min(lo_r, std::min(clampr(ip), clampr(in))); hi_r = std::max(hi_r, std::max(clampr(ip), clampr(in)));
+            }
+            r_min = lo_r; r_max = hi_r;
+        }
+        // one ascending list up to r_max, or one descending list down to r_min, or both split at the middle -- whichever is smallest
+        PartialLists C{};
+        const long long only_lo = r_max + 1, only_hi = mm - r_min;
+        long long split = only_lo;                          // ranks < mm/2+1 from the bottom, the others from the top
+        if (stat == ROCCO_STAT_IQR) {
+            // two rank pairs: the lower pair from the bottom, the upper pair from the top
+            long long pair_hi[2], pair_lo[2];
+            for (int k = 0; k < 2; ++k) {
+                const double vi = (double)(mm - 1) * ((k == 0 ? arg0 : arg1) / 100.0);
+                long long ip = (long long)floor(vi), in = ip + 1;
+                if (vi >= (double)(mm - 1)) { ip = mm - 1; in = mm - 1; }
+                if (vi < 0) { ip = 0; in = 0; }
+                pair_lo[k] = clampr(std::min(ip, in)); pair_hi[k] = clampr(std::max(ip, in));
+            }
+            const int a = pair_hi[0] <= pair_hi[1] ? 0 : 1, b = 1 - a;      // a: the lower percentile
+            const long long both = (pair_hi[a] + 1) + (mm - pair_lo[b]);
+            if (both < std::min(only_lo, only_hi) && pair_hi[a] + 1 <= pair_lo[b]) { C.cap_lo = (int)(pair_hi[a] + 1); C.cap_hi = (int)(mm - pair_lo[b]); split = -1; }
+        }
+        if (split >= 0) {
+            if (stat == ROCCO_STAT_MAD || only_lo <= only_hi) { C.cap_lo = (int)only_lo; C.cap_hi = 0; }     // (MAD reuses the ascending list)
+            else { C.cap_lo = 0; C.cap_hi = (int)only_hi; }
+        }
+        const size_t slots = (size_t)C.cap_lo + (size_t)C.cap_hi;
+        const size_t budget_r = 200 * 1024;
+        int tbr = 128;
+        while (tbr > 32 && slots * tbr * 8 > budget_r) tbr -= 32;
+        if (slots * tbr * 8 > budget_r) { set_error("column statistics support at most %zu samples", budget_r / (8 * 32)); return ST_INVALID; }
+        P.tb = tbr;
+        const size_t smem_r = slots * tbr * sizeof(double);
+        RB_CUDA(cudaFuncSetAttribute(k_colstat_ranks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget_r));
+        RB_PROF("k_colstat", st, (double)m * n * (dtype ? 4.0 : 8.0) + 8.0 * n);
+        k_colstat_ranks<<<(unsigned)((n + tbr - 1) / tbr), tbr, smem_r, st>>>(P, C);
         RB_LAUNCH_CHECK();
         return 0;
     }
