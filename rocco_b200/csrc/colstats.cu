@@ -132,42 +132,7 @@ __global__ void k_colstat(Params P)
             while (q > 0 && S(q - 1) > v) { S(q) = S(q - 1); --q; }
             S(q) = v;
         }
-        auto median_sorted = [&]() { return (m & 1) ? S(m / 2) : __dadd_rn(S(m / 2 - 1), S(m / 2)) / 2.0; };
-        if (stat == ROCCO_STAT_MEDIAN) {
-            result = median_sorted();
-        } else if (stat == ROCCO_STAT_QUANTILE) {
-            long long k = round_half_even((double)(m - 1) * P.arg0);
-            k = k < 0 ? 0 : (k >= m ? m - 1 : k);
-            result = S(k);
-        } else if (stat == ROCCO_STAT_MAD) {
-            const double med = median_sorted();
-            // |x - med| of a sorted column is V-shaped: merge the two monotone halves to reach the middle ranks
-            long long lo = 0;                                   // first index with S >= med
-            while (lo < m && S(lo) < med) ++lo;
-            long long a = lo - 1, b = lo;                       // a walks down (values below med), b walks up
-            double prev = 0.0, cur = 0.0;
-            const long long need = m / 2;                       // 0-based rank of the upper middle
-            for (long long r = 0; r <= need; ++r) {
-                const double da = (a >= 0) ? __dsub_rn(med, S(a)) : INFINITY;
-                const double db = (b < m) ? __dsub_rn(S(b), med) : INFINITY;
-                prev = cur;
-                if (da <= db) { cur = da; --a; } else { cur = db; ++b; }
-            }
-            result = (m & 1) ? cur : __dadd_rn(prev, cur) / 2.0;
-        } else if (stat == ROCCO_STAT_IQR) {
-            double pv[2];
-            for (int k = 0; k < 2; ++k) {
-                const double q = (k == 0 ? P.arg0 : P.arg1) / 100.0;
-                const double vi = (double)(m - 1) * q;
-                double prev = floor(vi);
-                long long ip = (long long)prev, in = ip + 1;
-                if (vi >= (double)(m - 1)) { ip = m - 1; in = m - 1; }
-                if (vi < 0) { ip = 0; in = 0; }
-                const double gamma = __dsub_rn(vi, prev);
-                pv[k] = lerp_np(S(ip), S(in), gamma);
-            }
-            result = __dsub_rn(pv[1], pv[0]);
-        } else {                                               // TMEAN / TSTD: nearest-rank limits, inclusive
+        {                                                      // TMEAN / TSTD: nearest-rank limits, inclusive (the rank-only modes run in k_colstat_ranks)
             long long kl = round_half_even((double)(m - 1) * P.arg0);
             long long kh = round_half_even((double)(m - 1) * (1.0 - P.arg0));
             kl = kl < 0 ? 0 : (kl >= m ? m - 1 : kl);
