@@ -149,3 +149,32 @@ def test_reorder_runs_equals_a_lexsort_of_the_records():
     assert np.array_equal(got[0], lex_rank[runs[0]][o]) and np.array_equal(got[1], runs[1][o]) and np.array_equal(got[2], runs[2][o])
     empty = pipeline.reorder_runs((np.zeros(0, np.int32), np.zeros(0, np.int64), np.zeros(0, np.int64)), lex_order)
     assert all(a.shape == (0,) for a in empty)
+
+
+def test_bed_text_sizes_and_positioned_writes_reproduce_the_plain_writer(tmp_path):
+    """the byte count announced per chromosome (digits of both coordinates, name, two tabs, newline) is exactly the text the
+    native formatter produces, also at digit-count boundaries; positioned writes of the parts rebuild the one-call file"""
+    from rocco_b200 import pipeline
+    names = ["chr1", "chr10", "chrUn_KI270742v1", "chrX"]
+    edge = np.array([0, 9, 10, 99, 100, 999, 1000, 99999, 100000, 4294967295, 4294967296, 10 ** 12], dtype=np.int64)
+    rng = np.random.default_rng(5)
+    chrom, starts = [], []
+    for k in range(len(names)):
+        vals = edge if k == 0 else (np.zeros(0, np.int64) if k == 2 else np.sort(rng.choice(5_000_000, 300, replace=False)))
+        chrom += [k] * len(vals)
+        starts += vals.tolist()
+    runs = (np.array(chrom, np.int32), np.array(starts, np.int64), np.array(starts, np.int64) + 7)
+    want = pipeline.runs_to_bed_text(names, runs, 1)
+    sizes = pipeline.bed_text_sizes(names, runs, 1)
+    per = [sum(len(line) + 1 for line in want.splitlines() if line.split("\t")[0] == nm) for nm in names]
+    assert sizes.tolist() == per and sizes[2] == 0
+    one = tmp_path / "one.bed"
+    pipeline.runs_to_bed_file(str(one), names, runs, 1)
+    assert one.read_text() == want
+    parts = tmp_path / "parts.bed"
+    parts.write_bytes(b"?" * (int(sizes.sum()) + 1000))                      # stale, longer content
+    offsets = np.concatenate([[0], np.cumsum(sizes)[:-1]])
+    assert pipeline.write_genome_bed_part(str(parts), names, runs, 1, offsets) == int(sizes.sum())
+    with open(parts, "ab") as fh:
+        fh.truncate(int(sizes.sum()))
+    assert parts.read_text() == want
